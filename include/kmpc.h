@@ -1,0 +1,131 @@
+/*
+ * kmpc.h -- C ABI of the B200-native batched unicycle-MPC solver (libkmpc.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of rtarun1/kiss-mpc: the per-step NLP solve
+ *     mpc/optimizer.py:319-400   MotionPlanner.solve(...)          (the call made by mpc/agent.py:139-152)
+ *     mpc/optimizer.py:354       ca.nlpsol("solver", "ipopt", ...) (rebuilt on every call)
+ *     mpc/optimizer.py:375-391   solver(x0=..., lbx, ubx, lbg, ubg, p=[current_state; goal_state])
+ * Every entry point below names the reference interface it replaces.  Plain C types only: no torch, no C++.
+ * All compute entry points launch hand-written sm_100a CUDA kernels; there is NO CPU fallback in this library.
+ *
+ * Conventions
+ *   - float64 everywhere (the reference computes in float64 through CasADi/IPOPT).
+ *   - B independent problem instances ("agents") per call; one CUDA thread solves one instance.
+ *   - I/O layouts, selected per handle by kmpc_config.layout:
+ *       KMPC_LAYOUT_INSTANCE_MAJOR (0): x_cur[B][3], goal[B][3], X[B][3][N+1], U[B][2][N], obs[B][O][2]
+ *            == what B stacked reference calls hold: states_matrix (3,N+1), controls_matrix (2,N) (optimizer.py:392-400)
+ *       KMPC_LAYOUT_BATCH_MINOR    (1): x_cur[3][B], goal[3][B], X[3][N+1][B], U[2][N][B], obs[O][2][B]
+ *            structure-of-arrays with the instance index fastest (fully coalesced loads/stores on the device).
+ *   - per-instance solver outcome uses IPOPT's ApplicationReturnStatus numbering (the reference discards it,
+ *     optimizer.py:375-400 reads only solution["x"]):
+ *         0 Solve_Succeeded, -1 Maximum_Iterations_Exceeded, -2 Restoration_Failed (restoration phase would be
+ *         needed), -3 Error_In_Step_Computation, 4 Diverging_Iterates, -13 Invalid_Number_Detected.
+ *   - functions return 0 on success, a negative KMPC_E_* code otherwise; nothing throws across the ABI.
+ */
+#ifndef KMPC_H
+#define KMPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMPC_VERSION 100
+
+#define KMPC_LAYOUT_INSTANCE_MAJOR 0
+#define KMPC_LAYOUT_BATCH_MINOR 1
+
+#define KMPC_COST_README 0       /* README.md:15-27: W_v- min(0,v)^2 + W_v+ max(0,v)^2 */
+#define KMPC_COST_CODE_LITERAL 1 /* optimizer.py:91-96: 300 * fmin(v, 0), linear */
+
+#define KMPC_E_BADARG (-1)
+#define KMPC_E_CUDA (-2)
+#define KMPC_E_NOMEM (-3)
+#define KMPC_E_NODEVICE (-4)
+
+#define KMPC_NO_BOUND 1e19 /* |bound| >= 1e19 means "no bound" (IPOPT nlp_lower/upper_bound_inf) */
+
+/* Problem + solver options.  Replaces MotionPlanner.__init__(time_step, horizon) (optimizer.py:40-77), the hard-coded
+ * weights (optimizer.py:57-60), the IPOPT option dict (optimizer.py:344-352) and the bound tuples that
+ * get_optimization_variable_bounds builds per call (optimizer.py:111-156). */
+typedef struct kmpc_config {
+    int32_t N;          /* horizon (optimizer.py:40)                                                       */
+    int32_t O_max;      /* obstacle slots per instance (0 = none); optimizer.py:198-258                     */
+    int32_t cost_mode;  /* KMPC_COST_*                                                                      */
+    int32_t goal_k_lo;  /* goal cost over k = goal_k_lo..goal_k_hi: README 1..N, code 1..N-1 (optimizer.py:80) */
+    int32_t goal_k_hi;
+    int32_t max_iter;   /* optimizer.py:346 (2000)                                                          */
+    int32_t B_max;      /* largest batch kmpc_solve will be called with (sizes the device workspace)        */
+    int32_t layout;     /* KMPC_LAYOUT_*                                                                    */
+    int32_t device;     /* CUDA device ordinal                                                              */
+    int32_t reserved;
+    double T;           /* time_step (optimizer.py:40)                                                      */
+    double W[3];        /* optimizer.py:57   diag(100,100,50)                                               */
+    double Wv_neg;      /* optimizer.py:59   300                                                            */
+    double Wv_pos;      /* README.md:24      0                                                              */
+    double Ww;          /* optimizer.py:60   10                                                             */
+    double lo[4];       /* lower bounds of x, y, v, omega (theta is free: optimizer.py:114-115)             */
+    double hi[4];
+    double tol;         /* IPOPT tol (1e-8; optimizer.py:348 sets acceptable_tol to the same value)         */
+} kmpc_config;
+
+typedef struct kmpc_handle kmpc_handle;
+
+/* Library identity / sizing (no reference equivalent). */
+int kmpc_version(void);
+size_t kmpc_workspace_bytes(const kmpc_config *cfg);
+
+/* Replaces MotionPlanner(time_step, horizon) (optimizer.py:40; called once per agent at agent.py:62):
+ * binds a device, allocates the device workspace for B_max instances.  One handle = one device = one host thread at a time. */
+int kmpc_create(const kmpc_config *cfg, kmpc_handle **out);
+void kmpc_destroy(kmpc_handle *h);
+const char *kmpc_last_error(const kmpc_handle *h);
+
+/* Replaces MotionPlanner.solve (optimizer.py:319-400) for B instances at once.  DEVICE pointers owned by the caller;
+ * asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream).
+ *   x_cur, goal           current_state / goal_state          (optimizer.py:390  p = [current_state; goal_state])
+ *   X0, U0                states_matrix / controls_matrix     (optimizer.py:376-385 primal warm start); both NULL = the
+ *                         cold start of agent.py:59-60 (X = tile(x_cur), U = 0) synthesised on chip
+ *   obs_centers, O        static/dynamic obstacle circle centres (optimizer.py:217-221), 0 <= O <= O_max; NULL iff O == 0
+ *   obs_radius            uniform obstacle radius (optimizer.py:231-245 uses the first obstacle's radius for all)
+ *   inflation             inflation_radius = lower bound of the distance rows (optimizer.py:254-258; agent.py:149)
+ *   X_out, U_out          the returned (3,N+1) / (2,N) matrices (optimizer.py:392-400)
+ *   obj_out, status_out, iters_out   new outputs (the reference never reads IPOPT's stats); each may be NULL. */
+int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
+               const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
+               double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream);
+
+/* Same call with HOST pointers (what a ctypes/NumPy caller such as the reference's agent.py holds): stages through the
+ * handle's pinned buffers, copies host->device, solves, copies device->host and synchronises before returning. */
+int kmpc_solve_host(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
+                    const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
+                    double *obj_out, int32_t *status_out, int32_t *iters_out);
+
+/* Batched EgoAgent.step hand-off (agent.py:139-155 + agent.py:70-72): after a solve, on the device,
+ *   applied[b] = U[:,0]  (agent.py:154-155),  x_cur[b] <- X[:,1] (the "perfect model" state hand-off, agent.py:70-72);
+ * X/U stay in place as the next solve's UNSHIFTED warm start (agent.py:139-145).  Device pointers, handle layout. */
+int kmpc_agent_handoff(kmpc_handle *h, int B, const double *X, const double *U, double *x_cur, double *applied_out,
+                       void *cuda_stream);
+
+/* Measurement helpers (no reference equivalent). */
+typedef struct kmpc_stats {
+    double last_kernel_ms;    /* device time of the solver kernel of the last kmpc_solve on this handle (CUDA events on its stream) */
+    int64_t launches;         /* kernels launched by this handle since creation */
+    int32_t slots;            /* resident solver threads (workspace slots) */
+    int32_t blocks;           /* grid size of the solver kernel */
+    int32_t threads_per_block;
+    int32_t sm_count;
+    int64_t trips;            /* total solver-loop trips of the last solve (sum over threads), if timing enabled */
+} kmpc_stats;
+int kmpc_set_timing(kmpc_handle *h, int enable); /* enable: kmpc_solve records events + syncs to fill last_kernel_ms */
+int kmpc_get_stats(kmpc_handle *h, kmpc_stats *out);
+/* FP64 FMA-pipe micro-benchmark on the handle's device: returns measured DFMA TFLOP/s (the roofline denominator of
+ * the solver kernel; MEASURED_PEAKS.json has no FP64 entry). */
+int kmpc_measure_fp64_peak(kmpc_handle *h, double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMPC_H */

@@ -1,0 +1,34 @@
+"""Builds libkmpc.so (the CUDA solver + C ABI) in-tree with nvcc for sm_100a.  nvcc cross-compiles without a GPU."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(_HERE, "csrc", "kmpc.cu")
+DEPS = [SRC, os.path.join(_HERE, "csrc", "kmpc_core.cuh"), os.path.join(_HERE, "..", "include", "kmpc.h")]
+SO = os.path.join(_HERE, "libkmpc.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
+              "-Xcompiler", "-fPIC", "-cudart", "shared"]
+
+
+def nvcc_path() -> str:
+    for p in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if p and (os.path.isabs(p) and os.path.exists(p) or not os.path.isabs(p)):
+            return p
+    return "nvcc"
+
+
+def stale() -> bool:
+    return not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(p) for p in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if force or stale():
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC]
+        subprocess.check_call(cmd)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,909 @@
+// kmpc_core.cuh -- per-instance primal-dual interior-point solver for the unicycle MPC NLP, written for ONE CUDA
+// thread per problem instance with all per-instance state in a structure-of-arrays HBM workspace (row r of slot s
+// lives at ws[r * S + s], so every load/store of a warp is one contiguous 256-byte segment).
+//
+// What it replaces: the arithmetic behind mpc/optimizer.py:354 (ca.nlpsol "ipopt") + :375-391 (the solve call):
+// IPOPT's filter line-search interior point method (Waechter & Biegler 2006; IPOPT 3.14 defaults + the options of
+// optimizer.py:344-352) applied to the NLP that optimizer.py:79-317 builds (README.md:15-81 form by default).
+// The linear algebra is NOT IPOPT's (MUMPS LDL^T on the 246x246 sparse KKT): the block-tridiagonal KKT system is
+// solved by a Riccati recursion over the 3-state/2-control stages, with the inertia test "every Q_uu is positive
+// definite" standing in for MUMPS' inertia count (equivalent because the dynamics Jacobian has full row rank).
+//
+// Control flow is a state machine ("trip" = [backward Riccati sweep] -> [forward roll-out] -> [trial-point
+// evaluation + speculative iterate/dual update] -> [scalar filter logic]) so that the 32 instances of a warp execute
+// the same heavy code every trip no matter whether a lane is in a Newton step, an inertia-correction retry, a
+// second-order correction, a back-tracking trial or the initial least-squares multiplier estimate.
+//
+// The code is plain C++ in KMPC_HD functions: the CUDA kernel in kmpc.cu wraps it; tests/host_emul compiles the very
+// same source with g++ to check the algorithm against the oracle on the GPU-less build machine (test harness only --
+// the product library contains only the CUDA path).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <float.h>
+
+#ifdef __CUDACC__
+#define KMPC_HD __host__ __device__ __forceinline__
+#define KMPC_HDN __host__ __device__
+#else
+#define KMPC_HD inline
+#define KMPC_HDN
+#endif
+
+namespace kmpc {
+
+// ---- IPOPT 3.14 defaults (option names in brackets) ----
+#define K_BOUND_RELAX 1e-8        /* bound_relax_factor */
+#define K_SCALING_MAX_GRAD 100.0  /* nlp_scaling_max_gradient */
+#define K_SCALING_MIN 1e-8        /* nlp_scaling_min_value */
+#define K_BOUND_PUSH 0.01         /* bound_push */
+#define K_BOUND_FRAC 0.01         /* bound_frac */
+#define K_YINIT_MAX 1e3           /* constr_mult_init_max */
+#define K_MU_INIT 0.1             /* mu_init */
+#define K_TAU_MIN 0.99            /* tau_min */
+#define K_KAPPA_EPS 10.0          /* barrier_tol_factor */
+#define K_MU_LIN 0.2              /* mu_linear_decrease_factor */
+#define K_MU_SUPER 1.5            /* mu_superlinear_decrease_power */
+#define K_S_MAX 100.0             /* s_max */
+#define K_KAPPA_SIGMA 1e10        /* kappa_sigma */
+#define K_KAPPA_D 1e-5            /* kappa_d */
+#define K_GAMMA_THETA 1e-5
+#define K_GAMMA_PHI 1e-8
+#define K_ETA_PHI 1e-8
+#define K_S_THETA 1.1
+#define K_S_PHI 2.3
+#define K_DELTA_LS 1.0
+#define K_THETA_MAX_FACT 1e4
+#define K_THETA_MIN_FACT 1e-4
+#define K_ALPHA_MIN_FRAC 0.05
+#define K_ALPHA_RED 0.5
+#define K_MAX_SOC 4
+#define K_KAPPA_SOC 0.99
+#define K_OBJ_MAX_INC 5.0
+#define K_DW_INIT 1e-4            /* first_hessian_perturbation */
+#define K_DW_MIN 1e-20
+#define K_DW_MAX 1e20
+#define K_DW_INC_FIRST 100.0
+#define K_DW_INC 8.0
+#define K_DW_DEC (1.0 / 3.0)
+#define K_DUAL_INF_TOL 1.0
+#define K_CONSTR_VIOL_TOL 1e-4
+#define K_COMPL_INF_TOL 1e-4
+#define K_DIVERGING 1e20
+#define K_FILTER_CAP 24
+
+enum { ST_SUCCESS = 0, ST_MAXITER = -1, ST_RESTORATION = -2, ST_STEP_ERROR = -3, ST_DIVERGING = 4, ST_INVALID = -13 };
+enum { M_FETCH = 0, M_LSQ = 1, M_NEWTON = 2, M_SOC = 3, M_TRIAL = 4, M_DONE = 5 };
+enum { TU_INIT = 0, TU_STEP = 1 };
+
+// Row map of the per-slot workspace (all offsets in rows of S doubles).
+struct Rows {
+    int N, O;
+    // inside one state buffer
+    int sX, sU, sY, sZ, sCS, sS, sYD, sVL, state_rows;
+    int rState[2];
+    int rK, rKff, rP, rPv;
+    // inside one step buffer
+    int dX, dU, dY, dS, dYD, step_rows;
+    int rStep[2];
+    int rCsoc, rDsoc, rFilt, rSc, total;
+};
+
+KMPC_HD Rows make_rows(int N, int O) {
+    Rows L;
+    L.N = N; L.O = O;
+    int NO = N * O, o = 0;
+    L.sX = o; o += 3 * (N + 1);
+    L.sU = o; o += 2 * N;
+    L.sY = o; o += 3 * (N + 1);
+    L.sZ = o; o += 8 * (N + 1);
+    L.sCS = o; o += 2 * N;
+    L.sS = o; o += NO;
+    L.sYD = o; o += NO;
+    L.sVL = o; o += NO;
+    L.state_rows = o;
+    int r = 0;
+    L.rState[0] = r; r += L.state_rows;
+    L.rState[1] = r; r += L.state_rows;
+    L.rK = r; r += 6 * N;
+    L.rKff = r; r += 2 * N;
+    L.rP = r; r += 6 * (N + 1);
+    L.rPv = r; r += 3 * (N + 1);
+    o = 0;
+    L.dX = o; o += 3 * (N + 1);
+    L.dU = o; o += 2 * N;
+    L.dY = o; o += 3 * (N + 1);
+    L.dS = o; o += NO;
+    L.dYD = o; o += NO;
+    L.step_rows = o;
+    L.rStep[0] = r; r += L.step_rows;
+    L.rStep[1] = r; r += L.step_rows;
+    L.rCsoc = r; r += 3 * (N + 1);
+    L.rDsoc = r; r += NO;
+    L.rFilt = r; r += 2 * K_FILTER_CAP;
+    L.rSc = r; r += 6 + 2 * O;
+    L.total = r;
+    return L;
+}
+
+// Per-solve constants (kernel parameter, by value).
+struct Cfg {
+    int N, O, cost_mode, gk_lo, gk_hi, max_iter, layout, B;
+    int hasL[4], hasU[4];  // x, y, v, omega
+    int nb, m;             // number of bound sides incl. obstacle slacks; number of constraint rows
+    double T, W[3], Wvn, Wvp, Ww;
+    double lb[4], ub[4];   // relaxed bounds
+    double tol, obs_radius, dL;
+    Rows L;
+};
+
+// I/O pointers (device memory owned by the caller)
+struct IO {
+    const double *x_cur, *goal, *X0, *U0, *obs;
+    double *X_out, *U_out, *obj;
+    int32_t *status, *iters;
+};
+
+struct Stats {  // residual norms + merit ingredients of one point
+    double f, bar, damp, theta, dinf, pinf, mn, mx, sumy, sumz, wmax;
+};
+
+struct Ctx {  // per-thread solver state (registers / local memory)
+    int mode, inst, iter, cur, nsteps, soc_count, fn, trips;
+    double mu, tau, delta, delta_last, df, theta_max, theta_min;
+    double alpha, alpha_test, alpha_min, alpha_du, alpha_du0, alpha_soc, gBD, theta_soc_old, theta_trial;
+    Stats c;  // current iterate
+};
+
+KMPC_HD double dmin0(double v) { return v < 0 ? 1.0 : (v == 0 ? 0.5 : 0.0); }
+KMPC_HD double dmax0(double v) { return v > 0 ? 1.0 : (v == 0 ? 0.5 : 0.0); }
+KMPC_HD bool cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * DBL_EPSILON * fabs(bas); }
+KMPC_HD void sincos_(double a, double *s, double *c) {
+#ifdef __CUDA_ARCH__
+    sincos(a, s, c);
+#else
+    *s = sin(a); *c = cos(a);
+#endif
+}
+
+#define RW(r) wsp[(size_t)(r) * S]
+
+// I/O index helpers (kmpc.h layouts)
+KMPC_HD size_t io_vec3(const Cfg &c, int b, int j) { return c.layout ? (size_t)j * c.B + b : (size_t)b * 3 + j; }
+KMPC_HD size_t io_X(const Cfg &c, int b, int j, int k) {
+    return c.layout ? ((size_t)j * (c.N + 1) + k) * c.B + b : ((size_t)b * 3 + j) * (c.N + 1) + k;
+}
+KMPC_HD size_t io_U(const Cfg &c, int b, int j, int k) {
+    return c.layout ? ((size_t)j * c.N + k) * c.B + b : ((size_t)b * 2 + j) * c.N + k;
+}
+KMPC_HD size_t io_obs(const Cfg &c, int b, int o, int j) {
+    return c.layout ? ((size_t)o * 2 + j) * c.B + b : ((size_t)b * c.O + o) * 2 + j;
+}
+
+// cost gradient of v (scaled) and its second derivative; optimizer.py:91-96 (literal) / README.md:23-24
+KMPC_HD void vcost(const Cfg &c, double df, double v, double *g, double *h) {
+    if (c.cost_mode == 0) {
+        double a = dmin0(v), b = dmax0(v);
+        *g = df * (2.0 * c.Wvn * fmin(v, 0.0) * a + 2.0 * c.Wvp * fmax(v, 0.0) * b);
+        *h = df * (2.0 * c.Wvn * a * a + 2.0 * c.Wvp * b * b);
+    } else {
+        *g = df * c.Wvn * dmin0(v);
+        *h = 0.0;
+    }
+}
+
+// barrier contributions of one bounded variable at the current iterate:
+//   sigma = zL/sl + zU/su,  rb = -mu/sl + mu/su (+- kappa_d mu for one-sided bounds)
+KMPC_HD void bound_terms(double val, double lb, double ub, int hL, int hU, double zL, double zU, double mu, double *sigma,
+                         double *rb) {
+    double sg = 0.0, r = 0.0;
+    if (hL) { double sl = val - lb; sg += zL / sl; r -= mu / sl; if (!hU) r += K_KAPPA_D * mu; }
+    if (hU) { double su = ub - val; sg += zU / su; r += mu / su; if (!hL) r -= K_KAPPA_D * mu; }
+    *sigma = sg; *rb = r;
+}
+
+// fraction-to-the-boundary of one bounded variable for the primal step d, and of its multipliers for the
+// induced dual steps; accumulates the directional derivative of the barrier term.
+KMPC_HD void bound_ftb(double val, double d, double lb, double ub, int hL, int hU, double zL, double zU, double mu,
+                       double tau, double *apr, double *adu) {
+    if (hL) {
+        double sl = val - lb;
+        if (d < 0) *apr = fmin(*apr, -tau * sl / d);
+        double dz = mu / sl - zL - zL / sl * d;
+        if (dz < 0) *adu = fmin(*adu, -tau * zL / dz);
+    }
+    if (hU) {
+        double su = ub - val;
+        if (d > 0) *apr = fmin(*apr, tau * su / d);
+        double dz = mu / su - zU + zU / su * d;
+        if (dz < 0) *adu = fmin(*adu, -tau * zU / dz);
+    }
+}
+
+// trial-point treatment of one bounded variable: new multipliers (with the kappa_sigma safeguard), barrier product,
+// damping, complementarity stats.  Returns false if the trial value is not strictly inside its bounds.
+KMPC_HD bool bound_trial(double val, double d, double vt, double lb, double ub, int hL, int hU, double zL, double zU,
+                         double mu, double adu, bool clamp, double *zLn, double *zUn, double *prod, double *damp,
+                         Stats *st) {
+    bool ok = true;
+    *zLn = 0.0; *zUn = 0.0;
+    if (hL) {
+        double sl = val - lb, sn = vt - lb;
+        if (!(sn > 0)) ok = false;
+        *prod *= sn;
+        if (!hU) *damp += sn;
+        double z = zL + adu * (mu / sl - zL - zL / sl * d);
+        if (clamp) z = fmax(fmin(z, K_KAPPA_SIGMA * mu / sn), mu / (K_KAPPA_SIGMA * sn));
+        *zLn = z;
+        double p = sn * z;
+        st->mn = fmin(st->mn, p); st->mx = fmax(st->mx, p); st->sumz += fabs(z);
+    }
+    if (hU) {
+        double su = ub - val, sn = ub - vt;
+        if (!(sn > 0)) ok = false;
+        *prod *= sn;
+        if (!hL) *damp += sn;
+        double z = zU + adu * (mu / su - zU + zU / su * d);
+        if (clamp) z = fmax(fmin(z, K_KAPPA_SIGMA * mu / sn), mu / (K_KAPPA_SIGMA * sn));
+        *zUn = z;
+        double p = sn * z;
+        st->mn = fmin(st->mn, p); st->mx = fmax(st->mx, p); st->sumz += fabs(z);
+    }
+    return ok;
+}
+
+KMPC_HD double maxabs_nan(double m, double v) { double t = fabs(v); return (t > m || t != t) ? t : m; }
+
+// ------------------------------------------------------------------------------------------------
+// INIT pass: starting point (optimizer.py:375-385; cold start agent.py:59-60), objective scaling, push into the
+// interior, z = 1, y = 0, slacks.  Writes state buffer 0.
+// ------------------------------------------------------------------------------------------------
+KMPC_HDN inline void pass_init(const Cfg &c, Ctx &t, double *wsp, size_t S, const IO &io) {
+    const int N = c.N, O = c.O, b = t.inst;
+    const Rows &L = c.L;
+    const int sb = L.rState[0];
+    double xc[3], gl[3];
+    for (int j = 0; j < 3; ++j) {
+        xc[j] = io.x_cur[io_vec3(c, b, j)]; gl[j] = io.goal[io_vec3(c, b, j)];
+        RW(L.rSc + j) = xc[j]; RW(L.rSc + 3 + j) = gl[j];
+    }
+    for (int o = 0; o < O; ++o) for (int j = 0; j < 2; ++j) RW(L.rSc + 6 + 2 * o + j) = io.obs[io_obs(c, b, o, j)];
+    double gm = 0.0;
+    const double dLpush = c.dL + K_BOUND_PUSH * fmax(1.0, fabs(c.dL));
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+        double x[3];
+        for (int j = 0; j < 3; ++j) x[j] = io.X0 ? io.X0[io_X(c, b, j, k)] : xc[j];
+        if (k >= c.gk_lo && k <= c.gk_hi)
+            for (int j = 0; j < 3; ++j) gm = maxabs_nan(gm, 2.0 * c.W[j] * (x[j] - gl[j]));
+        for (int j = 0; j < 2; ++j) {  // push x, y
+            int hL = c.hasL[j], hU = c.hasU[j];
+            double lb = c.lb[j], ub = c.ub[j];
+            if (hL && hU) {
+                double pl = fmin(K_BOUND_PUSH * fmax(1.0, fabs(lb)), K_BOUND_FRAC * (ub - lb));
+                double pu = fmin(K_BOUND_PUSH * fmax(1.0, fabs(ub)), K_BOUND_FRAC * (ub - lb));
+                x[j] = fmin(fmax(x[j], lb + pl), ub - pu);
+            } else if (hL) x[j] = fmax(x[j], lb + K_BOUND_PUSH * fmax(1.0, fabs(lb)));
+            else if (hU) x[j] = fmin(x[j], ub - K_BOUND_PUSH * fmax(1.0, fabs(ub)));
+            RW(sb + L.sZ + 8 * k + 2 * j) = hL ? 1.0 : 0.0;
+            RW(sb + L.sZ + 8 * k + 2 * j + 1) = hU ? 1.0 : 0.0;
+        }
+        for (int j = 0; j < 3; ++j) { RW(sb + L.sX + 3 * k + j) = x[j]; RW(sb + L.sY + 3 * k + j) = 0.0; }
+        if (k >= 1)
+            for (int o = 0; o < O; ++o) {
+                double ex = x[0] - RW(L.rSc + 6 + 2 * o), ey = x[1] - RW(L.rSc + 6 + 2 * o + 1);
+                double d = sqrt(ex * ex + ey * ey) - c.obs_radius;
+                int i = (k - 1) * O + o;
+                RW(sb + L.sS + i) = fmax(d, dLpush); RW(sb + L.sYD + i) = 0.0; RW(sb + L.sVL + i) = 1.0;
+            }
+        if (k < N) {
+            double u[2];
+            for (int j = 0; j < 2; ++j) u[j] = io.U0 ? io.U0[io_U(c, b, j, k)] : 0.0;
+            double gv, hv;
+            vcost(c, 1.0, u[0], &gv, &hv);
+            gm = maxabs_nan(gm, gv); gm = maxabs_nan(gm, 2.0 * c.Ww * u[1]);
+            for (int j = 0; j < 2; ++j) {
+                int hL = c.hasL[2 + j], hU = c.hasU[2 + j];
+                double lb = c.lb[2 + j], ub = c.ub[2 + j];
+                if (hL && hU) {
+                    double pl = fmin(K_BOUND_PUSH * fmax(1.0, fabs(lb)), K_BOUND_FRAC * (ub - lb));
+                    double pu = fmin(K_BOUND_PUSH * fmax(1.0, fabs(ub)), K_BOUND_FRAC * (ub - lb));
+                    u[j] = fmin(fmax(u[j], lb + pl), ub - pu);
+                } else if (hL) u[j] = fmax(u[j], lb + K_BOUND_PUSH * fmax(1.0, fabs(lb)));
+                else if (hU) u[j] = fmin(u[j], ub - K_BOUND_PUSH * fmax(1.0, fabs(ub)));
+                RW(sb + L.sZ + 8 * k + 4 + 2 * j) = hL ? 1.0 : 0.0;
+                RW(sb + L.sZ + 8 * k + 4 + 2 * j + 1) = hU ? 1.0 : 0.0;
+                RW(sb + L.sU + 2 * k + j) = u[j];
+            }
+            double sn, cs;
+            sincos_(x[2], &sn, &cs);
+            RW(sb + L.sCS + 2 * k) = cs; RW(sb + L.sCS + 2 * k + 1) = sn;
+        }
+    }
+    t.df = gm > K_SCALING_MAX_GRAD ? fmax(K_SCALING_MAX_GRAD / gm, K_SCALING_MIN) : 1.0;
+    t.cur = 0; t.iter = 0; t.mu = K_MU_INIT; t.tau = fmax(K_TAU_MIN, 1.0 - K_MU_INIT);
+    t.delta = 0.0; t.delta_last = 0.0; t.theta_max = -1.0; t.theta_min = -1.0; t.fn = 0;
+    t.nsteps = 0; t.soc_count = 0;
+    t.mode = M_LSQ;
+}
+
+// per-(stage, obstacle) quantities shared by the sweep and the roll-out
+struct ObsT { double nx, ny, rr, Ds, bd, bs; };
+KMPC_HD ObsT obs_terms(const Cfg &c, double px, double py, double cx, double cy, double s, double yd, double vL,
+                       double mu, double delta, bool lsq, bool soc, double dsoc) {
+    ObsT r;
+    double ex = px - cx, ey = py - cy;
+    r.rr = sqrt(ex * ex + ey * ey);
+    r.nx = ex / r.rr; r.ny = ey / r.rr;
+    if (lsq) { r.Ds = 1.0; r.bd = 0.0; r.bs = -yd - vL; }
+    else {
+        double sl = s - c.dL;
+        r.Ds = vL / sl + delta;
+        r.bs = yd + mu / sl - K_KAPPA_D * mu;
+        r.bd = soc ? -dsoc : -((r.rr - c.obs_radius) - s);
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SWEEP: backward Riccati recursion over the stages of the primal-dual system
+//   [W + Sigma + delta I   J^T] [dx ]   [bx]
+//   [J                      0 ] [dy ] = [bc]        (slacks of the obstacle rows condensed into the x-x blocks)
+// kind M_LSQ: W = 0, Sigma = I, rhs = (grad f - zL + zU, 0)  (least-squares multiplier estimate)
+// kind M_NEWTON: rhs = -(grad of the barrier Lagrangian, c);  kind M_SOC: same matrix, bc = -c_soc.
+// Stores the feedback gains K, k_ff and the cost-to-go (P, p).  Returns false when some Q_uu is not positive
+// definite (wrong inertia -> the caller raises delta, IPOPT's inertia correction).
+// ------------------------------------------------------------------------------------------------
+KMPC_HDN inline bool pass_sweep(const Cfg &c, const Ctx &t, double *wsp, size_t S) {
+    const int N = c.N, O = c.O;
+    const Rows &L = c.L;
+    const int sb = L.rState[t.cur];
+    const bool lsq = t.mode == M_LSQ, soc = t.mode == M_SOC;
+    const double mu = t.mu, delta = t.delta, df = t.df, T = c.T;
+    const double g0 = RW(L.rSc + 3), g1 = RW(L.rSc + 4), g2 = RW(L.rSc + 5);
+    double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0, p0 = 0, p1 = 0, p2 = 0;
+    double xn0 = 0, xn1 = 0, xn2 = 0, yn0 = 0, yn1 = 0, yn2 = 0;
+    bool ok = true;
+#pragma unroll 1
+    for (int k = N; k >= 0; --k) {
+        const double x0 = RW(sb + L.sX + 3 * k), x1 = RW(sb + L.sX + 3 * k + 1), x2 = RW(sb + L.sX + 3 * k + 2);
+        const double y0 = RW(sb + L.sY + 3 * k), y1 = RW(sb + L.sY + 3 * k + 1), y2 = RW(sb + L.sY + 3 * k + 2);
+        const bool ing = k >= c.gk_lo && k <= c.gk_hi;
+        double gx0 = 0, gx1 = 0, gx2 = 0, h0 = 0, h1 = 0, h2 = 0;
+        if (ing) {
+            gx0 = df * 2.0 * c.W[0] * (x0 - g0); gx1 = df * 2.0 * c.W[1] * (x1 - g1); gx2 = df * 2.0 * c.W[2] * (x2 - g2);
+            h0 = df * 2.0 * c.W[0]; h1 = df * 2.0 * c.W[1]; h2 = df * 2.0 * c.W[2];
+        }
+        // q = -bx (x part), Q = W_xx + Sigma_x + delta
+        double q0, q1, q2, Q00, Q01 = 0.0, Q11, Q22;
+        {
+            const double zLx = RW(sb + L.sZ + 8 * k), zUx = RW(sb + L.sZ + 8 * k + 1);
+            const double zLy = RW(sb + L.sZ + 8 * k + 2), zUy = RW(sb + L.sZ + 8 * k + 3);
+            if (lsq) {
+                q0 = -(gx0 - zLx + zUx); q1 = -(gx1 - zLy + zUy); q2 = -gx2;
+                Q00 = 1.0; Q11 = 1.0; Q22 = 1.0;
+            } else {
+                double sg0, rb0, sg1, rb1;
+                bound_terms(x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], zLx, zUx, mu, &sg0, &rb0);
+                bound_terms(x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], zLy, zUy, mu, &sg1, &rb1);
+                q0 = gx0 + y0 + rb0; q1 = gx1 + y1 + rb1; q2 = gx2 + y2;
+                Q00 = h0 + sg0 + delta; Q11 = h1 + sg1 + delta; Q22 = h2 + delta;
+            }
+        }
+        if (O > 0 && k >= 1) {
+#pragma unroll 1
+            for (int o = 0; o < O; ++o) {
+                const int i = (k - 1) * O + o;
+                const double yd = RW(sb + L.sYD + i);
+                ObsT ot = obs_terms(c, x0, x1, RW(L.rSc + 6 + 2 * o), RW(L.rSc + 7 + 2 * o), RW(sb + L.sS + i), yd,
+                                    RW(sb + L.sVL + i), mu, delta, lsq, soc, soc ? RW(L.rDsoc + i) : 0.0);
+                if (!lsq) {
+                    const double h = yd / ot.rr;
+                    Q00 += h * (1.0 - ot.nx * ot.nx); Q01 += h * (-ot.nx * ot.ny); Q11 += h * (1.0 - ot.ny * ot.ny);
+                    q0 += ot.nx * yd; q1 += ot.ny * yd;
+                }
+                Q00 += ot.Ds * ot.nx * ot.nx; Q01 += ot.Ds * ot.nx * ot.ny; Q11 += ot.Ds * ot.ny * ot.ny;
+                const double tt = ot.Ds * ot.bd + ot.bs;
+                q0 -= ot.nx * tt; q1 -= ot.ny * tt;
+            }
+        }
+        if (k == N) {
+            P00 = Q00; P10 = Q01; P11 = Q11; P20 = 0.0; P21 = 0.0; P22 = Q22;
+            p0 = q0; p1 = q1; p2 = q2;
+        } else {
+            const double v = RW(sb + L.sU + 2 * k), om = RW(sb + L.sU + 2 * k + 1);
+            const double cs = RW(sb + L.sCS + 2 * k), sn = RW(sb + L.sCS + 2 * k + 1);
+            const double a13 = -T * v * sn, a23 = T * v * cs, b11 = T * cs, b21 = T * sn, b32 = T;
+            double gv, hvv, qv, qw, Dv, Dw, htv = 0.0;
+            vcost(c, df, v, &gv, &hvv);
+            const double gw = df * 2.0 * c.Ww * om;
+            double hww = df * 2.0 * c.Ww;
+            {
+                const double zLv = RW(sb + L.sZ + 8 * k + 4), zUv = RW(sb + L.sZ + 8 * k + 5);
+                const double zLw = RW(sb + L.sZ + 8 * k + 6), zUw = RW(sb + L.sZ + 8 * k + 7);
+                if (lsq) {
+                    qv = -(gv - zLv + zUv); qw = -(gw - zLw + zUw);
+                    Dv = 1.0; Dw = 1.0; hvv = 0.0; hww = 0.0;
+                } else {
+                    double sgv, rbv, sgw, rbw;
+                    bound_terms(v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], zLv, zUv, mu, &sgv, &rbv);
+                    bound_terms(om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], zLw, zUw, mu, &sgw, &rbw);
+                    // J^T y of dynamics row k+1 (multiplier yn)
+                    q0 -= yn0; q1 -= yn1; q2 -= a13 * yn0 + a23 * yn1 + yn2;
+                    qv = gv - (b11 * yn0 + b21 * yn1) + rbv;
+                    qw = gw - b32 * yn2 + rbw;
+                    Dv = sgv + delta; Dw = sgw + delta;
+                    // curvature of the dynamics in the Lagrangian (the only indefinite terms)
+                    Q22 += T * v * (yn0 * cs + yn1 * sn);
+                    htv = T * (yn0 * sn - yn1 * cs);
+                }
+            }
+            // e = bc_{k+1}
+            double e0, e1, e2;
+            if (lsq) { e0 = e1 = e2 = 0.0; }
+            else if (soc) { e0 = -RW(L.rCsoc + 3 * (k + 1)); e1 = -RW(L.rCsoc + 3 * (k + 1) + 1); e2 = -RW(L.rCsoc + 3 * (k + 1) + 2); }
+            else { e0 = -(xn0 - (x0 + T * v * cs)); e1 = -(xn1 - (x1 + T * v * sn)); e2 = -(xn2 - (x2 + T * om)); }
+            // matrix recursion
+            const double PA02 = P00 * a13 + P10 * a23 + P20, PA12 = P10 * a13 + P11 * a23 + P21, PA22 = P20 * a13 + P21 * a23 + P22;
+            const double PB00 = P00 * b11 + P10 * b21, PB10 = P10 * b11 + P11 * b21, PB20 = P20 * b11 + P21 * b21;
+            const double PB01 = P20 * b32, PB11 = P21 * b32, PB21 = P22 * b32;
+            // Qxx = A^T P A + Q   (PA[:,0] = P[:,0], PA[:,1] = P[:,1])
+            double X00 = P00 + Q00, X01 = P10 + Q01, X02 = PA02;
+            double X10 = P10 + Q01, X11 = P11 + Q11, X12 = PA12;
+            double X20 = a13 * P00 + a23 * P10 + P20, X21 = a13 * P10 + a23 * P11 + P21, X22 = a13 * PA02 + a23 * PA12 + PA22 + Q22;
+            // Qux = B^T P A (+ W_v,theta)
+            const double U00 = b11 * P00 + b21 * P10, U01 = b11 * P10 + b21 * P11, U02 = b11 * PA02 + b21 * PA12 + htv;
+            const double U10 = b32 * P20, U11 = b32 * P21, U12 = b32 * PA22;
+            const double qa = b11 * PB00 + b21 * PB10 + hvv + Dv, qb = b11 * PB01 + b21 * PB11, qc = b32 * PB21 + hww + Dw;
+            if (!(qa > 0.0)) { ok = false; break; }
+            const double sch = qc - qb * qb / qa;
+            if (!(sch > 0.0)) { ok = false; break; }
+            const double det = qa * qc - qb * qb;
+            const double i00 = qc / det, i01 = -qb / det, i11 = qa / det;
+            const double K00 = -(i00 * U00 + i01 * U10), K01 = -(i00 * U01 + i01 * U11), K02 = -(i00 * U02 + i01 * U12);
+            const double K10 = -(i01 * U00 + i11 * U10), K11 = -(i01 * U01 + i11 * U11), K12 = -(i01 * U02 + i11 * U12);
+            // vector recursion
+            const double Pe0 = P00 * e0 + P10 * e1 + P20 * e2 + p0, Pe1 = P10 * e0 + P11 * e1 + P21 * e2 + p1,
+                         Pe2 = P20 * e0 + P21 * e1 + P22 * e2 + p2;
+            const double qu0 = qv + b11 * Pe0 + b21 * Pe1, qu1 = qw + b32 * Pe2;
+            const double qx0 = q0 + Pe0, qx1 = q1 + Pe1, qx2 = q2 + a13 * Pe0 + a23 * Pe1 + Pe2;
+            const double kf0 = -(i00 * qu0 + i01 * qu1), kf1 = -(i01 * qu0 + i11 * qu1);
+            p0 = qx0 + K00 * qu0 + K10 * qu1; p1 = qx1 + K01 * qu0 + K11 * qu1; p2 = qx2 + K02 * qu0 + K12 * qu1;
+            // P = Qxx + Qux^T K, symmetrised
+            const double N00 = X00 + U00 * K00 + U10 * K10, N01 = X01 + U00 * K01 + U10 * K11, N02 = X02 + U00 * K02 + U10 * K12;
+            const double N10 = X10 + U01 * K00 + U11 * K10, N11 = X11 + U01 * K01 + U11 * K11, N12 = X12 + U01 * K02 + U11 * K12;
+            const double N20 = X20 + U02 * K00 + U12 * K10, N21 = X21 + U02 * K01 + U12 * K11, N22 = X22 + U02 * K02 + U12 * K12;
+            P00 = N00; P10 = 0.5 * (N10 + N01); P11 = N11; P20 = 0.5 * (N20 + N02); P21 = 0.5 * (N21 + N12); P22 = N22;
+            RW(L.rK + 6 * k) = K00; RW(L.rK + 6 * k + 1) = K01; RW(L.rK + 6 * k + 2) = K02;
+            RW(L.rK + 6 * k + 3) = K10; RW(L.rK + 6 * k + 4) = K11; RW(L.rK + 6 * k + 5) = K12;
+            RW(L.rKff + 2 * k) = kf0; RW(L.rKff + 2 * k + 1) = kf1;
+        }
+        RW(L.rP + 6 * k) = P00; RW(L.rP + 6 * k + 1) = P10; RW(L.rP + 6 * k + 2) = P11;
+        RW(L.rP + 6 * k + 3) = P20; RW(L.rP + 6 * k + 4) = P21; RW(L.rP + 6 * k + 5) = P22;
+        RW(L.rPv + 3 * k) = p0; RW(L.rPv + 3 * k + 1) = p1; RW(L.rPv + 3 * k + 2) = p2;
+        xn0 = x0; xn1 = x1; xn2 = x2; yn0 = y0; yn1 = y1; yn2 = y2;
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ROLL-OUT: forward substitution dx_0 = bc_0, du = K dx + k_ff, dx+ = A dx + B du + e, dy = -(P dx + p);
+// fraction-to-the-boundary step sizes for the primal step and for the bound multipliers, and the
+// directional derivative of the barrier objective.  Writes step buffer `sel`.
+// ------------------------------------------------------------------------------------------------
+KMPC_HDN inline void pass_rollout(const Cfg &c, const Ctx &t, double *wsp, size_t S, int sel, double *alpha_pr,
+                                  double *alpha_du, double *gBD, double *ymax) {
+    const int N = c.N, O = c.O;
+    const Rows &L = c.L;
+    const int sb = L.rState[t.cur], db = L.rStep[sel];
+    const bool lsq = t.mode == M_LSQ, soc = t.mode == M_SOC;
+    const double mu = t.mu, delta = t.delta, df = t.df, T = c.T, tau = t.tau;
+    const double g0 = RW(L.rSc + 3), g1 = RW(L.rSc + 4), g2 = RW(L.rSc + 5);
+    double apr = 1.0, adu = 1.0, gbd = 0.0, ym = 0.0;
+    double x0 = RW(sb + L.sX), x1 = RW(sb + L.sX + 1), x2 = RW(sb + L.sX + 2);
+    double d0, d1, d2;
+    if (lsq) { d0 = d1 = d2 = 0.0; }
+    else if (soc) { d0 = -RW(L.rCsoc); d1 = -RW(L.rCsoc + 1); d2 = -RW(L.rCsoc + 2); }
+    else { d0 = -(x0 - RW(L.rSc)); d1 = -(x1 - RW(L.rSc + 1)); d2 = -(x2 - RW(L.rSc + 2)); }
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+        const double P00 = RW(L.rP + 6 * k), P10 = RW(L.rP + 6 * k + 1), P11 = RW(L.rP + 6 * k + 2);
+        const double P20 = RW(L.rP + 6 * k + 3), P21 = RW(L.rP + 6 * k + 4), P22 = RW(L.rP + 6 * k + 5);
+        const double dy0 = -(P00 * d0 + P10 * d1 + P20 * d2 + RW(L.rPv + 3 * k));
+        const double dy1 = -(P10 * d0 + P11 * d1 + P21 * d2 + RW(L.rPv + 3 * k + 1));
+        const double dy2 = -(P20 * d0 + P21 * d1 + P22 * d2 + RW(L.rPv + 3 * k + 2));
+        RW(db + L.dY + 3 * k) = dy0; RW(db + L.dY + 3 * k + 1) = dy1; RW(db + L.dY + 3 * k + 2) = dy2;
+        RW(db + L.dX + 3 * k) = d0; RW(db + L.dX + 3 * k + 1) = d1; RW(db + L.dX + 3 * k + 2) = d2;
+        ym = maxabs_nan(maxabs_nan(maxabs_nan(ym, dy0), dy1), dy2);
+        if (!lsq) {
+            const double zLx = RW(sb + L.sZ + 8 * k), zUx = RW(sb + L.sZ + 8 * k + 1);
+            const double zLy = RW(sb + L.sZ + 8 * k + 2), zUy = RW(sb + L.sZ + 8 * k + 3);
+            double sg, rb;
+            bound_ftb(x0, d0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], zLx, zUx, mu, tau, &apr, &adu);
+            bound_ftb(x1, d1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], zLy, zUy, mu, tau, &apr, &adu);
+            const bool ing = k >= c.gk_lo && k <= c.gk_hi;
+            bound_terms(x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], zLx, zUx, mu, &sg, &rb);
+            gbd += ((ing ? df * 2.0 * c.W[0] * (x0 - g0) : 0.0) + rb) * d0;
+            bound_terms(x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], zLy, zUy, mu, &sg, &rb);
+            gbd += ((ing ? df * 2.0 * c.W[1] * (x1 - g1) : 0.0) + rb) * d1;
+            gbd += (ing ? df * 2.0 * c.W[2] * (x2 - g2) : 0.0) * d2;
+        }
+        if (O > 0 && k >= 1) {
+#pragma unroll 1
+            for (int o = 0; o < O; ++o) {
+                const int i = (k - 1) * O + o;
+                const double s = RW(sb + L.sS + i), yd = RW(sb + L.sYD + i), vL = RW(sb + L.sVL + i);
+                ObsT ot = obs_terms(c, x0, x1, RW(L.rSc + 6 + 2 * o), RW(L.rSc + 7 + 2 * o), s, yd, vL, mu, delta, lsq,
+                                    soc, soc ? RW(L.rDsoc + i) : 0.0);
+                const double ds = ot.nx * d0 + ot.ny * d1 - ot.bd;
+                const double dyd = ot.Ds * ds - ot.bs;
+                RW(db + L.dS + i) = ds; RW(db + L.dYD + i) = dyd;
+                ym = maxabs_nan(ym, dyd);
+                if (!lsq) {
+                    const double sl = s - c.dL;
+                    if (ds < 0) apr = fmin(apr, -tau * sl / ds);
+                    const double dv = mu / sl - vL - vL / sl * ds;
+                    if (dv < 0) adu = fmin(adu, -tau * vL / dv);
+                    gbd += (-mu / sl + K_KAPPA_D * mu) * ds;
+                }
+            }
+        }
+        if (k < N) {
+            const double v = RW(sb + L.sU + 2 * k), om = RW(sb + L.sU + 2 * k + 1);
+            const double cs = RW(sb + L.sCS + 2 * k), sn = RW(sb + L.sCS + 2 * k + 1);
+            const double du0 = RW(L.rK + 6 * k) * d0 + RW(L.rK + 6 * k + 1) * d1 + RW(L.rK + 6 * k + 2) * d2 + RW(L.rKff + 2 * k);
+            const double du1 = RW(L.rK + 6 * k + 3) * d0 + RW(L.rK + 6 * k + 4) * d1 + RW(L.rK + 6 * k + 5) * d2 + RW(L.rKff + 2 * k + 1);
+            RW(db + L.dU + 2 * k) = du0; RW(db + L.dU + 2 * k + 1) = du1;
+            const double xn0 = RW(sb + L.sX + 3 * (k + 1)), xn1 = RW(sb + L.sX + 3 * (k + 1) + 1), xn2 = RW(sb + L.sX + 3 * (k + 1) + 2);
+            double e0, e1, e2;
+            if (lsq) { e0 = e1 = e2 = 0.0; }
+            else {
+                const double zLv = RW(sb + L.sZ + 8 * k + 4), zUv = RW(sb + L.sZ + 8 * k + 5);
+                const double zLw = RW(sb + L.sZ + 8 * k + 6), zUw = RW(sb + L.sZ + 8 * k + 7);
+                bound_ftb(v, du0, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], zLv, zUv, mu, tau, &apr, &adu);
+                bound_ftb(om, du1, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], zLw, zUw, mu, tau, &apr, &adu);
+                double gv, hv, sg, rb;
+                vcost(c, df, v, &gv, &hv);
+                bound_terms(v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], zLv, zUv, mu, &sg, &rb);
+                gbd += (gv + rb) * du0;
+                bound_terms(om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], zLw, zUw, mu, &sg, &rb);
+                gbd += (df * 2.0 * c.Ww * om + rb) * du1;
+                if (soc) { e0 = -RW(L.rCsoc + 3 * (k + 1)); e1 = -RW(L.rCsoc + 3 * (k + 1) + 1); e2 = -RW(L.rCsoc + 3 * (k + 1) + 2); }
+                else { e0 = -(xn0 - (x0 + T * v * cs)); e1 = -(xn1 - (x1 + T * v * sn)); e2 = -(xn2 - (x2 + T * om)); }
+            }
+            const double a13 = -T * v * sn, a23 = T * v * cs;
+            const double n0 = d0 + a13 * d2 + T * cs * du0 + e0;
+            const double n1 = d1 + a23 * d2 + T * sn * du0 + e1;
+            const double n2 = d2 + T * du1 + e2;
+            d0 = n0; d1 = n1; d2 = n2;
+            x0 = xn0; x1 = xn1; x2 = xn2;
+        }
+    }
+    *alpha_pr = apr; *alpha_du = adu; *gBD = gbd; *ymax = ym;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TRIAL + speculative UPDATE: evaluates the trial point w + alpha d (barrier objective ingredients, constraint
+// violation) and, in the same sweep over the stages, the iterate that would result from accepting it (multiplier
+// updates with their own step sizes, kappa_sigma safeguard) together with its optimality-error norms.  Everything
+// is written to the OTHER state buffer; accepting the trial point just flips t.cur.
+//   tu = TU_INIT : alpha = 0, y' = ay * dy (least-squares estimate), multipliers untouched (no safeguard)
+// ------------------------------------------------------------------------------------------------
+KMPC_HDN inline bool pass_trial(const Cfg &c, const Ctx &t, double *wsp, size_t S, int sel, int tu, double alpha, double ay,
+                                double adu, Stats *out) {
+    const int N = c.N, O = c.O;
+    const Rows &L = c.L;
+    const int sb = L.rState[t.cur], nb = L.rState[t.cur ^ 1], db = L.rStep[sel];
+    const double mu = t.mu, df = t.df, T = c.T;
+    const bool clamp = tu == TU_STEP;
+    const double g0 = RW(L.rSc + 3), g1 = RW(L.rSc + 4), g2 = RW(L.rSc + 5);
+    Stats st;
+    st.f = 0; st.bar = 0; st.damp = 0; st.theta = 0; st.dinf = 0; st.pinf = 0; st.mn = INFINITY; st.mx = 0; st.sumy = 0;
+    st.sumz = 0; st.wmax = 0;
+    bool valid = true;
+    double xp0 = RW(L.rSc), xp1 = RW(L.rSc + 1), xp2 = RW(L.rSc + 2);  // predicted state (k = 0: x_cur)
+    double yk0 = RW(sb + L.sY) + ay * RW(db + L.dY), yk1 = RW(sb + L.sY + 1) + ay * RW(db + L.dY + 1),
+           yk2 = RW(sb + L.sY + 2) + ay * RW(db + L.dY + 2);
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+        const double xo0 = RW(sb + L.sX + 3 * k), xo1 = RW(sb + L.sX + 3 * k + 1), xo2 = RW(sb + L.sX + 3 * k + 2);
+        const double d0 = RW(db + L.dX + 3 * k), d1 = RW(db + L.dX + 3 * k + 1), d2 = RW(db + L.dX + 3 * k + 2);
+        const double x0 = xo0 + alpha * d0, x1 = xo1 + alpha * d1, x2 = xo2 + alpha * d2;
+        RW(nb + L.sX + 3 * k) = x0; RW(nb + L.sX + 3 * k + 1) = x1; RW(nb + L.sX + 3 * k + 2) = x2;
+        RW(nb + L.sY + 3 * k) = yk0; RW(nb + L.sY + 3 * k + 1) = yk1; RW(nb + L.sY + 3 * k + 2) = yk2;
+        const double c0 = x0 - xp0, c1 = x1 - xp1, c2 = x2 - xp2;
+        st.theta += fabs(c0) + fabs(c1) + fabs(c2);
+        st.pinf = maxabs_nan(maxabs_nan(maxabs_nan(st.pinf, c0), c1), c2);
+        st.sumy += fabs(yk0) + fabs(yk1) + fabs(yk2);
+        st.wmax = fmax(st.wmax, fmax(fabs(x0), fmax(fabs(x1), fabs(x2))));
+        double r0 = yk0, r1 = yk1, r2 = yk2;  // dual residual of x_k
+        if (k >= c.gk_lo && k <= c.gk_hi) {
+            const double e0 = x0 - g0, e1 = x1 - g1, e2 = x2 - g2;
+            st.f += c.W[0] * e0 * e0; st.f += c.W[1] * e1 * e1; st.f += c.W[2] * e2 * e2;
+            r0 += df * 2.0 * c.W[0] * e0; r1 += df * 2.0 * c.W[1] * e1; r2 += df * 2.0 * c.W[2] * e2;
+        }
+        double prod = 1.0;
+        {
+            double zLn, zUn;
+            valid &= bound_trial(xo0, d0, x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], RW(sb + L.sZ + 8 * k), RW(sb + L.sZ + 8 * k + 1),
+                                 mu, adu, clamp, &zLn, &zUn, &prod, &st.damp, &st);
+            RW(nb + L.sZ + 8 * k) = zLn; RW(nb + L.sZ + 8 * k + 1) = zUn;
+            r0 += zUn - zLn;
+            valid &= bound_trial(xo1, d1, x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], RW(sb + L.sZ + 8 * k + 2), RW(sb + L.sZ + 8 * k + 3),
+                                 mu, adu, clamp, &zLn, &zUn, &prod, &st.damp, &st);
+            RW(nb + L.sZ + 8 * k + 2) = zLn; RW(nb + L.sZ + 8 * k + 3) = zUn;
+            r1 += zUn - zLn;
+        }
+        if (O > 0 && k >= 1) {
+#pragma unroll 1
+            for (int o = 0; o < O; ++o) {
+                const int i = (k - 1) * O + o;
+                const double so = RW(sb + L.sS + i), ds = RW(db + L.dS + i), vL = RW(sb + L.sVL + i);
+                const double s = so + alpha * ds;
+                const double ex = x0 - RW(L.rSc + 6 + 2 * o), ey = x1 - RW(L.rSc + 7 + 2 * o);
+                const double rr = sqrt(ex * ex + ey * ey), nx = ex / rr, ny = ey / rr;
+                const double dm = (rr - c.obs_radius) - s;
+                st.theta += fabs(dm); st.pinf = maxabs_nan(st.pinf, dm);
+                const double slo = so - c.dL, sln = s - c.dL;
+                if (!(sln > 0)) valid = false;
+                prod *= sln; st.damp += sln;
+                const double yd = RW(sb + L.sYD + i) + ay * RW(db + L.dYD + i);
+                double z = vL + adu * (mu / slo - vL - vL / slo * ds);
+                if (clamp) z = fmax(fmin(z, K_KAPPA_SIGMA * mu / sln), mu / (K_KAPPA_SIGMA * sln));
+                RW(nb + L.sS + i) = s; RW(nb + L.sYD + i) = yd; RW(nb + L.sVL + i) = z;
+                r0 += nx * yd; r1 += ny * yd;
+                st.dinf = maxabs_nan(st.dinf, -yd - z);
+                const double p = sln * z;
+                st.mn = fmin(st.mn, p); st.mx = fmax(st.mx, p); st.sumz += fabs(z); st.sumy += fabs(yd);
+            }
+        }
+        if (k < N) {
+            const double vo = RW(sb + L.sU + 2 * k), oo = RW(sb + L.sU + 2 * k + 1);
+            const double du0 = RW(db + L.dU + 2 * k), du1 = RW(db + L.dU + 2 * k + 1);
+            const double v = vo + alpha * du0, om = oo + alpha * du1;
+            RW(nb + L.sU + 2 * k) = v; RW(nb + L.sU + 2 * k + 1) = om;
+            double sn, cs;
+            sincos_(x2, &sn, &cs);
+            RW(nb + L.sCS + 2 * k) = cs; RW(nb + L.sCS + 2 * k + 1) = sn;
+            st.wmax = fmax(st.wmax, fmax(fabs(v), fabs(om)));
+            // multiplier of dynamics row k+1 at the updated point
+            const double yn0 = RW(sb + L.sY + 3 * (k + 1)) + ay * RW(db + L.dY + 3 * (k + 1));
+            const double yn1 = RW(sb + L.sY + 3 * (k + 1) + 1) + ay * RW(db + L.dY + 3 * (k + 1) + 1);
+            const double yn2 = RW(sb + L.sY + 3 * (k + 1) + 2) + ay * RW(db + L.dY + 3 * (k + 1) + 2);
+            const double a13 = -T * v * sn, a23 = T * v * cs;
+            r0 -= yn0; r1 -= yn1; r2 -= a13 * yn0 + a23 * yn1 + yn2;
+            double gv, hv;
+            vcost(c, df, v, &gv, &hv);
+            double rv = gv - (T * cs * yn0 + T * sn * yn1), rw = df * 2.0 * c.Ww * om - T * yn2;
+            if (c.cost_mode == 0) { const double vm = fmin(v, 0.0), vp = fmax(v, 0.0); st.f += c.Wvn * vm * vm + c.Wvp * vp * vp; }
+            else st.f += c.Wvn * fmin(v, 0.0);
+            st.f += c.Ww * om * om;
+            double zLn, zUn;
+            valid &= bound_trial(vo, du0, v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], RW(sb + L.sZ + 8 * k + 4), RW(sb + L.sZ + 8 * k + 5),
+                                 mu, adu, clamp, &zLn, &zUn, &prod, &st.damp, &st);
+            RW(nb + L.sZ + 8 * k + 4) = zLn; RW(nb + L.sZ + 8 * k + 5) = zUn;
+            rv += zUn - zLn;
+            valid &= bound_trial(oo, du1, om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], RW(sb + L.sZ + 8 * k + 6), RW(sb + L.sZ + 8 * k + 7),
+                                 mu, adu, clamp, &zLn, &zUn, &prod, &st.damp, &st);
+            RW(nb + L.sZ + 8 * k + 6) = zLn; RW(nb + L.sZ + 8 * k + 7) = zUn;
+            rw += zUn - zLn;
+            st.dinf = maxabs_nan(maxabs_nan(st.dinf, rv), rw);
+            xp0 = x0 + T * v * cs; xp1 = x1 + T * v * sn; xp2 = x2 + T * om;
+            yk0 = yn0; yk1 = yn1; yk2 = yn2;
+        }
+        st.dinf = maxabs_nan(maxabs_nan(maxabs_nan(st.dinf, r0), r1), r2);
+        st.bar += log(prod);
+    }
+    st.f *= df;
+    if (c.nb == 0) st.mn = 0.0;
+    *out = st;
+    const double phi = st.f - mu * st.bar + K_KAPPA_D * mu * st.damp;
+    return valid && isfinite(phi) && isfinite(st.theta);
+}
+
+// SOC right-hand side: c_soc <- a * base + c(trial), base = c(current) for the first correction, else the previous c_soc
+KMPC_HDN inline void pass_soc_rhs(const Cfg &c, const Ctx &t, double *wsp, size_t S, double a, bool first) {
+    const int N = c.N, O = c.O;
+    const Rows &L = c.L;
+    const int sb = L.rState[t.cur], nb = L.rState[t.cur ^ 1];
+    const double T = c.T;
+    double cp0 = RW(L.rSc), cp1 = RW(L.rSc + 1), cp2 = RW(L.rSc + 2);  // predicted (current point)
+    double tp0 = cp0, tp1 = cp1, tp2 = cp2;                            // predicted (trial point)
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+        const double x0 = RW(sb + L.sX + 3 * k), x1 = RW(sb + L.sX + 3 * k + 1), x2 = RW(sb + L.sX + 3 * k + 2);
+        const double t0 = RW(nb + L.sX + 3 * k), t1 = RW(nb + L.sX + 3 * k + 1), t2 = RW(nb + L.sX + 3 * k + 2);
+        double b0, b1, b2;
+        if (first) { b0 = x0 - cp0; b1 = x1 - cp1; b2 = x2 - cp2; }
+        else { b0 = RW(L.rCsoc + 3 * k); b1 = RW(L.rCsoc + 3 * k + 1); b2 = RW(L.rCsoc + 3 * k + 2); }
+        RW(L.rCsoc + 3 * k) = a * b0 + (t0 - tp0); RW(L.rCsoc + 3 * k + 1) = a * b1 + (t1 - tp1); RW(L.rCsoc + 3 * k + 2) = a * b2 + (t2 - tp2);
+        if (O > 0 && k >= 1)
+            for (int o = 0; o < O; ++o) {
+                const int i = (k - 1) * O + o;
+                const double cx = RW(L.rSc + 6 + 2 * o), cy = RW(L.rSc + 7 + 2 * o);
+                double base;
+                if (first) { const double ex = x0 - cx, ey = x1 - cy; base = (sqrt(ex * ex + ey * ey) - c.obs_radius) - RW(sb + L.sS + i); }
+                else base = RW(L.rDsoc + i);
+                const double ex = t0 - cx, ey = t1 - cy;
+                RW(L.rDsoc + i) = a * base + ((sqrt(ex * ex + ey * ey) - c.obs_radius) - RW(nb + L.sS + i));
+            }
+        if (k < N) {
+            const double v = RW(sb + L.sU + 2 * k), om = RW(sb + L.sU + 2 * k + 1);
+            const double cs = RW(sb + L.sCS + 2 * k), sn = RW(sb + L.sCS + 2 * k + 1);
+            cp0 = x0 + T * v * cs; cp1 = x1 + T * v * sn; cp2 = x2 + T * om;
+            const double vt = RW(nb + L.sU + 2 * k), ot = RW(nb + L.sU + 2 * k + 1);
+            const double ct = RW(nb + L.sCS + 2 * k), stt = RW(nb + L.sCS + 2 * k + 1);
+            tp0 = t0 + T * vt * ct; tp1 = t1 + T * vt * stt; tp2 = t2 + T * ot;
+        }
+    }
+}
+
+// OUTPUT pass: returned matrices (optimizer.py:392-400) + objective / status / iteration count
+KMPC_HDN inline void pass_output(const Cfg &c, const Ctx &t, double *wsp, size_t S, const IO &io, int status) {
+    const int N = c.N, b = t.inst;
+    const Rows &L = c.L;
+    const int sb = L.rState[t.cur];
+#pragma unroll 1
+    for (int k = 0; k <= N; ++k) {
+        for (int j = 0; j < 3; ++j) io.X_out[io_X(c, b, j, k)] = RW(sb + L.sX + 3 * k + j);
+        if (k < N) for (int j = 0; j < 2; ++j) io.U_out[io_U(c, b, j, k)] = RW(sb + L.sU + 2 * k + j);
+    }
+    if (io.obj) io.obj[b] = t.c.f / t.df;
+    if (io.status) io.status[b] = status;
+    if (io.iters) io.iters[b] = t.iter;
+}
+
+// ---- scalar logic -------------------------------------------------------------------------------
+KMPC_HD double compl_inf(const Cfg &c, const Stats &s, double mu) {
+    return c.nb ? fmax(fabs(s.mx - mu), fabs(s.mn - mu)) : 0.0;
+}
+KMPC_HD double opt_error(const Cfg &c, const Stats &s, double mu) {
+    const double sd = fmax(K_S_MAX, (s.sumy + s.sumz) / (double)(c.m + c.nb)) / K_S_MAX;
+    const double sc = c.nb ? fmax(K_S_MAX, s.sumz / (double)c.nb) / K_S_MAX : 1.0;
+    return fmax(s.dinf / sd, fmax(s.pinf, compl_inf(c, s, mu) / sc));
+}
+KMPC_HD double phi_of(const Stats &s, double mu) { return s.f - mu * s.bar + K_KAPPA_D * mu * s.damp; }
+
+KMPC_HD bool filter_ok(const Ctx &t, const Rows &L, const double *wsp, size_t S, double theta, double phi) {
+    for (int i = 0; i < t.fn; ++i)
+        if (!(theta <= RW(L.rFilt + 2 * i) || phi <= RW(L.rFilt + 2 * i + 1))) return false;
+    return true;
+}
+KMPC_HD void filter_add(Ctx &t, const Rows &L, double *wsp, size_t S, double theta, double phi) {
+    int m = 0;
+    for (int i = 0; i < t.fn; ++i) {
+        const double th = RW(L.rFilt + 2 * i), ph = RW(L.rFilt + 2 * i + 1);
+        if (!(th >= theta && ph >= phi)) { RW(L.rFilt + 2 * m) = th; RW(L.rFilt + 2 * m + 1) = ph; ++m; }
+    }
+    t.fn = m;
+    if (t.fn < K_FILTER_CAP) { RW(L.rFilt + 2 * t.fn) = theta; RW(L.rFilt + 2 * t.fn + 1) = phi; t.fn++; }
+}
+
+// FilterLSAcceptor::CheckAcceptabilityOfTrialPoint
+KMPC_HD bool is_ftype(const Ctx &t, double a) {
+    return t.gBD < 0 && a * pow(-t.gBD, K_S_PHI) > K_DELTA_LS * pow(t.c.theta, K_S_THETA);
+}
+KMPC_HD bool armijo(const Ctx &t, double a, double tphi, double cphi) { return cmp_le(tphi - cphi, K_ETA_PHI * a * t.gBD, cphi); }
+KMPC_HD bool acceptable(const Ctx &t, const Rows &L, const double *wsp, size_t S, const Stats &tri) {
+    const double cphi = phi_of(t.c, t.mu), tphi = phi_of(tri, t.mu), cth = t.c.theta;
+    bool acc;
+    if (tri.theta > t.theta_max) return false;
+    if (is_ftype(t, t.alpha_test) && cth <= t.theta_min) acc = armijo(t, t.alpha_test, tphi, cphi);
+    else {
+        acc = true;
+        if (tphi > cphi) {
+            const double bas = fabs(cphi) > 10.0 ? log10(fabs(cphi)) : 1.0;
+            if (log10(tphi - cphi) > K_OBJ_MAX_INC + bas) acc = false;
+        }
+        if (acc) acc = cmp_le(tri.theta, (1.0 - K_GAMMA_THETA) * cth, cth) || cmp_le(tphi - cphi, -K_GAMMA_PHI * cth, cphi);
+    }
+    if (acc) acc = filter_ok(t, L, wsp, S, tri.theta, tphi);
+    return acc;
+}
+
+// Top of IPOPT's main loop at a (new) current iterate: termination tests, monotone barrier update.
+// Returns a status < 100 to finish the instance, 100 to continue with a Newton step.
+KMPC_HD int begin_iteration(const Cfg &c, Ctx &t) {
+    const double E0 = opt_error(c, t.c, 0.0);
+    if (!isfinite(E0)) return ST_INVALID;
+    if (E0 <= c.tol && t.c.dinf / t.df <= K_DUAL_INF_TOL && t.c.pinf <= K_CONSTR_VIOL_TOL &&
+        compl_inf(c, t.c, 0.0) / t.df <= K_COMPL_INF_TOL)
+        return ST_SUCCESS;
+    if (t.iter >= c.max_iter) return ST_MAXITER;
+    if (t.c.wmax > K_DIVERGING) return ST_DIVERGING;
+    bool done = false;
+    while (!done && opt_error(c, t.c, t.mu) <= K_KAPPA_EPS * t.mu) {
+        const double nm = fmax(fmin(K_MU_LIN * t.mu, pow(t.mu, K_MU_SUPER)), fmin(c.tol, K_COMPL_INF_TOL) / (K_KAPPA_EPS + 1.0));
+        const bool changed = nm != t.mu;
+        t.mu = nm; t.tau = fmax(K_TAU_MIN, 1.0 - t.mu);
+        if (changed) t.fn = 0; else done = true;
+    }
+    t.delta = 0.0;
+    t.mode = M_NEWTON;
+    return 100;
+}
+
+// One trip of the state machine for one instance (mode != M_FETCH, != M_DONE).
+// Returns 100 while the instance is still being solved, else its final status (the caller writes the outputs).
+KMPC_HDN inline int trip(const Cfg &c, Ctx &t, double *wsp, size_t S) {
+    const Rows &L = c.L;
+    t.trips++;
+    int sel = 0, tu = TU_STEP;
+    double a_pr = 0.0, a_y = 0.0, a_du = 0.0;
+    if (t.mode != M_TRIAL) {
+        const bool ok = pass_sweep(c, t, wsp, S);
+        if (!ok) {
+            if (t.mode != M_NEWTON) return ST_STEP_ERROR;
+            // inertia correction (IPOPT PDPerturbationHandler)
+            if (t.delta == 0.0) t.delta = t.delta_last == 0.0 ? K_DW_INIT : fmax(K_DW_MIN, t.delta_last * K_DW_DEC);
+            else t.delta = (t.delta_last == 0.0 || 1e5 * t.delta_last < t.delta) ? K_DW_INC_FIRST * t.delta : K_DW_INC * t.delta;
+            if (t.delta > K_DW_MAX) return ST_STEP_ERROR;
+            return 100;
+        }
+        double apr, adu, gbd, ym;
+        sel = t.mode == M_SOC ? 1 : 0;
+        pass_rollout(c, t, wsp, S, sel, &apr, &adu, &gbd, &ym);
+        if (t.mode == M_LSQ) {
+            tu = TU_INIT; a_pr = 0.0; a_du = 0.0;
+            a_y = (ym <= K_YINIT_MAX && isfinite(ym)) ? -1.0 : 0.0;
+        } else if (t.mode == M_NEWTON) {
+            if (t.delta > 0.0) t.delta_last = t.delta;
+            t.gBD = gbd;
+            if (t.theta_max < 0) { t.theta_max = K_THETA_MAX_FACT * fmax(1.0, t.c.theta); t.theta_min = K_THETA_MIN_FACT * fmax(1.0, t.c.theta); }
+            double amin = K_GAMMA_THETA;
+            if (gbd < 0) {
+                amin = fmin(K_GAMMA_THETA, K_GAMMA_PHI * t.c.theta / (-gbd));
+                if (t.c.theta <= t.theta_min) amin = fmin(amin, K_DELTA_LS * pow(t.c.theta, K_S_THETA) / pow(-gbd, K_S_PHI));
+            }
+            t.alpha_min = amin * K_ALPHA_MIN_FRAC;
+            t.alpha = apr; t.alpha_test = apr; t.alpha_du0 = adu; t.nsteps = 0; t.soc_count = 0;
+            a_pr = apr; a_y = apr; a_du = adu;
+        } else {  // M_SOC
+            t.alpha_soc = apr;
+            a_pr = apr; a_y = apr; a_du = adu;
+        }
+    } else {
+        sel = 0; a_pr = t.alpha; a_y = t.alpha; a_du = t.alpha_du0;
+        t.alpha_test = t.alpha;
+    }
+    Stats tri;
+    const bool evok = pass_trial(c, t, wsp, S, sel, tu, a_pr, a_y, a_du, &tri);
+    bool accept = tu == TU_INIT;
+    int soc_rhs = 0;  // 1: first correction, 2: follow-up correction
+    if (tu == TU_STEP) {
+        if (evok) accept = acceptable(t, L, wsp, S, tri);
+        if (!accept && evok) {
+            if (t.mode == M_SOC) {
+                t.soc_count++; t.theta_trial = tri.theta;
+                if (t.soc_count < K_MAX_SOC && t.theta_trial <= K_KAPPA_SOC * t.theta_soc_old) soc_rhs = 2;
+            } else if (t.nsteps == 0 && t.c.theta <= tri.theta) {
+                // second-order correction from the first trial point (max_soc 4)
+                t.alpha_soc = t.alpha; t.soc_count = 0;
+                soc_rhs = 1;
+            }
+        }
+        if (soc_rhs) {
+            t.theta_soc_old = tri.theta; t.theta_trial = tri.theta;
+            pass_soc_rhs(c, t, wsp, S, t.alpha_soc, soc_rhs == 1);
+            t.mode = M_SOC;
+            return 100;
+        }
+        if (!accept) {
+            // back-track on the original step (also after a failed correction)
+            t.alpha *= K_ALPHA_RED; t.nsteps++;
+            if (!(t.alpha > t.alpha_min)) return ST_RESTORATION;  // IPOPT would enter the restoration phase here
+            t.mode = M_TRIAL;
+            return 100;
+        }
+        // accepted: filter augmentation (FilterLSAcceptor::UpdateForNextIteration)
+        const double cphi = phi_of(t.c, t.mu), tphi = phi_of(tri, t.mu);
+        if (!is_ftype(t, t.alpha_test) || !armijo(t, t.alpha_test, tphi, cphi))
+            filter_add(t, L, wsp, S, (1.0 - K_GAMMA_THETA) * t.c.theta, cphi - K_GAMMA_PHI * t.c.theta);
+        t.iter++;
+    }
+    // the trial buffer becomes the current iterate
+    t.c = tri; t.cur ^= 1;
+    return begin_iteration(c, t);
+}
+
+}  // namespace kmpc

@@ -1,0 +1,54 @@
+// TEST HARNESS ONLY -- never built into or loaded by the product package.
+// Compiles kiss_mpc_b200/csrc/kmpc_core.cuh (the per-thread solver the CUDA kernel runs) with g++ so that the
+// algorithm can be checked against the oracle on a machine without a GPU.  One "slot" is executed at a time; the
+// structure-of-arrays workspace indexing (row * S + slot) is exercised with S > 1.
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include "../../include/kmpc.h"
+#include "../../kiss_mpc_b200/csrc/kmpc_core.cuh"
+
+using namespace kmpc;
+
+extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, const double *goal, const double *X0,
+                          const double *U0, const double *obs, int O, double obs_radius, double inflation, double *X_out,
+                          double *U_out, double *obj, int32_t *status, int32_t *iters, int32_t *trips) {
+    Cfg c;
+    memset(&c, 0, sizeof c);
+    c.N = cf->N; c.O = O; c.cost_mode = cf->cost_mode; c.gk_lo = cf->goal_k_lo; c.gk_hi = cf->goal_k_hi;
+    c.max_iter = cf->max_iter; c.layout = cf->layout; c.B = B;
+    for (int i = 0; i < 4; ++i) {
+        c.hasL[i] = cf->lo[i] > -KMPC_NO_BOUND; c.hasU[i] = cf->hi[i] < KMPC_NO_BOUND;
+        c.lb[i] = c.hasL[i] ? cf->lo[i] - K_BOUND_RELAX * fmax(1.0, fabs(cf->lo[i])) : -INFINITY;
+        c.ub[i] = c.hasU[i] ? cf->hi[i] + K_BOUND_RELAX * fmax(1.0, fabs(cf->hi[i])) : INFINITY;
+    }
+    c.T = cf->T; c.W[0] = cf->W[0]; c.W[1] = cf->W[1]; c.W[2] = cf->W[2];
+    c.Wvn = cf->Wv_neg; c.Wvp = cf->Wv_pos; c.Ww = cf->Ww; c.tol = cf->tol;
+    c.obs_radius = obs_radius; c.dL = inflation - K_BOUND_RELAX * fmax(1.0, fabs(inflation));
+    c.L = make_rows(cf->N, O);
+    c.nb = (cf->N + 1) * (c.hasL[0] + c.hasU[0] + c.hasL[1] + c.hasU[1]) + cf->N * (c.hasL[2] + c.hasU[2] + c.hasL[3] + c.hasU[3]) + cf->N * O;
+    c.m = 3 * (cf->N + 1) + cf->N * O;
+    IO io;
+    io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs;
+    io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters;
+    const size_t S = 8;
+#pragma omp parallel
+    {
+        double *ws = (double *)malloc(sizeof(double) * S * c.L.total);
+        for (size_t i = 0; i < S * c.L.total; ++i) ws[i] = NAN;  // poison: reads of never-written rows show up
+#pragma omp for schedule(dynamic, 1)
+        for (int b = 0; b < B; ++b) {
+            double *wsp = ws + (b % S);
+            Ctx t;
+            memset(&t, 0, sizeof t);
+            t.inst = b; t.trips = 0;
+            pass_init(c, t, wsp, S, io);
+            int r;
+            do { r = trip(c, t, wsp, S); } while (r == 100);
+            pass_output(c, t, wsp, S, io, r);
+            if (trips) trips[b] = t.trips;
+        }
+        free(ws);
+    }
+    return 0;
+}

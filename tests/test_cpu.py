@@ -1,0 +1,167 @@
+"""CPU-side tests (no GPU): the oracle against its own cross-checks and committed golden vectors, the g++ build of the
+per-thread solver source against the oracle, the C ABI surface, host logic."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from kiss_mpc_b200.synthetic import cfg1_instance, make_batch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+# ---------------- oracle ----------------
+def test_oracle_dense_vs_riccati(oracle_mod):
+    b = make_batch(64, seed=1002)
+    rd = oracle_mod.solve(oracle_mod.OracleConfig(linsolve="dense"), b["x_cur"], b["goal"])
+    rr = oracle_mod.solve(oracle_mod.OracleConfig(linsolve="riccati"), b["x_cur"], b["goal"])
+    assert (rd.status == 0).all() and (rr.status == 0).all()
+    assert np.abs(rd.U - rr.U).max() < 1e-9
+    assert (rd.iters == rr.iters).all()
+
+
+def test_oracle_kkt_certificate_and_slsqp(oracle_mod):
+    """Solver-independent check of the oracle's answers: first-order certificate + SLSQP polish."""
+    from oracle.nlp_numpy import NLP, kkt_certificate, slsqp_polish
+    cfg = oracle_mod.OracleConfig(linsolve="dense")
+    b = make_batch(4, seed=3)
+    r = oracle_mod.solve(cfg, b["x_cur"], b["goal"])
+    for i in range(4):
+        nlp = NLP(cfg, b["x_cur"][i], b["goal"][i])
+        cert = kkt_certificate(nlp, r.X[i], r.U[i])
+        assert cert["primal"] < 1e-8 and cert["bound_violation"] < 1e-7 and cert["stationarity_rel"] < 1e-5
+        Xp, Up, fp = slsqp_polish(nlp, r.X[i], r.U[i])
+        assert abs(fp - r.obj[i]) <= 1e-6 * abs(r.obj[i])
+        assert np.abs(Up - r.U[i]).max() <= 1e-5
+
+
+def test_oracle_golden(oracle_mod):
+    """Golden vectors committed under tests/golden (made by tests/golden/make_golden.py from the oracle + SLSQP polish)."""
+    g = np.load(os.path.join(GOLD, "cfg1_and_batch.npz"))
+    cfg = oracle_mod.OracleConfig(linsolve="dense")
+    r = oracle_mod.solve(cfg, g["x_cur"], g["goal"])
+    assert (r.status == g["status"]).all()
+    assert np.abs(r.U - g["U"]).max() <= 1e-9
+    assert np.abs(r.obj - g["obj"]).max() <= 1e-9 * np.abs(g["obj"]).max()
+    # the polished (SLSQP) solutions are an independent solver's answer for the same instances
+    assert np.abs(r.U - g["U_slsqp"]).max() <= 1e-5
+    assert (np.abs(r.obj - g["obj_slsqp"]) / np.abs(g["obj_slsqp"])).max() <= 1e-6
+
+
+# ---------------- per-thread solver source (g++ build) vs oracle ----------------
+@pytest.mark.parametrize("case", ["box", "N50", "literal", "obs", "layout1", "infeasible"])
+def test_solver_source_matches_oracle(oracle_mod, case):
+    import emul
+    kw, B, seed, O, layout = {}, 96, 1002, 0, 0
+    if case == "N50":
+        kw, seed = dict(N=50), 1003
+    elif case == "literal":
+        kw = dict(cost_mode="code_literal", goal_range="code", y_bounds=(-oracle_mod.INF, oracle_mod.INF))
+    elif case == "obs":
+        kw, seed, O = dict(O=10), 1004, 10
+    elif case == "layout1":
+        layout = 1
+    elif case == "infeasible":
+        kw = dict(max_iter=300)
+    cfg = oracle_mod.OracleConfig(linsolve="riccati", **kw)
+    b = make_batch(B, seed=seed, O=O)
+    if case == "infeasible":
+        b["x_cur"][::4, 0] = 25.0
+    ref = oracle_mod.solve(cfg, b["x_cur"], b["goal"], obs=b["obs"])
+    X, U, obj, st, it, tp = emul.solve(cfg, b["x_cur"], b["goal"], obs=b["obs"], layout=layout)
+    assert (st == ref.status).all()
+    conv = st == 0
+    assert np.abs(U - ref.U)[conv].max() <= 1e-9
+    assert (it == ref.iters).mean() >= 0.95
+
+
+def test_solver_source_warm_start(oracle_mod):
+    import emul
+    cfg = oracle_mod.OracleConfig(linsolve="riccati")
+    b = make_batch(48, seed=11)
+    r0 = oracle_mod.solve(cfg, b["x_cur"], b["goal"])
+    r1 = oracle_mod.solve(cfg, r0.X[:, :, 1], b["goal"], X0=r0.X, U0=r0.U)
+    X, U, obj, st, it, tp = emul.solve(cfg, r0.X[:, :, 1], b["goal"], X0=r0.X, U0=r0.U)
+    assert (st == r1.status).all() and np.abs(U - r1.U).max() <= 1e-9
+
+
+# ---------------- C ABI surface ----------------
+def test_abi_exports_every_declared_symbol():
+    from kiss_mpc_b200 import _lib, build
+    so = build.build()
+    hdr = open(os.path.join(ROOT, "include", "kmpc.h")).read()
+    declared = set(re.findall(r"\b(kmpc_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"kmpc_config", "kmpc_handle", "kmpc_stats"}
+    assert declared == set(_lib.SYMBOLS)
+    L = C.CDLL(so)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert L.kmpc_version() == _lib.KMPC_VERSION
+
+
+def test_abi_struct_and_workspace_size():
+    from kiss_mpc_b200 import PlannerConfig, _lib
+    L = _lib.load()
+    c = PlannerConfig().to_c(65536, 0, 0)
+    assert C.sizeof(c) == 10 * 4 + 8 * (1 + 3 + 3 + 4 + 4 + 1)
+    nbytes = L.kmpc_workspace_bytes(C.byref(c))
+    assert 100e6 < nbytes < 4e9
+    bad = PlannerConfig(N=0).to_c(1, 0, 0)
+    assert L.kmpc_workspace_bytes(C.byref(bad)) == 0
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from kiss_mpc_b200 import BatchedMotionPlanner, KmpcError
+    with pytest.raises(KmpcError):
+        BatchedMotionPlanner(max_batch=4)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "kiss_mpc_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "kmpc_oracle" not in src, f
+
+
+# ---------------- host logic ----------------
+def test_shard_range_partitions():
+    from kiss_mpc_b200 import shard_range
+    for B in (0, 1, 7, 64, 65536, 65537):
+        for w in (1, 2, 3, 8):
+            parts = [shard_range(B, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == B
+            assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+
+
+def _gloo_worker(rank, world, port, B, q):
+    import torch
+    import torch.distributed as dist
+    from kiss_mpc_b200 import SolveResult, gather_results, shard_range
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = shard_range(B, rank, world)
+    idx = torch.arange(lo, hi, dtype=torch.float64)
+    local = SolveResult(idx[:, None, None].repeat(1, 3, 4), idx[:, None, None].repeat(1, 2, 3), idx * 2, idx.to(torch.int32), idx.to(torch.int32) + 1)
+    out = gather_results(local, B)
+    if rank == 0:
+        q.put((out.objective.tolist(), out.status.tolist(), tuple(out.states.shape)))
+    dist.destroy_process_group()
+
+
+def test_sharded_gather_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    B, world, port = 11, 2, 29731
+    ps = [ctx.Process(target=_gloo_worker, args=(r, world, port, B, q)) for r in range(world)]
+    [p.start() for p in ps]
+    obj, st, shp = q.get(timeout=120)
+    [p.join(60) for p in ps]
+    assert obj == [2.0 * i for i in range(B)] and st == list(range(B)) and shp == (B, 3, 4)

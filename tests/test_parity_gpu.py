@@ -1,0 +1,223 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via kiss_mpc_b200.BatchedMotionPlanner / MotionPlanner) against
+the CPU oracle on the same seeded inputs.  Tolerances are BASELINE.json's: objective rel. 1e-6, controls abs. 1e-5 on
+converged instances, identical status."""
+import numpy as np
+import pytest
+
+from kiss_mpc_b200.synthetic import cfg1_instance, make_batch
+
+pytestmark = pytest.mark.gpu
+
+OBJ_RTOL = 1e-6   # BASELINE.json north_star
+CTRL_ATOL = 1e-5  # BASELINE.json north_star
+
+
+def _torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _pair(ok, **kw):
+    from kiss_mpc_b200 import PlannerConfig
+    ocfg = ok.OracleConfig(linsolve="riccati", **kw)
+    pk = {k: v for k, v in kw.items() if k not in ("O", "obs_radius", "inflation")}
+    if "O" in kw:
+        pk["O_max"] = kw["O"]
+    for k in ("y_bounds", "x_bounds"):
+        if k in pk:
+            pk[k] = tuple(float(np.clip(v, -1e30, 1e30)) for v in pk[k])
+    return ocfg, PlannerConfig(**pk)
+
+
+def _check(res, ref, require_all_converged=True):
+    st = res.status.cpu().numpy() if hasattr(res.status, "cpu") else res.status
+    U = res.controls.cpu().numpy() if hasattr(res.controls, "cpu") else res.controls
+    X = res.states.cpu().numpy() if hasattr(res.states, "cpu") else res.states
+    obj = res.objective.cpu().numpy() if hasattr(res.objective, "cpu") else res.objective
+    assert (st == ref.status).all(), f"status mismatch at {np.where(st != ref.status)[0][:10]}"
+    conv = st == 0
+    if require_all_converged:
+        assert conv.all()
+    if conv.any():
+        assert np.abs(U - ref.U)[conv].max() <= CTRL_ATOL
+        assert np.abs(X - ref.X)[conv].max() <= 1e-4
+        assert (np.abs(obj - ref.obj) / np.maximum(1.0, np.abs(ref.obj)))[conv].max() <= OBJ_RTOL
+    return conv
+
+
+def _dev(a):
+    torch = _torch()
+    return None if a is None else torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda:0")
+
+
+@pytest.mark.parametrize("B", [1, 33, 1000])
+def test_box_bounds_cold_start(oracle_mod, B):
+    from kiss_mpc_b200 import BatchedMotionPlanner
+    ocfg, pcfg = _pair(oracle_mod)
+    b = make_batch(B, seed=1002)
+    ref = oracle_mod.solve(ocfg, b["x_cur"], b["goal"])
+    pl = BatchedMotionPlanner(pcfg, max_batch=B)
+    res = pl.solve(_dev(b["x_cur"]), _dev(b["goal"]))
+    _torch().cuda.synchronize()
+    _check(res, ref)
+    assert (res.iters.cpu().numpy() == ref.iters).mean() > 0.95
+
+
+def test_cfg2_4096(oracle_mod):
+    """BASELINE configs[1]: 4,096-instance batch, random start/goal, N=30, box bounds only."""
+    from kiss_mpc_b200 import BatchedMotionPlanner
+    ocfg, pcfg = _pair(oracle_mod)
+    b = make_batch(4096, seed=1002)
+    ref = oracle_mod.solve(ocfg, b["x_cur"], b["goal"])
+    res = BatchedMotionPlanner(pcfg, max_batch=4096).solve(_dev(b["x_cur"]), _dev(b["goal"]))
+    _check(res, ref)
+
+
+def test_horizon_50(oracle_mod):
+    from kiss_mpc_b200 import BatchedMotionPlanner
+    ocfg, pcfg = _pair(oracle_mod, N=50)
+    b = make_batch(512, seed=1003)
+    ref = oracle_mod.solve(ocfg, b["x_cur"], b["goal"])
+    res = BatchedMotionPlanner(pcfg, max_batch=512).solve(_dev(b["x_cur"]), _dev(b["goal"]))
+    _check(res, ref)
+
+
+def test_code_literal_form(oracle_mod):
+    from kiss_mpc_b200 import BatchedMotionPlanner, PlannerConfig
+    ocfg = oracle_mod.OracleConfig(linsolve="riccati", cost_mode="code_literal", goal_range="code",
+                                   y_bounds=(-oracle_mod.INF, oracle_mod.INF))
+    b = make_batch(512, seed=1002)
+    ref = oracle_mod.solve(ocfg, b["x_cur"], b["goal"])
+    res = BatchedMotionPlanner(PlannerConfig.code_literal(), max_batch=512).solve(_dev(b["x_cur"]), _dev(b["goal"]))
+    _check(res, ref)
+
+
+def test_obstacles_O10(oracle_mod):
+    """BASELINE configs[3]: O=10 static circular obstacle-distance constraints, N=30."""
+    from kiss_mpc_b200 import BatchedMotionPlanner
+    ocfg, pcfg = _pair(oracle_mod, O=10)
+    b = make_batch(512, seed=1004, O=10)
+    ref = oracle_mod.solve(ocfg, b["x_cur"], b["goal"], obs=b["obs"])
+    res = BatchedMotionPlanner(pcfg, max_batch=512).solve(_dev(b["x_cur"]), _dev(b["goal"]), obstacles=_dev(b["obs"]),
+                                                           obstacle_radius=ocfg.obs_radius, inflation_radius=ocfg.inflation)
+    conv = _check(res, ref, require_all_converged=False)
+    assert conv.mean() > 0.9
+    # constraint actually holds: distance >= inflation (up to IPOPT's bound relaxation)
+    X = res.states.cpu().numpy()[conv]
+    d = np.linalg.norm(X[:, None, :2, 1:] - b["obs"][conv][:, :, :, None], axis=2) - ocfg.obs_radius
+    assert d.min() >= ocfg.inflation - 1e-6
+
+
+def test_warm_start_and_handoff(oracle_mod):
+    """Closed-loop step semantics of agent.py:139-155: unshifted warm start from the previous solution, x_cur <- X[:,1]."""
+    from kiss_mpc_b200 import BatchedMotionPlanner
+    torch = _torch()
+    ocfg, pcfg = _pair(oracle_mod)
+    B = 256
+    b = make_batch(B, seed=1005)
+    pl = BatchedMotionPlanner(pcfg, max_batch=B)
+    x, g = _dev(b["x_cur"]), _dev(b["goal"])
+    r0 = pl.solve(x, g)
+    ref0 = oracle_mod.solve(ocfg, b["x_cur"], b["goal"])
+    _check(r0, ref0)
+    applied = torch.empty(B, 2, dtype=torch.float64, device="cuda:0")
+    pl.agent_handoff(r0.states, r0.controls, x, applied)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(x.cpu().numpy(), r0.states.cpu().numpy()[:, :, 1])
+    np.testing.assert_array_equal(applied.cpu().numpy(), r0.controls.cpu().numpy()[:, :, 0])
+    r1 = pl.solve(x, g, r0.states, r0.controls)
+    ref1 = oracle_mod.solve(ocfg, ref0.X[:, :, 1], b["goal"], X0=ref0.X, U0=ref0.U)
+    _check(r1, ref1)
+    assert r1.iters.float().mean() < r0.iters.float().mean()
+
+
+def test_status_parity_infeasible(oracle_mod):
+    """Status-parity batch: x_cur.x = +-25 violates the x bound -> the equality X_0 = x_cur is infeasible."""
+    from kiss_mpc_b200 import BatchedMotionPlanner
+    ocfg, pcfg = _pair(oracle_mod, max_iter=300)
+    b = make_batch(256, seed=77)
+    b["x_cur"][::4, 0] = 25.0
+    b["x_cur"][1::8, 0] = -25.0
+    ref = oracle_mod.solve(ocfg, b["x_cur"], b["goal"])
+    res = BatchedMotionPlanner(pcfg, max_batch=256).solve(_dev(b["x_cur"]), _dev(b["goal"]))
+    conv = _check(res, ref, require_all_converged=False)
+    assert (~conv).sum() >= 64
+
+
+def test_batch_minor_layout_and_host_path(oracle_mod):
+    from kiss_mpc_b200 import BatchedMotionPlanner
+    ocfg, pcfg = _pair(oracle_mod)
+    B = 300
+    b = make_batch(B, seed=5)
+    ref = oracle_mod.solve(ocfg, b["x_cur"], b["goal"])
+    pl = BatchedMotionPlanner(pcfg, max_batch=B, layout="batch_minor")
+    res = pl.solve(_dev(b["x_cur"].T), _dev(b["goal"].T))
+    from kiss_mpc_b200 import SolveResult
+    _check(SolveResult(res.states.permute(2, 0, 1), res.controls.permute(2, 0, 1), res.objective, res.status, res.iters), ref)
+    # host (NumPy) path through kmpc_solve_host
+    pl2 = BatchedMotionPlanner(pcfg, max_batch=B)
+    res2 = pl2.solve(b["x_cur"], b["goal"])
+    _check(res2, ref)
+
+
+def test_motion_planner_drop_in(oracle_mod):
+    """BASELINE configs[0]: single agent, N=30, T=0.1, exactly the reference's keyword call (agent.py:139-152)."""
+    from kiss_mpc_b200 import MotionPlanner
+    xc, gl = cfg1_instance()
+    N = 30
+    mp = MotionPlanner(time_step=0.1, horizon=N)
+    X0 = np.tile(xc.reshape(3, 1), (1, N + 1)); U0 = np.zeros((2, N))      # agent.py:59-60
+    X, U = mp.solve(current_state=xc[0], current_linear_velocity=0.0, current_angular_velocity=0.0, goal_state=gl[0],
+                    states_matrix=X0, controls_matrix=U0, state_bounds=(-20, 20), linear_velocity_bounds=(-0.2, 0.5),
+                    angular_velocity_bounds=(-0.5, 0.5), static_obstacles=[], dynamic_obstacles=[], inflation_radius=0.5)
+    assert X.shape == (3, N + 1) and U.shape == (2, N) and X.dtype == np.float64
+    ref = oracle_mod.solve(oracle_mod.OracleConfig(linsolve="dense"), xc, gl, X0=X0[None], U0=U0[None])
+    assert mp.last_status == ref.status[0] == 0
+    assert np.abs(U - ref.U[0]).max() <= CTRL_ATOL
+    assert abs(mp.last_objective - ref.obj[0]) <= OBJ_RTOL * abs(ref.obj[0])
+
+    class _Geo:  # duck-typed obstacle_handling.geometry.Circle
+        def __init__(self, c, r): self.center, self.radius = c, r
+
+    class _Obs:
+        def __init__(self, c, r): self.geometry = _Geo(c, r)
+
+    obs = [_Obs((1.0, 1.2), 0.3), _Obs((1.6, 2.6), 0.3)]
+    X2, U2 = mp.solve(current_state=xc[0], current_linear_velocity=0.0, current_angular_velocity=0.0, goal_state=gl[0],
+                      states_matrix=X0, controls_matrix=U0, state_bounds=(-20, 20), linear_velocity_bounds=(-0.2, 0.5),
+                      angular_velocity_bounds=(-0.5, 0.5), static_obstacles=obs[:1], dynamic_obstacles=obs[1:], inflation_radius=0.5)
+    oc = oracle_mod.OracleConfig(linsolve="dense", O=2)
+    ref2 = oracle_mod.solve(oc, xc, gl, X0=X0[None], U0=U0[None], obs=np.array([[[1.0, 1.2], [1.6, 2.6]]]))
+    assert mp.last_status == ref2.status[0]
+    assert np.abs(U2 - ref2.U[0]).max() <= CTRL_ATOL
+
+
+def test_full_size_properties():
+    """BASELINE full size (65,536 x N=30): size-independent properties -- every converged solution is dynamically
+    feasible, inside its bounds, and shards of the batch reproduce the full-batch result bit for bit."""
+    from kiss_mpc_b200 import BatchedMotionPlanner, PlannerConfig, shard_range
+    torch = _torch()
+    B, N, T = 65536, 30, 0.1
+    b = make_batch(B, seed=1000)
+    pl = BatchedMotionPlanner(PlannerConfig(), max_batch=B)
+    x, g = _dev(b["x_cur"]), _dev(b["goal"])
+    r = pl.solve(x, g)
+    st = r.status.cpu().numpy()
+    assert (st == 0).mean() > 0.999
+    X, U = r.states, r.controls
+    nxt = X[:, :, :-1] + T * torch.stack([U[:, 0] * torch.cos(X[:, 2, :-1]), U[:, 0] * torch.sin(X[:, 2, :-1]), U[:, 1]], 1)
+    conv = r.status == 0
+    assert (X[:, :, 1:] - nxt)[conv].abs().max().item() <= 1e-7
+    assert (X[:, :, 0] - x)[conv].abs().max().item() <= 1e-7
+    assert U[conv][:, 0].min().item() >= -0.2 - 1e-7 and U[conv][:, 0].max().item() <= 0.5 + 1e-7
+    assert U[conv][:, 1].abs().max().item() <= 0.5 + 1e-7
+    # objective recomputed from the returned trajectory
+    e = X[:, :, 1:] - g[:, :, None]
+    f = (torch.tensor([100.0, 100.0, 50.0], device=X.device, dtype=X.dtype)[None, :, None] * e * e).sum((1, 2)) \
+        + (300.0 * U[:, 0].clamp(max=0) ** 2 + 10.0 * U[:, 1] ** 2).sum(1)
+    assert ((f - r.objective).abs() / f.abs().clamp(min=1))[conv].max().item() <= 1e-10
+    # batch-slice shards (the multi-GPU partition) give bit-identical results
+    lo, hi = shard_range(B, 3, 8)
+    rs = pl.solve(x[lo:hi].contiguous(), g[lo:hi].contiguous())
+    assert torch.equal(rs.controls, U[lo:hi]) and torch.equal(rs.status, r.status[lo:hi])
