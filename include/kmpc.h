@@ -113,8 +113,8 @@ int kmpc_agent_handoff(kmpc_handle *h, int B, const double *X, const double *U, 
 typedef struct kmpc_stats {
     double last_kernel_ms;    /* device time of the solver kernel of the last kmpc_solve on this handle (CUDA events on its stream) */
     int64_t launches;         /* kernels launched by this handle since creation */
-    int32_t slots;            /* resident solver threads (workspace slots) */
-    int32_t blocks;           /* grid size of the solver kernel */
+    int32_t slots;            /* workspace columns (one per instance) */
+    int32_t blocks;           /* host-driven solver trips (3 launches each) of the last solve */
     int32_t threads_per_block;
     int32_t sm_count;
     int64_t trips;            /* total solver-loop trips of the last solve (sum over threads), if timing enabled */

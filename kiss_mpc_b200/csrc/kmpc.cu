@@ -1,10 +1,10 @@
 // kmpc.cu -- CUDA kernels (sm_100a) and the C ABI of include/kmpc.h.
 //
 // Replaces the numerical core of mpc/optimizer.py:319-400 (MotionPlanner.solve -> CasADi/IPOPT) for B instances at
-// once.  One persistent CUDA thread per problem instance; per-instance state lives in a structure-of-arrays HBM
-// workspace (see kmpc_core.cuh); finished lanes pull the next instance from a global work counter, so a warp keeps
-// all 32 lanes busy although iteration counts differ by 5x between instances.  No tensor cores: the stage blocks are
-// 3x3 / 2x2 / 2x3 and the work is FP64 FMA + HBM streaming.  No CPU fallback exists in this library.
+// once.  One CUDA thread per problem instance and phase; per-instance state lives in a structure-of-arrays HBM
+// workspace (see kmpc_core.cuh); each launch works on a compacted list of the instances that still need that phase.
+// No tensor cores: the stage blocks are 3x3 / 2x2 / 2x3 and the work is FP64 FMA + HBM streaming.
+// No CPU fallback exists in this library.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -18,37 +18,124 @@ using namespace kmpc;
 #define KMPC_TPB 128
 
 // ------------------------------------------------------------------------------------------------
-// The solver kernel: grid of resident threads; thread "slot" owns workspace column `slot`.
-// counter starts at the number of launched threads: the first instance of a slot is b = slot (coalesced I/O for the
-// batch-minor layout), later ones come from atomicAdd.
+// Solver kernels.  One CUDA thread advances one instance by one phase; instance b owns workspace column b.
+// Between launches all solver state lives in the workspace (HBM, structure of arrays), so every launch works on a
+// COMPACTED list of the instances that still need that phase: a warp always has 32 live lanes although iteration
+// counts differ by 5x between instances and although some instances need extra sweeps (inertia correction, second-
+// order correction) or extra trial points (back-tracking).
+//   lists: LA[p] = instances that need a sweep in trip parity p, LT[p] = instances that need a trial point.
+//   trip t (p = t & 1):  sweep(LA[p]) -> ok: LT[p], wrong inertia: LA[1-p]
+//                        rollout(LT[p]);  trial(LT[p]) -> Newton/SOC next: LA[1-p], back-track next: LT[1-p], done: outputs
+// Survivors are appended per block with one atomicAdd (order inside a block chunk is preserved, so the columns a
+// warp touches stay sorted and mostly adjacent -> coalesced 32-byte sectors).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(KMPC_TPB, 2)
-kmpc_ipm_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_t S, int *__restrict__ counter,
-                unsigned long long *__restrict__ trips_total) {
-    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    double *wsp = ws + slot;
+struct Lists {
+    int *LA[2], *LT[2];
+    int *cnt;  // [0,1] = |LA[0]|,|LA[1]|   [2,3] = |LT[0]|,|LT[1]|
+    unsigned long long *trips;
+};
+
+// block-wide ordered append: every thread of the block calls it; returns the list position or -1
+__device__ __forceinline__ int block_append(bool flag, int *counter) {
+    __shared__ int s_cnt[KMPC_TPB / 32];
+    __shared__ int s_base;
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) s_cnt[w] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int i = 0; i < KMPC_TPB / 32; ++i) { const int v = s_cnt[i]; s_cnt[i] = tot; tot += v; }
+        s_base = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    const int pos = s_base + s_cnt[w] + __popc(m & ((1u << lane) - 1u));
+    __syncthreads();  // s_cnt/s_base are reused by the next call
+    return flag ? pos : -1;
+}
+
+__global__ void __launch_bounds__(KMPC_TPB)
+kmpc_init_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_t S, int *__restrict__ LA0) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= c.B) return;
+    double *wsp = ws + b;
     Ctx t;
-    t.mode = M_FETCH; t.trips = 0; t.inst = -1;
-    bool first = true;
-    for (;;) {
-        if (t.mode == M_FETCH) {
-            const int b = first ? (int)slot : atomicAdd(counter, 1);
-            first = false;
-            if (b < c.B) { t.inst = b; pass_init(c, t, wsp, S, io); }
-            else t.mode = M_DONE;
-        }
-        __syncwarp();
-        if (__all_sync(0xffffffffu, t.mode == M_DONE)) break;
-        if (t.mode != M_DONE) {
-            const int r = trip(c, t, wsp, S);
-            if (r != 100) { pass_output(c, t, wsp, S, io, r); t.mode = M_FETCH; }
+    t.inst = b;
+    pass_init(c, t, wsp, S, io);
+    ctx_store(t, c.L, wsp, S);
+    LA0[b] = b;
+}
+
+template <bool OBS>
+__global__ void __launch_bounds__(KMPC_TPB, 3)
+kmpc_sweep_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_t S, const Lists ls, const int p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = ls.cnt[p];
+    if (blockIdx.x * blockDim.x >= n) return;  // whole block idle
+    int r = -1000, b = -1;
+    if (i < n) {
+        b = ls.LA[p][i];
+        double *wsp = ws + b;
+        Ctx t;
+        ctx_load(t, c.L, wsp, S);
+        t.inst = b;
+        r = phase_sweep<OBS>(c, t, wsp, S);
+        const double *px = wsp + (size_t)c.L.rCtx * S;
+        double *pw = wsp + (size_t)c.L.rCtx * S;
+        (void)px;
+        pw[(size_t)X_TRIPS * S] = t.trips; pw[(size_t)X_DELTA * S] = t.delta;
+        if (r != 100 && r != 101) {
+            pass_output(c, t, wsp, S, io, r);
+            if (ls.trips) atomicAdd(ls.trips, (unsigned long long)t.trips);
         }
     }
-    if (trips_total) {
-        unsigned long long v = (unsigned long long)t.trips;
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(trips_total, v);
+    const int pos_t = block_append(r == 100, ls.cnt + 2 + p);
+    if (pos_t >= 0) ls.LT[p][pos_t] = b;
+    const int pos_a = block_append(r == 101, ls.cnt + (1 - p));
+    if (pos_a >= 0) ls.LA[1 - p][pos_a] = b;
+}
+
+template <bool OBS>
+__global__ void __launch_bounds__(KMPC_TPB, 4)
+kmpc_rollout_kernel(const Cfg c, double *__restrict__ ws, const size_t S, const Lists ls, const int p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = ls.cnt[2 + p];
+    if (i >= n) return;
+    const int b = ls.LT[p][i];
+    double *wsp = ws + b;
+    Ctx t;
+    ctx_load(t, c.L, wsp, S);
+    if (t.mode == M_TRIAL) return;  // back-tracking instance: keeps its step, only a new trial point
+    t.inst = b;
+    phase_rollout<OBS>(c, t, wsp, S);
+    ctx_store(t, c.L, wsp, S);
+}
+
+template <bool OBS>
+__global__ void __launch_bounds__(KMPC_TPB, 3)
+kmpc_trial_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_t S, const Lists ls, const int p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = ls.cnt[2 + p];
+    if (blockIdx.x * blockDim.x >= n) return;
+    int r = -1000, b = -1, mode = -1;
+    if (i < n) {
+        b = ls.LT[p][i];
+        double *wsp = ws + b;
+        Ctx t;
+        ctx_load(t, c.L, wsp, S);
+        t.inst = b;
+        r = phase_trial<OBS>(c, t, wsp, S);
+        mode = t.mode;
+        if (r == 100) ctx_store(t, c.L, wsp, S);
+        else {
+            pass_output(c, t, wsp, S, io, r);
+            if (ls.trips) atomicAdd(ls.trips, (unsigned long long)t.trips);
+        }
     }
+    const int pos_t = block_append(r == 100 && mode == M_TRIAL, ls.cnt + 2 + (1 - p));
+    if (pos_t >= 0) ls.LT[1 - p][pos_t] = b;
+    const int pos_a = block_append(r == 100 && mode != M_TRIAL, ls.cnt + (1 - p));
+    if (pos_a >= 0) ls.LA[1 - p][pos_a] = b;
 }
 
 // Batched EgoAgent.step hand-off (agent.py:139-155, :70-72): applied control = U[:,0]; next current state = X[:,1].
@@ -86,17 +173,22 @@ __global__ void kmpc_dfma_kernel(double *out, int iters, double a, double b) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+#define KMPC_LOOKAHEAD 4 /* trips enqueued before the host looks at the active-instance count of an older trip */
+
 struct kmpc_handle {
     kmpc_config cfg;
     Rows rows;
-    int device, sm_count, blocks, slots;
+    int device, sm_count, cols;  // cols = workspace columns (B_max rounded up to a multiple of 32)
     double *ws;
-    int *counter;
+    int *lists;  // 4 x cols ints
+    int *cnt;    // 4 counters
     unsigned long long *trips;
-    cudaEvent_t ev0, ev1;
+    int *h_cnt;  // pinned: KMPC_LOOKAHEAD x 4 counters
+    cudaEvent_t ev0, ev1, evq[KMPC_LOOKAHEAD];
     int timing;
     double last_ms;
     long long launches, last_trips;
+    int last_host_trips;
     // staging for kmpc_solve_host
     double *d_in, *d_out, *h_in, *h_out;
     int32_t *d_iout, *h_iout;
@@ -130,21 +222,14 @@ static int check_cfg(const kmpc_config *cfg) {
     return 1;
 }
 
-static int slots_for(const kmpc_config *cfg, int sm_count, int blocks_per_sm) {
-    int want = (cfg->B_max + KMPC_TPB - 1) / KMPC_TPB;
-    int cap = sm_count * blocks_per_sm;
-    int blocks = want < cap ? want : cap;
-    return blocks * KMPC_TPB;
-}
+static int cols_for(const kmpc_config *cfg) { return (cfg->B_max + 31) / 32 * 32; }
 
 extern "C" int kmpc_version(void) { return KMPC_VERSION; }
 
 extern "C" size_t kmpc_workspace_bytes(const kmpc_config *cfg) {
     if (!check_cfg(cfg)) return 0;
     Rows r = make_rows(cfg->N, cfg->O_max);
-    // upper bound without querying a device: 148 SMs x 2 blocks
-    int slots = slots_for(cfg, 148, 2);
-    return (size_t)r.total * slots * sizeof(double);
+    return (size_t)r.total * cols_for(cfg) * sizeof(double) + (size_t)4 * cols_for(cfg) * sizeof(int);
 }
 
 extern "C" const char *kmpc_last_error(const kmpc_handle *h) { return h ? h->err : g_err; }
@@ -153,8 +238,10 @@ extern "C" void kmpc_destroy(kmpc_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->ws) cudaFree(h->ws);
-    if (h->counter) cudaFree(h->counter);
+    if (h->lists) cudaFree(h->lists);
+    if (h->cnt) cudaFree(h->cnt);
     if (h->trips) cudaFree(h->trips);
+    if (h->h_cnt) cudaFreeHost(h->h_cnt);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_iout) cudaFree(h->d_iout);
@@ -163,6 +250,7 @@ extern "C" void kmpc_destroy(kmpc_handle *h) {
     if (h->h_iout) cudaFreeHost(h->h_iout);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int i = 0; i < KMPC_LOOKAHEAD; ++i) if (h->evq[i]) cudaEventDestroy(h->evq[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
     free(h);
 }
@@ -181,20 +269,17 @@ extern "C" int kmpc_create(const kmpc_config *cfg, kmpc_handle **out) {
     h->cfg = *cfg;
     h->device = cfg->device;
     h->rows = make_rows(cfg->N, cfg->O_max);
+    h->cols = cols_for(cfg);
     cudaError_t e = cudaSetDevice(h->device);
-    int bps = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kmpc_ipm_kernel, KMPC_TPB, 0);
-    if (e == cudaSuccess && bps < 1) bps = 1;
-    if (e == cudaSuccess) {
-        h->slots = slots_for(cfg, h->sm_count, bps);
-        h->blocks = h->slots / KMPC_TPB;
-        e = cudaMalloc(&h->ws, (size_t)h->rows.total * h->slots * sizeof(double));
-    }
-    if (e == cudaSuccess) e = cudaMalloc(&h->counter, sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&h->ws, (size_t)h->rows.total * h->cols * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&h->lists, (size_t)4 * h->cols * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&h->cnt, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&h->trips, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_cnt, KMPC_LOOKAHEAD * 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev1);
+    for (int i = 0; i < KMPC_LOOKAHEAD && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->evq[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof g_err, "kmpc_create: %s", cudaGetErrorString(e));
@@ -214,6 +299,11 @@ static void relax_bounds(const kmpc_config *cfg, Cfg *c) {
     }
 }
 
+static inline int nblocks(int n) { return (n + KMPC_TPB - 1) / KMPC_TPB; }
+
+// The trip loop is driven from the host: three launches per trip on `cuda_stream`, KMPC_LOOKAHEAD trips in flight; the
+// active-instance count of an older trip (async copy into pinned memory) sizes the grids and ends the loop.  On return
+// every instance has finished and the outputs are complete on `cuda_stream`.
 extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
                           const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
                           double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream) {
@@ -240,14 +330,46 @@ extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const doub
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs_centers;
     io.X_out = X_out; io.U_out = U_out; io.obj = obj_out; io.status = status_out; io.iters = iters_out;
-    int blocks = (B + KMPC_TPB - 1) / KMPC_TPB;
-    if (blocks > h->blocks) blocks = h->blocks;
-    const int launched = blocks * KMPC_TPB;
-    CU(cudaMemcpyAsync(h->counter, &launched, sizeof(int), cudaMemcpyHostToDevice, st));
+    const size_t S = (size_t)h->cols;
+    Lists ls;
+    ls.LA[0] = h->lists; ls.LA[1] = h->lists + S; ls.LT[0] = h->lists + 2 * S; ls.LT[1] = h->lists + 3 * S;
+    ls.cnt = h->cnt; ls.trips = h->timing ? h->trips : NULL;
+
     if (h->timing) { CU(cudaMemsetAsync(h->trips, 0, sizeof(unsigned long long), st)); CU(cudaEventRecord(h->ev0, st)); }
-    kmpc_ipm_kernel<<<blocks, KMPC_TPB, 0, st>>>(c, io, h->ws, (size_t)h->slots, h->counter, h->timing ? h->trips : NULL);
-    CU(cudaGetLastError());
+    const int cnt0[4] = {B, 0, 0, 0};
+    CU(cudaMemcpyAsync(h->cnt, cnt0, sizeof cnt0, cudaMemcpyHostToDevice, st));
+    kmpc_init_kernel<<<nblocks(B), KMPC_TPB, 0, st>>>(c, io, h->ws, S, ls.LA[0]);
     h->launches++;
+    int ub = B;  // upper bound of the number of unfinished instances (non-increasing over the trips)
+    int t = 0;
+    for (;; ++t) {
+        const int p = t & 1, q = t % KMPC_LOOKAHEAD;
+        if (t >= KMPC_LOOKAHEAD) {
+            CU(cudaEventSynchronize(h->evq[q]));
+            const int *hc = h->h_cnt + 4 * q;  // counts after trip t - LOOKAHEAD (parity p: its "next" lists are 1-p)
+            const int active = hc[1 - p] + hc[2 + (1 - p)];
+            if (active == 0) break;
+            ub = active;
+        }
+        const int g = nblocks(ub);
+        if (O > 0) {
+            kmpc_sweep_kernel<true><<<g, KMPC_TPB, 0, st>>>(c, io, h->ws, S, ls, p);
+            kmpc_rollout_kernel<true><<<g, KMPC_TPB, 0, st>>>(c, h->ws, S, ls, p);
+            kmpc_trial_kernel<true><<<g, KMPC_TPB, 0, st>>>(c, io, h->ws, S, ls, p);
+        } else {
+            kmpc_sweep_kernel<false><<<g, KMPC_TPB, 0, st>>>(c, io, h->ws, S, ls, p);
+            kmpc_rollout_kernel<false><<<g, KMPC_TPB, 0, st>>>(c, h->ws, S, ls, p);
+            kmpc_trial_kernel<false><<<g, KMPC_TPB, 0, st>>>(c, io, h->ws, S, ls, p);
+        }
+        h->launches += 3;
+        CU(cudaMemcpyAsync(h->h_cnt + 4 * q, h->cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(h->evq[q], st));
+        // the lists of parity p are consumed: empty them for trip t+1's appends
+        CU(cudaMemsetAsync(h->cnt + p, 0, sizeof(int), st));
+        CU(cudaMemsetAsync(h->cnt + 2 + p, 0, sizeof(int), st));
+    }
+    CU(cudaGetLastError());
+    h->last_host_trips = t;
     if (h->timing) {
         CU(cudaEventRecord(h->ev1, st));
         CU(cudaEventSynchronize(h->ev1));
@@ -334,7 +456,7 @@ extern "C" int kmpc_set_timing(kmpc_handle *h, int enable) {
 
 extern "C" int kmpc_get_stats(kmpc_handle *h, kmpc_stats *out) {
     if (!h || !out) return KMPC_E_BADARG;
-    out->last_kernel_ms = h->last_ms; out->launches = h->launches; out->slots = h->slots; out->blocks = h->blocks;
+    out->last_kernel_ms = h->last_ms; out->launches = h->launches; out->slots = h->cols; out->blocks = h->last_host_trips;
     out->threads_per_block = KMPC_TPB; out->sm_count = h->sm_count; out->trips = h->last_trips;
     return 0;
 }

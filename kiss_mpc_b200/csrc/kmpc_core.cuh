@@ -71,57 +71,48 @@ namespace kmpc {
 #define K_COMPL_INF_TOL 1e-4
 #define K_DIVERGING 1e20
 #define K_FILTER_CAP 24
+#define KMPC_NCTX 40  /* rows reserved for the per-instance solver context in the workspace */
 
 enum { ST_SUCCESS = 0, ST_MAXITER = -1, ST_RESTORATION = -2, ST_STEP_ERROR = -3, ST_DIVERGING = 4, ST_INVALID = -13 };
 enum { M_FETCH = 0, M_LSQ = 1, M_NEWTON = 2, M_SOC = 3, M_TRIAL = 4, M_DONE = 5 };
 enum { TU_INIT = 0, TU_STEP = 1 };
 
+// Workspace records.  All per-instance data of one stage k that a pass touches together is one RECORD of consecutive
+// rows, so a pass walks one pointer per record type and prefetches the next record while it computes on this one.
+enum { F_X0 = 0, F_X1, F_X2, F_V, F_OM, F_Y0, F_Y1, F_Y2, F_ZLX, F_ZUX, F_ZLY, F_ZUY, F_ZLV, F_ZUV, F_ZLW, F_ZUW, F_CS, F_SN, NSTATE };
+enum { A_K00 = 0, A_K01, A_K02, A_K10, A_K11, A_K12, A_KF0, A_KF1, A_P00, A_P10, A_P11, A_P20, A_P21, A_P22, A_PV0, A_PV1, A_PV2, NFACT };
+enum { D_X0 = 0, D_X1, D_X2, D_U0, D_U1, D_Y0, D_Y1, D_Y2, NSTEP };
+
 // Row map of the per-slot workspace (all offsets in rows of S doubles).
 struct Rows {
     int N, O;
-    // inside one state buffer
-    int sX, sU, sY, sZ, sCS, sS, sYD, sVL, state_rows;
+    int sObs, state_rows;  // one state buffer: (N+1) STATE records, then N*O obstacle records [s, yd, vL]
     int rState[2];
-    int rK, rKff, rP, rPv;
-    // inside one step buffer
-    int dX, dU, dY, dS, dYD, step_rows;
+    int rFact;             // (N+1) FACT records
+    int dObs, step_rows;   // one step buffer: (N+1) STEP records, then N*O records [ds, dyd]
     int rStep[2];
-    int rCsoc, rDsoc, rFilt, rSc, total;
+    int rCsoc, rDsoc, rFilt, rSc, rCtx, total;
 };
 
 KMPC_HD Rows make_rows(int N, int O) {
     Rows L;
     L.N = N; L.O = O;
-    int NO = N * O, o = 0;
-    L.sX = o; o += 3 * (N + 1);
-    L.sU = o; o += 2 * N;
-    L.sY = o; o += 3 * (N + 1);
-    L.sZ = o; o += 8 * (N + 1);
-    L.sCS = o; o += 2 * N;
-    L.sS = o; o += NO;
-    L.sYD = o; o += NO;
-    L.sVL = o; o += NO;
-    L.state_rows = o;
+    const int NO = N * O;
+    L.sObs = NSTATE * (N + 1);
+    L.state_rows = L.sObs + 3 * NO;
     int r = 0;
     L.rState[0] = r; r += L.state_rows;
     L.rState[1] = r; r += L.state_rows;
-    L.rK = r; r += 6 * N;
-    L.rKff = r; r += 2 * N;
-    L.rP = r; r += 6 * (N + 1);
-    L.rPv = r; r += 3 * (N + 1);
-    o = 0;
-    L.dX = o; o += 3 * (N + 1);
-    L.dU = o; o += 2 * N;
-    L.dY = o; o += 3 * (N + 1);
-    L.dS = o; o += NO;
-    L.dYD = o; o += NO;
-    L.step_rows = o;
+    L.rFact = r; r += NFACT * (N + 1);
+    L.dObs = NSTEP * (N + 1);
+    L.step_rows = L.dObs + 2 * NO;
     L.rStep[0] = r; r += L.step_rows;
     L.rStep[1] = r; r += L.step_rows;
     L.rCsoc = r; r += 3 * (N + 1);
     L.rDsoc = r; r += NO;
     L.rFilt = r; r += 2 * K_FILTER_CAP;
     L.rSc = r; r += 6 + 2 * O;
+    L.rCtx = r; r += KMPC_NCTX;
     L.total = r;
     return L;
 }
@@ -149,9 +140,10 @@ struct Stats {  // residual norms + merit ingredients of one point
 };
 
 struct Ctx {  // per-thread solver state (registers / local memory)
-    int mode, inst, iter, cur, nsteps, soc_count, fn, trips;
+    int mode, inst, iter, cur, nsteps, soc_count, fn, trips, sel, tu;
     double mu, tau, delta, delta_last, df, theta_max, theta_min;
-    double alpha, alpha_test, alpha_min, alpha_du, alpha_du0, alpha_soc, gBD, theta_soc_old, theta_trial;
+    double alpha, alpha_test, alpha_min, alpha_du0, alpha_soc, gBD, theta_soc_old, theta_trial;
+    double a_pr, a_y, a_du;  // step sizes of the pending trial: primal, equality multipliers, bound multipliers
     Stats c;  // current iterate
 };
 
@@ -255,75 +247,91 @@ KMPC_HD bool bound_trial(double val, double d, double vt, double lb, double ub, 
 KMPC_HD double maxabs_nan(double m, double v) { double t = fabs(v); return (t > m || t != t) ? t : m; }
 
 // ------------------------------------------------------------------------------------------------
+// record access helpers.  ST(p, f): field f of the record p points at.
+// ------------------------------------------------------------------------------------------------
+#define FD(p, f) (p)[(size_t)(f) * S]
+
+template <int NR>
+KMPC_HD void rec_load(double (&r)[NR], const double *p, size_t S) {
+#pragma unroll
+    for (int j = 0; j < NR; ++j) r[j] = FD(p, j);
+}
+template <int NR>
+KMPC_HD void rec_copy(double (&d)[NR], const double (&s)[NR]) {
+#pragma unroll
+    for (int j = 0; j < NR; ++j) d[j] = s[j];
+}
+
+KMPC_HD double push_in(double v, double lb, double ub, int hL, int hU) {
+    if (hL && hU) {
+        const double pl = fmin(K_BOUND_PUSH * fmax(1.0, fabs(lb)), K_BOUND_FRAC * (ub - lb));
+        const double pu = fmin(K_BOUND_PUSH * fmax(1.0, fabs(ub)), K_BOUND_FRAC * (ub - lb));
+        return fmin(fmax(v, lb + pl), ub - pu);
+    }
+    if (hL) return fmax(v, lb + K_BOUND_PUSH * fmax(1.0, fabs(lb)));
+    if (hU) return fmin(v, ub - K_BOUND_PUSH * fmax(1.0, fabs(ub)));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
 // INIT pass: starting point (optimizer.py:375-385; cold start agent.py:59-60), objective scaling, push into the
 // interior, z = 1, y = 0, slacks.  Writes state buffer 0.
 // ------------------------------------------------------------------------------------------------
 KMPC_HDN inline void pass_init(const Cfg &c, Ctx &t, double *wsp, size_t S, const IO &io) {
     const int N = c.N, O = c.O, b = t.inst;
     const Rows &L = c.L;
-    const int sb = L.rState[0];
+    double *sc = wsp + (size_t)L.rSc * S;
     double xc[3], gl[3];
     for (int j = 0; j < 3; ++j) {
         xc[j] = io.x_cur[io_vec3(c, b, j)]; gl[j] = io.goal[io_vec3(c, b, j)];
-        RW(L.rSc + j) = xc[j]; RW(L.rSc + 3 + j) = gl[j];
+        FD(sc, j) = xc[j]; FD(sc, 3 + j) = gl[j];
     }
-    for (int o = 0; o < O; ++o) for (int j = 0; j < 2; ++j) RW(L.rSc + 6 + 2 * o + j) = io.obs[io_obs(c, b, o, j)];
+    for (int o = 0; o < O; ++o) for (int j = 0; j < 2; ++j) FD(sc, 6 + 2 * o + j) = io.obs[io_obs(c, b, o, j)];
     double gm = 0.0;
     const double dLpush = c.dL + K_BOUND_PUSH * fmax(1.0, fabs(c.dL));
+    double *ps = wsp + (size_t)L.rState[0] * S;
+    double *po = wsp + (size_t)(L.rState[0] + L.sObs) * S;
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
-        double x[3];
+    for (int k = 0; k <= N; ++k, ps += (size_t)NSTATE * S) {
+        double x[3], u[2] = {0.0, 0.0};
         for (int j = 0; j < 3; ++j) x[j] = io.X0 ? io.X0[io_X(c, b, j, k)] : xc[j];
+        if (k < N) for (int j = 0; j < 2; ++j) u[j] = io.U0 ? io.U0[io_U(c, b, j, k)] : 0.0;
         if (k >= c.gk_lo && k <= c.gk_hi)
             for (int j = 0; j < 3; ++j) gm = maxabs_nan(gm, 2.0 * c.W[j] * (x[j] - gl[j]));
-        for (int j = 0; j < 2; ++j) {  // push x, y
-            int hL = c.hasL[j], hU = c.hasU[j];
-            double lb = c.lb[j], ub = c.ub[j];
-            if (hL && hU) {
-                double pl = fmin(K_BOUND_PUSH * fmax(1.0, fabs(lb)), K_BOUND_FRAC * (ub - lb));
-                double pu = fmin(K_BOUND_PUSH * fmax(1.0, fabs(ub)), K_BOUND_FRAC * (ub - lb));
-                x[j] = fmin(fmax(x[j], lb + pl), ub - pu);
-            } else if (hL) x[j] = fmax(x[j], lb + K_BOUND_PUSH * fmax(1.0, fabs(lb)));
-            else if (hU) x[j] = fmin(x[j], ub - K_BOUND_PUSH * fmax(1.0, fabs(ub)));
-            RW(sb + L.sZ + 8 * k + 2 * j) = hL ? 1.0 : 0.0;
-            RW(sb + L.sZ + 8 * k + 2 * j + 1) = hU ? 1.0 : 0.0;
-        }
-        for (int j = 0; j < 3; ++j) { RW(sb + L.sX + 3 * k + j) = x[j]; RW(sb + L.sY + 3 * k + j) = 0.0; }
-        if (k >= 1)
-            for (int o = 0; o < O; ++o) {
-                double ex = x[0] - RW(L.rSc + 6 + 2 * o), ey = x[1] - RW(L.rSc + 6 + 2 * o + 1);
-                double d = sqrt(ex * ex + ey * ey) - c.obs_radius;
-                int i = (k - 1) * O + o;
-                RW(sb + L.sS + i) = fmax(d, dLpush); RW(sb + L.sYD + i) = 0.0; RW(sb + L.sVL + i) = 1.0;
-            }
-        if (k < N) {
-            double u[2];
-            for (int j = 0; j < 2; ++j) u[j] = io.U0 ? io.U0[io_U(c, b, j, k)] : 0.0;
+        x[0] = push_in(x[0], c.lb[0], c.ub[0], c.hasL[0], c.hasU[0]);
+        x[1] = push_in(x[1], c.lb[1], c.ub[1], c.hasL[1], c.hasU[1]);
+        FD(ps, F_X0) = x[0]; FD(ps, F_X1) = x[1]; FD(ps, F_X2) = x[2];
+        FD(ps, F_Y0) = 0.0; FD(ps, F_Y1) = 0.0; FD(ps, F_Y2) = 0.0;
+        FD(ps, F_ZLX) = c.hasL[0] ? 1.0 : 0.0; FD(ps, F_ZUX) = c.hasU[0] ? 1.0 : 0.0;
+        FD(ps, F_ZLY) = c.hasL[1] ? 1.0 : 0.0; FD(ps, F_ZUY) = c.hasU[1] ? 1.0 : 0.0;
+        double cs = 1.0, sn = 0.0;
+        const bool hasu = k < N;
+        if (hasu) {
             double gv, hv;
             vcost(c, 1.0, u[0], &gv, &hv);
             gm = maxabs_nan(gm, gv); gm = maxabs_nan(gm, 2.0 * c.Ww * u[1]);
-            for (int j = 0; j < 2; ++j) {
-                int hL = c.hasL[2 + j], hU = c.hasU[2 + j];
-                double lb = c.lb[2 + j], ub = c.ub[2 + j];
-                if (hL && hU) {
-                    double pl = fmin(K_BOUND_PUSH * fmax(1.0, fabs(lb)), K_BOUND_FRAC * (ub - lb));
-                    double pu = fmin(K_BOUND_PUSH * fmax(1.0, fabs(ub)), K_BOUND_FRAC * (ub - lb));
-                    u[j] = fmin(fmax(u[j], lb + pl), ub - pu);
-                } else if (hL) u[j] = fmax(u[j], lb + K_BOUND_PUSH * fmax(1.0, fabs(lb)));
-                else if (hU) u[j] = fmin(u[j], ub - K_BOUND_PUSH * fmax(1.0, fabs(ub)));
-                RW(sb + L.sZ + 8 * k + 4 + 2 * j) = hL ? 1.0 : 0.0;
-                RW(sb + L.sZ + 8 * k + 4 + 2 * j + 1) = hU ? 1.0 : 0.0;
-                RW(sb + L.sU + 2 * k + j) = u[j];
-            }
-            double sn, cs;
+            u[0] = push_in(u[0], c.lb[2], c.ub[2], c.hasL[2], c.hasU[2]);
+            u[1] = push_in(u[1], c.lb[3], c.ub[3], c.hasL[3], c.hasU[3]);
             sincos_(x[2], &sn, &cs);
-            RW(sb + L.sCS + 2 * k) = cs; RW(sb + L.sCS + 2 * k + 1) = sn;
         }
+        FD(ps, F_V) = u[0]; FD(ps, F_OM) = u[1];
+        FD(ps, F_ZLV) = (hasu && c.hasL[2]) ? 1.0 : 0.0; FD(ps, F_ZUV) = (hasu && c.hasU[2]) ? 1.0 : 0.0;
+        FD(ps, F_ZLW) = (hasu && c.hasL[3]) ? 1.0 : 0.0; FD(ps, F_ZUW) = (hasu && c.hasU[3]) ? 1.0 : 0.0;
+        FD(ps, F_CS) = cs; FD(ps, F_SN) = sn;
+        if (k >= 1)
+            for (int o = 0; o < O; ++o, po += (size_t)3 * S) {
+                const double ex = x[0] - FD(sc, 6 + 2 * o), ey = x[1] - FD(sc, 7 + 2 * o);
+                const double d = sqrt(ex * ex + ey * ey) - c.obs_radius;
+                FD(po, 0) = fmax(d, dLpush); FD(po, 1) = 0.0; FD(po, 2) = 1.0;
+            }
     }
     t.df = gm > K_SCALING_MAX_GRAD ? fmax(K_SCALING_MAX_GRAD / gm, K_SCALING_MIN) : 1.0;
     t.cur = 0; t.iter = 0; t.mu = K_MU_INIT; t.tau = fmax(K_TAU_MIN, 1.0 - K_MU_INIT);
     t.delta = 0.0; t.delta_last = 0.0; t.theta_max = -1.0; t.theta_min = -1.0; t.fn = 0;
-    t.nsteps = 0; t.soc_count = 0;
+    t.nsteps = 0; t.soc_count = 0; t.trips = 0; t.sel = 0; t.tu = TU_INIT;
+    t.alpha = t.alpha_test = t.alpha_min = t.alpha_du0 = t.alpha_soc = t.gBD = t.theta_soc_old = t.theta_trial = 0.0;
+    t.a_pr = t.a_y = t.a_du = 0.0;
+    t.c.f = t.c.bar = t.c.damp = t.c.theta = t.c.dinf = t.c.pinf = t.c.mn = t.c.mx = t.c.sumy = t.c.sumz = t.c.wmax = 0.0;
     t.mode = M_LSQ;
 }
 
@@ -332,12 +340,12 @@ struct ObsT { double nx, ny, rr, Ds, bd, bs; };
 KMPC_HD ObsT obs_terms(const Cfg &c, double px, double py, double cx, double cy, double s, double yd, double vL,
                        double mu, double delta, bool lsq, bool soc, double dsoc) {
     ObsT r;
-    double ex = px - cx, ey = py - cy;
+    const double ex = px - cx, ey = py - cy;
     r.rr = sqrt(ex * ex + ey * ey);
     r.nx = ex / r.rr; r.ny = ey / r.rr;
     if (lsq) { r.Ds = 1.0; r.bd = 0.0; r.bs = -yd - vL; }
     else {
-        double sl = s - c.dL;
+        const double sl = s - c.dL;
         r.Ds = vL / sl + delta;
         r.bs = yd + mu / sl - K_KAPPA_D * mu;
         r.bd = soc ? -dsoc : -((r.rr - c.obs_radius) - s);
@@ -351,23 +359,32 @@ KMPC_HD ObsT obs_terms(const Cfg &c, double px, double py, double cx, double cy,
 //   [J                      0 ] [dy ] = [bc]        (slacks of the obstacle rows condensed into the x-x blocks)
 // kind M_LSQ: W = 0, Sigma = I, rhs = (grad f - zL + zU, 0)  (least-squares multiplier estimate)
 // kind M_NEWTON: rhs = -(grad of the barrier Lagrangian, c);  kind M_SOC: same matrix, bc = -c_soc.
-// Stores the feedback gains K, k_ff and the cost-to-go (P, p).  Returns false when some Q_uu is not positive
-// definite (wrong inertia -> the caller raises delta, IPOPT's inertia correction).
+// Stores the feedback gains K, k_ff and the cost-to-go (P, p) as FACT records.  Returns false when some Q_uu is not
+// positive definite (wrong inertia -> the caller raises delta, IPOPT's inertia correction).
+// The STATE record of stage k-1 is loaded while stage k is being processed (register double buffer).
 // ------------------------------------------------------------------------------------------------
+template <bool OBS>
 KMPC_HDN inline bool pass_sweep(const Cfg &c, const Ctx &t, double *wsp, size_t S) {
-    const int N = c.N, O = c.O;
+    const int N = c.N, O = OBS ? c.O : 0;
     const Rows &L = c.L;
-    const int sb = L.rState[t.cur];
     const bool lsq = t.mode == M_LSQ, soc = t.mode == M_SOC;
     const double mu = t.mu, delta = t.delta, df = t.df, T = c.T;
-    const double g0 = RW(L.rSc + 3), g1 = RW(L.rSc + 4), g2 = RW(L.rSc + 5);
+    const double *__restrict__ sc = wsp + (size_t)L.rSc * S;
+    const double g0 = FD(sc, 3), g1 = FD(sc, 4), g2 = FD(sc, 5);
+    const double *__restrict__ ps = wsp + ((size_t)L.rState[t.cur] + (size_t)NSTATE * N) * S;
+    const double *__restrict__ po = wsp + ((size_t)L.rState[t.cur] + L.sObs + (size_t)3 * N * O) * S;  // one past the last obstacle record
+    const double *__restrict__ pcs = wsp + ((size_t)L.rCsoc + 3 * (N + 1)) * S;  // record k+1 once stage k is reached
+    const double *__restrict__ pds = wsp + ((size_t)L.rDsoc + (size_t)N * O) * S;
+    double *__restrict__ pf = wsp + ((size_t)L.rFact + (size_t)NFACT * N) * S;
     double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0, p0 = 0, p1 = 0, p2 = 0;
     double xn0 = 0, xn1 = 0, xn2 = 0, yn0 = 0, yn1 = 0, yn2 = 0;
+    double a[NSTATE], nx[NSTATE];
+    rec_load(a, ps, S);
     bool ok = true;
 #pragma unroll 1
     for (int k = N; k >= 0; --k) {
-        const double x0 = RW(sb + L.sX + 3 * k), x1 = RW(sb + L.sX + 3 * k + 1), x2 = RW(sb + L.sX + 3 * k + 2);
-        const double y0 = RW(sb + L.sY + 3 * k), y1 = RW(sb + L.sY + 3 * k + 1), y2 = RW(sb + L.sY + 3 * k + 2);
+        if (k > 0) rec_load(nx, ps - (size_t)NSTATE * S, S);
+        const double x0 = a[F_X0], x1 = a[F_X1], x2 = a[F_X2], y0 = a[F_Y0], y1 = a[F_Y1], y2 = a[F_Y2];
         const bool ing = k >= c.gk_lo && k <= c.gk_hi;
         double gx0 = 0, gx1 = 0, gx2 = 0, h0 = 0, h1 = 0, h2 = 0;
         if (ing) {
@@ -376,27 +393,23 @@ KMPC_HDN inline bool pass_sweep(const Cfg &c, const Ctx &t, double *wsp, size_t 
         }
         // q = -bx (x part), Q = W_xx + Sigma_x + delta
         double q0, q1, q2, Q00, Q01 = 0.0, Q11, Q22;
-        {
-            const double zLx = RW(sb + L.sZ + 8 * k), zUx = RW(sb + L.sZ + 8 * k + 1);
-            const double zLy = RW(sb + L.sZ + 8 * k + 2), zUy = RW(sb + L.sZ + 8 * k + 3);
-            if (lsq) {
-                q0 = -(gx0 - zLx + zUx); q1 = -(gx1 - zLy + zUy); q2 = -gx2;
-                Q00 = 1.0; Q11 = 1.0; Q22 = 1.0;
-            } else {
-                double sg0, rb0, sg1, rb1;
-                bound_terms(x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], zLx, zUx, mu, &sg0, &rb0);
-                bound_terms(x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], zLy, zUy, mu, &sg1, &rb1);
-                q0 = gx0 + y0 + rb0; q1 = gx1 + y1 + rb1; q2 = gx2 + y2;
-                Q00 = h0 + sg0 + delta; Q11 = h1 + sg1 + delta; Q22 = h2 + delta;
-            }
+        if (lsq) {
+            q0 = -(gx0 - a[F_ZLX] + a[F_ZUX]); q1 = -(gx1 - a[F_ZLY] + a[F_ZUY]); q2 = -gx2;
+            Q00 = 1.0; Q11 = 1.0; Q22 = 1.0;
+        } else {
+            double sg0, rb0, sg1, rb1;
+            bound_terms(x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], a[F_ZLX], a[F_ZUX], mu, &sg0, &rb0);
+            bound_terms(x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], a[F_ZLY], a[F_ZUY], mu, &sg1, &rb1);
+            q0 = gx0 + y0 + rb0; q1 = gx1 + y1 + rb1; q2 = gx2 + y2;
+            Q00 = h0 + sg0 + delta; Q11 = h1 + sg1 + delta; Q22 = h2 + delta;
         }
-        if (O > 0 && k >= 1) {
+        if (OBS && k >= 1) {
 #pragma unroll 1
-            for (int o = 0; o < O; ++o) {
-                const int i = (k - 1) * O + o;
-                const double yd = RW(sb + L.sYD + i);
-                ObsT ot = obs_terms(c, x0, x1, RW(L.rSc + 6 + 2 * o), RW(L.rSc + 7 + 2 * o), RW(sb + L.sS + i), yd,
-                                    RW(sb + L.sVL + i), mu, delta, lsq, soc, soc ? RW(L.rDsoc + i) : 0.0);
+            for (int o = O - 1; o >= 0; --o) {
+                po -= (size_t)3 * S; pds -= S;
+                const double yd = FD(po, 1);
+                ObsT ot = obs_terms(c, x0, x1, FD(sc, 6 + 2 * o), FD(sc, 7 + 2 * o), FD(po, 0), yd, FD(po, 2), mu, delta, lsq,
+                                    soc, soc ? FD(pds, 0) : 0.0);
                 if (!lsq) {
                     const double h = yd / ot.rr;
                     Q00 += h * (1.0 - ot.nx * ot.nx); Q01 += h * (-ot.nx * ot.ny); Q11 += h * (1.0 - ot.ny * ot.ny);
@@ -411,46 +424,41 @@ KMPC_HDN inline bool pass_sweep(const Cfg &c, const Ctx &t, double *wsp, size_t 
             P00 = Q00; P10 = Q01; P11 = Q11; P20 = 0.0; P21 = 0.0; P22 = Q22;
             p0 = q0; p1 = q1; p2 = q2;
         } else {
-            const double v = RW(sb + L.sU + 2 * k), om = RW(sb + L.sU + 2 * k + 1);
-            const double cs = RW(sb + L.sCS + 2 * k), sn = RW(sb + L.sCS + 2 * k + 1);
+            const double v = a[F_V], om = a[F_OM], cs = a[F_CS], sn = a[F_SN];
             const double a13 = -T * v * sn, a23 = T * v * cs, b11 = T * cs, b21 = T * sn, b32 = T;
             double gv, hvv, qv, qw, Dv, Dw, htv = 0.0;
             vcost(c, df, v, &gv, &hvv);
             const double gw = df * 2.0 * c.Ww * om;
             double hww = df * 2.0 * c.Ww;
-            {
-                const double zLv = RW(sb + L.sZ + 8 * k + 4), zUv = RW(sb + L.sZ + 8 * k + 5);
-                const double zLw = RW(sb + L.sZ + 8 * k + 6), zUw = RW(sb + L.sZ + 8 * k + 7);
-                if (lsq) {
-                    qv = -(gv - zLv + zUv); qw = -(gw - zLw + zUw);
-                    Dv = 1.0; Dw = 1.0; hvv = 0.0; hww = 0.0;
-                } else {
-                    double sgv, rbv, sgw, rbw;
-                    bound_terms(v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], zLv, zUv, mu, &sgv, &rbv);
-                    bound_terms(om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], zLw, zUw, mu, &sgw, &rbw);
-                    // J^T y of dynamics row k+1 (multiplier yn)
-                    q0 -= yn0; q1 -= yn1; q2 -= a13 * yn0 + a23 * yn1 + yn2;
-                    qv = gv - (b11 * yn0 + b21 * yn1) + rbv;
-                    qw = gw - b32 * yn2 + rbw;
-                    Dv = sgv + delta; Dw = sgw + delta;
-                    // curvature of the dynamics in the Lagrangian (the only indefinite terms)
-                    Q22 += T * v * (yn0 * cs + yn1 * sn);
-                    htv = T * (yn0 * sn - yn1 * cs);
-                }
+            if (lsq) {
+                qv = -(gv - a[F_ZLV] + a[F_ZUV]); qw = -(gw - a[F_ZLW] + a[F_ZUW]);
+                Dv = 1.0; Dw = 1.0; hvv = 0.0; hww = 0.0;
+            } else {
+                double sgv, rbv, sgw, rbw;
+                bound_terms(v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], a[F_ZLV], a[F_ZUV], mu, &sgv, &rbv);
+                bound_terms(om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], a[F_ZLW], a[F_ZUW], mu, &sgw, &rbw);
+                // J^T y of dynamics row k+1 (multiplier yn)
+                q0 -= yn0; q1 -= yn1; q2 -= a13 * yn0 + a23 * yn1 + yn2;
+                qv = gv - (b11 * yn0 + b21 * yn1) + rbv;
+                qw = gw - b32 * yn2 + rbw;
+                Dv = sgv + delta; Dw = sgw + delta;
+                // curvature of the dynamics in the Lagrangian (the only indefinite terms)
+                Q22 += T * v * (yn0 * cs + yn1 * sn);
+                htv = T * (yn0 * sn - yn1 * cs);
             }
             // e = bc_{k+1}
             double e0, e1, e2;
             if (lsq) { e0 = e1 = e2 = 0.0; }
-            else if (soc) { e0 = -RW(L.rCsoc + 3 * (k + 1)); e1 = -RW(L.rCsoc + 3 * (k + 1) + 1); e2 = -RW(L.rCsoc + 3 * (k + 1) + 2); }
+            else if (soc) { e0 = -FD(pcs, 0); e1 = -FD(pcs, 1); e2 = -FD(pcs, 2); }
             else { e0 = -(xn0 - (x0 + T * v * cs)); e1 = -(xn1 - (x1 + T * v * sn)); e2 = -(xn2 - (x2 + T * om)); }
             // matrix recursion
             const double PA02 = P00 * a13 + P10 * a23 + P20, PA12 = P10 * a13 + P11 * a23 + P21, PA22 = P20 * a13 + P21 * a23 + P22;
-            const double PB00 = P00 * b11 + P10 * b21, PB10 = P10 * b11 + P11 * b21, PB20 = P20 * b11 + P21 * b21;
+            const double PB00 = P00 * b11 + P10 * b21, PB10 = P10 * b11 + P11 * b21;
             const double PB01 = P20 * b32, PB11 = P21 * b32, PB21 = P22 * b32;
             // Qxx = A^T P A + Q   (PA[:,0] = P[:,0], PA[:,1] = P[:,1])
-            double X00 = P00 + Q00, X01 = P10 + Q01, X02 = PA02;
-            double X10 = P10 + Q01, X11 = P11 + Q11, X12 = PA12;
-            double X20 = a13 * P00 + a23 * P10 + P20, X21 = a13 * P10 + a23 * P11 + P21, X22 = a13 * PA02 + a23 * PA12 + PA22 + Q22;
+            const double X00 = P00 + Q00, X01 = P10 + Q01, X02 = PA02;
+            const double X10 = P10 + Q01, X11 = P11 + Q11, X12 = PA12;
+            const double X20 = a13 * P00 + a23 * P10 + P20, X21 = a13 * P10 + a23 * P11 + P21, X22 = a13 * PA02 + a23 * PA12 + PA22 + Q22;
             // Qux = B^T P A (+ W_v,theta)
             const double U00 = b11 * P00 + b21 * P10, U01 = b11 * P10 + b21 * P11, U02 = b11 * PA02 + b21 * PA12 + htv;
             const double U10 = b32 * P20, U11 = b32 * P21, U12 = b32 * PA22;
@@ -474,14 +482,16 @@ KMPC_HDN inline bool pass_sweep(const Cfg &c, const Ctx &t, double *wsp, size_t 
             const double N10 = X10 + U01 * K00 + U11 * K10, N11 = X11 + U01 * K01 + U11 * K11, N12 = X12 + U01 * K02 + U11 * K12;
             const double N20 = X20 + U02 * K00 + U12 * K10, N21 = X21 + U02 * K01 + U12 * K11, N22 = X22 + U02 * K02 + U12 * K12;
             P00 = N00; P10 = 0.5 * (N10 + N01); P11 = N11; P20 = 0.5 * (N20 + N02); P21 = 0.5 * (N21 + N12); P22 = N22;
-            RW(L.rK + 6 * k) = K00; RW(L.rK + 6 * k + 1) = K01; RW(L.rK + 6 * k + 2) = K02;
-            RW(L.rK + 6 * k + 3) = K10; RW(L.rK + 6 * k + 4) = K11; RW(L.rK + 6 * k + 5) = K12;
-            RW(L.rKff + 2 * k) = kf0; RW(L.rKff + 2 * k + 1) = kf1;
+            FD(pf, A_K00) = K00; FD(pf, A_K01) = K01; FD(pf, A_K02) = K02;
+            FD(pf, A_K10) = K10; FD(pf, A_K11) = K11; FD(pf, A_K12) = K12;
+            FD(pf, A_KF0) = kf0; FD(pf, A_KF1) = kf1;
         }
-        RW(L.rP + 6 * k) = P00; RW(L.rP + 6 * k + 1) = P10; RW(L.rP + 6 * k + 2) = P11;
-        RW(L.rP + 6 * k + 3) = P20; RW(L.rP + 6 * k + 4) = P21; RW(L.rP + 6 * k + 5) = P22;
-        RW(L.rPv + 3 * k) = p0; RW(L.rPv + 3 * k + 1) = p1; RW(L.rPv + 3 * k + 2) = p2;
+        FD(pf, A_P00) = P00; FD(pf, A_P10) = P10; FD(pf, A_P11) = P11;
+        FD(pf, A_P20) = P20; FD(pf, A_P21) = P21; FD(pf, A_P22) = P22;
+        FD(pf, A_PV0) = p0; FD(pf, A_PV1) = p1; FD(pf, A_PV2) = p2;
         xn0 = x0; xn1 = x1; xn2 = x2; yn0 = y0; yn1 = y1; yn2 = y2;
+        rec_copy(a, nx);
+        ps -= (size_t)NSTATE * S; pf -= (size_t)NFACT * S; pcs -= (size_t)3 * S;
     }
     return ok;
 }
@@ -489,55 +499,61 @@ KMPC_HDN inline bool pass_sweep(const Cfg &c, const Ctx &t, double *wsp, size_t 
 // ------------------------------------------------------------------------------------------------
 // ROLL-OUT: forward substitution dx_0 = bc_0, du = K dx + k_ff, dx+ = A dx + B du + e, dy = -(P dx + p);
 // fraction-to-the-boundary step sizes for the primal step and for the bound multipliers, and the
-// directional derivative of the barrier objective.  Writes step buffer `sel`.
+// directional derivative of the barrier objective.  Writes STEP records of step buffer `sel`.
 // ------------------------------------------------------------------------------------------------
+template <bool OBS>
 KMPC_HDN inline void pass_rollout(const Cfg &c, const Ctx &t, double *wsp, size_t S, int sel, double *alpha_pr,
                                   double *alpha_du, double *gBD, double *ymax) {
-    const int N = c.N, O = c.O;
+    const int N = c.N, O = OBS ? c.O : 0;
     const Rows &L = c.L;
-    const int sb = L.rState[t.cur], db = L.rStep[sel];
     const bool lsq = t.mode == M_LSQ, soc = t.mode == M_SOC;
     const double mu = t.mu, delta = t.delta, df = t.df, T = c.T, tau = t.tau;
-    const double g0 = RW(L.rSc + 3), g1 = RW(L.rSc + 4), g2 = RW(L.rSc + 5);
+    const double *__restrict__ sc = wsp + (size_t)L.rSc * S;
+    const double g0 = FD(sc, 3), g1 = FD(sc, 4), g2 = FD(sc, 5);
+    const double *__restrict__ ps = wsp + (size_t)L.rState[t.cur] * S;
+    const double *__restrict__ po = wsp + ((size_t)L.rState[t.cur] + L.sObs) * S;
+    const double *__restrict__ pf = wsp + (size_t)L.rFact * S;
+    const double *__restrict__ pcs = wsp + (size_t)L.rCsoc * S;
+    const double *__restrict__ pds = wsp + (size_t)L.rDsoc * S;
+    double *__restrict__ pd = wsp + (size_t)L.rStep[sel] * S;
+    double *__restrict__ pdo = wsp + ((size_t)L.rStep[sel] + L.dObs) * S;
     double apr = 1.0, adu = 1.0, gbd = 0.0, ym = 0.0;
-    double x0 = RW(sb + L.sX), x1 = RW(sb + L.sX + 1), x2 = RW(sb + L.sX + 2);
+    double a[NSTATE], an[NSTATE], f[NFACT], fn[NFACT];
+    rec_load(a, ps, S); rec_load(f, pf, S);
     double d0, d1, d2;
     if (lsq) { d0 = d1 = d2 = 0.0; }
-    else if (soc) { d0 = -RW(L.rCsoc); d1 = -RW(L.rCsoc + 1); d2 = -RW(L.rCsoc + 2); }
-    else { d0 = -(x0 - RW(L.rSc)); d1 = -(x1 - RW(L.rSc + 1)); d2 = -(x2 - RW(L.rSc + 2)); }
+    else if (soc) { d0 = -FD(pcs, 0); d1 = -FD(pcs, 1); d2 = -FD(pcs, 2); }
+    else { d0 = -(a[F_X0] - FD(sc, 0)); d1 = -(a[F_X1] - FD(sc, 1)); d2 = -(a[F_X2] - FD(sc, 2)); }
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-        const double P00 = RW(L.rP + 6 * k), P10 = RW(L.rP + 6 * k + 1), P11 = RW(L.rP + 6 * k + 2);
-        const double P20 = RW(L.rP + 6 * k + 3), P21 = RW(L.rP + 6 * k + 4), P22 = RW(L.rP + 6 * k + 5);
-        const double dy0 = -(P00 * d0 + P10 * d1 + P20 * d2 + RW(L.rPv + 3 * k));
-        const double dy1 = -(P10 * d0 + P11 * d1 + P21 * d2 + RW(L.rPv + 3 * k + 1));
-        const double dy2 = -(P20 * d0 + P21 * d1 + P22 * d2 + RW(L.rPv + 3 * k + 2));
-        RW(db + L.dY + 3 * k) = dy0; RW(db + L.dY + 3 * k + 1) = dy1; RW(db + L.dY + 3 * k + 2) = dy2;
-        RW(db + L.dX + 3 * k) = d0; RW(db + L.dX + 3 * k + 1) = d1; RW(db + L.dX + 3 * k + 2) = d2;
+        if (k < N) { rec_load(an, ps + (size_t)NSTATE * S, S); rec_load(fn, pf + (size_t)NFACT * S, S); }
+        const double x0 = a[F_X0], x1 = a[F_X1], x2 = a[F_X2];
+        const double dy0 = -(f[A_P00] * d0 + f[A_P10] * d1 + f[A_P20] * d2 + f[A_PV0]);
+        const double dy1 = -(f[A_P10] * d0 + f[A_P11] * d1 + f[A_P21] * d2 + f[A_PV1]);
+        const double dy2 = -(f[A_P20] * d0 + f[A_P21] * d1 + f[A_P22] * d2 + f[A_PV2]);
+        FD(pd, D_Y0) = dy0; FD(pd, D_Y1) = dy1; FD(pd, D_Y2) = dy2;
+        FD(pd, D_X0) = d0; FD(pd, D_X1) = d1; FD(pd, D_X2) = d2;
         ym = maxabs_nan(maxabs_nan(maxabs_nan(ym, dy0), dy1), dy2);
         if (!lsq) {
-            const double zLx = RW(sb + L.sZ + 8 * k), zUx = RW(sb + L.sZ + 8 * k + 1);
-            const double zLy = RW(sb + L.sZ + 8 * k + 2), zUy = RW(sb + L.sZ + 8 * k + 3);
             double sg, rb;
-            bound_ftb(x0, d0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], zLx, zUx, mu, tau, &apr, &adu);
-            bound_ftb(x1, d1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], zLy, zUy, mu, tau, &apr, &adu);
+            bound_ftb(x0, d0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], a[F_ZLX], a[F_ZUX], mu, tau, &apr, &adu);
+            bound_ftb(x1, d1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], a[F_ZLY], a[F_ZUY], mu, tau, &apr, &adu);
             const bool ing = k >= c.gk_lo && k <= c.gk_hi;
-            bound_terms(x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], zLx, zUx, mu, &sg, &rb);
+            bound_terms(x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], a[F_ZLX], a[F_ZUX], mu, &sg, &rb);
             gbd += ((ing ? df * 2.0 * c.W[0] * (x0 - g0) : 0.0) + rb) * d0;
-            bound_terms(x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], zLy, zUy, mu, &sg, &rb);
+            bound_terms(x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], a[F_ZLY], a[F_ZUY], mu, &sg, &rb);
             gbd += ((ing ? df * 2.0 * c.W[1] * (x1 - g1) : 0.0) + rb) * d1;
             gbd += (ing ? df * 2.0 * c.W[2] * (x2 - g2) : 0.0) * d2;
         }
-        if (O > 0 && k >= 1) {
+        if (OBS && k >= 1) {
 #pragma unroll 1
-            for (int o = 0; o < O; ++o) {
-                const int i = (k - 1) * O + o;
-                const double s = RW(sb + L.sS + i), yd = RW(sb + L.sYD + i), vL = RW(sb + L.sVL + i);
-                ObsT ot = obs_terms(c, x0, x1, RW(L.rSc + 6 + 2 * o), RW(L.rSc + 7 + 2 * o), s, yd, vL, mu, delta, lsq,
-                                    soc, soc ? RW(L.rDsoc + i) : 0.0);
+            for (int o = 0; o < O; ++o, po += (size_t)3 * S, pdo += (size_t)2 * S, pds += S) {
+                const double s = FD(po, 0), yd = FD(po, 1), vL = FD(po, 2);
+                ObsT ot = obs_terms(c, x0, x1, FD(sc, 6 + 2 * o), FD(sc, 7 + 2 * o), s, yd, vL, mu, delta, lsq, soc,
+                                    soc ? FD(pds, 0) : 0.0);
                 const double ds = ot.nx * d0 + ot.ny * d1 - ot.bd;
                 const double dyd = ot.Ds * ds - ot.bs;
-                RW(db + L.dS + i) = ds; RW(db + L.dYD + i) = dyd;
+                FD(pdo, 0) = ds; FD(pdo, 1) = dyd;
                 ym = maxabs_nan(ym, dyd);
                 if (!lsq) {
                     const double sl = s - c.dL;
@@ -549,35 +565,32 @@ KMPC_HDN inline void pass_rollout(const Cfg &c, const Ctx &t, double *wsp, size_
             }
         }
         if (k < N) {
-            const double v = RW(sb + L.sU + 2 * k), om = RW(sb + L.sU + 2 * k + 1);
-            const double cs = RW(sb + L.sCS + 2 * k), sn = RW(sb + L.sCS + 2 * k + 1);
-            const double du0 = RW(L.rK + 6 * k) * d0 + RW(L.rK + 6 * k + 1) * d1 + RW(L.rK + 6 * k + 2) * d2 + RW(L.rKff + 2 * k);
-            const double du1 = RW(L.rK + 6 * k + 3) * d0 + RW(L.rK + 6 * k + 4) * d1 + RW(L.rK + 6 * k + 5) * d2 + RW(L.rKff + 2 * k + 1);
-            RW(db + L.dU + 2 * k) = du0; RW(db + L.dU + 2 * k + 1) = du1;
-            const double xn0 = RW(sb + L.sX + 3 * (k + 1)), xn1 = RW(sb + L.sX + 3 * (k + 1) + 1), xn2 = RW(sb + L.sX + 3 * (k + 1) + 2);
+            const double v = a[F_V], om = a[F_OM], cs = a[F_CS], sn = a[F_SN];
+            const double du0 = f[A_K00] * d0 + f[A_K01] * d1 + f[A_K02] * d2 + f[A_KF0];
+            const double du1 = f[A_K10] * d0 + f[A_K11] * d1 + f[A_K12] * d2 + f[A_KF1];
+            FD(pd, D_U0) = du0; FD(pd, D_U1) = du1;
             double e0, e1, e2;
             if (lsq) { e0 = e1 = e2 = 0.0; }
             else {
-                const double zLv = RW(sb + L.sZ + 8 * k + 4), zUv = RW(sb + L.sZ + 8 * k + 5);
-                const double zLw = RW(sb + L.sZ + 8 * k + 6), zUw = RW(sb + L.sZ + 8 * k + 7);
-                bound_ftb(v, du0, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], zLv, zUv, mu, tau, &apr, &adu);
-                bound_ftb(om, du1, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], zLw, zUw, mu, tau, &apr, &adu);
+                bound_ftb(v, du0, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], a[F_ZLV], a[F_ZUV], mu, tau, &apr, &adu);
+                bound_ftb(om, du1, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], a[F_ZLW], a[F_ZUW], mu, tau, &apr, &adu);
                 double gv, hv, sg, rb;
                 vcost(c, df, v, &gv, &hv);
-                bound_terms(v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], zLv, zUv, mu, &sg, &rb);
+                bound_terms(v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], a[F_ZLV], a[F_ZUV], mu, &sg, &rb);
                 gbd += (gv + rb) * du0;
-                bound_terms(om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], zLw, zUw, mu, &sg, &rb);
+                bound_terms(om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], a[F_ZLW], a[F_ZUW], mu, &sg, &rb);
                 gbd += (df * 2.0 * c.Ww * om + rb) * du1;
-                if (soc) { e0 = -RW(L.rCsoc + 3 * (k + 1)); e1 = -RW(L.rCsoc + 3 * (k + 1) + 1); e2 = -RW(L.rCsoc + 3 * (k + 1) + 2); }
-                else { e0 = -(xn0 - (x0 + T * v * cs)); e1 = -(xn1 - (x1 + T * v * sn)); e2 = -(xn2 - (x2 + T * om)); }
+                if (soc) { e0 = -FD(pcs, 3); e1 = -FD(pcs, 4); e2 = -FD(pcs, 5); }
+                else { e0 = -(an[F_X0] - (x0 + T * v * cs)); e1 = -(an[F_X1] - (x1 + T * v * sn)); e2 = -(an[F_X2] - (x2 + T * om)); }
             }
             const double a13 = -T * v * sn, a23 = T * v * cs;
             const double n0 = d0 + a13 * d2 + T * cs * du0 + e0;
             const double n1 = d1 + a23 * d2 + T * sn * du0 + e1;
             const double n2 = d2 + T * du1 + e2;
             d0 = n0; d1 = n1; d2 = n2;
-            x0 = xn0; x1 = xn1; x2 = xn2;
-        }
+        } else { FD(pd, D_U0) = 0.0; FD(pd, D_U1) = 0.0; }
+        rec_copy(a, an); rec_copy(f, fn);
+        ps += (size_t)NSTATE * S; pf += (size_t)NFACT * S; pd += (size_t)NSTEP * S; pcs += (size_t)3 * S;
     }
     *alpha_pr = apr; *alpha_du = adu; *gBD = gbd; *ymax = ym;
 }
@@ -589,28 +602,35 @@ KMPC_HDN inline void pass_rollout(const Cfg &c, const Ctx &t, double *wsp, size_
 // is written to the OTHER state buffer; accepting the trial point just flips t.cur.
 //   tu = TU_INIT : alpha = 0, y' = ay * dy (least-squares estimate), multipliers untouched (no safeguard)
 // ------------------------------------------------------------------------------------------------
+template <bool OBS>
 KMPC_HDN inline bool pass_trial(const Cfg &c, const Ctx &t, double *wsp, size_t S, int sel, int tu, double alpha, double ay,
                                 double adu, Stats *out) {
-    const int N = c.N, O = c.O;
+    const int N = c.N, O = OBS ? c.O : 0;
     const Rows &L = c.L;
-    const int sb = L.rState[t.cur], nb = L.rState[t.cur ^ 1], db = L.rStep[sel];
     const double mu = t.mu, df = t.df, T = c.T;
     const bool clamp = tu == TU_STEP;
-    const double g0 = RW(L.rSc + 3), g1 = RW(L.rSc + 4), g2 = RW(L.rSc + 5);
+    const double *__restrict__ sc = wsp + (size_t)L.rSc * S;
+    const double g0 = FD(sc, 3), g1 = FD(sc, 4), g2 = FD(sc, 5);
+    const double *__restrict__ ps = wsp + (size_t)L.rState[t.cur] * S;
+    const double *__restrict__ po = wsp + ((size_t)L.rState[t.cur] + L.sObs) * S;
+    const double *__restrict__ pd = wsp + (size_t)L.rStep[sel] * S;
+    const double *__restrict__ pdo = wsp + ((size_t)L.rStep[sel] + L.dObs) * S;
+    double *__restrict__ pn = wsp + (size_t)L.rState[t.cur ^ 1] * S;
+    double *__restrict__ pno = wsp + ((size_t)L.rState[t.cur ^ 1] + L.sObs) * S;
     Stats st;
     st.f = 0; st.bar = 0; st.damp = 0; st.theta = 0; st.dinf = 0; st.pinf = 0; st.mn = INFINITY; st.mx = 0; st.sumy = 0;
     st.sumz = 0; st.wmax = 0;
     bool valid = true;
-    double xp0 = RW(L.rSc), xp1 = RW(L.rSc + 1), xp2 = RW(L.rSc + 2);  // predicted state (k = 0: x_cur)
-    double yk0 = RW(sb + L.sY) + ay * RW(db + L.dY), yk1 = RW(sb + L.sY + 1) + ay * RW(db + L.dY + 1),
-           yk2 = RW(sb + L.sY + 2) + ay * RW(db + L.dY + 2);
+    double xp0 = FD(sc, 0), xp1 = FD(sc, 1), xp2 = FD(sc, 2);  // predicted state (k = 0: x_cur)
+    double a[NSTATE - 2], an[NSTATE - 2], d[NSTEP], dn[NSTEP];  // CS/SN of the old point are not needed
+    rec_load(a, ps, S); rec_load(d, pd, S);
+    double yk0 = a[F_Y0] + ay * d[D_Y0], yk1 = a[F_Y1] + ay * d[D_Y1], yk2 = a[F_Y2] + ay * d[D_Y2];
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-        const double xo0 = RW(sb + L.sX + 3 * k), xo1 = RW(sb + L.sX + 3 * k + 1), xo2 = RW(sb + L.sX + 3 * k + 2);
-        const double d0 = RW(db + L.dX + 3 * k), d1 = RW(db + L.dX + 3 * k + 1), d2 = RW(db + L.dX + 3 * k + 2);
-        const double x0 = xo0 + alpha * d0, x1 = xo1 + alpha * d1, x2 = xo2 + alpha * d2;
-        RW(nb + L.sX + 3 * k) = x0; RW(nb + L.sX + 3 * k + 1) = x1; RW(nb + L.sX + 3 * k + 2) = x2;
-        RW(nb + L.sY + 3 * k) = yk0; RW(nb + L.sY + 3 * k + 1) = yk1; RW(nb + L.sY + 3 * k + 2) = yk2;
+        if (k < N) { rec_load(an, ps + (size_t)NSTATE * S, S); rec_load(dn, pd + (size_t)NSTEP * S, S); }
+        const double x0 = a[F_X0] + alpha * d[D_X0], x1 = a[F_X1] + alpha * d[D_X1], x2 = a[F_X2] + alpha * d[D_X2];
+        FD(pn, F_X0) = x0; FD(pn, F_X1) = x1; FD(pn, F_X2) = x2;
+        FD(pn, F_Y0) = yk0; FD(pn, F_Y1) = yk1; FD(pn, F_Y2) = yk2;
         const double c0 = x0 - xp0, c1 = x1 - xp1, c2 = x2 - xp2;
         st.theta += fabs(c0) + fabs(c1) + fabs(c2);
         st.pinf = maxabs_nan(maxabs_nan(maxabs_nan(st.pinf, c0), c1), c2);
@@ -625,32 +645,31 @@ KMPC_HDN inline bool pass_trial(const Cfg &c, const Ctx &t, double *wsp, size_t 
         double prod = 1.0;
         {
             double zLn, zUn;
-            valid &= bound_trial(xo0, d0, x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], RW(sb + L.sZ + 8 * k), RW(sb + L.sZ + 8 * k + 1),
-                                 mu, adu, clamp, &zLn, &zUn, &prod, &st.damp, &st);
-            RW(nb + L.sZ + 8 * k) = zLn; RW(nb + L.sZ + 8 * k + 1) = zUn;
+            valid &= bound_trial(a[F_X0], d[D_X0], x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], a[F_ZLX], a[F_ZUX], mu, adu, clamp,
+                                 &zLn, &zUn, &prod, &st.damp, &st);
+            FD(pn, F_ZLX) = zLn; FD(pn, F_ZUX) = zUn;
             r0 += zUn - zLn;
-            valid &= bound_trial(xo1, d1, x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], RW(sb + L.sZ + 8 * k + 2), RW(sb + L.sZ + 8 * k + 3),
-                                 mu, adu, clamp, &zLn, &zUn, &prod, &st.damp, &st);
-            RW(nb + L.sZ + 8 * k + 2) = zLn; RW(nb + L.sZ + 8 * k + 3) = zUn;
+            valid &= bound_trial(a[F_X1], d[D_X1], x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], a[F_ZLY], a[F_ZUY], mu, adu, clamp,
+                                 &zLn, &zUn, &prod, &st.damp, &st);
+            FD(pn, F_ZLY) = zLn; FD(pn, F_ZUY) = zUn;
             r1 += zUn - zLn;
         }
-        if (O > 0 && k >= 1) {
+        if (OBS && k >= 1) {
 #pragma unroll 1
-            for (int o = 0; o < O; ++o) {
-                const int i = (k - 1) * O + o;
-                const double so = RW(sb + L.sS + i), ds = RW(db + L.dS + i), vL = RW(sb + L.sVL + i);
+            for (int o = 0; o < O; ++o, po += (size_t)3 * S, pdo += (size_t)2 * S, pno += (size_t)3 * S) {
+                const double so = FD(po, 0), ds = FD(pdo, 0), vL = FD(po, 2);
                 const double s = so + alpha * ds;
-                const double ex = x0 - RW(L.rSc + 6 + 2 * o), ey = x1 - RW(L.rSc + 7 + 2 * o);
+                const double ex = x0 - FD(sc, 6 + 2 * o), ey = x1 - FD(sc, 7 + 2 * o);
                 const double rr = sqrt(ex * ex + ey * ey), nx = ex / rr, ny = ey / rr;
                 const double dm = (rr - c.obs_radius) - s;
                 st.theta += fabs(dm); st.pinf = maxabs_nan(st.pinf, dm);
                 const double slo = so - c.dL, sln = s - c.dL;
                 if (!(sln > 0)) valid = false;
                 prod *= sln; st.damp += sln;
-                const double yd = RW(sb + L.sYD + i) + ay * RW(db + L.dYD + i);
+                const double yd = FD(po, 1) + ay * FD(pdo, 1);
                 double z = vL + adu * (mu / slo - vL - vL / slo * ds);
                 if (clamp) z = fmax(fmin(z, K_KAPPA_SIGMA * mu / sln), mu / (K_KAPPA_SIGMA * sln));
-                RW(nb + L.sS + i) = s; RW(nb + L.sYD + i) = yd; RW(nb + L.sVL + i) = z;
+                FD(pno, 0) = s; FD(pno, 1) = yd; FD(pno, 2) = z;
                 r0 += nx * yd; r1 += ny * yd;
                 st.dinf = maxabs_nan(st.dinf, -yd - z);
                 const double p = sln * z;
@@ -658,18 +677,14 @@ KMPC_HDN inline bool pass_trial(const Cfg &c, const Ctx &t, double *wsp, size_t 
             }
         }
         if (k < N) {
-            const double vo = RW(sb + L.sU + 2 * k), oo = RW(sb + L.sU + 2 * k + 1);
-            const double du0 = RW(db + L.dU + 2 * k), du1 = RW(db + L.dU + 2 * k + 1);
-            const double v = vo + alpha * du0, om = oo + alpha * du1;
-            RW(nb + L.sU + 2 * k) = v; RW(nb + L.sU + 2 * k + 1) = om;
+            const double v = a[F_V] + alpha * d[D_U0], om = a[F_OM] + alpha * d[D_U1];
+            FD(pn, F_V) = v; FD(pn, F_OM) = om;
             double sn, cs;
             sincos_(x2, &sn, &cs);
-            RW(nb + L.sCS + 2 * k) = cs; RW(nb + L.sCS + 2 * k + 1) = sn;
+            FD(pn, F_CS) = cs; FD(pn, F_SN) = sn;
             st.wmax = fmax(st.wmax, fmax(fabs(v), fabs(om)));
             // multiplier of dynamics row k+1 at the updated point
-            const double yn0 = RW(sb + L.sY + 3 * (k + 1)) + ay * RW(db + L.dY + 3 * (k + 1));
-            const double yn1 = RW(sb + L.sY + 3 * (k + 1) + 1) + ay * RW(db + L.dY + 3 * (k + 1) + 1);
-            const double yn2 = RW(sb + L.sY + 3 * (k + 1) + 2) + ay * RW(db + L.dY + 3 * (k + 1) + 2);
+            const double yn0 = an[F_Y0] + ay * dn[D_Y0], yn1 = an[F_Y1] + ay * dn[D_Y1], yn2 = an[F_Y2] + ay * dn[D_Y2];
             const double a13 = -T * v * sn, a23 = T * v * cs;
             r0 -= yn0; r1 -= yn1; r2 -= a13 * yn0 + a23 * yn1 + yn2;
             double gv, hv;
@@ -679,20 +694,25 @@ KMPC_HDN inline bool pass_trial(const Cfg &c, const Ctx &t, double *wsp, size_t 
             else st.f += c.Wvn * fmin(v, 0.0);
             st.f += c.Ww * om * om;
             double zLn, zUn;
-            valid &= bound_trial(vo, du0, v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], RW(sb + L.sZ + 8 * k + 4), RW(sb + L.sZ + 8 * k + 5),
-                                 mu, adu, clamp, &zLn, &zUn, &prod, &st.damp, &st);
-            RW(nb + L.sZ + 8 * k + 4) = zLn; RW(nb + L.sZ + 8 * k + 5) = zUn;
+            valid &= bound_trial(a[F_V], d[D_U0], v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], a[F_ZLV], a[F_ZUV], mu, adu, clamp,
+                                 &zLn, &zUn, &prod, &st.damp, &st);
+            FD(pn, F_ZLV) = zLn; FD(pn, F_ZUV) = zUn;
             rv += zUn - zLn;
-            valid &= bound_trial(oo, du1, om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], RW(sb + L.sZ + 8 * k + 6), RW(sb + L.sZ + 8 * k + 7),
-                                 mu, adu, clamp, &zLn, &zUn, &prod, &st.damp, &st);
-            RW(nb + L.sZ + 8 * k + 6) = zLn; RW(nb + L.sZ + 8 * k + 7) = zUn;
+            valid &= bound_trial(a[F_OM], d[D_U1], om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], a[F_ZLW], a[F_ZUW], mu, adu, clamp,
+                                 &zLn, &zUn, &prod, &st.damp, &st);
+            FD(pn, F_ZLW) = zLn; FD(pn, F_ZUW) = zUn;
             rw += zUn - zLn;
             st.dinf = maxabs_nan(maxabs_nan(st.dinf, rv), rw);
             xp0 = x0 + T * v * cs; xp1 = x1 + T * v * sn; xp2 = x2 + T * om;
             yk0 = yn0; yk1 = yn1; yk2 = yn2;
+        } else {
+            FD(pn, F_V) = 0.0; FD(pn, F_OM) = 0.0; FD(pn, F_CS) = 1.0; FD(pn, F_SN) = 0.0;
+            FD(pn, F_ZLV) = 0.0; FD(pn, F_ZUV) = 0.0; FD(pn, F_ZLW) = 0.0; FD(pn, F_ZUW) = 0.0;
         }
         st.dinf = maxabs_nan(maxabs_nan(maxabs_nan(st.dinf, r0), r1), r2);
         st.bar += log(prod);
+        rec_copy(a, an); rec_copy(d, dn);
+        ps += (size_t)NSTATE * S; pd += (size_t)NSTEP * S; pn += (size_t)NSTATE * S;
     }
     st.f *= df;
     if (c.nb == 0) st.mn = 0.0;
@@ -702,39 +722,38 @@ KMPC_HDN inline bool pass_trial(const Cfg &c, const Ctx &t, double *wsp, size_t 
 }
 
 // SOC right-hand side: c_soc <- a * base + c(trial), base = c(current) for the first correction, else the previous c_soc
-KMPC_HDN inline void pass_soc_rhs(const Cfg &c, const Ctx &t, double *wsp, size_t S, double a, bool first) {
+KMPC_HDN inline void pass_soc_rhs(const Cfg &c, const Ctx &t, double *wsp, size_t S, double al, bool first) {
     const int N = c.N, O = c.O;
     const Rows &L = c.L;
-    const int sb = L.rState[t.cur], nb = L.rState[t.cur ^ 1];
     const double T = c.T;
-    double cp0 = RW(L.rSc), cp1 = RW(L.rSc + 1), cp2 = RW(L.rSc + 2);  // predicted (current point)
-    double tp0 = cp0, tp1 = cp1, tp2 = cp2;                            // predicted (trial point)
+    const double *sc = wsp + (size_t)L.rSc * S;
+    const double *ps = wsp + (size_t)L.rState[t.cur] * S, *pt = wsp + (size_t)L.rState[t.cur ^ 1] * S;
+    const double *po = wsp + ((size_t)L.rState[t.cur] + L.sObs) * S, *pto = wsp + ((size_t)L.rState[t.cur ^ 1] + L.sObs) * S;
+    double *pcs = wsp + (size_t)L.rCsoc * S, *pds = wsp + (size_t)L.rDsoc * S;
+    double cp0 = FD(sc, 0), cp1 = FD(sc, 1), cp2 = FD(sc, 2);  // predicted (current point)
+    double tp0 = cp0, tp1 = cp1, tp2 = cp2;                    // predicted (trial point)
 #pragma unroll 1
     for (int k = 0; k <= N; ++k) {
-        const double x0 = RW(sb + L.sX + 3 * k), x1 = RW(sb + L.sX + 3 * k + 1), x2 = RW(sb + L.sX + 3 * k + 2);
-        const double t0 = RW(nb + L.sX + 3 * k), t1 = RW(nb + L.sX + 3 * k + 1), t2 = RW(nb + L.sX + 3 * k + 2);
+        const double x0 = FD(ps, F_X0), x1 = FD(ps, F_X1), x2 = FD(ps, F_X2);
+        const double t0 = FD(pt, F_X0), t1 = FD(pt, F_X1), t2 = FD(pt, F_X2);
         double b0, b1, b2;
         if (first) { b0 = x0 - cp0; b1 = x1 - cp1; b2 = x2 - cp2; }
-        else { b0 = RW(L.rCsoc + 3 * k); b1 = RW(L.rCsoc + 3 * k + 1); b2 = RW(L.rCsoc + 3 * k + 2); }
-        RW(L.rCsoc + 3 * k) = a * b0 + (t0 - tp0); RW(L.rCsoc + 3 * k + 1) = a * b1 + (t1 - tp1); RW(L.rCsoc + 3 * k + 2) = a * b2 + (t2 - tp2);
+        else { b0 = FD(pcs, 0); b1 = FD(pcs, 1); b2 = FD(pcs, 2); }
+        FD(pcs, 0) = al * b0 + (t0 - tp0); FD(pcs, 1) = al * b1 + (t1 - tp1); FD(pcs, 2) = al * b2 + (t2 - tp2);
         if (O > 0 && k >= 1)
-            for (int o = 0; o < O; ++o) {
-                const int i = (k - 1) * O + o;
-                const double cx = RW(L.rSc + 6 + 2 * o), cy = RW(L.rSc + 7 + 2 * o);
+            for (int o = 0; o < O; ++o, po += (size_t)3 * S, pto += (size_t)3 * S, pds += S) {
+                const double cx = FD(sc, 6 + 2 * o), cy = FD(sc, 7 + 2 * o);
                 double base;
-                if (first) { const double ex = x0 - cx, ey = x1 - cy; base = (sqrt(ex * ex + ey * ey) - c.obs_radius) - RW(sb + L.sS + i); }
-                else base = RW(L.rDsoc + i);
+                if (first) { const double ex = x0 - cx, ey = x1 - cy; base = (sqrt(ex * ex + ey * ey) - c.obs_radius) - FD(po, 0); }
+                else base = FD(pds, 0);
                 const double ex = t0 - cx, ey = t1 - cy;
-                RW(L.rDsoc + i) = a * base + ((sqrt(ex * ex + ey * ey) - c.obs_radius) - RW(nb + L.sS + i));
+                FD(pds, 0) = al * base + ((sqrt(ex * ex + ey * ey) - c.obs_radius) - FD(pto, 0));
             }
         if (k < N) {
-            const double v = RW(sb + L.sU + 2 * k), om = RW(sb + L.sU + 2 * k + 1);
-            const double cs = RW(sb + L.sCS + 2 * k), sn = RW(sb + L.sCS + 2 * k + 1);
-            cp0 = x0 + T * v * cs; cp1 = x1 + T * v * sn; cp2 = x2 + T * om;
-            const double vt = RW(nb + L.sU + 2 * k), ot = RW(nb + L.sU + 2 * k + 1);
-            const double ct = RW(nb + L.sCS + 2 * k), stt = RW(nb + L.sCS + 2 * k + 1);
-            tp0 = t0 + T * vt * ct; tp1 = t1 + T * vt * stt; tp2 = t2 + T * ot;
+            cp0 = x0 + T * FD(ps, F_V) * FD(ps, F_CS); cp1 = x1 + T * FD(ps, F_V) * FD(ps, F_SN); cp2 = x2 + T * FD(ps, F_OM);
+            tp0 = t0 + T * FD(pt, F_V) * FD(pt, F_CS); tp1 = t1 + T * FD(pt, F_V) * FD(pt, F_SN); tp2 = t2 + T * FD(pt, F_OM);
         }
+        ps += (size_t)NSTATE * S; pt += (size_t)NSTATE * S; pcs += (size_t)3 * S;
     }
 }
 
@@ -742,11 +761,11 @@ KMPC_HDN inline void pass_soc_rhs(const Cfg &c, const Ctx &t, double *wsp, size_
 KMPC_HDN inline void pass_output(const Cfg &c, const Ctx &t, double *wsp, size_t S, const IO &io, int status) {
     const int N = c.N, b = t.inst;
     const Rows &L = c.L;
-    const int sb = L.rState[t.cur];
+    const double *ps = wsp + (size_t)L.rState[t.cur] * S;
 #pragma unroll 1
-    for (int k = 0; k <= N; ++k) {
-        for (int j = 0; j < 3; ++j) io.X_out[io_X(c, b, j, k)] = RW(sb + L.sX + 3 * k + j);
-        if (k < N) for (int j = 0; j < 2; ++j) io.U_out[io_U(c, b, j, k)] = RW(sb + L.sU + 2 * k + j);
+    for (int k = 0; k <= N; ++k, ps += (size_t)NSTATE * S) {
+        io.X_out[io_X(c, b, 0, k)] = FD(ps, F_X0); io.X_out[io_X(c, b, 1, k)] = FD(ps, F_X1); io.X_out[io_X(c, b, 2, k)] = FD(ps, F_X2);
+        if (k < N) { io.U_out[io_U(c, b, 0, k)] = FD(ps, F_V); io.U_out[io_U(c, b, 1, k)] = FD(ps, F_OM); }
     }
     if (io.obj) io.obj[b] = t.c.f / t.df;
     if (io.status) io.status[b] = status;
@@ -823,54 +842,66 @@ KMPC_HD int begin_iteration(const Cfg &c, Ctx &t) {
     return 100;
 }
 
-// One trip of the state machine for one instance (mode != M_FETCH, != M_DONE).
-// Returns 100 while the instance is still being solved, else its final status (the caller writes the outputs).
-KMPC_HDN inline int trip(const Cfg &c, Ctx &t, double *wsp, size_t S) {
-    const Rows &L = c.L;
+// ------------------------------------------------------------------------------------------------
+// The state machine of one instance, cut into the three phases the kernels run (kmpc.cu):
+//   phase_sweep   -> 100: factorisation ok, go on to the roll-out; 101: wrong inertia, delta raised, sweep again;
+//                    otherwise a final status
+//   phase_rollout -> search direction, step sizes, line-search set-up
+//   phase_trial   -> trial point + acceptance logic; 100: continue (t.mode tells which phase is next), else final status
+// ------------------------------------------------------------------------------------------------
+template <bool OBS>
+KMPC_HDN inline int phase_sweep(const Cfg &c, Ctx &t, double *wsp, size_t S) {
     t.trips++;
-    int sel = 0, tu = TU_STEP;
-    double a_pr = 0.0, a_y = 0.0, a_du = 0.0;
-    if (t.mode != M_TRIAL) {
-        const bool ok = pass_sweep(c, t, wsp, S);
-        if (!ok) {
-            if (t.mode != M_NEWTON) return ST_STEP_ERROR;
-            // inertia correction (IPOPT PDPerturbationHandler)
-            if (t.delta == 0.0) t.delta = t.delta_last == 0.0 ? K_DW_INIT : fmax(K_DW_MIN, t.delta_last * K_DW_DEC);
-            else t.delta = (t.delta_last == 0.0 || 1e5 * t.delta_last < t.delta) ? K_DW_INC_FIRST * t.delta : K_DW_INC * t.delta;
-            if (t.delta > K_DW_MAX) return ST_STEP_ERROR;
-            return 100;
+    const bool ok = pass_sweep<OBS>(c, t, wsp, S);
+    if (ok) return 100;
+    if (t.mode != M_NEWTON) return ST_STEP_ERROR;
+    // inertia correction (IPOPT PDPerturbationHandler)
+    if (t.delta == 0.0) t.delta = t.delta_last == 0.0 ? K_DW_INIT : fmax(K_DW_MIN, t.delta_last * K_DW_DEC);
+    else t.delta = (t.delta_last == 0.0 || 1e5 * t.delta_last < t.delta) ? K_DW_INC_FIRST * t.delta : K_DW_INC * t.delta;
+    if (t.delta > K_DW_MAX) return ST_STEP_ERROR;
+    return 101;
+}
+
+template <bool OBS>
+KMPC_HDN inline void phase_rollout(const Cfg &c, Ctx &t, double *wsp, size_t S) {
+    double apr, adu, gbd, ym;
+    t.sel = t.mode == M_SOC ? 1 : 0;
+    t.tu = TU_STEP;
+    pass_rollout<OBS>(c, t, wsp, S, t.sel, &apr, &adu, &gbd, &ym);
+    if (t.mode == M_LSQ) {
+        t.tu = TU_INIT; t.a_pr = 0.0; t.a_du = 0.0;
+        t.a_y = (ym <= K_YINIT_MAX && isfinite(ym)) ? -1.0 : 0.0;
+    } else if (t.mode == M_NEWTON) {
+        if (t.delta > 0.0) t.delta_last = t.delta;
+        t.gBD = gbd;
+        if (t.theta_max < 0) { t.theta_max = K_THETA_MAX_FACT * fmax(1.0, t.c.theta); t.theta_min = K_THETA_MIN_FACT * fmax(1.0, t.c.theta); }
+        double amin = K_GAMMA_THETA;
+        if (gbd < 0) {
+            amin = fmin(K_GAMMA_THETA, K_GAMMA_PHI * t.c.theta / (-gbd));
+            if (t.c.theta <= t.theta_min) amin = fmin(amin, K_DELTA_LS * pow(t.c.theta, K_S_THETA) / pow(-gbd, K_S_PHI));
         }
-        double apr, adu, gbd, ym;
-        sel = t.mode == M_SOC ? 1 : 0;
-        pass_rollout(c, t, wsp, S, sel, &apr, &adu, &gbd, &ym);
-        if (t.mode == M_LSQ) {
-            tu = TU_INIT; a_pr = 0.0; a_du = 0.0;
-            a_y = (ym <= K_YINIT_MAX && isfinite(ym)) ? -1.0 : 0.0;
-        } else if (t.mode == M_NEWTON) {
-            if (t.delta > 0.0) t.delta_last = t.delta;
-            t.gBD = gbd;
-            if (t.theta_max < 0) { t.theta_max = K_THETA_MAX_FACT * fmax(1.0, t.c.theta); t.theta_min = K_THETA_MIN_FACT * fmax(1.0, t.c.theta); }
-            double amin = K_GAMMA_THETA;
-            if (gbd < 0) {
-                amin = fmin(K_GAMMA_THETA, K_GAMMA_PHI * t.c.theta / (-gbd));
-                if (t.c.theta <= t.theta_min) amin = fmin(amin, K_DELTA_LS * pow(t.c.theta, K_S_THETA) / pow(-gbd, K_S_PHI));
-            }
-            t.alpha_min = amin * K_ALPHA_MIN_FRAC;
-            t.alpha = apr; t.alpha_test = apr; t.alpha_du0 = adu; t.nsteps = 0; t.soc_count = 0;
-            a_pr = apr; a_y = apr; a_du = adu;
-        } else {  // M_SOC
-            t.alpha_soc = apr;
-            a_pr = apr; a_y = apr; a_du = adu;
-        }
-    } else {
-        sel = 0; a_pr = t.alpha; a_y = t.alpha; a_du = t.alpha_du0;
+        t.alpha_min = amin * K_ALPHA_MIN_FRAC;
+        t.alpha = apr; t.alpha_test = apr; t.alpha_du0 = adu; t.nsteps = 0; t.soc_count = 0;
+        t.a_pr = apr; t.a_y = apr; t.a_du = adu;
+    } else {  // M_SOC
+        t.alpha_soc = apr;
+        t.a_pr = apr; t.a_y = apr; t.a_du = adu;
+    }
+}
+
+template <bool OBS>
+KMPC_HDN inline int phase_trial(const Cfg &c, Ctx &t, double *wsp, size_t S) {
+    const Rows &L = c.L;
+    if (t.mode == M_TRIAL) {  // back-tracking trial on the original step: no sweep / roll-out this trip
+        t.trips++;
+        t.sel = 0; t.tu = TU_STEP; t.a_pr = t.alpha; t.a_y = t.alpha; t.a_du = t.alpha_du0;
         t.alpha_test = t.alpha;
     }
     Stats tri;
-    const bool evok = pass_trial(c, t, wsp, S, sel, tu, a_pr, a_y, a_du, &tri);
-    bool accept = tu == TU_INIT;
+    const bool evok = pass_trial<OBS>(c, t, wsp, S, t.sel, t.tu, t.a_pr, t.a_y, t.a_du, &tri);
+    bool accept = t.tu == TU_INIT;
     int soc_rhs = 0;  // 1: first correction, 2: follow-up correction
-    if (tu == TU_STEP) {
+    if (t.tu == TU_STEP) {
         if (evok) accept = acceptable(t, L, wsp, S, tri);
         if (!accept && evok) {
             if (t.mode == M_SOC) {
@@ -904,6 +935,48 @@ KMPC_HDN inline int trip(const Cfg &c, Ctx &t, double *wsp, size_t S) {
     // the trial buffer becomes the current iterate
     t.c = tri; t.cur ^= 1;
     return begin_iteration(c, t);
+}
+
+// One whole trip for one instance (used by the sequential test harness): sweep -> roll-out -> trial.
+template <bool OBS>
+KMPC_HDN inline int trip(const Cfg &c, Ctx &t, double *wsp, size_t S) {
+    if (t.mode != M_TRIAL) {
+        const int r = phase_sweep<OBS>(c, t, wsp, S);
+        if (r == 101) return 100;
+        if (r != 100) return r;
+        phase_rollout<OBS>(c, t, wsp, S);
+    }
+    return phase_trial<OBS>(c, t, wsp, S);
+}
+
+// ---- solver context <-> workspace (the kernels keep no state between launches) -------------------
+enum { X_MODE = 0, X_ITER, X_CUR, X_NSTEPS, X_SOCC, X_FN, X_TRIPS, X_SEL, X_TU, X_MU, X_TAU, X_DELTA, X_DLAST, X_DF, X_THMAX,
+       X_THMIN, X_ALPHA, X_ATEST, X_AMIN, X_ADU0, X_ASOC, X_GBD, X_THSOC, X_THTRI, X_APR, X_AY, X_ADU, X_CF, X_CBAR, X_CDAMP,
+       X_CTHETA, X_CDINF, X_CPINF, X_CMN, X_CMX, X_CSUMY, X_CSUMZ, X_CWMAX, X_COUNT };
+
+KMPC_HD void ctx_store(const Ctx &t, const Rows &L, double *wsp, size_t S) {
+    double *p = wsp + (size_t)L.rCtx * S;
+    FD(p, X_MODE) = t.mode; FD(p, X_ITER) = t.iter; FD(p, X_CUR) = t.cur; FD(p, X_NSTEPS) = t.nsteps; FD(p, X_SOCC) = t.soc_count;
+    FD(p, X_FN) = t.fn; FD(p, X_TRIPS) = t.trips; FD(p, X_SEL) = t.sel; FD(p, X_TU) = t.tu;
+    FD(p, X_MU) = t.mu; FD(p, X_TAU) = t.tau; FD(p, X_DELTA) = t.delta; FD(p, X_DLAST) = t.delta_last; FD(p, X_DF) = t.df;
+    FD(p, X_THMAX) = t.theta_max; FD(p, X_THMIN) = t.theta_min; FD(p, X_ALPHA) = t.alpha; FD(p, X_ATEST) = t.alpha_test;
+    FD(p, X_AMIN) = t.alpha_min; FD(p, X_ADU0) = t.alpha_du0; FD(p, X_ASOC) = t.alpha_soc; FD(p, X_GBD) = t.gBD;
+    FD(p, X_THSOC) = t.theta_soc_old; FD(p, X_THTRI) = t.theta_trial; FD(p, X_APR) = t.a_pr; FD(p, X_AY) = t.a_y; FD(p, X_ADU) = t.a_du;
+    FD(p, X_CF) = t.c.f; FD(p, X_CBAR) = t.c.bar; FD(p, X_CDAMP) = t.c.damp; FD(p, X_CTHETA) = t.c.theta; FD(p, X_CDINF) = t.c.dinf;
+    FD(p, X_CPINF) = t.c.pinf; FD(p, X_CMN) = t.c.mn; FD(p, X_CMX) = t.c.mx; FD(p, X_CSUMY) = t.c.sumy; FD(p, X_CSUMZ) = t.c.sumz;
+    FD(p, X_CWMAX) = t.c.wmax;
+}
+KMPC_HD void ctx_load(Ctx &t, const Rows &L, const double *wsp, size_t S) {
+    const double *p = wsp + (size_t)L.rCtx * S;
+    t.mode = (int)FD(p, X_MODE); t.iter = (int)FD(p, X_ITER); t.cur = (int)FD(p, X_CUR); t.nsteps = (int)FD(p, X_NSTEPS);
+    t.soc_count = (int)FD(p, X_SOCC); t.fn = (int)FD(p, X_FN); t.trips = (int)FD(p, X_TRIPS); t.sel = (int)FD(p, X_SEL); t.tu = (int)FD(p, X_TU);
+    t.mu = FD(p, X_MU); t.tau = FD(p, X_TAU); t.delta = FD(p, X_DELTA); t.delta_last = FD(p, X_DLAST); t.df = FD(p, X_DF);
+    t.theta_max = FD(p, X_THMAX); t.theta_min = FD(p, X_THMIN); t.alpha = FD(p, X_ALPHA); t.alpha_test = FD(p, X_ATEST);
+    t.alpha_min = FD(p, X_AMIN); t.alpha_du0 = FD(p, X_ADU0); t.alpha_soc = FD(p, X_ASOC); t.gBD = FD(p, X_GBD);
+    t.theta_soc_old = FD(p, X_THSOC); t.theta_trial = FD(p, X_THTRI); t.a_pr = FD(p, X_APR); t.a_y = FD(p, X_AY); t.a_du = FD(p, X_ADU);
+    t.c.f = FD(p, X_CF); t.c.bar = FD(p, X_CBAR); t.c.damp = FD(p, X_CDAMP); t.c.theta = FD(p, X_CTHETA); t.c.dinf = FD(p, X_CDINF);
+    t.c.pinf = FD(p, X_CPINF); t.c.mn = FD(p, X_CMN); t.c.mx = FD(p, X_CMX); t.c.sumy = FD(p, X_CSUMY); t.c.sumz = FD(p, X_CSUMZ);
+    t.c.wmax = FD(p, X_CWMAX);
 }
 
 }  // namespace kmpc

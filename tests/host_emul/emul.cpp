@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdint.h>
+#include <vector>
 #include "../../include/kmpc.h"
 #include "../../kiss_mpc_b200/csrc/kmpc_core.cuh"
 
@@ -31,24 +32,59 @@ extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, con
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs;
     io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters;
-    const size_t S = 8;
-#pragma omp parallel
-    {
-        double *ws = (double *)malloc(sizeof(double) * S * c.L.total);
-        for (size_t i = 0; i < S * c.L.total; ++i) ws[i] = NAN;  // poison: reads of never-written rows show up
-#pragma omp for schedule(dynamic, 1)
-        for (int b = 0; b < B; ++b) {
-            double *wsp = ws + (b % S);
-            Ctx t;
-            memset(&t, 0, sizeof t);
-            t.inst = b; t.trips = 0;
-            pass_init(c, t, wsp, S, io);
-            int r;
-            do { r = trip(c, t, wsp, S); } while (r == 100);
-            pass_output(c, t, wsp, S, io, r);
-            if (trips) trips[b] = t.trips;
-        }
-        free(ws);
+    // Mirrors the launch structure of kmpc.cu on the host: per trip, sweep(LA[p]) -> rollout(LT[p]) -> trial(LT[p]), with the
+    // solver context stored in / reloaded from the workspace between the phases exactly as the kernels do.
+    const size_t S = (size_t)((B + 31) / 32 * 32);
+    double *ws = (double *)malloc(sizeof(double) * S * c.L.total);
+    for (size_t i = 0; i < S * c.L.total; ++i) ws[i] = NAN;  // poison: reads of never-written rows show up
+    std::vector<int> LA[2], LT[2];
+    for (int b = 0; b < B; ++b) {
+        Ctx t; memset(&t, 0, sizeof t); t.inst = b;
+        pass_init(c, t, ws + b, S, io);
+        ctx_store(t, c.L, ws + b, S);
+        LA[0].push_back(b);
     }
+    for (int tr = 0; !(LA[tr & 1].empty() && LT[tr & 1].empty()); ++tr) {
+        const int p = tr & 1;
+        std::vector<int> outcome(LA[p].size());
+#pragma omp parallel for schedule(dynamic, 8)
+        for (size_t i = 0; i < LA[p].size(); ++i) {
+            const int b = LA[p][i]; double *wsp = ws + b;
+            Ctx t; ctx_load(t, c.L, wsp, S); t.inst = b;
+            const int r = O > 0 ? phase_sweep<true>(c, t, wsp, S) : phase_sweep<false>(c, t, wsp, S);
+            double *pw = wsp + (size_t)c.L.rCtx * S;
+            pw[(size_t)X_TRIPS * S] = t.trips; pw[(size_t)X_DELTA * S] = t.delta;
+            if (r != 100 && r != 101) { pass_output(c, t, wsp, S, io, r); if (trips) trips[b] = t.trips; }
+            outcome[i] = r;
+        }
+        for (size_t i = 0; i < LA[p].size(); ++i) {
+            if (outcome[i] == 100) LT[p].push_back(LA[p][i]);
+            else if (outcome[i] == 101) LA[1 - p].push_back(LA[p][i]);
+        }
+#pragma omp parallel for schedule(dynamic, 8)
+        for (size_t i = 0; i < LT[p].size(); ++i) {
+            const int b = LT[p][i]; double *wsp = ws + b;
+            Ctx t; ctx_load(t, c.L, wsp, S);
+            if (t.mode == M_TRIAL) continue;
+            t.inst = b;
+            if (O > 0) phase_rollout<true>(c, t, wsp, S); else phase_rollout<false>(c, t, wsp, S);
+            ctx_store(t, c.L, wsp, S);
+        }
+        std::vector<int> out2(LT[p].size());
+#pragma omp parallel for schedule(dynamic, 8)
+        for (size_t i = 0; i < LT[p].size(); ++i) {
+            const int b = LT[p][i]; double *wsp = ws + b;
+            Ctx t; ctx_load(t, c.L, wsp, S); t.inst = b;
+            const int r = O > 0 ? phase_trial<true>(c, t, wsp, S) : phase_trial<false>(c, t, wsp, S);
+            if (r == 100) { ctx_store(t, c.L, wsp, S); out2[i] = t.mode == M_TRIAL ? 1 : 2; }
+            else { pass_output(c, t, wsp, S, io, r); if (trips) trips[b] = t.trips; out2[i] = 0; }
+        }
+        for (size_t i = 0; i < LT[p].size(); ++i) {
+            if (out2[i] == 1) LT[1 - p].push_back(LT[p][i]);
+            else if (out2[i] == 2) LA[1 - p].push_back(LT[p][i]);
+        }
+        LA[p].clear(); LT[p].clear();
+    }
+    free(ws);
     return 0;
 }
