@@ -342,6 +342,9 @@ extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const doub
     h->launches++;
     int ub = B;  // upper bound of the number of unfinished instances (non-increasing over the trips)
     int t = 0;
+    const bool trace = getenv("KMPC_TRACE") != NULL;  // debugging aid: per-trip device time + active counts on stderr
+    cudaEvent_t tev[2] = {NULL, NULL};
+    if (trace) { cudaEventCreate(&tev[0]); cudaEventCreate(&tev[1]); }
     for (;; ++t) {
         const int p = t & 1, q = t % KMPC_LOOKAHEAD;
         if (t >= KMPC_LOOKAHEAD) {
@@ -352,6 +355,7 @@ extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const doub
             ub = active;
         }
         const int g = nblocks(ub);
+        if (trace) cudaEventRecord(tev[0], st);
         if (O > 0) {
             kmpc_sweep_kernel<true><<<g, KMPC_TPB, 0, st>>>(c, io, h->ws, S, ls, p);
             kmpc_rollout_kernel<true><<<g, KMPC_TPB, 0, st>>>(c, h->ws, S, ls, p);
@@ -362,6 +366,12 @@ extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const doub
             kmpc_trial_kernel<false><<<g, KMPC_TPB, 0, st>>>(c, io, h->ws, S, ls, p);
         }
         h->launches += 3;
+        if (trace) {
+            int hc[4]; float ms = 0;
+            cudaEventRecord(tev[1], st); cudaEventSynchronize(tev[1]); cudaEventElapsedTime(&ms, tev[0], tev[1]);
+            cudaMemcpy(hc, h->cnt, sizeof hc, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "kmpc trip %4d  %8.3f ms  sweep %6d  trial %6d  -> next sweep %6d trial %6d\n", t, ms, hc[p], hc[2 + p], hc[1 - p], hc[2 + 1 - p]);
+        }
         CU(cudaMemcpyAsync(h->h_cnt + 4 * q, h->cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaEventRecord(h->evq[q], st));
         // the lists of parity p are consumed: empty them for trip t+1's appends
@@ -369,6 +379,7 @@ extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const doub
         CU(cudaMemsetAsync(h->cnt + 2 + p, 0, sizeof(int), st));
     }
     CU(cudaGetLastError());
+    if (trace) { cudaEventDestroy(tev[0]); cudaEventDestroy(tev[1]); }
     h->last_host_trips = t;
     if (h->timing) {
         CU(cudaEventRecord(h->ev1, st));
