@@ -12,6 +12,7 @@
 
 #include "../../include/kmpc.h"
 #include "kmpc_core.cuh"
+#include "kmpc_warp.cuh"
 
 using namespace kmpc;
 
@@ -136,6 +137,29 @@ kmpc_trial_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_
     if (pos_t >= 0) ls.LT[1 - p][pos_t] = b;
     const int pos_a = block_append(r == 100 && mode != M_TRIAL, ls.cnt + (1 - p));
     if (pos_a >= 0) ls.LA[1 - p][pos_a] = b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-per-instance solver (kmpc_warp.cuh): a persistent grid of warps, each pulling the next instance from a global
+// queue and solving it start to finish with the whole iterate in registers.  Used for problems without obstacle rows
+// and N + 1 <= 32 * SPL.
+// ------------------------------------------------------------------------------------------------
+#define KMPC_WARPS_PER_BLOCK 4
+template <int SPL>
+__global__ void __launch_bounds__(32 * KMPC_WARPS_PER_BLOCK, 3)
+kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned long long *__restrict__ trips_total) {
+    __shared__ double s_filt[KMPC_WARPS_PER_BLOCK][2 * K_FILTER_CAP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(queue, 1);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= c.B) break;
+        int tr = 0;
+        w_solve<SPL>(c, io, b, s_filt[warp], &tr);
+        if (lane == 0 && trips_total) atomicAdd(trips_total, (unsigned long long)tr);
+        __syncwarp();
+    }
 }
 
 // Batched EgoAgent.step hand-off (agent.py:139-155, :70-72): applied control = U[:,0]; next current state = X[:,1].
@@ -336,6 +360,34 @@ extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const doub
     ls.cnt = h->cnt; ls.trips = h->timing ? h->trips : NULL;
 
     if (h->timing) { CU(cudaMemsetAsync(h->trips, 0, sizeof(unsigned long long), st)); CU(cudaEventRecord(h->ev0, st)); }
+    const bool use_warp = O == 0 && cf->N + 1 <= 64 && getenv("KMPC_FORCE_THREAD") == NULL;
+    if (use_warp) {
+        // warp-per-instance path: one persistent launch, instances pulled from a queue, no workspace traffic
+        CU(cudaMemsetAsync(h->cnt, 0, sizeof(int), st));
+        int wpsm = 0;
+        const int spl = cf->N + 1 <= 32 ? 1 : 2;
+        if (spl == 1) { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wpsm, kmpc_warp_kernel<1>, 32 * KMPC_WARPS_PER_BLOCK, 0)); }
+        else { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wpsm, kmpc_warp_kernel<2>, 32 * KMPC_WARPS_PER_BLOCK, 0)); }
+        int grid = h->sm_count * (wpsm > 0 ? wpsm : 1);
+        const int need = (B + KMPC_WARPS_PER_BLOCK - 1) / KMPC_WARPS_PER_BLOCK;
+        if (grid > need) grid = need;
+        if (spl == 1) kmpc_warp_kernel<1><<<grid, 32 * KMPC_WARPS_PER_BLOCK, 0, st>>>(c, io, h->cnt, ls.trips);
+        else kmpc_warp_kernel<2><<<grid, 32 * KMPC_WARPS_PER_BLOCK, 0, st>>>(c, io, h->cnt, ls.trips);
+        CU(cudaGetLastError());
+        h->launches++;
+        h->last_host_trips = 0;
+        if (h->timing) {
+            CU(cudaEventRecord(h->ev1, st));
+            CU(cudaEventSynchronize(h->ev1));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            h->last_ms = ms;
+            unsigned long long tr = 0;
+            CU(cudaMemcpy(&tr, h->trips, sizeof tr, cudaMemcpyDeviceToHost));
+            h->last_trips = (long long)tr;
+        }
+        return 0;
+    }
     const int cnt0[4] = {B, 0, 0, 0};
     CU(cudaMemcpyAsync(h->cnt, cnt0, sizeof cnt0, cudaMemcpyHostToDevice, st));
     kmpc_init_kernel<<<nblocks(B), KMPC_TPB, 0, st>>>(c, io, h->ws, S, ls.LA[0]);

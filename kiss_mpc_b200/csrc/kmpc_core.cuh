@@ -783,19 +783,20 @@ KMPC_HD double opt_error(const Cfg &c, const Stats &s, double mu) {
 }
 KMPC_HD double phi_of(const Stats &s, double mu) { return s.f - mu * s.bar + K_KAPPA_D * mu * s.damp; }
 
-KMPC_HD bool filter_ok(const Ctx &t, const Rows &L, const double *wsp, size_t S, double theta, double phi) {
+// the filter: entry i = (theta, phi) at filt[(2 i) * FS], filt[(2 i + 1) * FS]
+KMPC_HD bool filter_ok(const Ctx &t, const double *filt, size_t FS, double theta, double phi) {
     for (int i = 0; i < t.fn; ++i)
-        if (!(theta <= RW(L.rFilt + 2 * i) || phi <= RW(L.rFilt + 2 * i + 1))) return false;
+        if (!(theta <= filt[(size_t)(2 * i) * FS] || phi <= filt[(size_t)(2 * i + 1) * FS])) return false;
     return true;
 }
-KMPC_HD void filter_add(Ctx &t, const Rows &L, double *wsp, size_t S, double theta, double phi) {
+KMPC_HD void filter_add(Ctx &t, double *filt, size_t FS, double theta, double phi) {
     int m = 0;
     for (int i = 0; i < t.fn; ++i) {
-        const double th = RW(L.rFilt + 2 * i), ph = RW(L.rFilt + 2 * i + 1);
-        if (!(th >= theta && ph >= phi)) { RW(L.rFilt + 2 * m) = th; RW(L.rFilt + 2 * m + 1) = ph; ++m; }
+        const double th = filt[(size_t)(2 * i) * FS], ph = filt[(size_t)(2 * i + 1) * FS];
+        if (!(th >= theta && ph >= phi)) { filt[(size_t)(2 * m) * FS] = th; filt[(size_t)(2 * m + 1) * FS] = ph; ++m; }
     }
     t.fn = m;
-    if (t.fn < K_FILTER_CAP) { RW(L.rFilt + 2 * t.fn) = theta; RW(L.rFilt + 2 * t.fn + 1) = phi; t.fn++; }
+    if (t.fn < K_FILTER_CAP) { filt[(size_t)(2 * t.fn) * FS] = theta; filt[(size_t)(2 * t.fn + 1) * FS] = phi; t.fn++; }
 }
 
 // FilterLSAcceptor::CheckAcceptabilityOfTrialPoint
@@ -803,7 +804,7 @@ KMPC_HD bool is_ftype(const Ctx &t, double a) {
     return t.gBD < 0 && a * pow(-t.gBD, K_S_PHI) > K_DELTA_LS * pow(t.c.theta, K_S_THETA);
 }
 KMPC_HD bool armijo(const Ctx &t, double a, double tphi, double cphi) { return cmp_le(tphi - cphi, K_ETA_PHI * a * t.gBD, cphi); }
-KMPC_HD bool acceptable(const Ctx &t, const Rows &L, const double *wsp, size_t S, const Stats &tri) {
+KMPC_HD bool acceptable(const Ctx &t, const double *filt, size_t FS, const Stats &tri) {
     const double cphi = phi_of(t.c, t.mu), tphi = phi_of(tri, t.mu), cth = t.c.theta;
     bool acc;
     if (tri.theta > t.theta_max) return false;
@@ -816,7 +817,7 @@ KMPC_HD bool acceptable(const Ctx &t, const Rows &L, const double *wsp, size_t S
         }
         if (acc) acc = cmp_le(tri.theta, (1.0 - K_GAMMA_THETA) * cth, cth) || cmp_le(tphi - cphi, -K_GAMMA_PHI * cth, cphi);
     }
-    if (acc) acc = filter_ok(t, L, wsp, S, tri.theta, tphi);
+    if (acc) acc = filter_ok(t, filt, FS, tri.theta, tphi);
     return acc;
 }
 
@@ -849,13 +850,8 @@ KMPC_HD int begin_iteration(const Cfg &c, Ctx &t) {
 //   phase_rollout -> search direction, step sizes, line-search set-up
 //   phase_trial   -> trial point + acceptance logic; 100: continue (t.mode tells which phase is next), else final status
 // ------------------------------------------------------------------------------------------------
-template <bool OBS>
-KMPC_HDN inline int phase_sweep(const Cfg &c, Ctx &t, double *wsp, size_t S) {
-    t.trips++;
-    const bool ok = pass_sweep<OBS>(c, t, wsp, S);
-    if (ok) return 100;
-    if (t.mode != M_NEWTON) return ST_STEP_ERROR;
-    // inertia correction (IPOPT PDPerturbationHandler)
+// inertia correction (IPOPT PDPerturbationHandler): raise delta_w; 101 = factorise again, else a final status
+KMPC_HD int inertia_update(Ctx &t) {
     if (t.delta == 0.0) t.delta = t.delta_last == 0.0 ? K_DW_INIT : fmax(K_DW_MIN, t.delta_last * K_DW_DEC);
     else t.delta = (t.delta_last == 0.0 || 1e5 * t.delta_last < t.delta) ? K_DW_INC_FIRST * t.delta : K_DW_INC * t.delta;
     if (t.delta > K_DW_MAX) return ST_STEP_ERROR;
@@ -863,11 +859,18 @@ KMPC_HDN inline int phase_sweep(const Cfg &c, Ctx &t, double *wsp, size_t S) {
 }
 
 template <bool OBS>
-KMPC_HDN inline void phase_rollout(const Cfg &c, Ctx &t, double *wsp, size_t S) {
-    double apr, adu, gbd, ym;
+KMPC_HDN inline int phase_sweep(const Cfg &c, Ctx &t, double *wsp, size_t S) {
+    t.trips++;
+    const bool ok = pass_sweep<OBS>(c, t, wsp, S);
+    if (ok) return 100;
+    if (t.mode != M_NEWTON) return ST_STEP_ERROR;
+    return inertia_update(t);
+}
+
+// line-search set-up once the search direction and its step-size limits are known
+KMPC_HD void rollout_logic(Ctx &t, double apr, double adu, double gbd, double ym) {
     t.sel = t.mode == M_SOC ? 1 : 0;
     t.tu = TU_STEP;
-    pass_rollout<OBS>(c, t, wsp, S, t.sel, &apr, &adu, &gbd, &ym);
     if (t.mode == M_LSQ) {
         t.tu = TU_INIT; t.a_pr = 0.0; t.a_du = 0.0;
         t.a_y = (ym <= K_YINIT_MAX && isfinite(ym)) ? -1.0 : 0.0;
@@ -890,48 +893,76 @@ KMPC_HDN inline void phase_rollout(const Cfg &c, Ctx &t, double *wsp, size_t S) 
 }
 
 template <bool OBS>
-KMPC_HDN inline int phase_trial(const Cfg &c, Ctx &t, double *wsp, size_t S) {
-    const Rows &L = c.L;
-    if (t.mode == M_TRIAL) {  // back-tracking trial on the original step: no sweep / roll-out this trip
+KMPC_HDN inline void phase_rollout(const Cfg &c, Ctx &t, double *wsp, size_t S) {
+    double apr, adu, gbd, ym;
+    pass_rollout<OBS>(c, t, wsp, S, t.mode == M_SOC ? 1 : 0, &apr, &adu, &gbd, &ym);
+    rollout_logic(t, apr, adu, gbd, ym);
+}
+
+// back-tracking trial on the original step: no sweep / roll-out this trip
+KMPC_HD void trial_setup(Ctx &t) {
+    if (t.mode == M_TRIAL) {
         t.trips++;
         t.sel = 0; t.tu = TU_STEP; t.a_pr = t.alpha; t.a_y = t.alpha; t.a_du = t.alpha_du0;
         t.alpha_test = t.alpha;
     }
+}
+
+// Acceptance logic of one evaluated trial point.  Returns
+//   R_SOC1 / R_SOC2  a (first / follow-up) second-order correction is due: caller builds c_soc with step t.alpha_soc
+//   R_BACKTRACK      next trip evaluates a shorter step;   R_ACCEPT  caller makes the trial point current, then begin_iteration
+//   a final status (ST_RESTORATION)
+enum { R_CONTINUE = 100, R_RETRY = 101, R_ACCEPT = 102, R_SOC1 = 103, R_SOC2 = 104, R_BACKTRACK = 105 };
+KMPC_HD int trial_decide(Ctx &t, const double *filt, size_t FS, const Stats &tri, bool evok, bool *augment, double *aug_theta,
+                        double *aug_phi) {
+    *augment = false; *aug_theta = 0.0; *aug_phi = 0.0;
+    if (t.tu == TU_INIT) return R_ACCEPT;
+    bool accept = false;
+    int soc_rhs = 0;
+    if (evok) accept = acceptable(t, filt, FS, tri);
+    if (!accept && evok) {
+        if (t.mode == M_SOC) {
+            t.soc_count++; t.theta_trial = tri.theta;
+            if (t.soc_count < K_MAX_SOC && t.theta_trial <= K_KAPPA_SOC * t.theta_soc_old) soc_rhs = 2;
+        } else if (t.nsteps == 0 && t.c.theta <= tri.theta) {
+            // second-order correction from the first trial point (max_soc 4)
+            t.alpha_soc = t.alpha; t.soc_count = 0;
+            soc_rhs = 1;
+        }
+    }
+    if (soc_rhs) {
+        t.theta_soc_old = tri.theta; t.theta_trial = tri.theta;
+        t.mode = M_SOC;
+        return soc_rhs == 1 ? R_SOC1 : R_SOC2;
+    }
+    if (!accept) {
+        // back-track on the original step (also after a failed correction)
+        t.alpha *= K_ALPHA_RED; t.nsteps++;
+        if (!(t.alpha > t.alpha_min)) return ST_RESTORATION;  // IPOPT would enter the restoration phase here
+        t.mode = M_TRIAL;
+        return R_BACKTRACK;
+    }
+    // accepted: filter augmentation (FilterLSAcceptor::UpdateForNextIteration)
+    const double cphi = phi_of(t.c, t.mu), tphi = phi_of(tri, t.mu);
+    if (!is_ftype(t, t.alpha_test) || !armijo(t, t.alpha_test, tphi, cphi)) {
+        *augment = true; *aug_theta = (1.0 - K_GAMMA_THETA) * t.c.theta; *aug_phi = cphi - K_GAMMA_PHI * t.c.theta;
+    }
+    t.iter++;
+    return R_ACCEPT;
+}
+
+template <bool OBS>
+KMPC_HDN inline int phase_trial(const Cfg &c, Ctx &t, double *wsp, size_t S) {
+    trial_setup(t);
     Stats tri;
     const bool evok = pass_trial<OBS>(c, t, wsp, S, t.sel, t.tu, t.a_pr, t.a_y, t.a_du, &tri);
-    bool accept = t.tu == TU_INIT;
-    int soc_rhs = 0;  // 1: first correction, 2: follow-up correction
-    if (t.tu == TU_STEP) {
-        if (evok) accept = acceptable(t, L, wsp, S, tri);
-        if (!accept && evok) {
-            if (t.mode == M_SOC) {
-                t.soc_count++; t.theta_trial = tri.theta;
-                if (t.soc_count < K_MAX_SOC && t.theta_trial <= K_KAPPA_SOC * t.theta_soc_old) soc_rhs = 2;
-            } else if (t.nsteps == 0 && t.c.theta <= tri.theta) {
-                // second-order correction from the first trial point (max_soc 4)
-                t.alpha_soc = t.alpha; t.soc_count = 0;
-                soc_rhs = 1;
-            }
-        }
-        if (soc_rhs) {
-            t.theta_soc_old = tri.theta; t.theta_trial = tri.theta;
-            pass_soc_rhs(c, t, wsp, S, t.alpha_soc, soc_rhs == 1);
-            t.mode = M_SOC;
-            return 100;
-        }
-        if (!accept) {
-            // back-track on the original step (also after a failed correction)
-            t.alpha *= K_ALPHA_RED; t.nsteps++;
-            if (!(t.alpha > t.alpha_min)) return ST_RESTORATION;  // IPOPT would enter the restoration phase here
-            t.mode = M_TRIAL;
-            return 100;
-        }
-        // accepted: filter augmentation (FilterLSAcceptor::UpdateForNextIteration)
-        const double cphi = phi_of(t.c, t.mu), tphi = phi_of(tri, t.mu);
-        if (!is_ftype(t, t.alpha_test) || !armijo(t, t.alpha_test, tphi, cphi))
-            filter_add(t, L, wsp, S, (1.0 - K_GAMMA_THETA) * t.c.theta, cphi - K_GAMMA_PHI * t.c.theta);
-        t.iter++;
-    }
+    bool aug; double ath, aph;
+    double *filt = wsp + (size_t)c.L.rFilt * S;
+    const int r = trial_decide(t, filt, S, tri, evok, &aug, &ath, &aph);
+    if (aug) filter_add(t, filt, S, ath, aph);
+    if (r == R_SOC1 || r == R_SOC2) { pass_soc_rhs(c, t, wsp, S, t.alpha_soc, r == R_SOC1); return 100; }
+    if (r == R_BACKTRACK) return 100;
+    if (r != R_ACCEPT) return r;
     // the trial buffer becomes the current iterate
     t.c = tri; t.cur ^= 1;
     return begin_iteration(c, t);

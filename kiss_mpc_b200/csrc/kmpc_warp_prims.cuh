@@ -1,0 +1,36 @@
+// kmpc_warp_prims.cuh -- the handful of warp-collective primitives the warp-per-instance solver uses.
+// Device build: CUDA shuffle / vote intrinsics.  Host build (tests/host_emul only): a cooperative 32-fibre emulator
+// (tests/host_emul/simt.h) supplies the same functions so the identical solver source runs on a GPU-less machine.
+#pragma once
+
+#ifdef __CUDACC__
+#define KMPC_W __device__ __forceinline__
+#define KMPC_WN __device__
+namespace kmpc {
+KMPC_W int w_lane() { return (int)(threadIdx.x & 31u); }
+KMPC_W double w_down(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+KMPC_W double w_up(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+KMPC_W double w_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+KMPC_W double w_bcast(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+KMPC_W int w_bcast_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+KMPC_W bool w_all(bool p) { return __all_sync(0xffffffffu, p); }
+KMPC_W bool w_any(bool p) { return __any_sync(0xffffffffu, p); }
+KMPC_W void w_sync() { __syncwarp(); }
+}  // namespace kmpc
+#else
+#define KMPC_W inline
+#define KMPC_WN
+#include "simt.h"  // tests/host_emul/simt.h (include path set by the test build only)
+#endif
+
+namespace kmpc {
+// butterfly reductions: every lane ends with the same bits
+KMPC_W double w_sum(double v) { for (int m = 16; m > 0; m >>= 1) v += w_xor(v, m); return v; }
+KMPC_W double w_min(double v) { for (int m = 16; m > 0; m >>= 1) v = fmin(v, w_xor(v, m)); return v; }
+KMPC_W double w_max(double v) { for (int m = 16; m > 0; m >>= 1) v = fmax(v, w_xor(v, m)); return v; }
+// max of |.| that propagates NaN (mirrors maxabs_nan of the thread solver)
+KMPC_W double w_maxabs_nan(double v) {
+    for (int m = 16; m > 0; m >>= 1) { const double o = w_xor(v, m); v = (o > v || o != o) ? o : v; }
+    return v;
+}
+}  // namespace kmpc

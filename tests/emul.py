@@ -9,6 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "host_emul", "emul.cpp")
 _SO = os.path.join(_HERE, "host_emul", "libkmpc_emul.so")
 _CORE = os.path.join(_HERE, "..", "kiss_mpc_b200", "csrc", "kmpc_core.cuh")
+_WARP = os.path.join(_HERE, "..", "kiss_mpc_b200", "csrc", "kmpc_warp.cuh")
 
 
 class KmpcConfig(C.Structure):
@@ -20,9 +21,9 @@ class KmpcConfig(C.Structure):
 
 
 def build():
-    newest = max(os.path.getmtime(_SRC), os.path.getmtime(_CORE))
+    newest = max(os.path.getmtime(p) for p in (_SRC, _CORE, _WARP, os.path.join(_HERE, "host_emul", "simt.h")))
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
-        subprocess.check_call(["g++", "-O2", "-fopenmp", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _SO, _SRC])
+        subprocess.check_call(["g++", "-O2", "-fopenmp", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", os.path.join(_HERE, "host_emul"), "-o", _SO, _SRC])
     return _SO
 
 
@@ -43,7 +44,7 @@ def cfg_from_oracle(ocfg, B_max=1, layout=0):
     return c
 
 
-def solve(ocfg, x_cur, goal, X0=None, U0=None, obs=None, layout=0):
+def solve(ocfg, x_cur, goal, X0=None, U0=None, obs=None, layout=0, warp=False):
     L = C.CDLL(build())
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
     L.emul_solve.restype = C.c_int
@@ -64,8 +65,15 @@ def solve(ocfg, x_cur, goal, X0=None, U0=None, obs=None, layout=0):
     Xo = np.full((3, N + 1, B) if layout else (B, 3, N + 1), np.nan); Uo = np.full((2, N, B) if layout else (B, 2, N), np.nan)
     obj = np.empty(B); st = np.empty(B, np.int32); it = np.empty(B, np.int32); tp = np.empty(B, np.int32)
     p = lambda a, t=C.c_double: None if a is None else a.ctypes.data_as(C.POINTER(t))
-    rc = L.emul_solve(C.byref(c), B, p(xi), p(gi), p(X0i), p(U0i), p(obi), O, ocfg.obs_radius, ocfg.inflation, p(Xo), p(Uo),
-                      p(obj), p(st, C.c_int32), p(it, C.c_int32), p(tp, C.c_int32))
+    if warp:
+        assert O == 0
+        L.emul_solve_warp.restype = C.c_int
+        L.emul_solve_warp.argtypes = [C.POINTER(KmpcConfig), C.c_int, dp, dp, dp, dp, dp, dp, dp, ip, ip, ip]
+        rc = L.emul_solve_warp(C.byref(c), B, p(xi), p(gi), p(X0i), p(U0i), p(Xo), p(Uo), p(obj), p(st, C.c_int32),
+                               p(it, C.c_int32), p(tp, C.c_int32))
+    else:
+        rc = L.emul_solve(C.byref(c), B, p(xi), p(gi), p(X0i), p(U0i), p(obi), O, ocfg.obs_radius, ocfg.inflation, p(Xo), p(Uo),
+                          p(obj), p(st, C.c_int32), p(it, C.c_int32), p(tp, C.c_int32))
     assert rc == 0
     if layout:
         Xo = np.ascontiguousarray(np.moveaxis(Xo, -1, 0)); Uo = np.ascontiguousarray(np.moveaxis(Uo, -1, 0))

@@ -8,12 +8,41 @@
 #include <vector>
 #include "../../include/kmpc.h"
 #include "../../kiss_mpc_b200/csrc/kmpc_core.cuh"
+#include "../../kiss_mpc_b200/csrc/kmpc_warp.cuh"
 
 using namespace kmpc;
 
-extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, const double *goal, const double *X0,
-                          const double *U0, const double *obs, int O, double obs_radius, double inflation, double *X_out,
-                          double *U_out, double *obj, int32_t *status, int32_t *iters, int32_t *trips) {
+// ---- 32-fibre warp emulator (see simt.h) ----
+namespace kmpc {
+thread_local Simt *g_simt = nullptr;
+static void simt_entry() {
+    Simt &s = *g_simt;
+    s.fn();
+    // this lane is finished: hand over to the next unfinished lane, the last one returns to the caller
+    const int me = s.cur;
+    if (me < 31) { s.cur = me + 1; setcontext(&s.ctx[me + 1]); }
+    setcontext(&s.main);
+}
+void simt_run(const std::function<void()> &fn) {
+    Simt s;
+    g_simt = &s;
+    s.fn = fn;
+    for (int i = 0; i < 32; ++i) {
+        s.parity[i] = 0;
+        s.stack[i].resize(1 << 20);
+        getcontext(&s.ctx[i]);
+        s.ctx[i].uc_stack.ss_sp = s.stack[i].data();
+        s.ctx[i].uc_stack.ss_size = s.stack[i].size();
+        s.ctx[i].uc_link = nullptr;
+        makecontext(&s.ctx[i], (void (*)())simt_entry, 0);
+    }
+    s.cur = 0;
+    swapcontext(&s.main, &s.ctx[0]);
+    g_simt = nullptr;
+}
+}  // namespace kmpc
+
+static Cfg make_cfg(const kmpc_config *cf, int B, int O, double obs_radius, double inflation) {
     Cfg c;
     memset(&c, 0, sizeof c);
     c.N = cf->N; c.O = O; c.cost_mode = cf->cost_mode; c.gk_lo = cf->goal_k_lo; c.gk_hi = cf->goal_k_hi;
@@ -29,6 +58,13 @@ extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, con
     c.L = make_rows(cf->N, O);
     c.nb = (cf->N + 1) * (c.hasL[0] + c.hasU[0] + c.hasL[1] + c.hasU[1]) + cf->N * (c.hasL[2] + c.hasU[2] + c.hasL[3] + c.hasU[3]) + cf->N * O;
     c.m = 3 * (cf->N + 1) + cf->N * O;
+    return c;
+}
+
+extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, const double *goal, const double *X0,
+                          const double *U0, const double *obs, int O, double obs_radius, double inflation, double *X_out,
+                          double *U_out, double *obj, int32_t *status, int32_t *iters, int32_t *trips) {
+    Cfg c = make_cfg(cf, B, O, obs_radius, inflation);
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs;
     io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters;
@@ -86,5 +122,25 @@ extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, con
         LA[p].clear(); LT[p].clear();
     }
     free(ws);
+    return 0;
+}
+
+// warp-per-instance solver (kmpc_warp.cuh) on the fibre emulator; O must be 0 and N + 1 <= 64
+extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur, const double *goal, const double *X0,
+                               const double *U0, double *X_out, double *U_out, double *obj, int32_t *status, int32_t *iters,
+                               int32_t *trips) {
+    if (cf->N + 1 > 64) return -1;
+    Cfg c = make_cfg(cf, B, 0, 0.0, 0.0);
+    IO io;
+    io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = NULL;
+    io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters;
+    const int spl = cf->N + 1 <= 32 ? 1 : 2;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < B; ++b) {
+        double filt[2 * K_FILTER_CAP];
+        int tr = 0;
+        simt_run([&]() { if (spl == 1) w_solve<1>(c, io, b, filt, &tr); else w_solve<2>(c, io, b, filt, &tr); });
+        if (trips) trips[b] = tr;
+    }
     return 0;
 }
