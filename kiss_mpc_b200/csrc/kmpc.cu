@@ -145,8 +145,11 @@ kmpc_trial_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_
 // and N + 1 <= 32 * SPL.
 // ------------------------------------------------------------------------------------------------
 #define KMPC_WARPS_PER_BLOCK 4
+#ifndef KMPC_WARP_MINB
+#define KMPC_WARP_MINB 2
+#endif
 template <int SPL>
-__global__ void __launch_bounds__(32 * KMPC_WARPS_PER_BLOCK, 3)
+__global__ void __launch_bounds__(32 * KMPC_WARPS_PER_BLOCK, KMPC_WARP_MINB)
 kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned long long *__restrict__ trips_total) {
     __shared__ double s_filt[KMPC_WARPS_PER_BLOCK][2 * K_FILTER_CAP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -360,12 +363,12 @@ extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const doub
     ls.cnt = h->cnt; ls.trips = h->timing ? h->trips : NULL;
 
     if (h->timing) { CU(cudaMemsetAsync(h->trips, 0, sizeof(unsigned long long), st)); CU(cudaEventRecord(h->ev0, st)); }
-    const bool use_warp = O == 0 && cf->N + 1 <= 64 && getenv("KMPC_FORCE_THREAD") == NULL;
+    const bool use_warp = O == 0 && cf->N + 1 < 64 && getenv("KMPC_FORCE_THREAD") == NULL;  // N + 1 < 32 * SPL
     if (use_warp) {
         // warp-per-instance path: one persistent launch, instances pulled from a queue, no workspace traffic
         CU(cudaMemsetAsync(h->cnt, 0, sizeof(int), st));
         int wpsm = 0;
-        const int spl = cf->N + 1 <= 32 ? 1 : 2;
+        const int spl = cf->N + 1 < 32 ? 1 : 2;
         if (spl == 1) { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wpsm, kmpc_warp_kernel<1>, 32 * KMPC_WARPS_PER_BLOCK, 0)); }
         else { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wpsm, kmpc_warp_kernel<2>, 32 * KMPC_WARPS_PER_BLOCK, 0)); }
         int grid = h->sm_count * (wpsm > 0 ? wpsm : 1);

@@ -144,6 +144,7 @@ struct Ctx {  // per-thread solver state (registers / local memory)
     double mu, tau, delta, delta_last, df, theta_max, theta_min;
     double alpha, alpha_test, alpha_min, alpha_du0, alpha_soc, gBD, theta_soc_old, theta_trial;
     double a_pr, a_y, a_du;  // step sizes of the pending trial: primal, equality multipliers, bound multipliers
+    double pw_g, pw_t;       // (-gBD)^s_phi and theta^s_theta of the current line search (switching condition)
     Stats c;  // current iterate
 };
 
@@ -184,13 +185,20 @@ KMPC_HD void vcost(const Cfg &c, double df, double v, double *g, double *h) {
     }
 }
 
+// correctly rounded reciprocal (one MUFU + Newton steps on the device instead of a full division)
+#ifdef __CUDA_ARCH__
+#define KRCP(x) __drcp_rn(x)
+#else
+#define KRCP(x) (1.0 / (x))
+#endif
+
 // barrier contributions of one bounded variable at the current iterate:
 //   sigma = zL/sl + zU/su,  rb = -mu/sl + mu/su (+- kappa_d mu for one-sided bounds)
 KMPC_HD void bound_terms(double val, double lb, double ub, int hL, int hU, double zL, double zU, double mu, double *sigma,
                          double *rb) {
     double sg = 0.0, r = 0.0;
-    if (hL) { double sl = val - lb; sg += zL / sl; r -= mu / sl; if (!hU) r += K_KAPPA_D * mu; }
-    if (hU) { double su = ub - val; sg += zU / su; r += mu / su; if (!hL) r -= K_KAPPA_D * mu; }
+    if (hL) { const double rs = KRCP(val - lb); sg += zL * rs; r -= mu * rs; if (!hU) r += K_KAPPA_D * mu; }
+    if (hU) { const double rs = KRCP(ub - val); sg += zU * rs; r += mu * rs; if (!hL) r -= K_KAPPA_D * mu; }
     *sigma = sg; *rb = r;
 }
 
@@ -199,15 +207,15 @@ KMPC_HD void bound_terms(double val, double lb, double ub, int hL, int hU, doubl
 KMPC_HD void bound_ftb(double val, double d, double lb, double ub, int hL, int hU, double zL, double zU, double mu,
                        double tau, double *apr, double *adu) {
     if (hL) {
-        double sl = val - lb;
+        const double sl = val - lb, rs = KRCP(sl);
         if (d < 0) *apr = fmin(*apr, -tau * sl / d);
-        double dz = mu / sl - zL - zL / sl * d;
+        const double dz = mu * rs - zL - zL * rs * d;
         if (dz < 0) *adu = fmin(*adu, -tau * zL / dz);
     }
     if (hU) {
-        double su = ub - val;
+        const double su = ub - val, rs = KRCP(su);
         if (d > 0) *apr = fmin(*apr, tau * su / d);
-        double dz = mu / su - zU + zU / su * d;
+        const double dz = mu * rs - zU + zU * rs * d;
         if (dz < 0) *adu = fmin(*adu, -tau * zU / dz);
     }
 }
@@ -220,23 +228,23 @@ KMPC_HD bool bound_trial(double val, double d, double vt, double lb, double ub, 
     bool ok = true;
     *zLn = 0.0; *zUn = 0.0;
     if (hL) {
-        double sl = val - lb, sn = vt - lb;
+        const double sl = val - lb, sn = vt - lb, rs = KRCP(sl);
         if (!(sn > 0)) ok = false;
         *prod *= sn;
         if (!hU) *damp += sn;
-        double z = zL + adu * (mu / sl - zL - zL / sl * d);
-        if (clamp) z = fmax(fmin(z, K_KAPPA_SIGMA * mu / sn), mu / (K_KAPPA_SIGMA * sn));
+        double z = zL + adu * (mu * rs - zL - zL * rs * d);
+        if (clamp) { const double mr = mu * KRCP(sn); z = fmax(fmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
         *zLn = z;
         double p = sn * z;
         st->mn = fmin(st->mn, p); st->mx = fmax(st->mx, p); st->sumz += fabs(z);
     }
     if (hU) {
-        double su = ub - val, sn = ub - vt;
+        const double su = ub - val, sn = ub - vt, rs = KRCP(su);
         if (!(sn > 0)) ok = false;
         *prod *= sn;
         if (!hL) *damp += sn;
-        double z = zU + adu * (mu / su - zU + zU / su * d);
-        if (clamp) z = fmax(fmin(z, K_KAPPA_SIGMA * mu / sn), mu / (K_KAPPA_SIGMA * sn));
+        double z = zU + adu * (mu * rs - zU + zU * rs * d);
+        if (clamp) { const double mr = mu * KRCP(sn); z = fmax(fmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
         *zUn = z;
         double p = sn * z;
         st->mn = fmin(st->mn, p); st->mx = fmax(st->mx, p); st->sumz += fabs(z);
@@ -245,6 +253,51 @@ KMPC_HD bool bound_trial(double val, double d, double vt, double lb, double ub, 
 }
 
 KMPC_HD double maxabs_nan(double m, double v) { double t = fabs(v); return (t > m || t != t) ? t : m; }
+
+// ------------------------------------------------------------------------------------------------
+// One step of the backward Riccati recursion for the unicycle stage
+//   A = I + a13 e1 e3^T + a23 e2 e3^T,   B = [b11 0; b21 0; 0 T],
+// in square-root-free LDL^T form: Q_uu = [d1 0; l d1, d2] pivots d1, d2 > 0 <=> Q_uu positive definite (the inertia test).
+//   in : (P, p) of stage k+1, stage blocks Q (xx, with Q01 only for obstacle rows), q, (qv, qw), (dv, dw) = diag of
+//        W_uu + Sigma_u + delta, htv = W_v,theta, e = bc_{k+1}
+//   out: (P, p) of stage k (overwritten), feedback K (2x3), feed-forward kf.  Returns false on a non-positive pivot.
+// ------------------------------------------------------------------------------------------------
+struct RicK { double K00, K01, K02, K10, K11, K12, kf0, kf1; };
+KMPC_HD bool riccati_step(double &P00, double &P10, double &P11, double &P20, double &P21, double &P22, double &p0, double &p1,
+                          double &p2, double a13, double a23, double b11, double b21, double T, double Q00, double Q01, double Q11,
+                          double Q22, double q0, double q1, double q2, double qv, double qw, double dv, double dw, double htv,
+                          double e0, double e1, double e2, RicK &o) {
+    // P A (third column), symmetric Qxx = A^T P A + Q
+    const double PA02 = fma(P00, a13, fma(P10, a23, P20)), PA12 = fma(P10, a13, fma(P11, a23, P21)), PA22 = fma(P20, a13, fma(P21, a23, P22));
+    const double X00 = P00 + Q00, X10 = P10 + Q01, X11 = P11 + Q11, X20 = PA02, X21 = PA12;
+    const double X22 = fma(a13, PA02, fma(a23, PA12, PA22)) + Q22;
+    // Qux = B^T P A (+ W_v,theta)
+    const double U00 = fma(b11, P00, b21 * P10), U01 = fma(b11, P10, b21 * P11), U02 = fma(b11, PA02, fma(b21, PA12, htv));
+    const double U10 = T * P20, U11 = T * P21, U12 = T * PA22;
+    // Quu = B^T P B + diag
+    const double d1 = fma(b11, U00, fma(b21, U01, dv)), qb = fma(b11, U10, b21 * U11), qc = fma(T * T, P22, dw);
+    const double r1 = KRCP(d1), l = qb * r1, d2 = fma(-l, qb, qc);
+    const double r2 = KRCP(d2);
+    const bool pd = d1 > 0.0 && d2 > 0.0;  // branch-free: the caller discards the outputs when a pivot is not positive
+    const double w0 = fma(-l, U00, U10), w1 = fma(-l, U01, U11), w2 = fma(-l, U02, U12);
+    const double s10 = r1 * U00, s11 = r1 * U01, s12 = r1 * U02, s20 = r2 * w0, s21 = r2 * w1, s22 = r2 * w2;
+    // vector part
+    const double Pe0 = fma(P00, e0, fma(P10, e1, fma(P20, e2, p0))), Pe1 = fma(P10, e0, fma(P11, e1, fma(P21, e2, p1))),
+                 Pe2 = fma(P20, e0, fma(P21, e1, fma(P22, e2, p2)));
+    const double qu0 = fma(b11, Pe0, fma(b21, Pe1, qv)), qu1 = fma(T, Pe2, qw);
+    const double g2 = fma(-l, qu0, qu1);
+    p0 = fma(-s10, qu0, fma(-s20, g2, q0 + Pe0));
+    p1 = fma(-s11, qu0, fma(-s21, g2, q1 + Pe1));
+    p2 = fma(-s12, qu0, fma(-s22, g2, fma(a13, Pe0, fma(a23, Pe1, q2 + Pe2))));
+    // P <- Qxx - Qux^T Quu^-1 Qux  (symmetric by construction)
+    P00 = fma(-s10, U00, fma(-s20, w0, X00)); P10 = fma(-s11, U00, fma(-s21, w0, X10)); P11 = fma(-s11, U01, fma(-s21, w1, X11));
+    P20 = fma(-s12, U00, fma(-s22, w0, X20)); P21 = fma(-s12, U01, fma(-s22, w1, X21)); P22 = fma(-s12, U02, fma(-s22, w2, X22));
+    // K = -Quu^-1 Qux, kf = -Quu^-1 qu
+    o.K10 = -s20; o.K11 = -s21; o.K12 = -s22;
+    o.K00 = fma(l, s20, -s10); o.K01 = fma(l, s21, -s11); o.K02 = fma(l, s22, -s12);
+    o.kf1 = -(g2 * r2); o.kf0 = fma(-l, o.kf1, -(qu0 * r1));
+    return pd;
+}
 
 // ------------------------------------------------------------------------------------------------
 // record access helpers.  ST(p, f): field f of the record p points at.
@@ -330,7 +383,7 @@ KMPC_HDN inline void pass_init(const Cfg &c, Ctx &t, double *wsp, size_t S, cons
     t.delta = 0.0; t.delta_last = 0.0; t.theta_max = -1.0; t.theta_min = -1.0; t.fn = 0;
     t.nsteps = 0; t.soc_count = 0; t.trips = 0; t.sel = 0; t.tu = TU_INIT;
     t.alpha = t.alpha_test = t.alpha_min = t.alpha_du0 = t.alpha_soc = t.gBD = t.theta_soc_old = t.theta_trial = 0.0;
-    t.a_pr = t.a_y = t.a_du = 0.0;
+    t.a_pr = t.a_y = t.a_du = 0.0; t.pw_g = t.pw_t = 0.0;
     t.c.f = t.c.bar = t.c.damp = t.c.theta = t.c.dinf = t.c.pinf = t.c.mn = t.c.mx = t.c.sumy = t.c.sumz = t.c.wmax = 0.0;
     t.mode = M_LSQ;
 }
@@ -425,7 +478,7 @@ KMPC_HDN inline bool pass_sweep(const Cfg &c, const Ctx &t, double *wsp, size_t 
             p0 = q0; p1 = q1; p2 = q2;
         } else {
             const double v = a[F_V], om = a[F_OM], cs = a[F_CS], sn = a[F_SN];
-            const double a13 = -T * v * sn, a23 = T * v * cs, b11 = T * cs, b21 = T * sn, b32 = T;
+            const double a13 = -T * v * sn, a23 = T * v * cs, b11 = T * cs, b21 = T * sn;
             double gv, hvv, qv, qw, Dv, Dw, htv = 0.0;
             vcost(c, df, v, &gv, &hvv);
             const double gw = df * 2.0 * c.Ww * om;
@@ -440,7 +493,7 @@ KMPC_HDN inline bool pass_sweep(const Cfg &c, const Ctx &t, double *wsp, size_t 
                 // J^T y of dynamics row k+1 (multiplier yn)
                 q0 -= yn0; q1 -= yn1; q2 -= a13 * yn0 + a23 * yn1 + yn2;
                 qv = gv - (b11 * yn0 + b21 * yn1) + rbv;
-                qw = gw - b32 * yn2 + rbw;
+                qw = gw - T * yn2 + rbw;
                 Dv = sgv + delta; Dw = sgw + delta;
                 // curvature of the dynamics in the Lagrangian (the only indefinite terms)
                 Q22 += T * v * (yn0 * cs + yn1 * sn);
@@ -451,37 +504,10 @@ KMPC_HDN inline bool pass_sweep(const Cfg &c, const Ctx &t, double *wsp, size_t 
             if (lsq) { e0 = e1 = e2 = 0.0; }
             else if (soc) { e0 = -FD(pcs, 0); e1 = -FD(pcs, 1); e2 = -FD(pcs, 2); }
             else { e0 = -(xn0 - (x0 + T * v * cs)); e1 = -(xn1 - (x1 + T * v * sn)); e2 = -(xn2 - (x2 + T * om)); }
-            // matrix recursion
-            const double PA02 = P00 * a13 + P10 * a23 + P20, PA12 = P10 * a13 + P11 * a23 + P21, PA22 = P20 * a13 + P21 * a23 + P22;
-            const double PB00 = P00 * b11 + P10 * b21, PB10 = P10 * b11 + P11 * b21;
-            const double PB01 = P20 * b32, PB11 = P21 * b32, PB21 = P22 * b32;
-            // Qxx = A^T P A + Q   (PA[:,0] = P[:,0], PA[:,1] = P[:,1])
-            const double X00 = P00 + Q00, X01 = P10 + Q01, X02 = PA02;
-            const double X10 = P10 + Q01, X11 = P11 + Q11, X12 = PA12;
-            const double X20 = a13 * P00 + a23 * P10 + P20, X21 = a13 * P10 + a23 * P11 + P21, X22 = a13 * PA02 + a23 * PA12 + PA22 + Q22;
-            // Qux = B^T P A (+ W_v,theta)
-            const double U00 = b11 * P00 + b21 * P10, U01 = b11 * P10 + b21 * P11, U02 = b11 * PA02 + b21 * PA12 + htv;
-            const double U10 = b32 * P20, U11 = b32 * P21, U12 = b32 * PA22;
-            const double qa = b11 * PB00 + b21 * PB10 + hvv + Dv, qb = b11 * PB01 + b21 * PB11, qc = b32 * PB21 + hww + Dw;
-            if (!(qa > 0.0)) { ok = false; break; }
-            const double sch = qc - qb * qb / qa;
-            if (!(sch > 0.0)) { ok = false; break; }
-            const double det = qa * qc - qb * qb;
-            const double i00 = qc / det, i01 = -qb / det, i11 = qa / det;
-            const double K00 = -(i00 * U00 + i01 * U10), K01 = -(i00 * U01 + i01 * U11), K02 = -(i00 * U02 + i01 * U12);
-            const double K10 = -(i01 * U00 + i11 * U10), K11 = -(i01 * U01 + i11 * U11), K12 = -(i01 * U02 + i11 * U12);
-            // vector recursion
-            const double Pe0 = P00 * e0 + P10 * e1 + P20 * e2 + p0, Pe1 = P10 * e0 + P11 * e1 + P21 * e2 + p1,
-                         Pe2 = P20 * e0 + P21 * e1 + P22 * e2 + p2;
-            const double qu0 = qv + b11 * Pe0 + b21 * Pe1, qu1 = qw + b32 * Pe2;
-            const double qx0 = q0 + Pe0, qx1 = q1 + Pe1, qx2 = q2 + a13 * Pe0 + a23 * Pe1 + Pe2;
-            const double kf0 = -(i00 * qu0 + i01 * qu1), kf1 = -(i01 * qu0 + i11 * qu1);
-            p0 = qx0 + K00 * qu0 + K10 * qu1; p1 = qx1 + K01 * qu0 + K11 * qu1; p2 = qx2 + K02 * qu0 + K12 * qu1;
-            // P = Qxx + Qux^T K, symmetrised
-            const double N00 = X00 + U00 * K00 + U10 * K10, N01 = X01 + U00 * K01 + U10 * K11, N02 = X02 + U00 * K02 + U10 * K12;
-            const double N10 = X10 + U01 * K00 + U11 * K10, N11 = X11 + U01 * K01 + U11 * K11, N12 = X12 + U01 * K02 + U11 * K12;
-            const double N20 = X20 + U02 * K00 + U12 * K10, N21 = X21 + U02 * K01 + U12 * K11, N22 = X22 + U02 * K02 + U12 * K12;
-            P00 = N00; P10 = 0.5 * (N10 + N01); P11 = N11; P20 = 0.5 * (N20 + N02); P21 = 0.5 * (N21 + N12); P22 = N22;
+            RicK rk;
+            if (!riccati_step(P00, P10, P11, P20, P21, P22, p0, p1, p2, a13, a23, b11, b21, T, Q00, Q01, Q11, Q22, q0, q1, q2, qv, qw,
+                              hvv + Dv, hww + Dw, htv, e0, e1, e2, rk)) { ok = false; break; }
+            const double K00 = rk.K00, K01 = rk.K01, K02 = rk.K02, K10 = rk.K10, K11 = rk.K11, K12 = rk.K12, kf0 = rk.kf0, kf1 = rk.kf1;
             FD(pf, A_K00) = K00; FD(pf, A_K01) = K01; FD(pf, A_K02) = K02;
             FD(pf, A_K10) = K10; FD(pf, A_K11) = K11; FD(pf, A_K12) = K12;
             FD(pf, A_KF0) = kf0; FD(pf, A_KF1) = kf1;
@@ -800,9 +826,7 @@ KMPC_HD void filter_add(Ctx &t, double *filt, size_t FS, double theta, double ph
 }
 
 // FilterLSAcceptor::CheckAcceptabilityOfTrialPoint
-KMPC_HD bool is_ftype(const Ctx &t, double a) {
-    return t.gBD < 0 && a * pow(-t.gBD, K_S_PHI) > K_DELTA_LS * pow(t.c.theta, K_S_THETA);
-}
+KMPC_HD bool is_ftype(const Ctx &t, double a) { return t.gBD < 0 && a * t.pw_g > K_DELTA_LS * t.pw_t; }
 KMPC_HD bool armijo(const Ctx &t, double a, double tphi, double cphi) { return cmp_le(tphi - cphi, K_ETA_PHI * a * t.gBD, cphi); }
 KMPC_HD bool acceptable(const Ctx &t, const double *filt, size_t FS, const Stats &tri) {
     const double cphi = phi_of(t.c, t.mu), tphi = phi_of(tri, t.mu), cth = t.c.theta;
@@ -879,9 +903,11 @@ KMPC_HD void rollout_logic(Ctx &t, double apr, double adu, double gbd, double ym
         t.gBD = gbd;
         if (t.theta_max < 0) { t.theta_max = K_THETA_MAX_FACT * fmax(1.0, t.c.theta); t.theta_min = K_THETA_MIN_FACT * fmax(1.0, t.c.theta); }
         double amin = K_GAMMA_THETA;
+        t.pw_g = 0.0; t.pw_t = 0.0;
         if (gbd < 0) {
+            t.pw_g = pow(-gbd, K_S_PHI); t.pw_t = pow(t.c.theta, K_S_THETA);
             amin = fmin(K_GAMMA_THETA, K_GAMMA_PHI * t.c.theta / (-gbd));
-            if (t.c.theta <= t.theta_min) amin = fmin(amin, K_DELTA_LS * pow(t.c.theta, K_S_THETA) / pow(-gbd, K_S_PHI));
+            if (t.c.theta <= t.theta_min) amin = fmin(amin, K_DELTA_LS * t.pw_t / t.pw_g);
         }
         t.alpha_min = amin * K_ALPHA_MIN_FRAC;
         t.alpha = apr; t.alpha_test = apr; t.alpha_du0 = adu; t.nsteps = 0; t.soc_count = 0;
@@ -983,7 +1009,8 @@ KMPC_HDN inline int trip(const Cfg &c, Ctx &t, double *wsp, size_t S) {
 // ---- solver context <-> workspace (the kernels keep no state between launches) -------------------
 enum { X_MODE = 0, X_ITER, X_CUR, X_NSTEPS, X_SOCC, X_FN, X_TRIPS, X_SEL, X_TU, X_MU, X_TAU, X_DELTA, X_DLAST, X_DF, X_THMAX,
        X_THMIN, X_ALPHA, X_ATEST, X_AMIN, X_ADU0, X_ASOC, X_GBD, X_THSOC, X_THTRI, X_APR, X_AY, X_ADU, X_CF, X_CBAR, X_CDAMP,
-       X_CTHETA, X_CDINF, X_CPINF, X_CMN, X_CMX, X_CSUMY, X_CSUMZ, X_CWMAX, X_COUNT };
+       X_CTHETA, X_CDINF, X_CPINF, X_CMN, X_CMX, X_CSUMY, X_CSUMZ, X_CWMAX, X_PWG, X_PWT, X_COUNT };
+static_assert(X_COUNT <= KMPC_NCTX, "context rows");
 
 KMPC_HD void ctx_store(const Ctx &t, const Rows &L, double *wsp, size_t S) {
     double *p = wsp + (size_t)L.rCtx * S;
@@ -995,7 +1022,7 @@ KMPC_HD void ctx_store(const Ctx &t, const Rows &L, double *wsp, size_t S) {
     FD(p, X_THSOC) = t.theta_soc_old; FD(p, X_THTRI) = t.theta_trial; FD(p, X_APR) = t.a_pr; FD(p, X_AY) = t.a_y; FD(p, X_ADU) = t.a_du;
     FD(p, X_CF) = t.c.f; FD(p, X_CBAR) = t.c.bar; FD(p, X_CDAMP) = t.c.damp; FD(p, X_CTHETA) = t.c.theta; FD(p, X_CDINF) = t.c.dinf;
     FD(p, X_CPINF) = t.c.pinf; FD(p, X_CMN) = t.c.mn; FD(p, X_CMX) = t.c.mx; FD(p, X_CSUMY) = t.c.sumy; FD(p, X_CSUMZ) = t.c.sumz;
-    FD(p, X_CWMAX) = t.c.wmax;
+    FD(p, X_CWMAX) = t.c.wmax; FD(p, X_PWG) = t.pw_g; FD(p, X_PWT) = t.pw_t;
 }
 KMPC_HD void ctx_load(Ctx &t, const Rows &L, const double *wsp, size_t S) {
     const double *p = wsp + (size_t)L.rCtx * S;
@@ -1007,7 +1034,7 @@ KMPC_HD void ctx_load(Ctx &t, const Rows &L, const double *wsp, size_t S) {
     t.theta_soc_old = FD(p, X_THSOC); t.theta_trial = FD(p, X_THTRI); t.a_pr = FD(p, X_APR); t.a_y = FD(p, X_AY); t.a_du = FD(p, X_ADU);
     t.c.f = FD(p, X_CF); t.c.bar = FD(p, X_CBAR); t.c.damp = FD(p, X_CDAMP); t.c.theta = FD(p, X_CTHETA); t.c.dinf = FD(p, X_CDINF);
     t.c.pinf = FD(p, X_CPINF); t.c.mn = FD(p, X_CMN); t.c.mx = FD(p, X_CMX); t.c.sumy = FD(p, X_CSUMY); t.c.sumz = FD(p, X_CSUMZ);
-    t.c.wmax = FD(p, X_CWMAX);
+    t.c.wmax = FD(p, X_CWMAX); t.pw_g = FD(p, X_PWG); t.pw_t = FD(p, X_PWT);
 }
 
 }  // namespace kmpc

@@ -28,6 +28,8 @@ struct WFact { double K00[SPL], K01[SPL], K02[SPL], K10[SPL], K11[SPL], K12[SPL]
                double P00[SPL], P10[SPL], P11[SPL], P20[SPL], P21[SPL], P22[SPL], pv0[SPL], pv1[SPL], pv2[SPL]; };
 template <int SPL>
 struct WVec3 { double a[SPL], b[SPL], c[SPL]; };
+template <int SPL>
+struct WLin { double a13[SPL], a23[SPL], b11[SPL], b21[SPL]; };  // non-trivial entries of A_k, B_k (zero for stages >= N)
 
 // value of the next / previous stage (neighbouring slot, or the neighbouring lane's edge slot)
 template <int SPL>
@@ -85,7 +87,7 @@ KMPC_WN inline void w_init(const Cfg &c, Ctx &t, const IO &io, int b, WState<SPL
     t.delta = 0.0; t.delta_last = 0.0; t.theta_max = -1.0; t.theta_min = -1.0; t.fn = 0;
     t.nsteps = 0; t.soc_count = 0; t.trips = 0; t.sel = 0; t.tu = TU_INIT;
     t.alpha = t.alpha_test = t.alpha_min = t.alpha_du0 = t.alpha_soc = t.gBD = t.theta_soc_old = t.theta_trial = 0.0;
-    t.a_pr = t.a_y = t.a_du = 0.0;
+    t.a_pr = t.a_y = t.a_du = 0.0; t.pw_g = t.pw_t = 0.0;
     t.c.f = t.c.bar = t.c.damp = t.c.theta = t.c.dinf = t.c.pinf = t.c.mn = t.c.mx = t.c.sumy = t.c.sumz = t.c.wmax = 0.0;
     t.mode = M_LSQ;
 }
@@ -95,7 +97,7 @@ KMPC_WN inline void w_init(const Cfg &c, Ctx &t, const IO &io, int b, WState<SPL
 // the roll-out.
 template <int SPL>
 KMPC_WN inline bool w_sweep(const Cfg &c, const Ctx &t, const WState<SPL> &w, const WVec3<SPL> &csoc, const double (&gl)[3],
-                            WFact<SPL> &f, WVec3<SPL> &e) {
+                            WFact<SPL> &f, WVec3<SPL> &e, WLin<SPL> &lin) {
     const int N = c.N, lane = w_lane();
     const bool lsq = t.mode == M_LSQ, soc = t.mode == M_SOC;
     const double mu = t.mu, delta = t.delta, df = t.df, T = c.T;
@@ -105,7 +107,7 @@ KMPC_WN inline bool w_sweep(const Cfg &c, const Ctx &t, const WState<SPL> &w, co
     w_next<SPL>(csoc.a, cn0); w_next<SPL>(csoc.b, cn1); w_next<SPL>(csoc.c, cn2);
     // per-stage blocks that do not depend on the cost-to-go
     double q0[SPL], q1[SPL], q2[SPL], Q00[SPL], Q11[SPL], Q22[SPL], qv[SPL], qw[SPL], dv[SPL], dw[SPL], htv[SPL];
-    double a13[SPL], a23[SPL], b11[SPL], b21[SPL];
+    double (&a13)[SPL] = lin.a13, (&a23)[SPL] = lin.a23, (&b11)[SPL] = lin.b11, (&b21)[SPL] = lin.b21;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
         const int s = lane * SPL + j;
@@ -154,102 +156,78 @@ KMPC_WN inline bool w_sweep(const Cfg &c, const Ctx &t, const WState<SPL> &w, co
             else { e.a[j] = -(xn0[j] - (x0 + T * v * cs)); e.b[j] = -(xn1[j] - (x1 + T * v * sn)); e.c[j] = -(xn2[j] - (x2 + T * om)); }
         }
     }
-    // backward recursion: lane l takes the cost-to-go of lane l+1 (its slot 0)
-    double C00 = 0, C10 = 0, C11 = 0, C20 = 0, C21 = 0, C22 = 0, c0 = 0, c1 = 0, c2 = 0;  // carried (P, p)
-    bool okl = true;
-    const int top = N / SPL;
-#pragma unroll 1
-    for (int l = top; l >= 0; --l) {
-        const double I00 = w_down(C00, 1), I10 = w_down(C10, 1), I11 = w_down(C11, 1), I20 = w_down(C20, 1), I21 = w_down(C21, 1),
-                     I22 = w_down(C22, 1), i0 = w_down(c0, 1), i1 = w_down(c1, 1), i2 = w_down(c2, 1);
-        if (lane == l) {
-            double P00 = I00, P10 = I10, P11 = I11, P20 = I20, P21 = I21, P22 = I22, p0 = i0, p1 = i1, p2 = i2;
+    // Stages without a control (the terminal stage N and the padding stages behind it) become pass-through steps:
+    // zero dynamics, unit Quu, zero rhs -> P_out = P_in + Q, p_out = p_in + q; the padding stages carry Q = q = 0.
 #pragma unroll
-            for (int j = SPL - 1; j >= 0; --j) {
-                const int s = l * SPL + j;
-                if (s > N || !okl) continue;
-                if (s == N) {
-                    P00 = Q00[j]; P10 = 0.0; P11 = Q11[j]; P20 = 0.0; P21 = 0.0; P22 = Q22[j];
-                    p0 = q0[j]; p1 = q1[j]; p2 = q2[j];
-                } else {
-                    const double A13 = a13[j], A23 = a23[j], B11 = b11[j], B21 = b21[j], B32 = T;
-                    const double PA02 = P00 * A13 + P10 * A23 + P20, PA12 = P10 * A13 + P11 * A23 + P21, PA22 = P20 * A13 + P21 * A23 + P22;
-                    const double PB00 = P00 * B11 + P10 * B21, PB10 = P10 * B11 + P11 * B21;
-                    const double PB01 = P20 * B32, PB11 = P21 * B32, PB21 = P22 * B32;
-                    const double X00 = P00 + Q00[j], X01 = P10, X02 = PA02;
-                    const double X10 = P10, X11 = P11 + Q11[j], X12 = PA12;
-                    const double X20 = A13 * P00 + A23 * P10 + P20, X21 = A13 * P10 + A23 * P11 + P21, X22 = A13 * PA02 + A23 * PA12 + PA22 + Q22[j];
-                    const double U00 = B11 * P00 + B21 * P10, U01 = B11 * P10 + B21 * P11, U02 = B11 * PA02 + B21 * PA12 + htv[j];
-                    const double U10 = B32 * P20, U11 = B32 * P21, U12 = B32 * PA22;
-                    const double qa = B11 * PB00 + B21 * PB10 + dv[j], qb = B11 * PB01 + B21 * PB11, qc = B32 * PB21 + dw[j];
-                    if (!(qa > 0.0)) { okl = false; continue; }
-                    const double sch = qc - qb * qb / qa;
-                    if (!(sch > 0.0)) { okl = false; continue; }
-                    const double det = qa * qc - qb * qb;
-                    const double i00 = qc / det, i01 = -qb / det, i11 = qa / det;
-                    const double K00 = -(i00 * U00 + i01 * U10), K01 = -(i00 * U01 + i01 * U11), K02 = -(i00 * U02 + i01 * U12);
-                    const double K10 = -(i01 * U00 + i11 * U10), K11 = -(i01 * U01 + i11 * U11), K12 = -(i01 * U02 + i11 * U12);
-                    const double e0 = e.a[j], e1 = e.b[j], e2 = e.c[j];
-                    const double Pe0 = P00 * e0 + P10 * e1 + P20 * e2 + p0, Pe1 = P10 * e0 + P11 * e1 + P21 * e2 + p1,
-                                 Pe2 = P20 * e0 + P21 * e1 + P22 * e2 + p2;
-                    const double qu0 = qv[j] + B11 * Pe0 + B21 * Pe1, qu1 = qw[j] + B32 * Pe2;
-                    const double qx0 = q0[j] + Pe0, qx1 = q1[j] + Pe1, qx2 = q2[j] + A13 * Pe0 + A23 * Pe1 + Pe2;
-                    f.kf0[j] = -(i00 * qu0 + i01 * qu1); f.kf1[j] = -(i01 * qu0 + i11 * qu1);
-                    p0 = qx0 + K00 * qu0 + K10 * qu1; p1 = qx1 + K01 * qu0 + K11 * qu1; p2 = qx2 + K02 * qu0 + K12 * qu1;
-                    const double N00 = X00 + U00 * K00 + U10 * K10, N01 = X01 + U00 * K01 + U10 * K11, N02 = X02 + U00 * K02 + U10 * K12;
-                    const double N10 = X10 + U01 * K00 + U11 * K10, N11 = X11 + U01 * K01 + U11 * K11, N12 = X12 + U01 * K02 + U11 * K12;
-                    const double N20 = X20 + U02 * K00 + U12 * K10, N21 = X21 + U02 * K01 + U12 * K11, N22 = X22 + U02 * K02 + U12 * K12;
-                    P00 = N00; P10 = 0.5 * (N10 + N01); P11 = N11; P20 = 0.5 * (N20 + N02); P21 = 0.5 * (N21 + N12); P22 = N22;
-                    f.K00[j] = K00; f.K01[j] = K01; f.K02[j] = K02; f.K10[j] = K10; f.K11[j] = K11; f.K12[j] = K12;
-                }
-                f.P00[j] = P00; f.P10[j] = P10; f.P11[j] = P11; f.P20[j] = P20; f.P21[j] = P21; f.P22[j] = P22;
-                f.pv0[j] = p0; f.pv1[j] = p1; f.pv2[j] = p2;
-            }
-            C00 = P00; C10 = P10; C11 = P11; C20 = P20; C21 = P21; C22 = P22; c0 = p0; c1 = p1; c2 = p2;
+    for (int j = 0; j < SPL; ++j) {
+        const int s = lane * SPL + j;
+        if (s >= N) {
+            a13[j] = a23[j] = b11[j] = b21[j] = 0.0; qv[j] = qw[j] = htv[j] = 0.0; dv[j] = dw[j] = 1.0;
+            e.a[j] = e.b[j] = e.c[j] = 0.0;
         }
-        if (!w_all(okl)) return false;
+        if (s > N) { q0[j] = q1[j] = q2[j] = 0.0; Q00[j] = Q11[j] = Q22[j] = 0.0; }
     }
-    return true;
+    // Backward recursion as a warp-uniform fixed-point loop: every lane applies its stage step(s) to whatever its right
+    // neighbour produced in the previous round.  The dependency is triangular, so lane top-i is exact from round i on and
+    // stays exact: after top+1 rounds every lane holds its true K, k_ff, P, p -- no branches, no predicated commits.
+    // (The last lane's last slot is always a padding stage -- the launcher guarantees N + 1 < 32 * SPL -- so the chain
+    // end feeds zeros.)
+    double C00 = 0, C10 = 0, C11 = 0, C20 = 0, C21 = 0, C22 = 0, c0 = 0, c1 = 0, c2 = 0;  // this lane's slot-0 (P, p)
+    const int top = N / SPL;
+    bool pd = true;
+#pragma unroll 1
+    for (int it = 0; it <= top; ++it) {
+        double P00 = w_down(C00, 1), P10 = w_down(C10, 1), P11 = w_down(C11, 1), P20 = w_down(C20, 1), P21 = w_down(C21, 1),
+               P22 = w_down(C22, 1), p0 = w_down(c0, 1), p1 = w_down(c1, 1), p2 = w_down(c2, 1);
+        pd = true;
+#pragma unroll
+        for (int j = SPL - 1; j >= 0; --j) {
+            RicK rk;
+            pd &= riccati_step(P00, P10, P11, P20, P21, P22, p0, p1, p2, a13[j], a23[j], b11[j], b21[j], T, Q00[j], 0.0, Q11[j], Q22[j],
+                               q0[j], q1[j], q2[j], qv[j], qw[j], dv[j], dw[j], htv[j], e.a[j], e.b[j], e.c[j], rk);
+            f.K00[j] = rk.K00; f.K01[j] = rk.K01; f.K02[j] = rk.K02; f.K10[j] = rk.K10; f.K11[j] = rk.K11; f.K12[j] = rk.K12;
+            f.kf0[j] = rk.kf0; f.kf1[j] = rk.kf1;
+            f.P00[j] = P00; f.P10[j] = P10; f.P11[j] = P11; f.P20[j] = P20; f.P21[j] = P21; f.P22[j] = P22;
+            f.pv0[j] = p0; f.pv1[j] = p1; f.pv2[j] = p2;
+        }
+        C00 = P00; C10 = P10; C11 = P11; C20 = P20; C21 = P21; C22 = P22; c0 = p0; c1 = p1; c2 = p2;
+        // wrong inertia detected by a lane that is already exact: stop early (looked at every 8th round)
+        if ((it & 7) == 7 && w_any(!pd && lane >= top - it)) return false;
+    }
+    return w_all(pd);
 }
 
 // ---- ROLL-OUT: forward substitution lane by lane, then stage-parallel step-size limits ----
 template <int SPL>
 KMPC_WN inline void w_rollout(const Cfg &c, const Ctx &t, const WState<SPL> &w, const WFact<SPL> &f, const WVec3<SPL> &e,
-                              const WVec3<SPL> &csoc, const double (&xc)[3], const double (&gl)[3], WStep<SPL> &d,
+                              const WLin<SPL> &lin, const WVec3<SPL> &csoc, const double (&xc)[3], const double (&gl)[3], WStep<SPL> &d,
                               double *alpha_pr, double *alpha_du, double *gBD, double *ymax) {
     const int N = c.N, lane = w_lane();
     const bool lsq = t.mode == M_LSQ, soc = t.mode == M_SOC;
     const double mu = t.mu, df = t.df, T = c.T, tau = t.tau;
-    double r0 = 0, r1 = 0, r2 = 0;  // carried dx of the next stage
-    if (lane == 0) {
-        if (lsq) { r0 = r1 = r2 = 0.0; }
-        else if (soc) { r0 = -csoc.a[0]; r1 = -csoc.b[0]; r2 = -csoc.c[0]; }
-        else { r0 = -(w.x0[0] - xc[0]); r1 = -(w.x1[0] - xc[1]); r2 = -(w.x2[0] - xc[2]); }
-    }
+    // forward substitution, again as a warp-uniform fixed-point loop (lane i is exact from round i on)
+    double i0, i1, i2;  // dx of stage 0
+    if (lsq) { i0 = i1 = i2 = 0.0; }
+    else if (soc) { i0 = -csoc.a[0]; i1 = -csoc.b[0]; i2 = -csoc.c[0]; }
+    else { i0 = -(w.x0[0] - xc[0]); i1 = -(w.x1[0] - xc[1]); i2 = -(w.x2[0] - xc[2]); }
+    double r0 = 0, r1 = 0, r2 = 0;  // dx of the stage after this lane's last slot
     const int top = N / SPL;
 #pragma unroll 1
-    for (int l = 0; l <= top; ++l) {
-        const double i0 = w_up(r0, 1), i1 = w_up(r1, 1), i2 = w_up(r2, 1);
-        if (lane == l) {
-            double d0 = l == 0 ? r0 : i0, d1 = l == 0 ? r1 : i1, d2 = l == 0 ? r2 : i2;
+    for (int it = 0; it <= top; ++it) {
+        const double u0 = w_up(r0, 1), u1 = w_up(r1, 1), u2 = w_up(r2, 1);
+        double d0 = lane == 0 ? i0 : u0, d1 = lane == 0 ? i1 : u1, d2 = lane == 0 ? i2 : u2;
 #pragma unroll
-            for (int j = 0; j < SPL; ++j) {
-                const int s = l * SPL + j;
-                if (s > N) continue;
-                d.dx0[j] = d0; d.dx1[j] = d1; d.dx2[j] = d2;
-                if (s < N) {
-                    const double du0 = f.K00[j] * d0 + f.K01[j] * d1 + f.K02[j] * d2 + f.kf0[j];
-                    const double du1 = f.K10[j] * d0 + f.K11[j] * d1 + f.K12[j] * d2 + f.kf1[j];
-                    d.du0[j] = du0; d.du1[j] = du1;
-                    const double v = w.v[j], cs = w.cs[j], sn = w.sn[j];
-                    const double n0 = d0 + (-T * v * sn) * d2 + T * cs * du0 + e.a[j];
-                    const double n1 = d1 + (T * v * cs) * d2 + T * sn * du0 + e.b[j];
-                    const double n2 = d2 + T * du1 + e.c[j];
-                    d0 = n0; d1 = n1; d2 = n2;
-                } else { d.du0[j] = 0.0; d.du1[j] = 0.0; }
-            }
-            r0 = d0; r1 = d1; r2 = d2;
+        for (int j = 0; j < SPL; ++j) {
+            d.dx0[j] = d0; d.dx1[j] = d1; d.dx2[j] = d2;
+            const double du0 = fma(f.K00[j], d0, fma(f.K01[j], d1, fma(f.K02[j], d2, f.kf0[j])));
+            const double du1 = fma(f.K10[j], d0, fma(f.K11[j], d1, fma(f.K12[j], d2, f.kf1[j])));
+            d.du0[j] = du0; d.du1[j] = du1;
+            const double n0 = d0 + lin.a13[j] * d2 + lin.b11[j] * du0 + e.a[j];
+            const double n1 = d1 + lin.a23[j] * d2 + lin.b21[j] * du0 + e.b[j];
+            const double n2 = d2 + T * du1 + e.c[j];
+            d0 = n0; d1 = n1; d2 = n2;
         }
+        r0 = d0; r1 = d1; r2 = d2;
     }
     double apr = 1.0, adu = 1.0, gbd = 0.0, ym = 0.0;
 #pragma unroll
@@ -415,6 +393,7 @@ KMPC_WN inline void w_solve(const Cfg &c, const IO &io, int b, double *filt, int
     WStep<SPL> st0, st1, act;
     WFact<SPL> fact;
     WVec3<SPL> e, csoc, ct;
+    WLin<SPL> lin;
     double xc[3], gl[3];
 #pragma unroll
     for (int j = 0; j < SPL; ++j) { csoc.a[j] = csoc.b[j] = csoc.c[j] = 0.0; ct.a[j] = ct.b[j] = ct.c[j] = 0.0; }
@@ -424,7 +403,7 @@ KMPC_WN inline void w_solve(const Cfg &c, const IO &io, int b, double *filt, int
     while (status == 100) {
         if (t.mode != M_TRIAL) {
             t.trips++;
-            const bool ok = w_sweep<SPL>(c, t, cur, csoc, gl, fact, e);
+            const bool ok = w_sweep<SPL>(c, t, cur, csoc, gl, fact, e, lin);
             if (!ok) {
                 if (t.mode != M_NEWTON) { status = ST_STEP_ERROR; break; }
                 const int r = inertia_update(t);
@@ -432,7 +411,7 @@ KMPC_WN inline void w_solve(const Cfg &c, const IO &io, int b, double *filt, int
                 continue;
             }
             double apr, adu, gbd, ym;
-            w_rollout<SPL>(c, t, cur, fact, e, csoc, xc, gl, act, &apr, &adu, &gbd, &ym);
+            w_rollout<SPL>(c, t, cur, fact, e, lin, csoc, xc, gl, act, &apr, &adu, &gbd, &ym);
             rollout_logic(t, apr, adu, gbd, ym);
             if (t.sel) st1 = act; else st0 = act;
         } else {
