@@ -188,8 +188,19 @@ KMPC_HD void vcost(const Cfg &c, double df, double v, double *g, double *h) {
 // correctly rounded reciprocal (one MUFU + Newton steps on the device instead of a full division)
 #ifdef __CUDA_ARCH__
 #define KRCP(x) __drcp_rn(x)
+// reciprocal for the Riccati pivots: MUFU.RCP64H seed (~20 bits) + two Newton steps (<= 1-2 ulp), branch-free.  Operands
+// are positive and far from the denormal/overflow range whenever the result is used (the pivot test discards the rest).
+__device__ __forceinline__ double krcp_fast(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    return r;
+}
+#define KRCPF(x) krcp_fast(x)
 #else
 #define KRCP(x) (1.0 / (x))
+#define KRCPF(x) (1.0 / (x))
 #endif
 
 // barrier contributions of one bounded variable at the current iterate:
@@ -257,7 +268,7 @@ KMPC_HD double maxabs_nan(double m, double v) { double t = fabs(v); return (t > 
 // ------------------------------------------------------------------------------------------------
 // One step of the backward Riccati recursion for the unicycle stage
 //   A = I + a13 e1 e3^T + a23 e2 e3^T,   B = [b11 0; b21 0; 0 T],
-// in square-root-free LDL^T form: Q_uu = [d1 0; l d1, d2] pivots d1, d2 > 0 <=> Q_uu positive definite (the inertia test).
+// Q_uu (2x2) is inverted through its determinant: d1 > 0 and det > 0 <=> Q_uu positive definite (the inertia test).
 //   in : (P, p) of stage k+1, stage blocks Q (xx, with Q01 only for obstacle rows), q, (qv, qw), (dv, dw) = diag of
 //        W_uu + Sigma_u + delta, htv = W_v,theta, e = bc_{k+1}
 //   out: (P, p) of stage k (overwritten), feedback K (2x3), feed-forward kf.  Returns false on a non-positive pivot.
@@ -274,28 +285,26 @@ KMPC_HD bool riccati_step(double &P00, double &P10, double &P11, double &P20, do
     // Qux = B^T P A (+ W_v,theta)
     const double U00 = fma(b11, P00, b21 * P10), U01 = fma(b11, P10, b21 * P11), U02 = fma(b11, PA02, fma(b21, PA12, htv));
     const double U10 = T * P20, U11 = T * P21, U12 = T * PA22;
-    // Quu = B^T P B + diag
+    // Quu = B^T P B + diag = [d1 qb; qb qc];  positive definite <=> d1 > 0 and det > 0
     const double d1 = fma(b11, U00, fma(b21, U01, dv)), qb = fma(b11, U10, b21 * U11), qc = fma(T * T, P22, dw);
-    const double r1 = KRCP(d1), l = qb * r1, d2 = fma(-l, qb, qc);
-    const double r2 = KRCP(d2);
-    const bool pd = d1 > 0.0 && d2 > 0.0;  // branch-free: the caller discards the outputs when a pivot is not positive
-    const double w0 = fma(-l, U00, U10), w1 = fma(-l, U01, U11), w2 = fma(-l, U02, U12);
-    const double s10 = r1 * U00, s11 = r1 * U01, s12 = r1 * U02, s20 = r2 * w0, s21 = r2 * w1, s22 = r2 * w2;
+    const double det = fma(d1, qc, -(qb * qb));
+    const bool pd = d1 > 0.0 && det > 0.0;  // branch-free: the caller discards the outputs when Quu is not positive definite
+    const double r = KRCPF(det), i00 = qc * r, i01 = -(qb * r), i11 = d1 * r;
+    // K = -Quu^-1 Qux
+    const double K00 = -fma(i00, U00, i01 * U10), K01 = -fma(i00, U01, i01 * U11), K02 = -fma(i00, U02, i01 * U12);
+    const double K10 = -fma(i01, U00, i11 * U10), K11 = -fma(i01, U01, i11 * U11), K12 = -fma(i01, U02, i11 * U12);
     // vector part
     const double Pe0 = fma(P00, e0, fma(P10, e1, fma(P20, e2, p0))), Pe1 = fma(P10, e0, fma(P11, e1, fma(P21, e2, p1))),
                  Pe2 = fma(P20, e0, fma(P21, e1, fma(P22, e2, p2)));
     const double qu0 = fma(b11, Pe0, fma(b21, Pe1, qv)), qu1 = fma(T, Pe2, qw);
-    const double g2 = fma(-l, qu0, qu1);
-    p0 = fma(-s10, qu0, fma(-s20, g2, q0 + Pe0));
-    p1 = fma(-s11, qu0, fma(-s21, g2, q1 + Pe1));
-    p2 = fma(-s12, qu0, fma(-s22, g2, fma(a13, Pe0, fma(a23, Pe1, q2 + Pe2))));
-    // P <- Qxx - Qux^T Quu^-1 Qux  (symmetric by construction)
-    P00 = fma(-s10, U00, fma(-s20, w0, X00)); P10 = fma(-s11, U00, fma(-s21, w0, X10)); P11 = fma(-s11, U01, fma(-s21, w1, X11));
-    P20 = fma(-s12, U00, fma(-s22, w0, X20)); P21 = fma(-s12, U01, fma(-s22, w1, X21)); P22 = fma(-s12, U02, fma(-s22, w2, X22));
-    // K = -Quu^-1 Qux, kf = -Quu^-1 qu
-    o.K10 = -s20; o.K11 = -s21; o.K12 = -s22;
-    o.K00 = fma(l, s20, -s10); o.K01 = fma(l, s21, -s11); o.K02 = fma(l, s22, -s12);
-    o.kf1 = -(g2 * r2); o.kf0 = fma(-l, o.kf1, -(qu0 * r1));
+    p0 = fma(K00, qu0, fma(K10, qu1, q0 + Pe0));
+    p1 = fma(K01, qu0, fma(K11, qu1, q1 + Pe1));
+    p2 = fma(K02, qu0, fma(K12, qu1, fma(a13, Pe0, fma(a23, Pe1, q2 + Pe2))));
+    // P <- Qxx + Qux^T K  (lower triangle; symmetric in exact arithmetic)
+    P00 = fma(U00, K00, fma(U10, K10, X00)); P10 = fma(U01, K00, fma(U11, K10, X10)); P11 = fma(U01, K01, fma(U11, K11, X11));
+    P20 = fma(U02, K00, fma(U12, K10, X20)); P21 = fma(U02, K01, fma(U12, K11, X21)); P22 = fma(U02, K02, fma(U12, K12, X22));
+    o.K00 = K00; o.K01 = K01; o.K02 = K02; o.K10 = K10; o.K11 = K11; o.K12 = K12;
+    o.kf0 = -fma(i00, qu0, i01 * qu1); o.kf1 = -fma(i01, qu0, i11 * qu1);
     return pd;
 }
 
