@@ -144,7 +144,9 @@ kmpc_trial_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_
 // queue and solving it start to finish with the whole iterate in registers.  Used for problems without obstacle rows
 // and N + 1 <= 32 * SPL.
 // ------------------------------------------------------------------------------------------------
-#define KMPC_WARPS_PER_BLOCK 4
+#ifndef KMPC_WARPS_PER_BLOCK
+#define KMPC_WARPS_PER_BLOCK 6
+#endif
 #ifndef KMPC_WARP_MINB
 #define KMPC_WARP_MINB 2
 #endif
@@ -152,17 +154,7 @@ template <int SPL>
 __global__ void __launch_bounds__(32 * KMPC_WARPS_PER_BLOCK, KMPC_WARP_MINB)
 kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned long long *__restrict__ trips_total) {
     __shared__ double s_filt[KMPC_WARPS_PER_BLOCK][2 * K_FILTER_CAP];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (;;) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(queue, 1);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= c.B) break;
-        int tr = 0;
-        w_solve<SPL>(c, io, b, s_filt[warp], &tr);
-        if (lane == 0 && trips_total) atomicAdd(trips_total, (unsigned long long)tr);
-        __syncwarp();
-    }
+    w_worker<SPL>(c, io, s_filt[threadIdx.x >> 5], queue, trips_total);
 }
 
 // Batched EgoAgent.step hand-off (agent.py:139-155, :70-72): applied control = U[:,0]; next current state = X[:,1].

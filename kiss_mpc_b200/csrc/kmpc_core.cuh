@@ -208,8 +208,8 @@ __device__ __forceinline__ double krcp_fast(double d) {
 KMPC_HD void bound_terms(double val, double lb, double ub, int hL, int hU, double zL, double zU, double mu, double *sigma,
                          double *rb) {
     double sg = 0.0, r = 0.0;
-    if (hL) { const double rs = KRCP(val - lb); sg += zL * rs; r -= mu * rs; if (!hU) r += K_KAPPA_D * mu; }
-    if (hU) { const double rs = KRCP(ub - val); sg += zU * rs; r += mu * rs; if (!hL) r -= K_KAPPA_D * mu; }
+    if (hL) { const double rs = KRCPF(val - lb); sg += zL * rs; r -= mu * rs; if (!hU) r += K_KAPPA_D * mu; }
+    if (hU) { const double rs = KRCPF(ub - val); sg += zU * rs; r += mu * rs; if (!hL) r -= K_KAPPA_D * mu; }
     *sigma = sg; *rb = r;
 }
 
@@ -218,13 +218,13 @@ KMPC_HD void bound_terms(double val, double lb, double ub, int hL, int hU, doubl
 KMPC_HD void bound_ftb(double val, double d, double lb, double ub, int hL, int hU, double zL, double zU, double mu,
                        double tau, double *apr, double *adu) {
     if (hL) {
-        const double sl = val - lb, rs = KRCP(sl);
+        const double sl = val - lb, rs = KRCPF(sl);
         if (d < 0) *apr = fmin(*apr, -tau * sl / d);
         const double dz = mu * rs - zL - zL * rs * d;
         if (dz < 0) *adu = fmin(*adu, -tau * zL / dz);
     }
     if (hU) {
-        const double su = ub - val, rs = KRCP(su);
+        const double su = ub - val, rs = KRCPF(su);
         if (d > 0) *apr = fmin(*apr, tau * su / d);
         const double dz = mu * rs - zU + zU * rs * d;
         if (dz < 0) *adu = fmin(*adu, -tau * zU / dz);
@@ -239,23 +239,23 @@ KMPC_HD bool bound_trial(double val, double d, double vt, double lb, double ub, 
     bool ok = true;
     *zLn = 0.0; *zUn = 0.0;
     if (hL) {
-        const double sl = val - lb, sn = vt - lb, rs = KRCP(sl);
+        const double sl = val - lb, sn = vt - lb, rs = KRCPF(sl);
         if (!(sn > 0)) ok = false;
         *prod *= sn;
         if (!hU) *damp += sn;
         double z = zL + adu * (mu * rs - zL - zL * rs * d);
-        if (clamp) { const double mr = mu * KRCP(sn); z = fmax(fmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
+        if (clamp) { const double mr = mu * KRCPF(sn); z = fmax(fmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
         *zLn = z;
         double p = sn * z;
         st->mn = fmin(st->mn, p); st->mx = fmax(st->mx, p); st->sumz += fabs(z);
     }
     if (hU) {
-        const double su = ub - val, sn = ub - vt, rs = KRCP(su);
+        const double su = ub - val, sn = ub - vt, rs = KRCPF(su);
         if (!(sn > 0)) ok = false;
         *prod *= sn;
         if (!hL) *damp += sn;
         double z = zU + adu * (mu * rs - zU + zU * rs * d);
-        if (clamp) { const double mr = mu * KRCP(sn); z = fmax(fmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
+        if (clamp) { const double mr = mu * KRCPF(sn); z = fmax(fmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
         *zUn = z;
         double p = sn * z;
         st->mn = fmin(st->mn, p); st->mx = fmax(st->mx, p); st->sumz += fabs(z);

@@ -384,9 +384,12 @@ KMPC_W void w_step_select(WStep<SPL> &o, const WStep<SPL> &a, const WStep<SPL> &
     }
 }
 
-// ---- the whole solve of instance b by one warp.  filt: 2*K_FILTER_CAP doubles of warp-private scratch. ----
+// ---- persistent worker: one warp pulls instances from a queue and solves each start to finish. ----
+// filt: 2*K_FILTER_CAP doubles of warp-private scratch.  The warps of a block walk through the three phases of a trip in
+// step (block barriers): at any time they execute the same few KB of code, so the instruction cache is shared instead of
+// being thrashed by warps that sit in different phases of a ~140 KB kernel.
 template <int SPL>
-KMPC_WN inline void w_solve(const Cfg &c, const IO &io, int b, double *filt, int *trips_out) {
+KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *filt, int *queue, unsigned long long *trips_total) {
     const int N = c.N, lane = w_lane();
     Ctx t;
     WState<SPL> cur, tri;
@@ -394,57 +397,75 @@ KMPC_WN inline void w_solve(const Cfg &c, const IO &io, int b, double *filt, int
     WFact<SPL> fact;
     WVec3<SPL> e, csoc, ct;
     WLin<SPL> lin;
-    double xc[3], gl[3];
-#pragma unroll
-    for (int j = 0; j < SPL; ++j) { csoc.a[j] = csoc.b[j] = csoc.c[j] = 0.0; ct.a[j] = ct.b[j] = ct.c[j] = 0.0; }
-    w_init<SPL>(c, t, io, b, cur, xc, gl);
-    int status = 100;
+    double xc[3] = {0, 0, 0}, gl[3] = {0, 0, 0};
+    bool have = false;
+    int b = -1;
+    t.mode = M_DONE;
 #pragma unroll 1
-    while (status == 100) {
-        if (t.mode != M_TRIAL) {
-            t.trips++;
-            const bool ok = w_sweep<SPL>(c, t, cur, csoc, gl, fact, e, lin);
-            if (!ok) {
-                if (t.mode != M_NEWTON) { status = ST_STEP_ERROR; break; }
-                const int r = inertia_update(t);
-                if (r != R_RETRY) { status = r; break; }
-                continue;
+    for (;;) {
+        if (!have) {
+            b = w_fetch(queue);
+            if (b < c.B) {
+#pragma unroll
+                for (int j = 0; j < SPL; ++j) { csoc.a[j] = csoc.b[j] = csoc.c[j] = 0.0; ct.a[j] = ct.b[j] = ct.c[j] = 0.0; }
+                w_init<SPL>(c, t, io, b, cur, xc, gl);
+                have = true;
             }
-            double apr, adu, gbd, ym;
-            w_rollout<SPL>(c, t, cur, fact, e, lin, csoc, xc, gl, act, &apr, &adu, &gbd, &ym);
-            rollout_logic(t, apr, adu, gbd, ym);
-            if (t.sel) st1 = act; else st0 = act;
-        } else {
+        }
+        if (!w_block_any(have)) break;  // also the barrier in front of phase 1
+        int status = 100;
+        // ---- phase 1: backward sweep ----
+        const bool do_sweep = have && t.mode != M_TRIAL;
+        bool ok = false;
+        if (do_sweep) { t.trips++; ok = w_sweep<SPL>(c, t, cur, csoc, gl, fact, e, lin); }
+        w_block_sync();
+        // ---- phase 2: roll-out + line-search set-up (or inertia correction) ----
+        bool go_trial = have && !do_sweep;
+        if (do_sweep) {
+            if (!ok) status = t.mode != M_NEWTON ? (int)ST_STEP_ERROR : inertia_update(t);  // R_RETRY: sweep again next trip
+            else {
+                double apr, adu, gbd, ym;
+                w_rollout<SPL>(c, t, cur, fact, e, lin, csoc, xc, gl, act, &apr, &adu, &gbd, &ym);
+                rollout_logic(t, apr, adu, gbd, ym);
+                if (t.sel) st1 = act; else st0 = act;
+                go_trial = true;
+            }
+        } else if (have) {
             trial_setup(t);
             w_step_select<SPL>(act, st0, st1, false);
         }
-        Stats ts;
-        const bool evok = w_trial<SPL>(c, t, cur, act, xc, gl, t.a_pr, t.a_y, t.a_du, t.tu == TU_STEP, tri, ct, &ts);
-        bool aug; double ath, aph;
-        const int r = trial_decide(t, filt, 1, ts, evok, &aug, &ath, &aph);
-        if (aug) {  // one lane edits the warp's filter, everybody learns the new length
-            if (lane == 0) filter_add(t, filt, 1, ath, aph);
-            t.fn = w_bcast_i(t.fn, 0);
+        w_block_sync();
+        // ---- phase 3: trial point + acceptance logic ----
+        if (go_trial) {
+            Stats ts;
+            const bool evok = w_trial<SPL>(c, t, cur, act, xc, gl, t.a_pr, t.a_y, t.a_du, t.tu == TU_STEP, tri, ct, &ts);
+            bool aug; double ath, aph;
+            const int r = trial_decide(t, filt, 1, ts, evok, &aug, &ath, &aph);
+            if (aug) {  // one lane edits the warp's filter, everybody learns the new length
+                if (lane == 0) filter_add(t, filt, 1, ath, aph);
+                t.fn = w_bcast_i(t.fn, 0);
+            }
+            w_sync();
+            if (r == R_SOC1 || r == R_SOC2) w_soc_rhs<SPL>(c, cur, ct, xc, t.alpha_soc, r == R_SOC1, csoc);
+            else if (r == R_ACCEPT) { cur = tri; t.c = ts; status = begin_iteration(c, t); }
+            else if (r != R_BACKTRACK) status = r;
         }
-        w_sync();
-        if (r == R_SOC1 || r == R_SOC2) { w_soc_rhs<SPL>(c, cur, ct, xc, t.alpha_soc, r == R_SOC1, csoc); continue; }
-        if (r == R_BACKTRACK) continue;
-        if (r != R_ACCEPT) { status = r; break; }
-        cur = tri; t.c = ts;
-        status = begin_iteration(c, t);
-    }
-    // returned matrices (optimizer.py:392-400): every lane writes its stages
+        if (have && status != 100 && status != R_RETRY) {
+            // returned matrices (optimizer.py:392-400): every lane writes its stages
 #pragma unroll
-    for (int j = 0; j < SPL; ++j) {
-        const int s = lane * SPL + j;
-        if (s <= N) { io.X_out[io_X(c, b, 0, s)] = cur.x0[j]; io.X_out[io_X(c, b, 1, s)] = cur.x1[j]; io.X_out[io_X(c, b, 2, s)] = cur.x2[j]; }
-        if (s < N) { io.U_out[io_U(c, b, 0, s)] = cur.v[j]; io.U_out[io_U(c, b, 1, s)] = cur.om[j]; }
-    }
-    if (lane == 0) {
-        if (io.obj) io.obj[b] = t.c.f / t.df;
-        if (io.status) io.status[b] = status;
-        if (io.iters) io.iters[b] = t.iter;
-        if (trips_out) *trips_out = t.trips;
+            for (int j = 0; j < SPL; ++j) {
+                const int s = lane * SPL + j;
+                if (s <= N) { io.X_out[io_X(c, b, 0, s)] = cur.x0[j]; io.X_out[io_X(c, b, 1, s)] = cur.x1[j]; io.X_out[io_X(c, b, 2, s)] = cur.x2[j]; }
+                if (s < N) { io.U_out[io_U(c, b, 0, s)] = cur.v[j]; io.U_out[io_U(c, b, 1, s)] = cur.om[j]; }
+            }
+            if (lane == 0) {
+                if (io.obj) io.obj[b] = t.c.f / t.df;
+                if (io.status) io.status[b] = status;
+                if (io.iters) io.iters[b] = t.iter;
+                w_count_trips(trips_total, t.trips);
+            }
+            have = false;
+        }
     }
 }
 

@@ -16,6 +16,14 @@ KMPC_W int w_bcast_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); 
 KMPC_W bool w_all(bool p) { return __all_sync(0xffffffffu, p); }
 KMPC_W bool w_any(bool p) { return __any_sync(0xffffffffu, p); }
 KMPC_W void w_sync() { __syncwarp(); }
+KMPC_W void w_block_sync() { __syncthreads(); }
+KMPC_W bool w_block_any(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
+KMPC_W int w_fetch(int *queue) {  // next instance index for this warp
+    int b = 0;
+    if ((threadIdx.x & 31u) == 0) b = atomicAdd(queue, 1);
+    return __shfl_sync(0xffffffffu, b, 0);
+}
+KMPC_W void w_count_trips(unsigned long long *total, int trips) { if (total) atomicAdd(total, (unsigned long long)trips); }
 }  // namespace kmpc
 #else
 #define KMPC_W inline

@@ -138,9 +138,11 @@ extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur
 #pragma omp parallel for schedule(dynamic, 1)
     for (int b = 0; b < B; ++b) {
         double filt[2 * K_FILTER_CAP];
-        int tr = 0;
-        simt_run([&]() { if (spl == 1) w_solve<1>(c, io, b, filt, &tr); else w_solve<2>(c, io, b, filt, &tr); });
-        if (trips) trips[b] = tr;
+        unsigned long long tr = 0;
+        int queue = b;          // this emulated warp is handed exactly instance b
+        Cfg cb = c; cb.B = b + 1;
+        simt_run([&]() { if (spl == 1) w_worker<1>(cb, io, filt, &queue, &tr); else w_worker<2>(cb, io, filt, &queue, &tr); });
+        if (trips) trips[b] = (int)tr;
     }
     return 0;
 }

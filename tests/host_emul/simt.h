@@ -42,6 +42,16 @@ inline int w_bcast_i(int v, int src) { const double *b = simt_rendezvous((double
 inline bool w_all(bool p) { const double *b = simt_rendezvous(p ? 1.0 : 0.0); bool r = true; for (int i = 0; i < 32; ++i) r = r && b[i] != 0.0; return r; }
 inline bool w_any(bool p) { const double *b = simt_rendezvous(p ? 1.0 : 0.0); bool r = false; for (int i = 0; i < 32; ++i) r = r || b[i] != 0.0; return r; }
 inline void w_sync() { simt_rendezvous(0.0); }
+// one emulated warp = one block
+inline void w_block_sync() { simt_rendezvous(0.0); }
+inline bool w_block_any(bool p) { return w_any(p); }
+inline int w_fetch(int *queue) {  // lane 0 takes the next index, everybody learns it
+    double v = 0.0;
+    if (w_lane() == 0) { v = (double)*queue; *queue += 1; }
+    const double *b = simt_rendezvous(v);
+    return (int)b[0];
+}
+inline void w_count_trips(unsigned long long *total, int trips) { if (total) *total += (unsigned long long)trips; }
 
 void simt_run(const std::function<void()> &fn);  // runs fn on 32 lanes (simt.cpp part of emul.cpp)
 }  // namespace kmpc
