@@ -144,17 +144,40 @@ kmpc_trial_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_
 // queue and solving it start to finish with the whole iterate in registers.  Used for problems without obstacle rows
 // and N + 1 <= 32 * SPL.
 // ------------------------------------------------------------------------------------------------
-#ifndef KMPC_WARPS_PER_BLOCK
-#define KMPC_WARPS_PER_BLOCK 6
+// launch shape per stage-slot count: warps (= instances) per block, resident blocks per SM the register budget is cut for
+#ifndef KMPC_WPB1
+#define KMPC_WPB1 8
 #endif
-#ifndef KMPC_WARP_MINB
-#define KMPC_WARP_MINB 2
+#ifndef KMPC_MINB1
+#define KMPC_MINB1 2
 #endif
-template <int SPL>
-__global__ void __launch_bounds__(32 * KMPC_WARPS_PER_BLOCK, KMPC_WARP_MINB)
+#ifndef KMPC_WPB2
+#define KMPC_WPB2 5
+#endif
+#ifndef KMPC_MINB2
+#define KMPC_MINB2 2
+#endif
+template <int SPL, int WPB, int MINB>
+__global__ void __launch_bounds__(32 * WPB, MINB)
 kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned long long *__restrict__ trips_total) {
-    __shared__ double s_filt[KMPC_WARPS_PER_BLOCK][2 * K_FILTER_CAP];
-    w_worker<SPL>(c, io, s_filt[threadIdx.x >> 5], queue, trips_total);
+    extern __shared__ double s_dyn[];  // WLay<SPL>::bytes(WPB)
+    w_worker<SPL>(c, io, s_dyn, queue, trips_total);
+}
+
+template <int SPL, int WPB, int MINB>
+static cudaError_t launch_warp_kernel(int sm_count, int B, const Cfg &c, const IO &io, int *queue, unsigned long long *trips, cudaStream_t st) {
+    const size_t smem = WLay<SPL>::bytes(WPB);
+    auto kern = kmpc_warp_kernel<SPL, WPB, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int bpsm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsm, kern, 32 * WPB, smem);
+    if (e != cudaSuccess) return e;
+    int grid = sm_count * (bpsm > 0 ? bpsm : 1);
+    const int need = (B + WPB - 1) / WPB;
+    if (grid > need) grid = need;
+    kern<<<grid, 32 * WPB, smem, st>>>(c, io, queue, trips);
+    return cudaGetLastError();
 }
 
 // Batched EgoAgent.step hand-off (agent.py:139-155, :70-72): applied control = U[:,0]; next current state = X[:,1].
@@ -355,19 +378,12 @@ extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const doub
     ls.cnt = h->cnt; ls.trips = h->timing ? h->trips : NULL;
 
     if (h->timing) { CU(cudaMemsetAsync(h->trips, 0, sizeof(unsigned long long), st)); CU(cudaEventRecord(h->ev0, st)); }
-    const bool use_warp = O == 0 && cf->N + 1 < 64 && getenv("KMPC_FORCE_THREAD") == NULL;  // N + 1 < 32 * SPL
+    const bool use_warp = O == 0 && cf->N + 1 <= 64 && getenv("KMPC_FORCE_THREAD") == NULL;  // N + 1 <= 32 * SPL
     if (use_warp) {
         // warp-per-instance path: one persistent launch, instances pulled from a queue, no workspace traffic
         CU(cudaMemsetAsync(h->cnt, 0, sizeof(int), st));
-        int wpsm = 0;
-        const int spl = cf->N + 1 < 32 ? 1 : 2;
-        if (spl == 1) { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wpsm, kmpc_warp_kernel<1>, 32 * KMPC_WARPS_PER_BLOCK, 0)); }
-        else { CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wpsm, kmpc_warp_kernel<2>, 32 * KMPC_WARPS_PER_BLOCK, 0)); }
-        int grid = h->sm_count * (wpsm > 0 ? wpsm : 1);
-        const int need = (B + KMPC_WARPS_PER_BLOCK - 1) / KMPC_WARPS_PER_BLOCK;
-        if (grid > need) grid = need;
-        if (spl == 1) kmpc_warp_kernel<1><<<grid, 32 * KMPC_WARPS_PER_BLOCK, 0, st>>>(c, io, h->cnt, ls.trips);
-        else kmpc_warp_kernel<2><<<grid, 32 * KMPC_WARPS_PER_BLOCK, 0, st>>>(c, io, h->cnt, ls.trips);
+        if (cf->N + 1 <= 32) { CU((launch_warp_kernel<1, KMPC_WPB1, KMPC_MINB1>(h->sm_count, B, c, io, h->cnt, ls.trips, st))); }
+        else { CU((launch_warp_kernel<2, KMPC_WPB2, KMPC_MINB2>(h->sm_count, B, c, io, h->cnt, ls.trips, st))); }
         CU(cudaGetLastError());
         h->launches++;
         h->last_host_trips = 0;

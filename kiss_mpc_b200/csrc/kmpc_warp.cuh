@@ -1,15 +1,19 @@
-// kmpc_warp.cuh -- warp-per-instance form of the interior-point solver: the stages of ONE problem instance are spread
-// over the 32 lanes of a warp (stage s lives in lane s / SPL, slot s % SPL), the whole iterate (primal, duals, step,
-// Riccati factors) stays in registers for the entire solve, and nothing but the problem data and the result touches HBM.
-//   - stage-parallel work (linearisation, barrier terms, trial-point evaluation, multiplier updates, residual norms)
-//     runs on all lanes at once, reductions are shuffle butterflies;
-//   - the two serial recursions (backward Riccati, forward roll-out) walk lane by lane, handing the 3x3 cost-to-go /
-//     the 3-vector state step to the neighbour with register shuffles;
-//   - the scalar IPOPT logic (filter, barrier update, inertia correction, termination) is computed redundantly and
-//     identically by all lanes (kmpc_core.cuh functions), so control flow is warp-uniform.
-// Same algorithm and formulas as the thread-per-instance passes in kmpc_core.cuh (which it replaces for problems
-// without obstacle rows and N < 32*SPL); what it replaces in the reference is the same: the IPOPT solve behind
-// mpc/optimizer.py:354/:375-391.
+// kmpc_warp.cuh -- warp-per-instance form of the interior-point solver with a block-cooperative Riccati phase.
+//
+// One warp owns one problem instance for the whole solve: stage s lives in lane s / SPL, slot s % SPL, the iterate
+// (primal, duals) stays in registers, the rest of the per-instance state in shared memory; nothing but the problem data
+// and the result touches HBM.  A trip of the solver state machine (kmpc_core.cuh) is cut into block-synchronous phases:
+//   1a  ASSEMBLE  (owner warps, stage-parallel)   KKT stage blocks of every instance that needs a factorisation
+//                                                 -> shared "coop" area  coop[instance][field][stage]
+//   1b  RICCATI   (warp 0, lane = instance)       the two serial recursions -- backward Riccati sweep with the inertia
+//                                                 test, forward roll-out -- of ALL the block's instances at once, one
+//                                                 lane per instance, reading/writing the coop area
+//   2   STEP      (owner warps, stage-parallel)   multiplier step, fraction-to-the-boundary limits, directional derivative
+//   3   TRIAL     (owner warps, stage-parallel)   trial point, residual norms (shuffle butterflies), filter logic
+// The serial recursions are thus executed once per instance (by one lane) instead of once per lane, and the lanes of
+// the Riccati warp are filled with the block's instances.  The scalar IPOPT logic (filter, barrier update, inertia
+// correction, termination; kmpc_core.cuh functions) runs on lane 0 of the owner warp on a Ctx kept in shared memory.
+// What it replaces in the reference is the IPOPT solve behind mpc/optimizer.py:354/:375-391.
 #pragma once
 #include "kmpc_core.cuh"
 #include "kmpc_warp_prims.cuh"
@@ -23,13 +27,36 @@ struct WState {  // one iterate: this lane's SPL stages
 };
 template <int SPL>
 struct WStep { double dx0[SPL], dx1[SPL], dx2[SPL], du0[SPL], du1[SPL], dy0[SPL], dy1[SPL], dy2[SPL]; };
+
+// ---- shared-memory layout ----------------------------------------------------------------------------------------
+// coop area of one instance: C_NF fields x NSTG stages (field-major: the owner lanes touch consecutive stages, the
+// Riccati lanes -- one per instance -- are COOP doubles apart, COOP odd => both patterns are bank-conflict free).
+// Fields 7..17 are the stage blocks going in; the backward sweep overwrites them (and fields 18..23) with K, k_ff, P, p;
+// the forward roll-out overwrites K with (dx, du).
+enum { C_A13 = 0, C_A23, C_B11, C_B21, C_E0, C_E1, C_E2,
+       C_Q00 = 7, C_Q11, C_Q22, C_Q0, C_Q1, C_Q2, C_QV, C_QW, C_DV, C_DW, C_HTV,
+       C_NF = 24 };
+enum { C_K00 = 7, C_K01, C_K02, C_K10, C_K11, C_K12, C_KF0, C_KF1,
+       C_P00 = 15, C_P10, C_P11, C_P20, C_P21, C_P22, C_PV0, C_PV1, C_PV2 };
+enum { C_DX0 = 7, C_DX1, C_DX2, C_DU0, C_DU1 };
+// private area of one instance (owner warp only): the kept Newton step (back-tracking / failed corrections return to
+// it), the second-order-correction rhs, the constraint values of the last trial point
+enum { V_DX0 = 0, V_DX1, V_DX2, V_DU0, V_DU1, V_DY0, V_DY1, V_DY2, V_CS0, V_CS1, V_CS2, V_CT0, V_CT1, V_CT2, V_NF };
+
+struct WScal {  // warp-uniform per-instance scalars
+    Ctx t;
+    double filt[2 * K_FILTER_CAP];
+    double xc[3], gl[3], d0[3];
+    int flag, ok, r, status;
+};
+
 template <int SPL>
-struct WFact { double K00[SPL], K01[SPL], K02[SPL], K10[SPL], K11[SPL], K12[SPL], kf0[SPL], kf1[SPL];
-               double P00[SPL], P10[SPL], P11[SPL], P20[SPL], P21[SPL], P22[SPL], pv0[SPL], pv1[SPL], pv2[SPL]; };
-template <int SPL>
-struct WVec3 { double a[SPL], b[SPL], c[SPL]; };
-template <int SPL>
-struct WLin { double a13[SPL], a23[SPL], b11[SPL], b21[SPL]; };  // non-trivial entries of A_k, B_k (zero for stages >= N)
+struct WLay {
+    static constexpr int NSTG = 32 * SPL;
+    static constexpr int COOP = C_NF * NSTG + 1;
+    static constexpr int PRIV = V_NF * NSTG;
+    static size_t bytes(int warps) { return (size_t)warps * ((COOP + PRIV) * sizeof(double) + sizeof(WScal)); }
+};
 
 // value of the next / previous stage (neighbouring slot, or the neighbouring lane's edge slot)
 template <int SPL>
@@ -49,8 +76,9 @@ KMPC_W void w_prev(const double (&a)[SPL], double (&p)[SPL]) {
 
 // ---- starting point: optimizer.py:375-385 (warm start) / agent.py:59-60 (cold start); IPOPT initialisation ----
 template <int SPL>
-KMPC_WN inline void w_init(const Cfg &c, Ctx &t, const IO &io, int b, WState<SPL> &w, double (&xc)[3], double (&gl)[3]) {
+KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<SPL> &w) {
     const int N = c.N, lane = w_lane();
+    double xc[3], gl[3];
     for (int j = 0; j < 3; ++j) { xc[j] = io.x_cur[io_vec3(c, b, j)]; gl[j] = io.goal[io_vec3(c, b, j)]; }
     double gm = 0.0;
 #pragma unroll
@@ -82,162 +110,173 @@ KMPC_WN inline void w_init(const Cfg &c, Ctx &t, const IO &io, int b, WState<SPL
         w.cs[j] = cs; w.sn[j] = sn;
     }
     gm = w_maxabs_nan(gm);
-    t.df = gm > K_SCALING_MAX_GRAD ? fmax(K_SCALING_MAX_GRAD / gm, K_SCALING_MIN) : 1.0;
-    t.inst = b; t.cur = 0; t.iter = 0; t.mu = K_MU_INIT; t.tau = fmax(K_TAU_MIN, 1.0 - K_MU_INIT);
-    t.delta = 0.0; t.delta_last = 0.0; t.theta_max = -1.0; t.theta_min = -1.0; t.fn = 0;
-    t.nsteps = 0; t.soc_count = 0; t.trips = 0; t.sel = 0; t.tu = TU_INIT;
-    t.alpha = t.alpha_test = t.alpha_min = t.alpha_du0 = t.alpha_soc = t.gBD = t.theta_soc_old = t.theta_trial = 0.0;
-    t.a_pr = t.a_y = t.a_du = 0.0; t.pw_g = t.pw_t = 0.0;
-    t.c.f = t.c.bar = t.c.damp = t.c.theta = t.c.dinf = t.c.pinf = t.c.mn = t.c.mx = t.c.sumy = t.c.sumz = t.c.wmax = 0.0;
-    t.mode = M_LSQ;
+    if (lane == 0) {
+        Ctx &t = sc->t;
+        for (int j = 0; j < 3; ++j) { sc->xc[j] = xc[j]; sc->gl[j] = gl[j]; }
+        t.df = gm > K_SCALING_MAX_GRAD ? fmax(K_SCALING_MAX_GRAD / gm, K_SCALING_MIN) : 1.0;
+        t.inst = b; t.cur = 0; t.iter = 0; t.mu = K_MU_INIT; t.tau = fmax(K_TAU_MIN, 1.0 - K_MU_INIT);
+        t.delta = 0.0; t.delta_last = 0.0; t.theta_max = -1.0; t.theta_min = -1.0; t.fn = 0;
+        t.nsteps = 0; t.soc_count = 0; t.trips = 0; t.sel = 0; t.tu = TU_INIT;
+        t.alpha = t.alpha_test = t.alpha_min = t.alpha_du0 = t.alpha_soc = t.gBD = t.theta_soc_old = t.theta_trial = 0.0;
+        t.a_pr = t.a_y = t.a_du = 0.0; t.pw_g = t.pw_t = 0.0;
+        t.c.f = t.c.bar = t.c.damp = t.c.theta = t.c.dinf = t.c.pinf = t.c.mn = t.c.mx = t.c.sumy = t.c.sumz = t.c.wmax = 0.0;
+        t.mode = M_LSQ;
+    }
+    w_sync();
 }
 
-// ---- SWEEP: stage-parallel assembly of the KKT blocks, then the backward Riccati recursion lane by lane ----
-// Returns false on wrong inertia (some Q_uu not positive definite).  e = bc of the NEXT stage's dynamics row, kept for
-// the roll-out.
+// ---- phase 1a, ASSEMBLE: stage blocks of the KKT system -> coop area (all stages at once) ----
+// Stages without a control (the terminal stage N) become pass-through steps of the recursion: zero dynamics, unit Q_uu,
+// zero rhs -> P_out = P_in + Q, p_out = p_in + q.
 template <int SPL>
-KMPC_WN inline bool w_sweep(const Cfg &c, const Ctx &t, const WState<SPL> &w, const WVec3<SPL> &csoc, const double (&gl)[3],
-                            WFact<SPL> &f, WVec3<SPL> &e, WLin<SPL> &lin) {
+KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, const double *priv, double *coop) {
+    constexpr int NSTG = WLay<SPL>::NSTG;
     const int N = c.N, lane = w_lane();
-    const bool lsq = t.mode == M_LSQ, soc = t.mode == M_SOC;
-    const double mu = t.mu, delta = t.delta, df = t.df, T = c.T;
-    double yn0[SPL], yn1[SPL], yn2[SPL], xn0[SPL], xn1[SPL], xn2[SPL], cn0[SPL], cn1[SPL], cn2[SPL];
+    const int mode = sc->t.mode;
+    const bool lsq = mode == M_LSQ, soc = mode == M_SOC;
+    const double mu = sc->t.mu, delta = sc->t.delta, df = sc->t.df, T = c.T;
+    const double gl0 = sc->gl[0], gl1 = sc->gl[1], gl2 = sc->gl[2];
+    double yn0[SPL], yn1[SPL], yn2[SPL], xn0[SPL], xn1[SPL], xn2[SPL];
     w_next<SPL>(w.y0, yn0); w_next<SPL>(w.y1, yn1); w_next<SPL>(w.y2, yn2);
     w_next<SPL>(w.x0, xn0); w_next<SPL>(w.x1, xn1); w_next<SPL>(w.x2, xn2);
-    w_next<SPL>(csoc.a, cn0); w_next<SPL>(csoc.b, cn1); w_next<SPL>(csoc.c, cn2);
-    // per-stage blocks that do not depend on the cost-to-go
-    double q0[SPL], q1[SPL], q2[SPL], Q00[SPL], Q11[SPL], Q22[SPL], qv[SPL], qw[SPL], dv[SPL], dw[SPL], htv[SPL];
-    double (&a13)[SPL] = lin.a13, (&a23)[SPL] = lin.a23, (&b11)[SPL] = lin.b11, (&b21)[SPL] = lin.b21;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
         const int s = lane * SPL + j;
+        if (s > N) continue;
         const double x0 = w.x0[j], x1 = w.x1[j], x2 = w.x2[j];
         const bool ing = s >= c.gk_lo && s <= c.gk_hi;
         double gx0 = 0, gx1 = 0, gx2 = 0, h0 = 0, h1 = 0, h2 = 0;
         if (ing) {
-            gx0 = df * 2.0 * c.W[0] * (x0 - gl[0]); gx1 = df * 2.0 * c.W[1] * (x1 - gl[1]); gx2 = df * 2.0 * c.W[2] * (x2 - gl[2]);
+            gx0 = df * 2.0 * c.W[0] * (x0 - gl0); gx1 = df * 2.0 * c.W[1] * (x1 - gl1); gx2 = df * 2.0 * c.W[2] * (x2 - gl2);
             h0 = df * 2.0 * c.W[0]; h1 = df * 2.0 * c.W[1]; h2 = df * 2.0 * c.W[2];
         }
+        double q0, q1, q2, Q00, Q11, Q22;
         if (lsq) {
-            q0[j] = -(gx0 - w.zLx[j] + w.zUx[j]); q1[j] = -(gx1 - w.zLy[j] + w.zUy[j]); q2[j] = -gx2;
-            Q00[j] = 1.0; Q11[j] = 1.0; Q22[j] = 1.0;
+            q0 = -(gx0 - w.zLx[j] + w.zUx[j]); q1 = -(gx1 - w.zLy[j] + w.zUy[j]); q2 = -gx2;
+            Q00 = 1.0; Q11 = 1.0; Q22 = 1.0;
         } else {
             double sg0, rb0, sg1, rb1;
             bound_terms(x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], w.zLx[j], w.zUx[j], mu, &sg0, &rb0);
             bound_terms(x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], w.zLy[j], w.zUy[j], mu, &sg1, &rb1);
-            q0[j] = gx0 + w.y0[j] + rb0; q1[j] = gx1 + w.y1[j] + rb1; q2[j] = gx2 + w.y2[j];
-            Q00[j] = h0 + sg0 + delta; Q11[j] = h1 + sg1 + delta; Q22[j] = h2 + delta;
+            q0 = gx0 + w.y0[j] + rb0; q1 = gx1 + w.y1[j] + rb1; q2 = gx2 + w.y2[j];
+            Q00 = h0 + sg0 + delta; Q11 = h1 + sg1 + delta; Q22 = h2 + delta;
         }
         const double v = w.v[j], om = w.om[j], cs = w.cs[j], sn = w.sn[j];
-        a13[j] = -T * v * sn; a23[j] = T * v * cs; b11[j] = T * cs; b21[j] = T * sn;
+        double a13 = -T * v * sn, a23 = T * v * cs, b11 = T * cs, b21 = T * sn;
         double gv, hvv;
         vcost(c, df, v, &gv, &hvv);
         const double gw = df * 2.0 * c.Ww * om;
-        double hww = df * 2.0 * c.Ww;
-        htv[j] = 0.0;
+        const double hww = df * 2.0 * c.Ww;
+        double htv = 0.0, qv, qw, dv, dw, e0, e1, e2;
         if (lsq) {
-            qv[j] = -(gv - w.zLv[j] + w.zUv[j]); qw[j] = -(gw - w.zLw[j] + w.zUw[j]);
-            dv[j] = 1.0; dw[j] = 1.0;
-            e.a[j] = e.b[j] = e.c[j] = 0.0;
+            qv = -(gv - w.zLv[j] + w.zUv[j]); qw = -(gw - w.zLw[j] + w.zUw[j]);
+            dv = 1.0; dw = 1.0;
+            e0 = e1 = e2 = 0.0;
         } else {
             double sgv, rbv, sgw, rbw;
             bound_terms(v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], w.zLv[j], w.zUv[j], mu, &sgv, &rbv);
             bound_terms(om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], w.zLw[j], w.zUw[j], mu, &sgw, &rbw);
             if (s < N) {
                 // J^T y of dynamics row s+1 and the curvature of the dynamics in the Lagrangian
-                q0[j] -= yn0[j]; q1[j] -= yn1[j]; q2[j] -= a13[j] * yn0[j] + a23[j] * yn1[j] + yn2[j];
-                Q22[j] += T * v * (yn0[j] * cs + yn1[j] * sn);
-                htv[j] = T * (yn0[j] * sn - yn1[j] * cs);
+                q0 -= yn0[j]; q1 -= yn1[j]; q2 -= a13 * yn0[j] + a23 * yn1[j] + yn2[j];
+                Q22 += T * v * (yn0[j] * cs + yn1[j] * sn);
+                htv = T * (yn0[j] * sn - yn1[j] * cs);
             }
-            qv[j] = gv - (b11[j] * yn0[j] + b21[j] * yn1[j]) + rbv;
-            qw[j] = gw - T * yn2[j] + rbw;
-            dv[j] = hvv + (sgv + delta); dw[j] = hww + (sgw + delta);
-            if (soc) { e.a[j] = -cn0[j]; e.b[j] = -cn1[j]; e.c[j] = -cn2[j]; }
-            else { e.a[j] = -(xn0[j] - (x0 + T * v * cs)); e.b[j] = -(xn1[j] - (x1 + T * v * sn)); e.c[j] = -(xn2[j] - (x2 + T * om)); }
+            qv = gv - (b11 * yn0[j] + b21 * yn1[j]) + rbv;
+            qw = gw - T * yn2[j] + rbw;
+            dv = hvv + (sgv + delta); dw = hww + (sgw + delta);
+            if (soc) {  // rhs of the dynamics row s+1 = -c_soc of stage s+1
+                const double *pn = priv + (s + 1 < NSTG ? s + 1 : s);
+                e0 = -pn[V_CS0 * NSTG]; e1 = -pn[V_CS1 * NSTG]; e2 = -pn[V_CS2 * NSTG];
+            } else { e0 = -(xn0[j] - (x0 + T * v * cs)); e1 = -(xn1[j] - (x1 + T * v * sn)); e2 = -(xn2[j] - (x2 + T * om)); }
         }
-    }
-    // Stages without a control (the terminal stage N and the padding stages behind it) become pass-through steps:
-    // zero dynamics, unit Quu, zero rhs -> P_out = P_in + Q, p_out = p_in + q; the padding stages carry Q = q = 0.
-#pragma unroll
-    for (int j = 0; j < SPL; ++j) {
-        const int s = lane * SPL + j;
         if (s >= N) {
-            a13[j] = a23[j] = b11[j] = b21[j] = 0.0; qv[j] = qw[j] = htv[j] = 0.0; dv[j] = dw[j] = 1.0;
-            e.a[j] = e.b[j] = e.c[j] = 0.0;
+            a13 = a23 = b11 = b21 = 0.0; qv = qw = htv = 0.0; dv = dw = 1.0;
+            e0 = e1 = e2 = 0.0;
         }
-        if (s > N) { q0[j] = q1[j] = q2[j] = 0.0; Q00[j] = Q11[j] = Q22[j] = 0.0; }
-    }
-    // Backward recursion as a warp-uniform fixed-point loop: every lane applies its stage step(s) to whatever its right
-    // neighbour produced in the previous round.  The dependency is triangular, so lane top-i is exact from round i on and
-    // stays exact: after top+1 rounds every lane holds its true K, k_ff, P, p -- no branches, no predicated commits.
-    // (The last lane's last slot is always a padding stage -- the launcher guarantees N + 1 < 32 * SPL -- so the chain
-    // end feeds zeros.)
-    double C00 = 0, C10 = 0, C11 = 0, C20 = 0, C21 = 0, C22 = 0, c0 = 0, c1 = 0, c2 = 0;  // this lane's slot-0 (P, p)
-    const int top = N / SPL;
-    bool pd = true;
-#pragma unroll 1
-    for (int it = 0; it <= top; ++it) {
-        double P00 = w_down(C00, 1), P10 = w_down(C10, 1), P11 = w_down(C11, 1), P20 = w_down(C20, 1), P21 = w_down(C21, 1),
-               P22 = w_down(C22, 1), p0 = w_down(c0, 1), p1 = w_down(c1, 1), p2 = w_down(c2, 1);
-        pd = true;
-#pragma unroll
-        for (int j = SPL - 1; j >= 0; --j) {
-            RicK rk;
-            pd &= riccati_step(P00, P10, P11, P20, P21, P22, p0, p1, p2, a13[j], a23[j], b11[j], b21[j], T, Q00[j], 0.0, Q11[j], Q22[j],
-                               q0[j], q1[j], q2[j], qv[j], qw[j], dv[j], dw[j], htv[j], e.a[j], e.b[j], e.c[j], rk);
-            f.K00[j] = rk.K00; f.K01[j] = rk.K01; f.K02[j] = rk.K02; f.K10[j] = rk.K10; f.K11[j] = rk.K11; f.K12[j] = rk.K12;
-            f.kf0[j] = rk.kf0; f.kf1[j] = rk.kf1;
-            f.P00[j] = P00; f.P10[j] = P10; f.P11[j] = P11; f.P20[j] = P20; f.P21[j] = P21; f.P22[j] = P22;
-            f.pv0[j] = p0; f.pv1[j] = p1; f.pv2[j] = p2;
+        double *q = coop + s;
+        q[C_A13 * NSTG] = a13; q[C_A23 * NSTG] = a23; q[C_B11 * NSTG] = b11; q[C_B21 * NSTG] = b21;
+        q[C_E0 * NSTG] = e0; q[C_E1 * NSTG] = e1; q[C_E2 * NSTG] = e2;
+        q[C_Q00 * NSTG] = Q00; q[C_Q11 * NSTG] = Q11; q[C_Q22 * NSTG] = Q22;
+        q[C_Q0 * NSTG] = q0; q[C_Q1 * NSTG] = q1; q[C_Q2 * NSTG] = q2;
+        q[C_QV * NSTG] = qv; q[C_QW * NSTG] = qw; q[C_DV * NSTG] = dv; q[C_DW * NSTG] = dw; q[C_HTV * NSTG] = htv;
+        if (s == 0) {  // dx of stage 0 (the rhs of the initial-state row)
+            if (lsq) { sc->d0[0] = sc->d0[1] = sc->d0[2] = 0.0; }
+            else if (soc) { sc->d0[0] = -priv[V_CS0 * NSTG]; sc->d0[1] = -priv[V_CS1 * NSTG]; sc->d0[2] = -priv[V_CS2 * NSTG]; }
+            else { sc->d0[0] = -(x0 - sc->xc[0]); sc->d0[1] = -(x1 - sc->xc[1]); sc->d0[2] = -(x2 - sc->xc[2]); }
         }
-        C00 = P00; C10 = P10; C11 = P11; C20 = P20; C21 = P21; C22 = P22; c0 = p0; c1 = p1; c2 = p2;
-        // wrong inertia detected by a lane that is already exact: stop early (looked at every 8th round)
-        if ((it & 7) == 7 && w_any(!pd && lane >= top - it)) return false;
     }
-    return w_all(pd);
 }
 
-// ---- ROLL-OUT: forward substitution lane by lane, then stage-parallel step-size limits ----
-template <int SPL>
-KMPC_WN inline void w_rollout(const Cfg &c, const Ctx &t, const WState<SPL> &w, const WFact<SPL> &f, const WVec3<SPL> &e,
-                              const WLin<SPL> &lin, const WVec3<SPL> &csoc, const double (&xc)[3], const double (&gl)[3], WStep<SPL> &d,
-                              double *alpha_pr, double *alpha_du, double *gBD, double *ymax) {
-    const int N = c.N, lane = w_lane();
-    const bool lsq = t.mode == M_LSQ, soc = t.mode == M_SOC;
-    const double mu = t.mu, df = t.df, T = c.T, tau = t.tau;
-    // forward substitution, again as a warp-uniform fixed-point loop (lane i is exact from round i on)
-    double i0, i1, i2;  // dx of stage 0
-    if (lsq) { i0 = i1 = i2 = 0.0; }
-    else if (soc) { i0 = -csoc.a[0]; i1 = -csoc.b[0]; i2 = -csoc.c[0]; }
-    else { i0 = -(w.x0[0] - xc[0]); i1 = -(w.x1[0] - xc[1]); i2 = -(w.x2[0] - xc[2]); }
-    double r0 = 0, r1 = 0, r2 = 0;  // dx of the stage after this lane's last slot
-    const int top = N / SPL;
+// ---- phase 1b, RICCATI: the two serial recursions of ONE instance, executed by ONE lane of the block's Riccati warp ----
+// Backward sweep (K, k_ff, P, p of every stage; false = some Q_uu not positive definite = wrong inertia), then the
+// forward substitution dx+ = A dx + B du + e, du = K dx + k_ff.
+KMPC_WN inline bool w_serial(const Cfg &c, double *coop, const int NSTG, const double *d0) {
+    const int N = c.N;
+    const double T = c.T;
+    double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0, p0 = 0, p1 = 0, p2 = 0;
 #pragma unroll 1
-    for (int it = 0; it <= top; ++it) {
-        const double u0 = w_up(r0, 1), u1 = w_up(r1, 1), u2 = w_up(r2, 1);
-        double d0 = lane == 0 ? i0 : u0, d1 = lane == 0 ? i1 : u1, d2 = lane == 0 ? i2 : u2;
-#pragma unroll
-        for (int j = 0; j < SPL; ++j) {
-            d.dx0[j] = d0; d.dx1[j] = d1; d.dx2[j] = d2;
-            const double du0 = fma(f.K00[j], d0, fma(f.K01[j], d1, fma(f.K02[j], d2, f.kf0[j])));
-            const double du1 = fma(f.K10[j], d0, fma(f.K11[j], d1, fma(f.K12[j], d2, f.kf1[j])));
-            d.du0[j] = du0; d.du1[j] = du1;
-            const double n0 = d0 + lin.a13[j] * d2 + lin.b11[j] * du0 + e.a[j];
-            const double n1 = d1 + lin.a23[j] * d2 + lin.b21[j] * du0 + e.b[j];
-            const double n2 = d2 + T * du1 + e.c[j];
-            d0 = n0; d1 = n1; d2 = n2;
-        }
-        r0 = d0; r1 = d1; r2 = d2;
+    for (int s = N; s >= 0; --s) {
+        double *q = coop + s;
+        const double a13 = q[C_A13 * NSTG], a23 = q[C_A23 * NSTG], b11 = q[C_B11 * NSTG], b21 = q[C_B21 * NSTG];
+        const double e0 = q[C_E0 * NSTG], e1 = q[C_E1 * NSTG], e2 = q[C_E2 * NSTG];
+        const double Q00 = q[C_Q00 * NSTG], Q11 = q[C_Q11 * NSTG], Q22 = q[C_Q22 * NSTG];
+        const double q0 = q[C_Q0 * NSTG], q1 = q[C_Q1 * NSTG], q2 = q[C_Q2 * NSTG];
+        const double qv = q[C_QV * NSTG], qw = q[C_QW * NSTG], dv = q[C_DV * NSTG], dw = q[C_DW * NSTG], htv = q[C_HTV * NSTG];
+        RicK rk;
+        if (!riccati_step(P00, P10, P11, P20, P21, P22, p0, p1, p2, a13, a23, b11, b21, T, Q00, 0.0, Q11, Q22, q0, q1, q2, qv, qw,
+                          dv, dw, htv, e0, e1, e2, rk))
+            return false;
+        q[C_K00 * NSTG] = rk.K00; q[C_K01 * NSTG] = rk.K01; q[C_K02 * NSTG] = rk.K02;
+        q[C_K10 * NSTG] = rk.K10; q[C_K11 * NSTG] = rk.K11; q[C_K12 * NSTG] = rk.K12;
+        q[C_KF0 * NSTG] = rk.kf0; q[C_KF1 * NSTG] = rk.kf1;
+        q[C_P00 * NSTG] = P00; q[C_P10 * NSTG] = P10; q[C_P11 * NSTG] = P11;
+        q[C_P20 * NSTG] = P20; q[C_P21 * NSTG] = P21; q[C_P22 * NSTG] = P22;
+        q[C_PV0 * NSTG] = p0; q[C_PV1 * NSTG] = p1; q[C_PV2 * NSTG] = p2;
     }
+    double x0 = d0[0], x1 = d0[1], x2 = d0[2];
+#pragma unroll 1
+    for (int s = 0; s <= N; ++s) {
+        double *q = coop + s;
+        const double K00 = q[C_K00 * NSTG], K01 = q[C_K01 * NSTG], K02 = q[C_K02 * NSTG];
+        const double K10 = q[C_K10 * NSTG], K11 = q[C_K11 * NSTG], K12 = q[C_K12 * NSTG];
+        const double kf0 = q[C_KF0 * NSTG], kf1 = q[C_KF1 * NSTG];
+        const double a13 = q[C_A13 * NSTG], a23 = q[C_A23 * NSTG], b11 = q[C_B11 * NSTG], b21 = q[C_B21 * NSTG];
+        const double e0 = q[C_E0 * NSTG], e1 = q[C_E1 * NSTG], e2 = q[C_E2 * NSTG];
+        const double du0 = fma(K00, x0, fma(K01, x1, fma(K02, x2, kf0)));
+        const double du1 = fma(K10, x0, fma(K11, x1, fma(K12, x2, kf1)));
+        q[C_DX0 * NSTG] = x0; q[C_DX1 * NSTG] = x1; q[C_DX2 * NSTG] = x2; q[C_DU0 * NSTG] = du0; q[C_DU1 * NSTG] = du1;
+        const double n0 = x0 + a13 * x2 + b11 * du0 + e0;
+        const double n1 = x1 + a23 * x2 + b21 * du0 + e1;
+        const double n2 = x2 + T * du1 + e2;
+        x0 = n0; x1 = n1; x2 = n2;
+    }
+    return true;
+}
+
+// ---- phase 2, STEP: multiplier step dy = -(P dx + p), step-size limits, directional derivative (all stages at once) ----
+template <int SPL>
+KMPC_WN inline void w_step(const Cfg &c, const WScal *sc, const WState<SPL> &w, const double *coop, WStep<SPL> &d,
+                           double *alpha_pr, double *alpha_du, double *gBD, double *ymax) {
+    constexpr int NSTG = WLay<SPL>::NSTG;
+    const int N = c.N, lane = w_lane();
+    const bool lsq = sc->t.mode == M_LSQ;
+    const double mu = sc->t.mu, df = sc->t.df, tau = sc->t.tau;
+    const double gl0 = sc->gl[0], gl1 = sc->gl[1], gl2 = sc->gl[2];
     double apr = 1.0, adu = 1.0, gbd = 0.0, ym = 0.0;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
         const int s = lane * SPL + j;
         if (s > N) { d.dx0[j] = d.dx1[j] = d.dx2[j] = d.du0[j] = d.du1[j] = d.dy0[j] = d.dy1[j] = d.dy2[j] = 0.0; continue; }
-        const double d0 = d.dx0[j], d1 = d.dx1[j], d2 = d.dx2[j];
-        const double dy0 = -(f.P00[j] * d0 + f.P10[j] * d1 + f.P20[j] * d2 + f.pv0[j]);
-        const double dy1 = -(f.P10[j] * d0 + f.P11[j] * d1 + f.P21[j] * d2 + f.pv1[j]);
-        const double dy2 = -(f.P20[j] * d0 + f.P21[j] * d1 + f.P22[j] * d2 + f.pv2[j]);
+        const double *q = coop + s;
+        const double d0 = q[C_DX0 * NSTG], d1 = q[C_DX1 * NSTG], d2 = q[C_DX2 * NSTG];
+        const double du0 = s < N ? q[C_DU0 * NSTG] : 0.0, du1 = s < N ? q[C_DU1 * NSTG] : 0.0;
+        const double P00 = q[C_P00 * NSTG], P10 = q[C_P10 * NSTG], P11 = q[C_P11 * NSTG], P20 = q[C_P20 * NSTG],
+                     P21 = q[C_P21 * NSTG], P22 = q[C_P22 * NSTG];
+        const double dy0 = -(P00 * d0 + P10 * d1 + P20 * d2 + q[C_PV0 * NSTG]);
+        const double dy1 = -(P10 * d0 + P11 * d1 + P21 * d2 + q[C_PV1 * NSTG]);
+        const double dy2 = -(P20 * d0 + P21 * d1 + P22 * d2 + q[C_PV2 * NSTG]);
+        d.dx0[j] = d0; d.dx1[j] = d1; d.dx2[j] = d2; d.du0[j] = du0; d.du1[j] = du1;
         d.dy0[j] = dy0; d.dy1[j] = dy1; d.dy2[j] = dy2;
         ym = maxabs_nan(maxabs_nan(maxabs_nan(ym, dy0), dy1), dy2);
         if (lsq) continue;
@@ -247,12 +286,12 @@ KMPC_WN inline void w_rollout(const Cfg &c, const Ctx &t, const WState<SPL> &w, 
         bound_ftb(x1, d1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], w.zLy[j], w.zUy[j], mu, tau, &apr, &adu);
         const bool ing = s >= c.gk_lo && s <= c.gk_hi;
         bound_terms(x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], w.zLx[j], w.zUx[j], mu, &sg, &rb);
-        gbd += ((ing ? df * 2.0 * c.W[0] * (x0 - gl[0]) : 0.0) + rb) * d0;
+        gbd += ((ing ? df * 2.0 * c.W[0] * (x0 - gl0) : 0.0) + rb) * d0;
         bound_terms(x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], w.zLy[j], w.zUy[j], mu, &sg, &rb);
-        gbd += ((ing ? df * 2.0 * c.W[1] * (x1 - gl[1]) : 0.0) + rb) * d1;
-        gbd += (ing ? df * 2.0 * c.W[2] * (x2 - gl[2]) : 0.0) * d2;
+        gbd += ((ing ? df * 2.0 * c.W[1] * (x1 - gl1) : 0.0) + rb) * d1;
+        gbd += (ing ? df * 2.0 * c.W[2] * (x2 - gl2) : 0.0) * d2;
         if (s < N) {
-            const double v = w.v[j], om = w.om[j], du0 = d.du0[j], du1 = d.du1[j];
+            const double v = w.v[j], om = w.om[j];
             bound_ftb(v, du0, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], w.zLv[j], w.zUv[j], mu, tau, &apr, &adu);
             bound_ftb(om, du1, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], w.zLw[j], w.zUw[j], mu, tau, &apr, &adu);
             double gv, hv;
@@ -266,13 +305,36 @@ KMPC_WN inline void w_rollout(const Cfg &c, const Ctx &t, const WState<SPL> &w, 
     *alpha_pr = w_min(apr); *alpha_du = w_min(adu); *gBD = w_sum(gbd); *ymax = w_maxabs_nan(ym);
 }
 
-// ---- TRIAL + speculative update (all stages at once) ----
+// kept Newton step <-> private area
 template <int SPL>
-KMPC_WN inline bool w_trial(const Cfg &c, const Ctx &t, const WState<SPL> &w, const WStep<SPL> &d, const double (&xc)[3],
-                            const double (&gl)[3], double alpha, double ay, double adu, bool clamp, WState<SPL> &n,
-                            WVec3<SPL> &ct, Stats *out) {
+KMPC_W void w_step_store(const WStep<SPL> &d, double *priv) {
+    constexpr int NSTG = WLay<SPL>::NSTG;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        double *p = priv + w_lane() * SPL + j;
+        p[V_DX0 * NSTG] = d.dx0[j]; p[V_DX1 * NSTG] = d.dx1[j]; p[V_DX2 * NSTG] = d.dx2[j]; p[V_DU0 * NSTG] = d.du0[j];
+        p[V_DU1 * NSTG] = d.du1[j]; p[V_DY0 * NSTG] = d.dy0[j]; p[V_DY1 * NSTG] = d.dy1[j]; p[V_DY2 * NSTG] = d.dy2[j];
+    }
+}
+template <int SPL>
+KMPC_W void w_step_load(WStep<SPL> &d, const double *priv) {
+    constexpr int NSTG = WLay<SPL>::NSTG;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const double *p = priv + w_lane() * SPL + j;
+        d.dx0[j] = p[V_DX0 * NSTG]; d.dx1[j] = p[V_DX1 * NSTG]; d.dx2[j] = p[V_DX2 * NSTG]; d.du0[j] = p[V_DU0 * NSTG];
+        d.du1[j] = p[V_DU1 * NSTG]; d.dy0[j] = p[V_DY0 * NSTG]; d.dy1[j] = p[V_DY1 * NSTG]; d.dy2[j] = p[V_DY2 * NSTG];
+    }
+}
+
+// ---- phase 3, TRIAL: trial point + speculative multiplier update + residual norms (all stages at once) ----
+template <int SPL>
+KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w, const WStep<SPL> &d, double alpha, double ay,
+                            double adu, bool clamp, WState<SPL> &n, double *priv, Stats *out) {
+    constexpr int NSTG = WLay<SPL>::NSTG;
     const int N = c.N, lane = w_lane();
-    const double mu = t.mu, df = t.df, T = c.T;
+    const double mu = sc->t.mu, df = sc->t.df, T = c.T;
+    const double xc0 = sc->xc[0], xc1 = sc->xc[1], xc2 = sc->xc[2], gl0 = sc->gl[0], gl1 = sc->gl[1], gl2 = sc->gl[2];
     Stats st;
     st.f = 0; st.bar = 0; st.damp = 0; st.theta = 0; st.dinf = 0; st.pinf = 0; st.mn = INFINITY; st.mx = 0; st.sumy = 0;
     st.sumz = 0; st.wmax = 0;
@@ -296,17 +358,18 @@ KMPC_WN inline bool w_trial(const Cfg &c, const Ctx &t, const WState<SPL> &w, co
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
         const int s = lane * SPL + j;
-        if (s > N) { ct.a[j] = ct.b[j] = ct.c[j] = 0.0; continue; }
+        if (s > N) continue;
         const double x0 = n.x0[j], x1 = n.x1[j], x2 = n.x2[j];
-        const double c0 = x0 - (s == 0 ? xc[0] : pp0[j]), c1 = x1 - (s == 0 ? xc[1] : pp1[j]), c2 = x2 - (s == 0 ? xc[2] : pp2[j]);
-        ct.a[j] = c0; ct.b[j] = c1; ct.c[j] = c2;
+        const double c0 = x0 - (s == 0 ? xc0 : pp0[j]), c1 = x1 - (s == 0 ? xc1 : pp1[j]), c2 = x2 - (s == 0 ? xc2 : pp2[j]);
+        double *pv = priv + s;
+        pv[V_CT0 * NSTG] = c0; pv[V_CT1 * NSTG] = c1; pv[V_CT2 * NSTG] = c2;
         st.theta += fabs(c0) + fabs(c1) + fabs(c2);
         st.pinf = maxabs_nan(maxabs_nan(maxabs_nan(st.pinf, c0), c1), c2);
         st.sumy += fabs(n.y0[j]) + fabs(n.y1[j]) + fabs(n.y2[j]);
         st.wmax = fmax(st.wmax, fmax(fabs(x0), fmax(fabs(x1), fabs(x2))));
         double r0 = n.y0[j], r1 = n.y1[j], r2 = n.y2[j];
         if (s >= c.gk_lo && s <= c.gk_hi) {
-            const double e0 = x0 - gl[0], e1 = x1 - gl[1], e2 = x2 - gl[2];
+            const double e0 = x0 - gl0, e1 = x1 - gl1, e2 = x2 - gl2;
             st.f += c.W[0] * e0 * e0; st.f += c.W[1] * e1 * e1; st.f += c.W[2] * e2 * e2;
             r0 += df * 2.0 * c.W[0] * e0; r1 += df * 2.0 * c.W[1] * e1; r2 += df * 2.0 * c.W[2] * e2;
         }
@@ -353,8 +416,8 @@ KMPC_WN inline bool w_trial(const Cfg &c, const Ctx &t, const WState<SPL> &w, co
 
 // c_soc <- al * base + c(trial); base = c(current) for the first correction, else the previous c_soc
 template <int SPL>
-KMPC_WN inline void w_soc_rhs(const Cfg &c, const WState<SPL> &w, const WVec3<SPL> &ct, const double (&xc)[3], double al, bool first,
-                              WVec3<SPL> &csoc) {
+KMPC_WN inline void w_soc_rhs(const Cfg &c, const WScal *sc, const WState<SPL> &w, double al, bool first, double *priv) {
+    constexpr int NSTG = WLay<SPL>::NSTG;
     const int N = c.N, lane = w_lane();
     const double T = c.T;
     double xp0[SPL], xp1[SPL], xp2[SPL], pp0[SPL], pp1[SPL], pp2[SPL];
@@ -366,89 +429,94 @@ KMPC_WN inline void w_soc_rhs(const Cfg &c, const WState<SPL> &w, const WVec3<SP
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
         const int s = lane * SPL + j;
-        if (s > N) { csoc.a[j] = csoc.b[j] = csoc.c[j] = 0.0; continue; }
+        if (s > N) continue;
+        double *pv = priv + s;
         double b0, b1, b2;
-        if (first) { b0 = w.x0[j] - (s == 0 ? xc[0] : pp0[j]); b1 = w.x1[j] - (s == 0 ? xc[1] : pp1[j]); b2 = w.x2[j] - (s == 0 ? xc[2] : pp2[j]); }
-        else { b0 = csoc.a[j]; b1 = csoc.b[j]; b2 = csoc.c[j]; }
-        csoc.a[j] = al * b0 + ct.a[j]; csoc.b[j] = al * b1 + ct.b[j]; csoc.c[j] = al * b2 + ct.c[j];
+        if (first) { b0 = w.x0[j] - (s == 0 ? sc->xc[0] : pp0[j]); b1 = w.x1[j] - (s == 0 ? sc->xc[1] : pp1[j]); b2 = w.x2[j] - (s == 0 ? sc->xc[2] : pp2[j]); }
+        else { b0 = pv[V_CS0 * NSTG]; b1 = pv[V_CS1 * NSTG]; b2 = pv[V_CS2 * NSTG]; }
+        pv[V_CS0 * NSTG] = al * b0 + pv[V_CT0 * NSTG]; pv[V_CS1 * NSTG] = al * b1 + pv[V_CT1 * NSTG]; pv[V_CS2 * NSTG] = al * b2 + pv[V_CT2 * NSTG];
     }
+    w_sync();
 }
 
+// ---- persistent worker: one warp pulls instances from a queue and solves each start to finish; the warps of a block
+// walk through the phases of a trip in step (block barriers) so that warp 0 can run every instance's serial recursions.
+// smem: WLay<SPL>::bytes(warps per block) bytes of block-shared scratch.
 template <int SPL>
-KMPC_W void w_step_select(WStep<SPL> &o, const WStep<SPL> &a, const WStep<SPL> &b, bool pick_b) {
-#pragma unroll
-    for (int j = 0; j < SPL; ++j) {
-        o.dx0[j] = pick_b ? b.dx0[j] : a.dx0[j]; o.dx1[j] = pick_b ? b.dx1[j] : a.dx1[j]; o.dx2[j] = pick_b ? b.dx2[j] : a.dx2[j];
-        o.du0[j] = pick_b ? b.du0[j] : a.du0[j]; o.du1[j] = pick_b ? b.du1[j] : a.du1[j];
-        o.dy0[j] = pick_b ? b.dy0[j] : a.dy0[j]; o.dy1[j] = pick_b ? b.dy1[j] : a.dy1[j]; o.dy2[j] = pick_b ? b.dy2[j] : a.dy2[j];
-    }
-}
-
-// ---- persistent worker: one warp pulls instances from a queue and solves each start to finish. ----
-// filt: 2*K_FILTER_CAP doubles of warp-private scratch.  The warps of a block walk through the three phases of a trip in
-// step (block barriers): at any time they execute the same few KB of code, so the instruction cache is shared instead of
-// being thrashed by warps that sit in different phases of a ~140 KB kernel.
-template <int SPL>
-KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *filt, int *queue, unsigned long long *trips_total) {
-    const int N = c.N, lane = w_lane();
-    Ctx t;
-    WState<SPL> cur, tri;
-    WStep<SPL> st0, st1, act;
-    WFact<SPL> fact;
-    WVec3<SPL> e, csoc, ct;
-    WLin<SPL> lin;
-    double xc[3] = {0, 0, 0}, gl[3] = {0, 0, 0};
+KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queue, unsigned long long *trips_total) {
+    typedef WLay<SPL> LY;
+    const int N = c.N, lane = w_lane(), wid = w_warp(), W = w_warps();
+    double *coop = smem + (size_t)wid * LY::COOP;
+    double *priv = smem + (size_t)W * LY::COOP + (size_t)wid * LY::PRIV;
+    WScal *scal0 = (WScal *)(smem + (size_t)W * (LY::COOP + LY::PRIV));
+    WScal *sc = scal0 + wid;
+    Ctx &t = sc->t;
+    WState<SPL> cur;
+    WStep<SPL> act;
     bool have = false;
     int b = -1;
-    t.mode = M_DONE;
+    if (lane == 0) { t.mode = M_DONE; sc->flag = 0; sc->ok = 0; }
+    w_sync();
 #pragma unroll 1
     for (;;) {
         if (!have) {
             b = w_fetch(queue);
-            if (b < c.B) {
-#pragma unroll
-                for (int j = 0; j < SPL; ++j) { csoc.a[j] = csoc.b[j] = csoc.c[j] = 0.0; ct.a[j] = ct.b[j] = ct.c[j] = 0.0; }
-                w_init<SPL>(c, t, io, b, cur, xc, gl);
-                have = true;
-            }
+            if (b < c.B) { w_init<SPL>(c, sc, io, b, cur); have = true; }
         }
-        if (!w_block_any(have)) break;  // also the barrier in front of phase 1
+        if (!w_block_any(have)) break;
         int status = 100;
-        // ---- phase 1: backward sweep ----
-        const bool do_sweep = have && t.mode != M_TRIAL;
-        bool ok = false;
-        if (do_sweep) { t.trips++; ok = w_sweep<SPL>(c, t, cur, csoc, gl, fact, e, lin); }
+        // ---- phase 1a: assemble the stage blocks ----
+        const int mode = t.mode;
+        const bool do_sweep = have && mode != M_TRIAL;
+        if (do_sweep) w_assemble<SPL>(c, sc, cur, priv, coop);
+        if (lane == 0) { sc->flag = do_sweep ? 1 : 0; if (do_sweep) t.trips++; }
         w_block_sync();
-        // ---- phase 2: roll-out + line-search set-up (or inertia correction) ----
+        // ---- phase 1b: the serial recursions of all the block's instances, one lane each ----
+        if (wid == 0 && lane < W) {
+            WScal *so = scal0 + lane;
+            if (so->flag) so->ok = w_serial(c, smem + (size_t)lane * LY::COOP, LY::NSTG, so->d0) ? 1 : 0;
+        }
+        w_block_sync();
+        // ---- phase 2: search direction, step sizes, line-search set-up (or inertia correction) ----
         bool go_trial = have && !do_sweep;
         if (do_sweep) {
-            if (!ok) status = t.mode != M_NEWTON ? (int)ST_STEP_ERROR : inertia_update(t);  // R_RETRY: sweep again next trip
-            else {
+            if (!sc->ok) {
+                if (lane == 0) sc->status = mode != M_NEWTON ? (int)ST_STEP_ERROR : inertia_update(t);  // R_RETRY: sweep again next trip
+                w_sync();
+                status = sc->status;
+            } else {
                 double apr, adu, gbd, ym;
-                w_rollout<SPL>(c, t, cur, fact, e, lin, csoc, xc, gl, act, &apr, &adu, &gbd, &ym);
-                rollout_logic(t, apr, adu, gbd, ym);
-                if (t.sel) st1 = act; else st0 = act;
+                w_step<SPL>(c, sc, cur, coop, act, &apr, &adu, &gbd, &ym);
+                if (lane == 0) rollout_logic(t, apr, adu, gbd, ym);
+                w_sync();
+                if (t.sel == 0) w_step_store<SPL>(act, priv);
                 go_trial = true;
             }
         } else if (have) {
-            trial_setup(t);
-            w_step_select<SPL>(act, st0, st1, false);
+            if (lane == 0) trial_setup(t);
+            w_sync();
+            w_step_load<SPL>(act, priv);
         }
-        w_block_sync();
         // ---- phase 3: trial point + acceptance logic ----
         if (go_trial) {
             Stats ts;
-            const bool evok = w_trial<SPL>(c, t, cur, act, xc, gl, t.a_pr, t.a_y, t.a_du, t.tu == TU_STEP, tri, ct, &ts);
-            bool aug; double ath, aph;
-            const int r = trial_decide(t, filt, 1, ts, evok, &aug, &ath, &aph);
-            if (aug) {  // one lane edits the warp's filter, everybody learns the new length
-                if (lane == 0) filter_add(t, filt, 1, ath, aph);
-                t.fn = w_bcast_i(t.fn, 0);
+            WState<SPL> tri;
+            const bool evok = w_trial<SPL>(c, sc, cur, act, t.a_pr, t.a_y, t.a_du, t.tu == TU_STEP, tri, priv, &ts);
+            if (lane == 0) {
+                bool aug; double ath, aph;
+                const int r = trial_decide(t, sc->filt, 1, ts, evok, &aug, &ath, &aph);
+                if (aug) filter_add(t, sc->filt, 1, ath, aph);
+                sc->r = r;
             }
             w_sync();
-            if (r == R_SOC1 || r == R_SOC2) w_soc_rhs<SPL>(c, cur, ct, xc, t.alpha_soc, r == R_SOC1, csoc);
-            else if (r == R_ACCEPT) { cur = tri; t.c = ts; status = begin_iteration(c, t); }
-            else if (r != R_BACKTRACK) status = r;
+            const int r = sc->r;
+            if (r == R_SOC1 || r == R_SOC2) w_soc_rhs<SPL>(c, sc, cur, t.alpha_soc, r == R_SOC1, priv);
+            else if (r == R_ACCEPT) {
+                cur = tri;
+                if (lane == 0) { t.c = ts; sc->status = begin_iteration(c, t); }
+                w_sync();
+                status = sc->status;
+            } else if (r != R_BACKTRACK) status = r;
         }
         if (have && status != 100 && status != R_RETRY) {
             // returned matrices (optimizer.py:392-400): every lane writes its stages
@@ -463,6 +531,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *filt, int *queu
                 if (io.status) io.status[b] = status;
                 if (io.iters) io.iters[b] = t.iter;
                 w_count_trips(trips_total, t.trips);
+                t.mode = M_DONE;
             }
             have = false;
         }

@@ -129,19 +129,19 @@ extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, con
 extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur, const double *goal, const double *X0,
                                const double *U0, double *X_out, double *U_out, double *obj, int32_t *status, int32_t *iters,
                                int32_t *trips) {
-    if (cf->N + 1 >= 64) return -1;
+    if (cf->N + 1 > 64) return -1;
     Cfg c = make_cfg(cf, B, 0, 0.0, 0.0);
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = NULL;
     io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters;
-    const int spl = cf->N + 1 < 32 ? 1 : 2;
+    const int spl = cf->N + 1 <= 32 ? 1 : 2;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int b = 0; b < B; ++b) {
-        double filt[2 * K_FILTER_CAP];
+        std::vector<double> smem((spl == 1 ? WLay<1>::bytes(1) : WLay<2>::bytes(1)) / sizeof(double), NAN);  // one emulated warp = one block
         unsigned long long tr = 0;
         int queue = b;          // this emulated warp is handed exactly instance b
         Cfg cb = c; cb.B = b + 1;
-        simt_run([&]() { if (spl == 1) w_worker<1>(cb, io, filt, &queue, &tr); else w_worker<2>(cb, io, filt, &queue, &tr); });
+        simt_run([&]() { if (spl == 1) w_worker<1>(cb, io, smem.data(), &queue, &tr); else w_worker<2>(cb, io, smem.data(), &queue, &tr); });
         if (trips) trips[b] = (int)tr;
     }
     return 0;
