@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libkmpc.so")
+SO_PATH = os.environ.get("KMPC_LIB") or os.path.join(_HERE, "libkmpc.so")  # KMPC_LIB: alternative build (kernel tuning only)
 
 KMPC_VERSION = 100
 LAYOUT_INSTANCE_MAJOR, LAYOUT_BATCH_MINOR = 0, 1

@@ -152,22 +152,23 @@ kmpc_trial_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_
 #define KMPC_MINB1 2
 #endif
 #ifndef KMPC_WPB2
-#define KMPC_WPB2 5
+#define KMPC_WPB2 9
 #endif
 #ifndef KMPC_MINB2
-#define KMPC_MINB2 2
+#define KMPC_MINB2 1
 #endif
-template <int SPL, int WPB, int MINB>
+// FULL: every bound of x, y, v, omega exists (the default problem), so the per-side tests are compiled away.
+template <int SPL, bool FULL, int WPB, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB)
 kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned long long *__restrict__ trips_total) {
     extern __shared__ double s_dyn[];  // WLay<SPL>::bytes(WPB)
-    w_worker<SPL>(c, io, s_dyn, queue, trips_total);
+    w_worker<SPL, FULL>(c, io, s_dyn, queue, trips_total);
 }
 
-template <int SPL, int WPB, int MINB>
+template <int SPL, bool FULL, int WPB, int MINB>
 static cudaError_t launch_warp_kernel(int sm_count, int B, const Cfg &c, const IO &io, int *queue, unsigned long long *trips, cudaStream_t st) {
     const size_t smem = WLay<SPL>::bytes(WPB);
-    auto kern = kmpc_warp_kernel<SPL, WPB, MINB>;
+    auto kern = kmpc_warp_kernel<SPL, FULL, WPB, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int bpsm = 0;
@@ -369,6 +370,7 @@ extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const doub
     c.L = make_rows(cf->N, O);
     c.nb = (cf->N + 1) * (c.hasL[0] + c.hasU[0] + c.hasL[1] + c.hasU[1]) + cf->N * (c.hasL[2] + c.hasU[2] + c.hasL[3] + c.hasU[3]) + cf->N * O;
     c.m = 3 * (cf->N + 1) + cf->N * O;
+    c.r_mnb = 1.0 / (double)(c.m + c.nb); c.r_nb = c.nb ? 1.0 / (double)c.nb : 0.0;
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs_centers;
     io.X_out = X_out; io.U_out = U_out; io.obj = obj_out; io.status = status_out; io.iters = iters_out;
@@ -382,8 +384,15 @@ extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const doub
     if (use_warp) {
         // warp-per-instance path: one persistent launch, instances pulled from a queue, no workspace traffic
         CU(cudaMemsetAsync(h->cnt, 0, sizeof(int), st));
-        if (cf->N + 1 <= 32) { CU((launch_warp_kernel<1, KMPC_WPB1, KMPC_MINB1>(h->sm_count, B, c, io, h->cnt, ls.trips, st))); }
-        else { CU((launch_warp_kernel<2, KMPC_WPB2, KMPC_MINB2>(h->sm_count, B, c, io, h->cnt, ls.trips, st))); }
+        bool full = true;
+        for (int i = 0; i < 4; ++i) full = full && c.hasL[i] && c.hasU[i];
+        if (cf->N + 1 <= 32) {
+            if (full) { CU((launch_warp_kernel<1, true, KMPC_WPB1, KMPC_MINB1>(h->sm_count, B, c, io, h->cnt, ls.trips, st))); }
+            else { CU((launch_warp_kernel<1, false, KMPC_WPB1, KMPC_MINB1>(h->sm_count, B, c, io, h->cnt, ls.trips, st))); }
+        } else {
+            if (full) { CU((launch_warp_kernel<2, true, KMPC_WPB2, KMPC_MINB2>(h->sm_count, B, c, io, h->cnt, ls.trips, st))); }
+            else { CU((launch_warp_kernel<2, false, KMPC_WPB2, KMPC_MINB2>(h->sm_count, B, c, io, h->cnt, ls.trips, st))); }
+        }
         CU(cudaGetLastError());
         h->launches++;
         h->last_host_trips = 0;
@@ -521,6 +530,17 @@ extern "C" int kmpc_agent_handoff(kmpc_handle *h, int B, const double *X, const 
     h->launches++;
     return 0;
 }
+
+#ifdef KMPC_PHASE_TIMING
+// tuning builds only: read and reset the phase timers of kmpc_warp.cuh
+extern "C" int kmpc_debug_phase_cycles(double *out) {
+    unsigned long long h[KMPC_NPHASE], z[KMPC_NPHASE] = {0};
+    if (cudaMemcpyFromSymbol(h, g_phase_cycles, sizeof h) != cudaSuccess) return -1;
+    cudaMemcpyToSymbol(g_phase_cycles, z, sizeof z);
+    for (int i = 0; i < KMPC_NPHASE; ++i) out[i] = (double)h[i];
+    return KMPC_NPHASE;
+}
+#endif
 
 extern "C" int kmpc_set_timing(kmpc_handle *h, int enable) {
     if (!h) return KMPC_E_BADARG;

@@ -122,6 +122,7 @@ struct Cfg {
     int N, O, cost_mode, gk_lo, gk_hi, max_iter, layout, B;
     int hasL[4], hasU[4];  // x, y, v, omega
     int nb, m;             // number of bound sides incl. obstacle slacks; number of constraint rows
+    double r_mnb, r_nb;    // 1 / (m + nb), 1 / nb (0 if nb == 0): the averaging factors of IPOPT's s_d, s_c
     double T, W[3], Wvn, Wvp, Ww;
     double lb[4], ub[4];   // relaxed bounds
     double tol, obs_radius, dL;
@@ -812,9 +813,11 @@ KMPC_HD double compl_inf(const Cfg &c, const Stats &s, double mu) {
     return c.nb ? fmax(fabs(s.mx - mu), fabs(s.mn - mu)) : 0.0;
 }
 KMPC_HD double opt_error(const Cfg &c, const Stats &s, double mu) {
-    const double sd = fmax(K_S_MAX, (s.sumy + s.sumz) / (double)(c.m + c.nb)) / K_S_MAX;
-    const double sc = c.nb ? fmax(K_S_MAX, s.sumz / (double)c.nb) / K_S_MAX : 1.0;
-    return fmax(s.dinf / sd, fmax(s.pinf, compl_inf(c, s, mu) / sc));
+    // s_d = max(s_max, (|y|_1 + |z|_1) / (m + n_b)) / s_max, s_c likewise; both are >= 1 and almost always exactly 1
+    const double sd = fmax(K_S_MAX, (s.sumy + s.sumz) * c.r_mnb) * (1.0 / K_S_MAX);
+    const double sc = c.nb ? fmax(K_S_MAX, s.sumz * c.r_nb) * (1.0 / K_S_MAX) : 1.0;
+    const double di = sd > 1.0 ? s.dinf / sd : s.dinf, ci = compl_inf(c, s, mu);
+    return fmax(di, fmax(s.pinf, sc > 1.0 ? ci / sc : ci));
 }
 KMPC_HD double phi_of(const Stats &s, double mu) { return s.f - mu * s.bar + K_KAPPA_D * mu * s.damp; }
 
@@ -866,7 +869,7 @@ KMPC_HD int begin_iteration(const Cfg &c, Ctx &t) {
     if (t.c.wmax > K_DIVERGING) return ST_DIVERGING;
     bool done = false;
     while (!done && opt_error(c, t.c, t.mu) <= K_KAPPA_EPS * t.mu) {
-        const double nm = fmax(fmin(K_MU_LIN * t.mu, pow(t.mu, K_MU_SUPER)), fmin(c.tol, K_COMPL_INF_TOL) / (K_KAPPA_EPS + 1.0));
+        const double nm = fmax(fmin(K_MU_LIN * t.mu, t.mu * sqrt(t.mu)), fmin(c.tol, K_COMPL_INF_TOL) / (K_KAPPA_EPS + 1.0));  // mu^1.5 (mu_superlinear_decrease_power)
         const bool changed = nm != t.mu;
         t.mu = nm; t.tau = fmax(K_TAU_MIN, 1.0 - t.mu);
         if (changed) t.fn = 0; else done = true;

@@ -31,17 +31,20 @@ struct WStep { double dx0[SPL], dx1[SPL], dx2[SPL], du0[SPL], du1[SPL], dy0[SPL]
 // ---- shared-memory layout ----------------------------------------------------------------------------------------
 // coop area of one instance: C_NF fields x NSTG stages (field-major: the owner lanes touch consecutive stages, the
 // Riccati lanes -- one per instance -- are COOP doubles apart, COOP odd => both patterns are bank-conflict free).
-// Fields 7..17 are the stage blocks going in; the backward sweep overwrites them (and fields 18..23) with K, k_ff, P, p;
+// Fields 7..17 are the stage blocks going in.  The backward sweep overwrites the blocks its matrix part has consumed
+// (Q00 Q11 Q22 dv dw htv) with K, the ones its vector part has consumed (q, qv, qw) with p and k_ff, and adds P;
 // the forward roll-out overwrites K with (dx, du).
 enum { C_A13 = 0, C_A23, C_B11, C_B21, C_E0, C_E1, C_E2,
        C_Q00 = 7, C_Q11, C_Q22, C_Q0, C_Q1, C_Q2, C_QV, C_QW, C_DV, C_DW, C_HTV,
-       C_NF = 24 };
-enum { C_K00 = 7, C_K01, C_K02, C_K10, C_K11, C_K12, C_KF0, C_KF1,
-       C_P00 = 15, C_P10, C_P11, C_P20, C_P21, C_P22, C_PV0, C_PV1, C_PV2 };
-enum { C_DX0 = 7, C_DX1, C_DX2, C_DU0, C_DU1 };
+       C_P00 = 18, C_P10, C_P11, C_P20, C_P21, C_P22, C_NF = 24 };
+enum { C_K00 = C_Q00, C_K01 = C_Q11, C_K02 = C_Q22, C_K10 = C_DV, C_K11 = C_DW, C_K12 = C_HTV,
+       C_PV0 = C_Q0, C_PV1 = C_Q1, C_PV2 = C_Q2, C_KF0 = C_QV, C_KF1 = C_QW };
+enum { C_DX0 = C_K00, C_DX1 = C_K01, C_DX2 = C_K02, C_DU0 = C_K10, C_DU1 = C_K11 };
 // private area of one instance (owner warp only): the kept Newton step (back-tracking / failed corrections return to
 // it), the second-order-correction rhs, the constraint values of the last trial point
-enum { V_DX0 = 0, V_DX1, V_DX2, V_DU0, V_DU1, V_DY0, V_DY1, V_DY2, V_CS0, V_CS1, V_CS2, V_CT0, V_CT1, V_CT2, V_NF };
+// + the reciprocal slacks 1/(x - l), 1/(u - x) of the current iterate's four bounded variables (x, y, v, omega)
+enum { V_DX0 = 0, V_DX1, V_DX2, V_DU0, V_DU1, V_DY0, V_DY1, V_DY2, V_CS0, V_CS1, V_CS2, V_CT0, V_CT1, V_CT2,
+       V_RL0, V_RL1, V_RL2, V_RL3, V_RU0, V_RU1, V_RU2, V_RU3, V_NF };
 
 struct WScal {  // warp-uniform per-instance scalars
     Ctx t;
@@ -72,6 +75,74 @@ KMPC_W void w_prev(const double (&a)[SPL], double (&p)[SPL]) {
     p[0] = h;
 #pragma unroll
     for (int j = 1; j < SPL; ++j) p[j] = a[j - 1];
+}
+
+
+// ---- bound helpers of the warp solver.  FULL = every bound of x, y, v, omega exists (compile-time), so the per-side
+// tests fold away; otherwise hL / hU say which sides exist.  The reciprocal slacks rsL = 1/(val - l), rsU = 1/(u - val)
+// are computed once per assembled iterate and reused by the step-size and trial-point passes. ----
+template <bool FULL>
+KMPC_W void wb_terms(double val, double lb, double ub, bool hL, bool hU, double zL, double zU, double mu, double &rsL,
+                     double &rsU, double &sigma, double &rb) {
+    double sg = 0.0, r = 0.0;
+    rsL = 0.0; rsU = 0.0;
+    if (FULL || hL) { rsL = KRCPF(val - lb); sg = zL * rsL; r = -(mu * rsL); if (!FULL && !hU) r += K_KAPPA_D * mu; }
+    if (FULL || hU) { rsU = KRCPF(ub - val); sg = fma(zU, rsU, sg); r = fma(mu, rsU, r); if (!FULL && !hL) r -= K_KAPPA_D * mu; }
+    sigma = sg; rb = r;
+}
+template <bool FULL>
+KMPC_W double wb_rb(bool hL, bool hU, double rsL, double rsU, double mu) {
+    double r = 0.0;
+    if (FULL || hL) { r = -(mu * rsL); if (!FULL && !hU) r += K_KAPPA_D * mu; }
+    if (FULL || hU) { r = fma(mu, rsU, r); if (!FULL && !hL) r -= K_KAPPA_D * mu; }
+    return r;
+}
+// fraction-to-the-boundary as "largest relative decrease": rpr = max(-d / slack), rdu = max(-dz / z); the step limits are
+// min(1, tau / rpr), min(1, tau / rdu) (one division per instance instead of one per bound side).
+template <bool FULL>
+KMPC_W void wb_ftb(double d, bool hL, bool hU, double zL, double zU, double rsL, double rsU, double mu, double &rpr, double &rdu) {
+    if (FULL || hL) {
+        rpr = fmax(rpr, -d * rsL);
+        const double dz = fma(rsL, fma(-zL, d, mu), -zL);  // mu/s - z - z d/s
+        rdu = fmax(rdu, -dz * KRCPF(zL));
+    }
+    if (FULL || hU) {
+        rpr = fmax(rpr, d * rsU);
+        const double dz = fma(rsU, fma(zU, d, mu), -zU);   // mu/s - z + z d/s
+        rdu = fmax(rdu, -dz * KRCPF(zU));
+    }
+}
+KMPC_W double w_ftb_alpha(double rmax, double tau) { return rmax > tau ? tau / rmax : 1.0; }
+// trial-point treatment of one bounded variable (cf. bound_trial): new multipliers with the kappa_sigma safeguard,
+// barrier product, damping, complementarity stats.  False if the trial value is not strictly inside its bounds.
+template <bool FULL>
+KMPC_W bool wb_trial(double d, double vt, double lb, double ub, bool hL, bool hU, double zL, double zU, double rsL, double rsU,
+                     double mu, double adu, bool clamp, double &zLn, double &zUn, double &prod, Stats &st) {
+    bool ok = true;
+    zLn = 0.0; zUn = 0.0;
+    if (FULL || hL) {
+        const double sn = vt - lb;
+        ok = sn > 0;
+        prod *= sn;
+        if (!FULL && !hU) st.damp += sn;
+        double z = fma(adu, fma(rsL, fma(-zL, d, mu), -zL), zL);
+        if (clamp) { const double mr = mu * KRCPF(sn); z = fmax(fmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
+        zLn = z;
+        const double p = sn * z;
+        st.mn = fmin(st.mn, p); st.mx = fmax(st.mx, p); st.sumz += fabs(z);
+    }
+    if (FULL || hU) {
+        const double sn = ub - vt;
+        ok = ok && sn > 0;
+        prod *= sn;
+        if (!FULL && !hL) st.damp += sn;
+        double z = fma(adu, fma(rsU, fma(zU, d, mu), -zU), zU);
+        if (clamp) { const double mr = mu * KRCPF(sn); z = fmax(fmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
+        zUn = z;
+        const double p = sn * z;
+        st.mn = fmin(st.mn, p); st.mx = fmax(st.mx, p); st.sumz += fabs(z);
+    }
+    return ok;
 }
 
 // ---- starting point: optimizer.py:375-385 (warm start) / agent.py:59-60 (cold start); IPOPT initialisation ----
@@ -127,15 +198,16 @@ KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<
 
 // ---- phase 1a, ASSEMBLE: stage blocks of the KKT system -> coop area (all stages at once) ----
 // Stages without a control (the terminal stage N) become pass-through steps of the recursion: zero dynamics, unit Q_uu,
-// zero rhs -> P_out = P_in + Q, p_out = p_in + q.
-template <int SPL>
-KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, const double *priv, double *coop) {
+// zero rhs -> P_out = P_in + Q, p_out = p_in + q.  Also leaves the reciprocal slacks of the iterate in the private area.
+template <int SPL, bool FULL>
+KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, double *priv, double *coop) {
     constexpr int NSTG = WLay<SPL>::NSTG;
     const int N = c.N, lane = w_lane();
     const int mode = sc->t.mode;
     const bool lsq = mode == M_LSQ, soc = mode == M_SOC;
     const double mu = sc->t.mu, delta = sc->t.delta, df = sc->t.df, T = c.T;
     const double gl0 = sc->gl[0], gl1 = sc->gl[1], gl2 = sc->gl[2];
+    const bool hL0 = c.hasL[0], hU0 = c.hasU[0], hL1 = c.hasL[1], hU1 = c.hasU[1], hL2 = c.hasL[2], hU2 = c.hasU[2], hL3 = c.hasL[3], hU3 = c.hasU[3];
     double yn0[SPL], yn1[SPL], yn2[SPL], xn0[SPL], xn1[SPL], xn2[SPL];
     w_next<SPL>(w.y0, yn0); w_next<SPL>(w.y1, yn1); w_next<SPL>(w.y2, yn2);
     w_next<SPL>(w.x0, xn0); w_next<SPL>(w.x1, xn1); w_next<SPL>(w.x2, xn2);
@@ -144,24 +216,30 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, co
         const int s = lane * SPL + j;
         if (s > N) continue;
         const double x0 = w.x0[j], x1 = w.x1[j], x2 = w.x2[j];
+        const double v = w.v[j], om = w.om[j], cs = w.cs[j], sn = w.sn[j];
         const bool ing = s >= c.gk_lo && s <= c.gk_hi;
         double gx0 = 0, gx1 = 0, gx2 = 0, h0 = 0, h1 = 0, h2 = 0;
         if (ing) {
             gx0 = df * 2.0 * c.W[0] * (x0 - gl0); gx1 = df * 2.0 * c.W[1] * (x1 - gl1); gx2 = df * 2.0 * c.W[2] * (x2 - gl2);
             h0 = df * 2.0 * c.W[0]; h1 = df * 2.0 * c.W[1]; h2 = df * 2.0 * c.W[2];
         }
+        // barrier terms of the four bounded variables (their reciprocal slacks are kept for the later passes)
+        double rl0, ru0, rl1, ru1, rl2, ru2, rl3, ru3, sg0, rb0, sg1, rb1, sgv, rbv, sgw, rbw;
+        wb_terms<FULL>(x0, c.lb[0], c.ub[0], hL0, hU0, w.zLx[j], w.zUx[j], mu, rl0, ru0, sg0, rb0);
+        wb_terms<FULL>(x1, c.lb[1], c.ub[1], hL1, hU1, w.zLy[j], w.zUy[j], mu, rl1, ru1, sg1, rb1);
+        wb_terms<FULL>(v, c.lb[2], c.ub[2], hL2, hU2, w.zLv[j], w.zUv[j], mu, rl2, ru2, sgv, rbv);
+        wb_terms<FULL>(om, c.lb[3], c.ub[3], hL3, hU3, w.zLw[j], w.zUw[j], mu, rl3, ru3, sgw, rbw);
+        double *pv = priv + s;
+        pv[V_RL0 * NSTG] = rl0; pv[V_RU0 * NSTG] = ru0; pv[V_RL1 * NSTG] = rl1; pv[V_RU1 * NSTG] = ru1;
+        pv[V_RL2 * NSTG] = rl2; pv[V_RU2 * NSTG] = ru2; pv[V_RL3 * NSTG] = rl3; pv[V_RU3 * NSTG] = ru3;
         double q0, q1, q2, Q00, Q11, Q22;
         if (lsq) {
             q0 = -(gx0 - w.zLx[j] + w.zUx[j]); q1 = -(gx1 - w.zLy[j] + w.zUy[j]); q2 = -gx2;
             Q00 = 1.0; Q11 = 1.0; Q22 = 1.0;
         } else {
-            double sg0, rb0, sg1, rb1;
-            bound_terms(x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], w.zLx[j], w.zUx[j], mu, &sg0, &rb0);
-            bound_terms(x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], w.zLy[j], w.zUy[j], mu, &sg1, &rb1);
             q0 = gx0 + w.y0[j] + rb0; q1 = gx1 + w.y1[j] + rb1; q2 = gx2 + w.y2[j];
             Q00 = h0 + sg0 + delta; Q11 = h1 + sg1 + delta; Q22 = h2 + delta;
         }
-        const double v = w.v[j], om = w.om[j], cs = w.cs[j], sn = w.sn[j];
         double a13 = -T * v * sn, a23 = T * v * cs, b11 = T * cs, b21 = T * sn;
         double gv, hvv;
         vcost(c, df, v, &gv, &hvv);
@@ -173,9 +251,6 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, co
             dv = 1.0; dw = 1.0;
             e0 = e1 = e2 = 0.0;
         } else {
-            double sgv, rbv, sgw, rbw;
-            bound_terms(v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], w.zLv[j], w.zUv[j], mu, &sgv, &rbv);
-            bound_terms(om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], w.zLw[j], w.zUw[j], mu, &sgw, &rbw);
             if (s < N) {
                 // J^T y of dynamics row s+1 and the curvature of the dynamics in the Lagrangian
                 q0 -= yn0[j]; q1 -= yn1[j]; q2 -= a13 * yn0[j] + a23 * yn1[j] + yn2[j];
@@ -210,60 +285,111 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, co
 
 // ---- phase 1b, RICCATI: the two serial recursions of ONE instance, executed by ONE lane of the block's Riccati warp ----
 // Backward sweep (K, k_ff, P, p of every stage; false = some Q_uu not positive definite = wrong inertia), then the
-// forward substitution dx+ = A dx + B du + e, du = K dx + k_ff.
+// forward substitution dx+ = A dx + B du + e, du = K dx + k_ff.  Same algebra as riccati_step (kmpc_core.cuh) for the
+// unicycle stage A = I + a13 e1 e3^T + a23 e2 e3^T, B = [b11 0; b21 0; 0 T].  The lane is alone on its dependency chain,
+// so the loop is software-pipelined: iteration s runs the MATRIX part of stage s (P, K: the long chain through the
+// Q_uu inverse) together with the independent VECTOR part of stage s+1 (p, k_ff: a short chain), and no sign flips are
+// left on either chain.
+struct WRicCarry { double P00, P10, P11, P20, P21, P22, K00, K01, K02, K10, K11, K12, m00, m01, m11, a13, a23, b11, b21; };
+// vector part of stage k (q = coop + k): uses the cost-to-go P of stage k+1 (in cy) and p of stage k+1 (p0..p2, updated)
+KMPC_W void w_ric_vec(const WRicCarry &cy, double *q, const int NSTG, const double T, double &p0, double &p1, double &p2) {
+    const double e0 = q[C_E0 * NSTG], e1 = q[C_E1 * NSTG], e2 = q[C_E2 * NSTG];
+    const double q0 = q[C_Q0 * NSTG], q1 = q[C_Q1 * NSTG], q2 = q[C_Q2 * NSTG], qv = q[C_QV * NSTG], qw = q[C_QW * NSTG];
+    const double Pe0 = fma(cy.P00, e0, fma(cy.P10, e1, cy.P20 * e2)) + p0, Pe1 = fma(cy.P10, e0, fma(cy.P11, e1, cy.P21 * e2)) + p1,
+                 Pe2 = fma(cy.P20, e0, fma(cy.P21, e1, cy.P22 * e2)) + p2;
+    const double qu0 = fma(cy.b11, Pe0, fma(cy.b21, Pe1, qv)), qu1 = fma(T, Pe2, qw);
+    p0 = fma(cy.K00, qu0, fma(cy.K10, qu1, q0 + Pe0));
+    p1 = fma(cy.K01, qu0, fma(cy.K11, qu1, q1 + Pe1));
+    p2 = fma(cy.K02, qu0, fma(cy.K12, qu1, fma(cy.a13, Pe0, fma(cy.a23, Pe1, q2 + Pe2))));
+    q[C_KF0 * NSTG] = fma(cy.m00, qu0, cy.m01 * qu1); q[C_KF1 * NSTG] = fma(cy.m01, qu0, cy.m11 * qu1);
+    q[C_PV0 * NSTG] = p0; q[C_PV1 * NSTG] = p1; q[C_PV2 * NSTG] = p2;
+}
+// matrix part of stage k: (P of stage k+1 in P..) -> K, M = -Quu^-1, P of stage k; leaves what the vector part needs in cy
+KMPC_W bool w_ric_mat(WRicCarry &cy, double *q, const int NSTG, const double T, const double TT, double &P00, double &P10,
+                      double &P11, double &P20, double &P21, double &P22) {
+    const double a13 = q[C_A13 * NSTG], a23 = q[C_A23 * NSTG], b11 = q[C_B11 * NSTG], b21 = q[C_B21 * NSTG];
+    const double Q00 = q[C_Q00 * NSTG], Q11 = q[C_Q11 * NSTG], Q22 = q[C_Q22 * NSTG];
+    const double dv = q[C_DV * NSTG], dw = q[C_DW * NSTG], htv = q[C_HTV * NSTG];
+    cy.P00 = P00; cy.P10 = P10; cy.P11 = P11; cy.P20 = P20; cy.P21 = P21; cy.P22 = P22;
+    cy.a13 = a13; cy.a23 = a23; cy.b11 = b11; cy.b21 = b21;
+    // P A (third column), symmetric Qxx = A^T P A + Q
+    const double PA02 = fma(P00, a13, fma(P10, a23, P20)), PA12 = fma(P10, a13, fma(P11, a23, P21)), PA22 = fma(P20, a13, fma(P21, a23, P22));
+    const double X00 = P00 + Q00, X10 = P10, X11 = P11 + Q11, X20 = PA02, X21 = PA12;
+    const double X22 = fma(a13, PA02, fma(a23, PA12, PA22)) + Q22;
+    // Qux = B^T P A (+ W_v,theta)
+    const double U00 = fma(b11, P00, b21 * P10), U01 = fma(b11, P10, b21 * P11), U02 = fma(b11, PA02, fma(b21, PA12, htv));
+    const double U10 = T * P20, U11 = T * P21, U12 = T * PA22;
+    // Quu = B^T P B + diag = [d1 qb; qb qc];  positive definite <=> d1 > 0 and det > 0
+    const double d1 = fma(b11, U00, fma(b21, U01, dv)), qb = fma(b11, U10, b21 * U11), qc = fma(TT, P22, dw);
+    const double ndet = fma(qb, qb, -(d1 * qc));  // -det
+    // M = -Quu^-1 = [m00 m01; m01 m11]
+    const double rn = KRCPF(ndet), m00 = qc * rn, m01 = qb * -rn, m11 = d1 * rn;
+    // K = -Quu^-1 Qux
+    const double K00 = fma(m00, U00, m01 * U10), K01 = fma(m00, U01, m01 * U11), K02 = fma(m00, U02, m01 * U12);
+    const double K10 = fma(m01, U00, m11 * U10), K11 = fma(m01, U01, m11 * U11), K12 = fma(m01, U02, m11 * U12);
+    // P <- Qxx + Qux^T K  (lower triangle; symmetric in exact arithmetic)
+    P00 = fma(U00, K00, fma(U10, K10, X00)); P10 = fma(U01, K00, fma(U11, K10, X10)); P11 = fma(U01, K01, fma(U11, K11, X11));
+    P20 = fma(U02, K00, fma(U12, K10, X20)); P21 = fma(U02, K01, fma(U12, K11, X21)); P22 = fma(U02, K02, fma(U12, K12, X22));
+    cy.K00 = K00; cy.K01 = K01; cy.K02 = K02; cy.K10 = K10; cy.K11 = K11; cy.K12 = K12; cy.m00 = m00; cy.m01 = m01; cy.m11 = m11;
+    q[C_K00 * NSTG] = K00; q[C_K01 * NSTG] = K01; q[C_K02 * NSTG] = K02;
+    q[C_K10 * NSTG] = K10; q[C_K11 * NSTG] = K11; q[C_K12 * NSTG] = K12;
+    q[C_P00 * NSTG] = P00; q[C_P10 * NSTG] = P10; q[C_P11 * NSTG] = P11;
+    q[C_P20 * NSTG] = P20; q[C_P21 * NSTG] = P21; q[C_P22 * NSTG] = P22;
+    return d1 > 0.0 && ndet < 0.0;
+}
+struct WFwdIn { double K00, K01, K02, K10, K11, K12, kf0, kf1, a13, a23, b11, b21, e0, e1, e2; };
+KMPC_W void w_fwd_load(WFwdIn &r, const double *q, const int NSTG) {
+    r.K00 = q[C_K00 * NSTG]; r.K01 = q[C_K01 * NSTG]; r.K02 = q[C_K02 * NSTG];
+    r.K10 = q[C_K10 * NSTG]; r.K11 = q[C_K11 * NSTG]; r.K12 = q[C_K12 * NSTG];
+    r.kf0 = q[C_KF0 * NSTG]; r.kf1 = q[C_KF1 * NSTG];
+    r.a13 = q[C_A13 * NSTG]; r.a23 = q[C_A23 * NSTG]; r.b11 = q[C_B11 * NSTG]; r.b21 = q[C_B21 * NSTG];
+    r.e0 = q[C_E0 * NSTG]; r.e1 = q[C_E1 * NSTG]; r.e2 = q[C_E2 * NSTG];
+}
 KMPC_WN inline bool w_serial(const Cfg &c, double *coop, const int NSTG, const double *d0) {
     const int N = c.N;
-    const double T = c.T;
+    const double T = c.T, TT = T * T;
     double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0, p0 = 0, p1 = 0, p2 = 0;
+    WRicCarry cy;
+    bool pd = w_ric_mat(cy, coop + N, NSTG, T, TT, P00, P10, P11, P20, P21, P22);
 #pragma unroll 1
-    for (int s = N; s >= 0; --s) {
+    for (int s = N - 1; s >= 0; --s) {
         double *q = coop + s;
-        const double a13 = q[C_A13 * NSTG], a23 = q[C_A23 * NSTG], b11 = q[C_B11 * NSTG], b21 = q[C_B21 * NSTG];
-        const double e0 = q[C_E0 * NSTG], e1 = q[C_E1 * NSTG], e2 = q[C_E2 * NSTG];
-        const double Q00 = q[C_Q00 * NSTG], Q11 = q[C_Q11 * NSTG], Q22 = q[C_Q22 * NSTG];
-        const double q0 = q[C_Q0 * NSTG], q1 = q[C_Q1 * NSTG], q2 = q[C_Q2 * NSTG];
-        const double qv = q[C_QV * NSTG], qw = q[C_QW * NSTG], dv = q[C_DV * NSTG], dw = q[C_DW * NSTG], htv = q[C_HTV * NSTG];
-        RicK rk;
-        if (!riccati_step(P00, P10, P11, P20, P21, P22, p0, p1, p2, a13, a23, b11, b21, T, Q00, 0.0, Q11, Q22, q0, q1, q2, qv, qw,
-                          dv, dw, htv, e0, e1, e2, rk))
-            return false;
-        q[C_K00 * NSTG] = rk.K00; q[C_K01 * NSTG] = rk.K01; q[C_K02 * NSTG] = rk.K02;
-        q[C_K10 * NSTG] = rk.K10; q[C_K11 * NSTG] = rk.K11; q[C_K12 * NSTG] = rk.K12;
-        q[C_KF0 * NSTG] = rk.kf0; q[C_KF1 * NSTG] = rk.kf1;
-        q[C_P00 * NSTG] = P00; q[C_P10 * NSTG] = P10; q[C_P11 * NSTG] = P11;
-        q[C_P20 * NSTG] = P20; q[C_P21 * NSTG] = P21; q[C_P22 * NSTG] = P22;
-        q[C_PV0 * NSTG] = p0; q[C_PV1 * NSTG] = p1; q[C_PV2 * NSTG] = p2;
+        const WRicCarry cp = cy;
+        pd = w_ric_mat(cy, q, NSTG, T, TT, P00, P10, P11, P20, P21, P22) && pd;
+        w_ric_vec(cp, q + 1, NSTG, T, p0, p1, p2);
     }
+    w_ric_vec(cy, coop, NSTG, T, p0, p1, p2);
+    if (!pd) return false;
     double x0 = d0[0], x1 = d0[1], x2 = d0[2];
+    WFwdIn fn;
+    w_fwd_load(fn, coop, NSTG);
 #pragma unroll 1
     for (int s = 0; s <= N; ++s) {
         double *q = coop + s;
-        const double K00 = q[C_K00 * NSTG], K01 = q[C_K01 * NSTG], K02 = q[C_K02 * NSTG];
-        const double K10 = q[C_K10 * NSTG], K11 = q[C_K11 * NSTG], K12 = q[C_K12 * NSTG];
-        const double kf0 = q[C_KF0 * NSTG], kf1 = q[C_KF1 * NSTG];
-        const double a13 = q[C_A13 * NSTG], a23 = q[C_A23 * NSTG], b11 = q[C_B11 * NSTG], b21 = q[C_B21 * NSTG];
-        const double e0 = q[C_E0 * NSTG], e1 = q[C_E1 * NSTG], e2 = q[C_E2 * NSTG];
-        const double du0 = fma(K00, x0, fma(K01, x1, fma(K02, x2, kf0)));
-        const double du1 = fma(K10, x0, fma(K11, x1, fma(K12, x2, kf1)));
+        const WFwdIn f = fn;
+        if (s < N) w_fwd_load(fn, q + 1, NSTG);
+        const double du0 = fma(f.K00, x0, fma(f.K01, x1, fma(f.K02, x2, f.kf0)));
+        const double du1 = fma(f.K10, x0, fma(f.K11, x1, fma(f.K12, x2, f.kf1)));
         q[C_DX0 * NSTG] = x0; q[C_DX1 * NSTG] = x1; q[C_DX2 * NSTG] = x2; q[C_DU0 * NSTG] = du0; q[C_DU1 * NSTG] = du1;
-        const double n0 = x0 + a13 * x2 + b11 * du0 + e0;
-        const double n1 = x1 + a23 * x2 + b21 * du0 + e1;
-        const double n2 = x2 + T * du1 + e2;
+        const double n0 = x0 + f.a13 * x2 + f.b11 * du0 + f.e0;
+        const double n1 = x1 + f.a23 * x2 + f.b21 * du0 + f.e1;
+        const double n2 = x2 + T * du1 + f.e2;
         x0 = n0; x1 = n1; x2 = n2;
     }
     return true;
 }
 
 // ---- phase 2, STEP: multiplier step dy = -(P dx + p), step-size limits, directional derivative (all stages at once) ----
-template <int SPL>
-KMPC_WN inline void w_step(const Cfg &c, const WScal *sc, const WState<SPL> &w, const double *coop, WStep<SPL> &d,
-                           double *alpha_pr, double *alpha_du, double *gBD, double *ymax) {
+template <int SPL, bool FULL>
+KMPC_WN inline void w_step(const Cfg &c, const WScal *sc, const WState<SPL> &w, const double *coop, const double *priv,
+                           WStep<SPL> &d, double *alpha_pr, double *alpha_du, double *gBD, double *ymax) {
     constexpr int NSTG = WLay<SPL>::NSTG;
     const int N = c.N, lane = w_lane();
     const bool lsq = sc->t.mode == M_LSQ;
     const double mu = sc->t.mu, df = sc->t.df, tau = sc->t.tau;
     const double gl0 = sc->gl[0], gl1 = sc->gl[1], gl2 = sc->gl[2];
-    double apr = 1.0, adu = 1.0, gbd = 0.0, ym = 0.0;
+    const bool hL0 = c.hasL[0], hU0 = c.hasU[0], hL1 = c.hasL[1], hU1 = c.hasU[1], hL2 = c.hasL[2], hU2 = c.hasU[2], hL3 = c.hasL[3], hU3 = c.hasU[3];
+    double rpr = 0.0, rdu = 0.0, gbd = 0.0, ym = 0.0;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
         const int s = lane * SPL + j;
@@ -280,29 +406,28 @@ KMPC_WN inline void w_step(const Cfg &c, const WScal *sc, const WState<SPL> &w, 
         d.dy0[j] = dy0; d.dy1[j] = dy1; d.dy2[j] = dy2;
         ym = maxabs_nan(maxabs_nan(maxabs_nan(ym, dy0), dy1), dy2);
         if (lsq) continue;
+        const double *pv = priv + s;
         const double x0 = w.x0[j], x1 = w.x1[j], x2 = w.x2[j];
-        double sg, rb;
-        bound_ftb(x0, d0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], w.zLx[j], w.zUx[j], mu, tau, &apr, &adu);
-        bound_ftb(x1, d1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], w.zLy[j], w.zUy[j], mu, tau, &apr, &adu);
+        const double rl0 = pv[V_RL0 * NSTG], ru0 = pv[V_RU0 * NSTG], rl1 = pv[V_RL1 * NSTG], ru1 = pv[V_RU1 * NSTG];
+        wb_ftb<FULL>(d0, hL0, hU0, w.zLx[j], w.zUx[j], rl0, ru0, mu, rpr, rdu);
+        wb_ftb<FULL>(d1, hL1, hU1, w.zLy[j], w.zUy[j], rl1, ru1, mu, rpr, rdu);
         const bool ing = s >= c.gk_lo && s <= c.gk_hi;
-        bound_terms(x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], w.zLx[j], w.zUx[j], mu, &sg, &rb);
-        gbd += ((ing ? df * 2.0 * c.W[0] * (x0 - gl0) : 0.0) + rb) * d0;
-        bound_terms(x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], w.zLy[j], w.zUy[j], mu, &sg, &rb);
-        gbd += ((ing ? df * 2.0 * c.W[1] * (x1 - gl1) : 0.0) + rb) * d1;
+        gbd += ((ing ? df * 2.0 * c.W[0] * (x0 - gl0) : 0.0) + wb_rb<FULL>(hL0, hU0, rl0, ru0, mu)) * d0;
+        gbd += ((ing ? df * 2.0 * c.W[1] * (x1 - gl1) : 0.0) + wb_rb<FULL>(hL1, hU1, rl1, ru1, mu)) * d1;
         gbd += (ing ? df * 2.0 * c.W[2] * (x2 - gl2) : 0.0) * d2;
         if (s < N) {
             const double v = w.v[j], om = w.om[j];
-            bound_ftb(v, du0, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], w.zLv[j], w.zUv[j], mu, tau, &apr, &adu);
-            bound_ftb(om, du1, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], w.zLw[j], w.zUw[j], mu, tau, &apr, &adu);
+            const double rl2 = pv[V_RL2 * NSTG], ru2 = pv[V_RU2 * NSTG], rl3 = pv[V_RL3 * NSTG], ru3 = pv[V_RU3 * NSTG];
+            wb_ftb<FULL>(du0, hL2, hU2, w.zLv[j], w.zUv[j], rl2, ru2, mu, rpr, rdu);
+            wb_ftb<FULL>(du1, hL3, hU3, w.zLw[j], w.zUw[j], rl3, ru3, mu, rpr, rdu);
             double gv, hv;
             vcost(c, df, v, &gv, &hv);
-            bound_terms(v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], w.zLv[j], w.zUv[j], mu, &sg, &rb);
-            gbd += (gv + rb) * du0;
-            bound_terms(om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], w.zLw[j], w.zUw[j], mu, &sg, &rb);
-            gbd += (df * 2.0 * c.Ww * om + rb) * du1;
+            gbd += (gv + wb_rb<FULL>(hL2, hU2, rl2, ru2, mu)) * du0;
+            gbd += (df * 2.0 * c.Ww * om + wb_rb<FULL>(hL3, hU3, rl3, ru3, mu)) * du1;
         }
     }
-    *alpha_pr = w_min(apr); *alpha_du = w_min(adu); *gBD = w_sum(gbd); *ymax = w_maxabs_nan(ym);
+    *alpha_pr = w_ftb_alpha(w_max(rpr), tau); *alpha_du = w_ftb_alpha(w_max(rdu), tau);
+    *gBD = w_sum(gbd); *ymax = w_maxabs_nan(ym);
 }
 
 // kept Newton step <-> private area
@@ -328,13 +453,14 @@ KMPC_W void w_step_load(WStep<SPL> &d, const double *priv) {
 }
 
 // ---- phase 3, TRIAL: trial point + speculative multiplier update + residual norms (all stages at once) ----
-template <int SPL>
+template <int SPL, bool FULL>
 KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w, const WStep<SPL> &d, double alpha, double ay,
                             double adu, bool clamp, WState<SPL> &n, double *priv, Stats *out) {
     constexpr int NSTG = WLay<SPL>::NSTG;
     const int N = c.N, lane = w_lane();
     const double mu = sc->t.mu, df = sc->t.df, T = c.T;
     const double xc0 = sc->xc[0], xc1 = sc->xc[1], xc2 = sc->xc[2], gl0 = sc->gl[0], gl1 = sc->gl[1], gl2 = sc->gl[2];
+    const bool hL0 = c.hasL[0], hU0 = c.hasU[0], hL1 = c.hasL[1], hU1 = c.hasU[1], hL2 = c.hasL[2], hU2 = c.hasU[2], hL3 = c.hasL[3], hU3 = c.hasU[3];
     Stats st;
     st.f = 0; st.bar = 0; st.damp = 0; st.theta = 0; st.dinf = 0; st.pinf = 0; st.mn = INFINITY; st.mx = 0; st.sumy = 0;
     st.sumz = 0; st.wmax = 0;
@@ -374,11 +500,11 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
             r0 += df * 2.0 * c.W[0] * e0; r1 += df * 2.0 * c.W[1] * e1; r2 += df * 2.0 * c.W[2] * e2;
         }
         double prod = 1.0, zLn, zUn;
-        valid &= bound_trial(w.x0[j], d.dx0[j], x0, c.lb[0], c.ub[0], c.hasL[0], c.hasU[0], w.zLx[j], w.zUx[j], mu, adu, clamp,
-                             &zLn, &zUn, &prod, &st.damp, &st);
+        valid &= wb_trial<FULL>(d.dx0[j], x0, c.lb[0], c.ub[0], hL0, hU0, w.zLx[j], w.zUx[j], pv[V_RL0 * NSTG], pv[V_RU0 * NSTG], mu, adu,
+                                clamp, zLn, zUn, prod, st);
         n.zLx[j] = zLn; n.zUx[j] = zUn; r0 += zUn - zLn;
-        valid &= bound_trial(w.x1[j], d.dx1[j], x1, c.lb[1], c.ub[1], c.hasL[1], c.hasU[1], w.zLy[j], w.zUy[j], mu, adu, clamp,
-                             &zLn, &zUn, &prod, &st.damp, &st);
+        valid &= wb_trial<FULL>(d.dx1[j], x1, c.lb[1], c.ub[1], hL1, hU1, w.zLy[j], w.zUy[j], pv[V_RL1 * NSTG], pv[V_RU1 * NSTG], mu, adu,
+                                clamp, zLn, zUn, prod, st);
         n.zLy[j] = zLn; n.zUy[j] = zUn; r1 += zUn - zLn;
         if (s < N) {
             const double v = n.v[j], om = n.om[j], cs = n.cs[j], sn = n.sn[j];
@@ -391,11 +517,11 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
             if (c.cost_mode == 0) { const double vm = fmin(v, 0.0), vp = fmax(v, 0.0); st.f += c.Wvn * vm * vm + c.Wvp * vp * vp; }
             else st.f += c.Wvn * fmin(v, 0.0);
             st.f += c.Ww * om * om;
-            valid &= bound_trial(w.v[j], d.du0[j], v, c.lb[2], c.ub[2], c.hasL[2], c.hasU[2], w.zLv[j], w.zUv[j], mu, adu, clamp,
-                                 &zLn, &zUn, &prod, &st.damp, &st);
+            valid &= wb_trial<FULL>(d.du0[j], v, c.lb[2], c.ub[2], hL2, hU2, w.zLv[j], w.zUv[j], pv[V_RL2 * NSTG], pv[V_RU2 * NSTG], mu, adu,
+                                    clamp, zLn, zUn, prod, st);
             n.zLv[j] = zLn; n.zUv[j] = zUn; rv += zUn - zLn;
-            valid &= bound_trial(w.om[j], d.du1[j], om, c.lb[3], c.ub[3], c.hasL[3], c.hasU[3], w.zLw[j], w.zUw[j], mu, adu, clamp,
-                                 &zLn, &zUn, &prod, &st.damp, &st);
+            valid &= wb_trial<FULL>(d.du1[j], om, c.lb[3], c.ub[3], hL3, hU3, w.zLw[j], w.zUw[j], pv[V_RL3 * NSTG], pv[V_RU3 * NSTG], mu, adu,
+                                    clamp, zLn, zUn, prod, st);
             n.zLw[j] = zLn; n.zUw[j] = zUn; rw += zUn - zLn;
             st.dinf = maxabs_nan(maxabs_nan(st.dinf, rv), rw);
         } else {
@@ -439,10 +565,25 @@ KMPC_WN inline void w_soc_rhs(const Cfg &c, const WScal *sc, const WState<SPL> &
     w_sync();
 }
 
+// Optional phase timers (tuning builds only, -DKMPC_PHASE_TIMING): cycles per phase summed over all owner warps.
+#if defined(KMPC_PHASE_TIMING) && defined(__CUDACC__)
+#define KMPC_NPHASE 16
+__device__ unsigned long long g_phase_cycles[KMPC_NPHASE];
+#define PT_DECL long long pt_acc[KMPC_NPHASE] = {0}; long long pt_last = clock64();
+#define PT(i) { const long long pt_now = clock64(); pt_acc[i] += pt_now - pt_last; pt_last = pt_now; }
+#define PT_COUNT(i) pt_acc[i] += 1;
+#define PT_FLUSH if (lane == 0) { for (int i = 0; i < KMPC_NPHASE; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)pt_acc[i]); }
+#else
+#define PT_DECL
+#define PT(i)
+#define PT_COUNT(i)
+#define PT_FLUSH
+#endif
+
 // ---- persistent worker: one warp pulls instances from a queue and solves each start to finish; the warps of a block
 // walk through the phases of a trip in step (block barriers) so that warp 0 can run every instance's serial recursions.
 // smem: WLay<SPL>::bytes(warps per block) bytes of block-shared scratch.
-template <int SPL>
+template <int SPL, bool FULL>
 KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queue, unsigned long long *trips_total) {
     typedef WLay<SPL> LY;
     const int N = c.N, lane = w_lane(), wid = w_warp(), W = w_warps();
@@ -457,36 +598,53 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     int b = -1;
     if (lane == 0) { t.mode = M_DONE; sc->flag = 0; sc->ok = 0; }
     w_sync();
+    PT_DECL
+    bool drained = false;  // the queue has no more instances for this warp
 #pragma unroll 1
     for (;;) {
-        if (!have) {
+        // warp 0 is busy in the serial window below, so it takes its next instance here; the other warps take theirs
+        // in that window (the global-memory round trip then costs the block nothing)
+        if (!have && !drained && wid == 0) {
             b = w_fetch(queue);
-            if (b < c.B) { w_init<SPL>(c, sc, io, b, cur); have = true; }
+            if (b < c.B) { w_init<SPL>(c, sc, io, b, cur); have = true; } else drained = true;
         }
+        PT(0)
         if (!w_block_any(have)) break;
+        PT(1)
         int status = 100;
         // ---- phase 1a: assemble the stage blocks ----
         const int mode = t.mode;
         const bool do_sweep = have && mode != M_TRIAL;
-        if (do_sweep) w_assemble<SPL>(c, sc, cur, priv, coop);
+        if (do_sweep) w_assemble<SPL, FULL>(c, sc, cur, priv, coop);
         if (lane == 0) { sc->flag = do_sweep ? 1 : 0; if (do_sweep) t.trips++; }
+        PT(2)
         w_block_sync();
+        PT(3)
         // ---- phase 1b: the serial recursions of all the block's instances, one lane each ----
-        if (wid == 0 && lane < W) {
-            WScal *so = scal0 + lane;
-            if (so->flag) so->ok = w_serial(c, smem + (size_t)lane * LY::COOP, LY::NSTG, so->d0) ? 1 : 0;
+        bool fresh = false;  // an instance taken in this window joins the next trip
+        if (wid == 0) {
+            if (lane < W) {
+                WScal *so = scal0 + lane;
+                if (so->flag) so->ok = w_serial(c, smem + (size_t)lane * LY::COOP, LY::NSTG, so->d0) ? 1 : 0;
+            }
+        } else if (!have && !drained) {
+            b = w_fetch(queue);
+            if (b < c.B) { w_init<SPL>(c, sc, io, b, cur); fresh = true; } else drained = true;
         }
+        PT(4)
         w_block_sync();
+        PT(5)
         // ---- phase 2: search direction, step sizes, line-search set-up (or inertia correction) ----
         bool go_trial = have && !do_sweep;
         if (do_sweep) {
             if (!sc->ok) {
+                PT_COUNT(10)
                 if (lane == 0) sc->status = mode != M_NEWTON ? (int)ST_STEP_ERROR : inertia_update(t);  // R_RETRY: sweep again next trip
                 w_sync();
                 status = sc->status;
             } else {
                 double apr, adu, gbd, ym;
-                w_step<SPL>(c, sc, cur, coop, act, &apr, &adu, &gbd, &ym);
+                w_step<SPL, FULL>(c, sc, cur, coop, priv, act, &apr, &adu, &gbd, &ym);
                 if (lane == 0) rollout_logic(t, apr, adu, gbd, ym);
                 w_sync();
                 if (t.sel == 0) w_step_store<SPL>(act, priv);
@@ -497,11 +655,13 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             w_sync();
             w_step_load<SPL>(act, priv);
         }
+        PT(6)
         // ---- phase 3: trial point + acceptance logic ----
         if (go_trial) {
             Stats ts;
             WState<SPL> tri;
-            const bool evok = w_trial<SPL>(c, sc, cur, act, t.a_pr, t.a_y, t.a_du, t.tu == TU_STEP, tri, priv, &ts);
+            const bool evok = w_trial<SPL, FULL>(c, sc, cur, act, t.a_pr, t.a_y, t.a_du, t.tu == TU_STEP, tri, priv, &ts);
+            PT(7)
             if (lane == 0) {
                 bool aug; double ath, aph;
                 const int r = trial_decide(t, sc->filt, 1, ts, evok, &aug, &ath, &aph);
@@ -510,14 +670,18 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             }
             w_sync();
             const int r = sc->r;
-            if (r == R_SOC1 || r == R_SOC2) w_soc_rhs<SPL>(c, sc, cur, t.alpha_soc, r == R_SOC1, priv);
+            if (r == R_SOC1 || r == R_SOC2) { PT_COUNT(11) w_soc_rhs<SPL>(c, sc, cur, t.alpha_soc, r == R_SOC1, priv); }
             else if (r == R_ACCEPT) {
+                PT_COUNT(12)
+                if (mode == M_SOC) { PT_COUNT(14) }
                 cur = tri;
                 if (lane == 0) { t.c = ts; sc->status = begin_iteration(c, t); }
                 w_sync();
                 status = sc->status;
             } else if (r != R_BACKTRACK) status = r;
+            else { PT_COUNT(13) }
         }
+        PT(8)
         if (have && status != 100 && status != R_RETRY) {
             // returned matrices (optimizer.py:392-400): every lane writes its stages
 #pragma unroll
@@ -535,7 +699,10 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             }
             have = false;
         }
+        if (fresh) have = true;
+        PT(9)
     }
+    PT_FLUSH
 }
 
 }  // namespace kmpc

@@ -1,0 +1,87 @@
+// Micro-benchmark: cycles of the serial Riccati phase (w_serial of kmpc_warp.cuh) for one warp with LANES active lanes,
+// alone on an SM or next to NBG background warps running dependent FP64 chains.
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../kiss_mpc_b200/csrc/kmpc_warp.cuh"
+using namespace kmpc;
+__global__ void bench(Cfg c, int lanes, int reps, long long *cyc, double *sink, int mode) {
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int COOP = WLay<1>::COOP, NSTG = 32;
+    for (int i = threadIdx.x; i < 8 * COOP; i += blockDim.x) sm[i] = 0.0;
+    __syncthreads();
+    // plausible stage blocks: Q = 2, R = 1, small dynamics terms
+    if (wid == 0 && lane < 8)
+        for (int s = 0; s <= c.N; ++s) {
+            double *q = sm + lane * COOP + s;
+            q[C_A13 * NSTG] = -0.01; q[C_A23 * NSTG] = 0.02; q[C_B11 * NSTG] = 0.08; q[C_B21 * NSTG] = 0.06;
+            q[C_Q00 * NSTG] = 2; q[C_Q11 * NSTG] = 2; q[C_Q22 * NSTG] = 1; q[C_DV * NSTG] = 1; q[C_DW * NSTG] = 1; q[C_HTV * NSTG] = 0.01;
+            q[C_Q0 * NSTG] = 0.3; q[C_Q1 * NSTG] = -0.2; q[C_Q2 * NSTG] = 0.1; q[C_QV * NSTG] = 0.05; q[C_QW * NSTG] = 0.02;
+            q[C_E0 * NSTG] = 0.001; q[C_E1 * NSTG] = 0.002; q[C_E2 * NSTG] = 0.0;
+        }
+    __syncthreads();
+    double d0[3] = {0.1, 0.2, 0.3};
+    if (wid == 0) {
+        long long t0 = clock64();
+        bool ok = true;
+        for (int r = 0; r < reps; ++r) {
+            if (lane < lanes) {
+                // re-arm the inputs the sweep overwrote (cheap relative to the sweep; same for every variant)
+                for (int s = 0; s <= c.N; ++s) {
+                    double *q = sm + lane * COOP + s;
+                    q[C_Q00 * NSTG] = 2; q[C_Q11 * NSTG] = 2; q[C_Q22 * NSTG] = 1; q[C_DV * NSTG] = 1; q[C_DW * NSTG] = 1; q[C_HTV * NSTG] = 0.01;
+                    q[C_Q0 * NSTG] = 0.3; q[C_Q1 * NSTG] = -0.2; q[C_Q2 * NSTG] = 0.1; q[C_QV * NSTG] = 0.05; q[C_QW * NSTG] = 0.02;
+                }
+            }
+            __syncwarp();
+            long long a = clock64();
+            if (lane < lanes) {
+                if (mode == 0) ok = w_serial(c, sm + lane * COOP, NSTG, d0) && ok;
+                else if (mode == 1) {  // backward sweep only
+                    double *coop = sm + lane * COOP; const double T = c.T, TT = T * T;
+                    double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0, p0 = 0, p1 = 0, p2 = 0;
+                    WRicCarry cy;
+                    bool pd = w_ric_mat(cy, coop + c.N, NSTG, T, TT, P00, P10, P11, P20, P21, P22);
+#pragma unroll 1
+                    for (int s = c.N - 1; s >= 0; --s) {
+                        double *q = coop + s; const WRicCarry cp = cy;
+                        pd = w_ric_mat(cy, q, NSTG, T, TT, P00, P10, P11, P20, P21, P22) && pd;
+                        w_ric_vec(cp, q + 1, NSTG, T, p0, p1, p2);
+                    }
+                    w_ric_vec(cy, coop, NSTG, T, p0, p1, p2);
+                    ok = ok && pd;
+                } else {  // matrix part only
+                    double *coop = sm + lane * COOP; const double T = c.T, TT = T * T;
+                    double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0;
+                    WRicCarry cy; bool pd = true;
+#pragma unroll 1
+                    for (int s = c.N; s >= 0; --s) pd = w_ric_mat(cy, coop + s, NSTG, T, TT, P00, P10, P11, P20, P21, P22) && pd;
+                    ok = ok && pd;
+                }
+            }
+            __syncwarp();
+            long long b = clock64();
+            t0 += 0; if (lane == 0) cyc[r] = b - a;
+        }
+        if (lane == 0) sink[0] = ok ? sm[C_DX0 * NSTG + 5] : -1.0;
+    } else {
+        // background: dependent FP64 chain (ILP 1) until warp 0 is done (fixed iteration count)
+        double x = threadIdx.x;
+        for (int i = 0; i < reps * 6000; ++i) x = fma(x, 0.999, 1e-9);
+        sink[threadIdx.x] = x;
+    }
+}
+int main() {
+    Cfg c; memset(&c, 0, sizeof c); c.N = 30; c.T = 0.1;
+    long long *cyc; double *sink; cudaMalloc(&cyc, 8 * 64); cudaMalloc(&sink, 8 * 2048);
+    const size_t smem = 8 * WLay<1>::COOP * 8;
+    cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int mode : {0, 1, 2}) for (int nbg : {0, 15}) for (int lanes : {8}) {
+        const int reps = 8; long long h[8];
+        bench<<<1, 32 * (1 + nbg), smem>>>(c, lanes, reps, cyc, sink, mode);
+        cudaError_t e = cudaDeviceSynchronize();
+        cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
+        printf("mode %d (0 full, 1 backward, 2 matrix part) background warps %2d lanes %d: %lld cycles per sweep (%.0f per stage)  [%s]\n", mode, nbg, lanes, h[5], h[5] / 31.0, cudaGetErrorString(e));
+    }
+    return 0;
+}

@@ -1,7 +1,13 @@
 #!/bin/bash
-# build + time launch-bound variants of the warp kernel on the GPU box:  "warps_per_block min_blocks"
-for v in "4 2" "8 1" "2 4" "6 2" "4 3"; do
+# Build launch-shape variants of the warp kernel HERE (nvcc cross-compiles), time them on the GPU box with
+#   KMPC_LIB=gpurun_variants/libkmpc_<tag>.so python scripts/one_solve.py 65536 30 3
+# usage: scripts/variants.sh "WPB1 MINB1 WPB2 MINB2" ...
+mkdir -p gpurun_variants
+for v in "$@"; do
   set -- $v
-  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC -cudart shared -DKMPC_WARPS_PER_BLOCK=$1 -DKMPC_WARP_MINB=$2 -o kiss_mpc_b200/libkmpc.so kiss_mpc_b200/csrc/kmpc.cu
-  echo "== WPB=$1 MINB=$2"; python scripts/one_solve.py 65536 30 2 | tail -1; python scripts/one_solve.py 65536 50 1 | tail -1
+  tag="$1_$2_$3_$4"
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC -cudart shared \
+    -DKMPC_WPB1=$1 -DKMPC_MINB1=$2 -DKMPC_WPB2=$3 -DKMPC_MINB2=$4 -o gpurun_variants/libkmpc_$tag.so kiss_mpc_b200/csrc/kmpc.cu &
 done
+wait
+ls -la gpurun_variants

@@ -58,6 +58,7 @@ static Cfg make_cfg(const kmpc_config *cf, int B, int O, double obs_radius, doub
     c.L = make_rows(cf->N, O);
     c.nb = (cf->N + 1) * (c.hasL[0] + c.hasU[0] + c.hasL[1] + c.hasU[1]) + cf->N * (c.hasL[2] + c.hasU[2] + c.hasL[3] + c.hasU[3]) + cf->N * O;
     c.m = 3 * (cf->N + 1) + cf->N * O;
+    c.r_mnb = 1.0 / (double)(c.m + c.nb); c.r_nb = c.nb ? 1.0 / (double)c.nb : 0.0;
     return c;
 }
 
@@ -141,7 +142,12 @@ extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur
         unsigned long long tr = 0;
         int queue = b;          // this emulated warp is handed exactly instance b
         Cfg cb = c; cb.B = b + 1;
-        simt_run([&]() { if (spl == 1) w_worker<1>(cb, io, smem.data(), &queue, &tr); else w_worker<2>(cb, io, smem.data(), &queue, &tr); });
+        bool full = true;
+        for (int i = 0; i < 4; ++i) full = full && c.hasL[i] && c.hasU[i];
+        simt_run([&]() {
+            if (spl == 1) { if (full) w_worker<1, true>(cb, io, smem.data(), &queue, &tr); else w_worker<1, false>(cb, io, smem.data(), &queue, &tr); }
+            else { if (full) w_worker<2, true>(cb, io, smem.data(), &queue, &tr); else w_worker<2, false>(cb, io, smem.data(), &queue, &tr); }
+        });
         if (trips) trips[b] = (int)tr;
     }
     return 0;
