@@ -177,9 +177,10 @@ KMPC_HD size_t io_obs(const Cfg &c, int b, int o, int j) {
 // cost gradient of v (scaled) and its second derivative; optimizer.py:91-96 (literal) / README.md:23-24
 KMPC_HD void vcost(const Cfg &c, double df, double v, double *g, double *h) {
     if (c.cost_mode == 0) {
-        double a = dmin0(v), b = dmax0(v);
-        *g = df * (2.0 * c.Wvn * fmin(v, 0.0) * a + 2.0 * c.Wvp * fmax(v, 0.0) * b);
-        *h = df * (2.0 * c.Wvn * a * a + 2.0 * c.Wvp * b * b);
+        // W_v- min(0,v)^2 + W_v+ max(0,v)^2 with CasADi's derivative convention at the kink (both halves weigh 1/2 at v == 0)
+        const double w = v < 0 ? c.Wvn : c.Wvp;
+        *g = df * (2.0 * w * v);
+        *h = v == 0 ? df * (0.5 * c.Wvn + 0.5 * c.Wvp) : df * (2.0 * w);
     } else {
         *g = df * c.Wvn * dmin0(v);
         *h = 0.0;
@@ -264,6 +265,10 @@ KMPC_HD bool bound_trial(double val, double d, double vt, double lb, double ub, 
     return ok;
 }
 
+// compare-and-select min / max (3 instructions on the device; fmin / fmax expand to ~9 with their NaN canonicalisation).
+// A NaN in the FIRST argument is ignored (as fmin / fmax would), so candidates go first, accumulators second.
+KMPC_HD double kmin(double cand, double acc) { return cand < acc ? cand : acc; }
+KMPC_HD double kmax(double cand, double acc) { return cand > acc ? cand : acc; }
 KMPC_HD double maxabs_nan(double m, double v) { double t = fabs(v); return (t > m || t != t) ? t : m; }
 
 // ------------------------------------------------------------------------------------------------
@@ -917,7 +922,9 @@ KMPC_HD void rollout_logic(Ctx &t, double apr, double adu, double gbd, double ym
         double amin = K_GAMMA_THETA;
         t.pw_g = 0.0; t.pw_t = 0.0;
         if (gbd < 0) {
-            t.pw_g = pow(-gbd, K_S_PHI); t.pw_t = pow(t.c.theta, K_S_THETA);
+            // switching condition a (-gBD)^s_phi > delta theta^s_theta, kept as a > delta * ratio with
+            // ratio = theta^s_theta / (-gBD)^s_phi = exp(s_theta log theta - s_phi log(-gBD))  (pw_g = 1, pw_t = ratio)
+            t.pw_g = 1.0; t.pw_t = exp(K_S_THETA * log(t.c.theta) - K_S_PHI * log(-gbd));
             amin = fmin(K_GAMMA_THETA, K_GAMMA_PHI * t.c.theta / (-gbd));
             if (t.c.theta <= t.theta_min) amin = fmin(amin, K_DELTA_LS * t.pw_t / t.pw_g);
         }

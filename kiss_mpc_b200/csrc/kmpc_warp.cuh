@@ -102,14 +102,14 @@ KMPC_W double wb_rb(bool hL, bool hU, double rsL, double rsU, double mu) {
 template <bool FULL>
 KMPC_W void wb_ftb(double d, bool hL, bool hU, double zL, double zU, double rsL, double rsU, double mu, double &rpr, double &rdu) {
     if (FULL || hL) {
-        rpr = fmax(rpr, -d * rsL);
+        rpr = kmax(-d * rsL, rpr);
         const double dz = fma(rsL, fma(-zL, d, mu), -zL);  // mu/s - z - z d/s
-        rdu = fmax(rdu, -dz * KRCPF(zL));
+        rdu = kmax(-dz * KRCPF(zL), rdu);
     }
     if (FULL || hU) {
-        rpr = fmax(rpr, d * rsU);
+        rpr = kmax(d * rsU, rpr);
         const double dz = fma(rsU, fma(zU, d, mu), -zU);   // mu/s - z + z d/s
-        rdu = fmax(rdu, -dz * KRCPF(zU));
+        rdu = kmax(-dz * KRCPF(zU), rdu);
     }
 }
 KMPC_W double w_ftb_alpha(double rmax, double tau) { return rmax > tau ? tau / rmax : 1.0; }
@@ -126,10 +126,10 @@ KMPC_W bool wb_trial(double d, double vt, double lb, double ub, bool hL, bool hU
         prod *= sn;
         if (!FULL && !hU) st.damp += sn;
         double z = fma(adu, fma(rsL, fma(-zL, d, mu), -zL), zL);
-        if (clamp) { const double mr = mu * KRCPF(sn); z = fmax(fmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
+        if (clamp) { const double mr = mu * KRCPF(sn); z = kmax(kmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
         zLn = z;
         const double p = sn * z;
-        st.mn = fmin(st.mn, p); st.mx = fmax(st.mx, p); st.sumz += fabs(z);
+        st.mn = kmin(p, st.mn); st.mx = kmax(p, st.mx); st.sumz += fabs(z);
     }
     if (FULL || hU) {
         const double sn = ub - vt;
@@ -137,10 +137,10 @@ KMPC_W bool wb_trial(double d, double vt, double lb, double ub, bool hL, bool hU
         prod *= sn;
         if (!FULL && !hL) st.damp += sn;
         double z = fma(adu, fma(rsU, fma(zU, d, mu), -zU), zU);
-        if (clamp) { const double mr = mu * KRCPF(sn); z = fmax(fmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
+        if (clamp) { const double mr = mu * KRCPF(sn); z = kmax(kmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
         zUn = z;
         const double p = sn * z;
-        st.mn = fmin(st.mn, p); st.mx = fmax(st.mx, p); st.sumz += fabs(z);
+        st.mn = kmin(p, st.mn); st.mx = kmax(p, st.mx); st.sumz += fabs(z);
     }
     return ok;
 }
@@ -180,7 +180,7 @@ KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<
         w.zLw[j] = (hasu && c.hasL[3]) ? 1.0 : 0.0; w.zUw[j] = (hasu && c.hasU[3]) ? 1.0 : 0.0;
         w.cs[j] = cs; w.sn[j] = sn;
     }
-    gm = w_maxabs_nan(gm);
+    gm = w_max_nn(gm);
     if (lane == 0) {
         Ctx &t = sc->t;
         for (int j = 0; j < 3; ++j) { sc->xc[j] = xc[j]; sc->gl[j] = gl[j]; }
@@ -426,8 +426,8 @@ KMPC_WN inline void w_step(const Cfg &c, const WScal *sc, const WState<SPL> &w, 
             gbd += (df * 2.0 * c.Ww * om + wb_rb<FULL>(hL3, hU3, rl3, ru3, mu)) * du1;
         }
     }
-    *alpha_pr = w_ftb_alpha(w_max(rpr), tau); *alpha_du = w_ftb_alpha(w_max(rdu), tau);
-    *gBD = w_sum(gbd); *ymax = w_maxabs_nan(ym);
+    *alpha_pr = w_ftb_alpha(w_max_nn(rpr), tau); *alpha_du = w_ftb_alpha(w_max_nn(rdu), tau);
+    *gBD = w_sum(gbd); *ymax = w_max_nn(ym);
 }
 
 // kept Newton step <-> private area
@@ -455,7 +455,7 @@ KMPC_W void w_step_load(WStep<SPL> &d, const double *priv) {
 // ---- phase 3, TRIAL: trial point + speculative multiplier update + residual norms (all stages at once) ----
 template <int SPL, bool FULL>
 KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w, const WStep<SPL> &d, double alpha, double ay,
-                            double adu, bool clamp, WState<SPL> &n, double *priv, Stats *out) {
+                            double adu, bool clamp, WState<SPL> &n, double *priv, double *scr, Stats *out) {
     constexpr int NSTG = WLay<SPL>::NSTG;
     const int N = c.N, lane = w_lane();
     const double mu = sc->t.mu, df = sc->t.df, T = c.T;
@@ -492,7 +492,7 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
         st.theta += fabs(c0) + fabs(c1) + fabs(c2);
         st.pinf = maxabs_nan(maxabs_nan(maxabs_nan(st.pinf, c0), c1), c2);
         st.sumy += fabs(n.y0[j]) + fabs(n.y1[j]) + fabs(n.y2[j]);
-        st.wmax = fmax(st.wmax, fmax(fabs(x0), fmax(fabs(x1), fabs(x2))));
+        st.wmax = kmax(fabs(x0), kmax(fabs(x1), kmax(fabs(x2), st.wmax)));
         double r0 = n.y0[j], r1 = n.y1[j], r2 = n.y2[j];
         if (s >= c.gk_lo && s <= c.gk_hi) {
             const double e0 = x0 - gl0, e1 = x1 - gl1, e2 = x2 - gl2;
@@ -508,14 +508,14 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
         n.zLy[j] = zLn; n.zUy[j] = zUn; r1 += zUn - zLn;
         if (s < N) {
             const double v = n.v[j], om = n.om[j], cs = n.cs[j], sn = n.sn[j];
-            st.wmax = fmax(st.wmax, fmax(fabs(v), fabs(om)));
+            st.wmax = kmax(fabs(v), kmax(fabs(om), st.wmax));
             const double a13 = -T * v * sn, a23 = T * v * cs;
             r0 -= yn0[j]; r1 -= yn1[j]; r2 -= a13 * yn0[j] + a23 * yn1[j] + yn2[j];
             double gv, hv;
             vcost(c, df, v, &gv, &hv);
             double rv = gv - (T * cs * yn0[j] + T * sn * yn1[j]), rw = df * 2.0 * c.Ww * om - T * yn2[j];
-            if (c.cost_mode == 0) { const double vm = fmin(v, 0.0), vp = fmax(v, 0.0); st.f += c.Wvn * vm * vm + c.Wvp * vp * vp; }
-            else st.f += c.Wvn * fmin(v, 0.0);
+            if (c.cost_mode == 0) { const double vm = v < 0 ? v : 0.0, vp = v > 0 ? v : 0.0; st.f += c.Wvn * vm * vm + c.Wvp * vp * vp; }
+            else st.f += c.Wvn * (v < 0 ? v : 0.0);
             st.f += c.Ww * om * om;
             valid &= wb_trial<FULL>(d.du0[j], v, c.lb[2], c.ub[2], hL2, hU2, w.zLv[j], w.zUv[j], pv[V_RL2 * NSTG], pv[V_RU2 * NSTG], mu, adu,
                                     clamp, zLn, zUn, prod, st);
@@ -530,10 +530,27 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
         st.dinf = maxabs_nan(maxabs_nan(maxabs_nan(st.dinf, r0), r1), r2);
         st.bar += log(prod);
     }
+    // Sums: every lane drops its partials into the (now dead) coop area, six lanes add up one column each (33-double
+    // rows: conflict-free); max / min: two CREDUX each.  One barrier pair instead of eleven shuffle butterflies.
     Stats g;
-    g.f = w_sum(st.f) * df; g.bar = w_sum(st.bar); g.damp = w_sum(st.damp); g.theta = w_sum(st.theta);
-    g.dinf = w_maxabs_nan(st.dinf); g.pinf = w_maxabs_nan(st.pinf); g.mn = w_min(st.mn); g.mx = w_max(st.mx);
-    g.sumy = w_sum(st.sumy); g.sumz = w_sum(st.sumz); g.wmax = w_max(st.wmax);
+    {
+        constexpr int NS = FULL ? 5 : 6;
+        scr[0 * 33 + lane] = st.f; scr[1 * 33 + lane] = st.bar; scr[2 * 33 + lane] = st.theta; scr[3 * 33 + lane] = st.sumy;
+        scr[4 * 33 + lane] = st.sumz;
+        if (!FULL) scr[5 * 33 + lane] = st.damp;
+        w_sync();
+        if (lane < NS) {
+            const double *r = scr + lane * 33;
+            double a0 = r[0], a1 = r[1], a2 = r[2], a3 = r[3];
+#pragma unroll
+            for (int i = 4; i < 32; i += 4) { a0 += r[i]; a1 += r[i + 1]; a2 += r[i + 2]; a3 += r[i + 3]; }
+            scr[6 * 33 + lane] = (a0 + a1) + (a2 + a3);
+        }
+        w_sync();
+        g.f = scr[6 * 33 + 0] * df; g.bar = scr[6 * 33 + 1]; g.theta = scr[6 * 33 + 2]; g.sumy = scr[6 * 33 + 3];
+        g.sumz = scr[6 * 33 + 4]; g.damp = FULL ? 0.0 : scr[6 * 33 + 5];
+    }
+    g.dinf = w_max_nn(st.dinf); g.pinf = w_max_nn(st.pinf); g.mn = w_min_nn(st.mn); g.mx = w_max_nn(st.mx); g.wmax = w_max_nn(st.wmax);
     if (c.nb == 0) g.mn = 0.0;
     *out = g;
     const double phi = g.f - mu * g.bar + K_KAPPA_D * mu * g.damp;
@@ -660,7 +677,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         if (go_trial) {
             Stats ts;
             WState<SPL> tri;
-            const bool evok = w_trial<SPL, FULL>(c, sc, cur, act, t.a_pr, t.a_y, t.a_du, t.tu == TU_STEP, tri, priv, &ts);
+            const bool evok = w_trial<SPL, FULL>(c, sc, cur, act, t.a_pr, t.a_y, t.a_du, t.tu == TU_STEP, tri, priv, coop, &ts);
             PT(7)
             if (lane == 0) {
                 bool aug; double ath, aph;

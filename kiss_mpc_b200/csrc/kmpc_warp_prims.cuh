@@ -26,6 +26,21 @@ KMPC_W int w_fetch(int *queue) {  // next instance index for this warp
     return __shfl_sync(0xffffffffu, b, 0);
 }
 KMPC_W void w_count_trips(unsigned long long *total, int trips) { if (total) atomicAdd(total, (unsigned long long)trips); }
+// max / min over the warp of doubles whose sign bit is clear (non-negative numbers, +inf, NaN with a clear sign bit): their
+// bit patterns order like unsigned integers, so two 32-bit warp reductions (CREDUX) replace a 5-level shuffle butterfly.
+// A NaN (pattern above +inf) wins the max, i.e. it propagates, exactly like w_maxabs_nan.
+KMPC_W double w_max_nn(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    return __hiloint2double((int)mh, (int)ml);
+}
+KMPC_W double w_min_nn(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return __hiloint2double((int)mh, (int)ml);
+}
 }  // namespace kmpc
 #else
 #define KMPC_W inline
@@ -36,8 +51,8 @@ KMPC_W void w_count_trips(unsigned long long *total, int trips) { if (total) ato
 namespace kmpc {
 // butterfly reductions: every lane ends with the same bits
 KMPC_W double w_sum(double v) { for (int m = 16; m > 0; m >>= 1) v += w_xor(v, m); return v; }
-KMPC_W double w_min(double v) { for (int m = 16; m > 0; m >>= 1) v = fmin(v, w_xor(v, m)); return v; }
-KMPC_W double w_max(double v) { for (int m = 16; m > 0; m >>= 1) v = fmax(v, w_xor(v, m)); return v; }
+KMPC_W double w_min(double v) { for (int m = 16; m > 0; m >>= 1) { const double o = w_xor(v, m); v = o < v ? o : v; } return v; }
+KMPC_W double w_max(double v) { for (int m = 16; m > 0; m >>= 1) { const double o = w_xor(v, m); v = o > v ? o : v; } return v; }
 // max of |.| that propagates NaN (mirrors maxabs_nan of the thread solver)
 KMPC_W double w_maxabs_nan(double v) {
     for (int m = 16; m > 0; m >>= 1) { const double o = w_xor(v, m); v = (o > v || o != o) ? o : v; }
