@@ -103,6 +103,13 @@ int kmpc_solve_host(kmpc_handle *h, int B, const double *x_cur, const double *go
                     const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
                     double *obj_out, int32_t *status_out, int32_t *iters_out);
 
+/* Zero-copy variant of the host path: when kmpc_solve_host is called with X_out == U_out == NULL the results are left in
+ * the handle's pinned staging buffers; this call returns their addresses (layout as kmpc_config.layout, sized for the
+ * B of that call).  The pointers stay valid until the next solve on, or the destruction of, the handle.  Replaces the
+ * `.full()` copies of optimizer.py:392-400 for callers that consume the result before the next solve. */
+int kmpc_host_result(kmpc_handle *h, const double **X, const double **U, const double **obj, const int32_t **status,
+                     const int32_t **iters);
+
 /* Batched EgoAgent.step hand-off (agent.py:139-155 + agent.py:70-72): after a solve, on the device,
  *   applied[b] = U[:,0]  (agent.py:154-155),  x_cur[b] <- X[:,1] (the "perfect model" state hand-off, agent.py:70-72);
  * X/U stay in place as the next solve's UNSHIFTED warm start (agent.py:139-145).  Device pointers, handle layout. */

@@ -15,7 +15,7 @@ NO_BOUND = 1e19
 
 # symbols include/kmpc.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["kmpc_version", "kmpc_workspace_bytes", "kmpc_create", "kmpc_destroy", "kmpc_last_error", "kmpc_solve",
-           "kmpc_solve_host", "kmpc_agent_handoff", "kmpc_set_timing", "kmpc_get_stats", "kmpc_measure_fp64_peak"]
+           "kmpc_solve_host", "kmpc_host_result", "kmpc_agent_handoff", "kmpc_set_timing", "kmpc_get_stats", "kmpc_measure_fp64_peak"]
 
 
 class KmpcConfig(C.Structure):
@@ -62,6 +62,8 @@ def load():
     L.kmpc_solve.argtypes = solve_args + [vp]
     L.kmpc_solve_host.restype = C.c_int
     L.kmpc_solve_host.argtypes = solve_args
+    L.kmpc_host_result.restype = C.c_int
+    L.kmpc_host_result.argtypes = [vp] + [C.POINTER(C.c_void_p)] * 5
     L.kmpc_agent_handoff.restype = C.c_int
     L.kmpc_agent_handoff.argtypes = [vp, C.c_int, dp, dp, dp, dp, vp]
     L.kmpc_set_timing.restype = C.c_int

@@ -236,6 +236,7 @@ struct kmpc_handle {
     double *d_in, *d_out, *h_in, *h_out;
     int32_t *d_iout, *h_iout;
     size_t in_doubles, out_doubles;
+    int host_B;  // batch of the last kmpc_solve_host (addresses kmpc_host_result hands out)
     cudaStream_t stream;
     char err[256];
 };
@@ -489,7 +490,7 @@ extern "C" int kmpc_solve_host(kmpc_handle *h, int B, const double *x_cur, const
     if (O < 0 || O > h->cfg.O_max || (O > 0 && !obs_centers)) return fail(h, KMPC_E_BADARG, "kmpc_solve_host: bad obstacle arguments%s", "");
     if ((X0 == NULL) != (U0 == NULL)) return fail(h, KMPC_E_BADARG, "kmpc_solve_host: X0 and U0 must both be given or both be NULL%s", "");
     if (B == 0) return 0;
-    if (!x_cur || !goal || !X_out || !U_out) return fail(h, KMPC_E_BADARG, "kmpc_solve_host: NULL required pointer%s", "");
+    if (!x_cur || !goal || ((X_out == NULL) != (U_out == NULL))) return fail(h, KMPC_E_BADARG, "kmpc_solve_host: NULL required pointer%s", "");
     CU(cudaSetDevice(h->device));
     int rc = ensure_staging(h);
     if (rc) return rc;
@@ -511,11 +512,26 @@ extern "C" int kmpc_solve_host(kmpc_handle *h, int B, const double *x_cur, const
     CU(cudaMemcpyAsync(h->h_out, h->d_out, (nX + nU + b) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_iout, h->d_iout, b * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    h->host_B = B;
+    if (!X_out) return 0;  // zero-copy: the caller reads the pinned buffers through kmpc_host_result
     memcpy(X_out, h->h_out, nX * sizeof(double));
     memcpy(U_out, h->h_out + nX, nU * sizeof(double));
     if (obj_out) memcpy(obj_out, h->h_out + nX + nU, b * sizeof(double));
     if (status_out) memcpy(status_out, h->h_iout, b * sizeof(int32_t));
     if (iters_out) memcpy(iters_out, h->h_iout + b, b * sizeof(int32_t));
+    return 0;
+}
+
+extern "C" int kmpc_host_result(kmpc_handle *h, const double **X, const double **U, const double **obj, const int32_t **status,
+                                const int32_t **iters) {
+    if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_host_result: NULL handle%s", "");
+    if (!h->h_out || h->host_B <= 0) return fail(h, KMPC_E_BADARG, "kmpc_host_result: no kmpc_solve_host result on this handle%s", "");
+    const size_t N = h->cfg.N, b = h->host_B, nX = b * 3 * (N + 1), nU = b * 2 * N;
+    if (X) *X = h->h_out;
+    if (U) *U = h->h_out + nX;
+    if (obj) *obj = h->h_out + nX + nU;
+    if (status) *status = h->h_iout;
+    if (iters) *iters = h->h_iout + b;
     return 0;
 }
 

@@ -131,16 +131,18 @@ class BatchedMotionPlanner:
 
     # -- solve ----------------------------------------------------------------------------------
     def solve(self, current_state, goal_state, states_matrix=None, controls_matrix=None, obstacles=None,
-              obstacle_radius: float = 0.3, inflation_radius: float = 0.0) -> SolveResult:
+              obstacle_radius: float = 0.3, inflation_radius: float = 0.0, copy: bool = True) -> SolveResult:
         """current_state/goal_state [B,3]; states_matrix [B,3,N+1] and controls_matrix [B,2,N] = primal warm start
         (both None: the cold start of agent.py:59-60); obstacles [B,O,2] circle centres.  CUDA tensors stay on the
-        device (asynchronous on the current torch stream); NumPy arrays / CPU tensors go through kmpc_solve_host."""
+        device (asynchronous on the current torch stream); NumPy arrays / CPU tensors go through kmpc_solve_host.
+        Host path only: ``copy=False`` returns NumPy views of the planner's pinned result buffers (no 80 MB memcpy at
+        B = 65,536); they are overwritten by the next solve on this planner."""
         torch = _torch()
         if isinstance(current_state, torch.Tensor) and current_state.is_cuda:
             return self._solve_device(current_state, goal_state, states_matrix, controls_matrix, obstacles,
                                       obstacle_radius, inflation_radius)
         return self._solve_host(current_state, goal_state, states_matrix, controls_matrix, obstacles, obstacle_radius,
-                                inflation_radius)
+                                inflation_radius, copy)
 
     def _check_O(self, obstacles):
         if obstacles is None:
@@ -184,7 +186,7 @@ class BatchedMotionPlanner:
         _lib.check(rc, self._h, "kmpc_solve")
         return SolveResult(Xo, Uo, obj, st, it)
 
-    def _solve_host(self, x, goal, X0, U0, obs, obs_radius, inflation) -> SolveResult:
+    def _solve_host(self, x, goal, X0, U0, obs, obs_radius, inflation, copy=True) -> SolveResult:
         def np64(a):
             if a is None:
                 return None
@@ -202,8 +204,22 @@ class BatchedMotionPlanner:
                 raise ValueError(f"{n}: expected shape {s}, got {a.shape}")
         if (X0 is None) != (U0 is None):
             raise ValueError("states_matrix and controls_matrix must both be given or both be None")
-        Xo = np.empty(sX); Uo = np.empty(sU); obj = np.empty(B); st = np.empty(B, np.int32); it = np.empty(B, np.int32)
         p = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+        if not copy:
+            rc = self._L.kmpc_solve_host(self._h, B, p(x), p(goal), p(X0), p(U0), p(obs) if O else None, O, float(obs_radius),
+                                         float(inflation), None, None, None, None, None)
+            _lib.check(rc, self._h, "kmpc_solve_host")
+            ptr = [C.c_void_p() for _ in range(5)]
+            _lib.check(self._L.kmpc_host_result(self._h, *[C.byref(q) for q in ptr]), self._h, "kmpc_host_result")
+
+            def view(q, shape, ct, dt):
+                n = int(np.prod(shape))
+                return np.frombuffer((ct * n).from_address(q.value), dtype=dt).reshape(shape)
+
+            return SolveResult(view(ptr[0], sX, C.c_double, np.float64), view(ptr[1], sU, C.c_double, np.float64),
+                               view(ptr[2], (B,), C.c_double, np.float64), view(ptr[3], (B,), C.c_int32, np.int32),
+                               view(ptr[4], (B,), C.c_int32, np.int32))
+        Xo = np.empty(sX); Uo = np.empty(sU); obj = np.empty(B); st = np.empty(B, np.int32); it = np.empty(B, np.int32)
         rc = self._L.kmpc_solve_host(self._h, B, p(x), p(goal), p(X0), p(U0), p(obs) if O else None, O, float(obs_radius),
                                      float(inflation), p(Xo), p(Uo), p(obj), p(st), p(it))
         _lib.check(rc, self._h, "kmpc_solve_host")

@@ -167,6 +167,11 @@ def test_batch_minor_layout_and_host_path(oracle_mod):
     pl2 = BatchedMotionPlanner(pcfg, max_batch=B)
     res2 = pl2.solve(b["x_cur"], b["goal"])
     _check(res2, ref)
+    # zero-copy host path (kmpc_host_result): views of the pinned result buffers
+    res3 = pl2.solve(b["x_cur"], b["goal"], copy=False)
+    np.testing.assert_array_equal(res3.controls, res2.controls)
+    np.testing.assert_array_equal(res3.status, res2.status)
+    np.testing.assert_array_equal(res3.objective, res2.objective)
 
 
 def test_motion_planner_drop_in(oracle_mod):
