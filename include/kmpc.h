@@ -116,6 +116,20 @@ int kmpc_host_result(kmpc_handle *h, const double **X, const double **U, const d
 int kmpc_agent_handoff(kmpc_handle *h, int B, const double *X, const double *U, double *x_cur, double *applied_out,
                        void *cuda_stream);
 
+/* Device-resident receding-horizon loop: `steps` repetitions of EgoAgent.step (agent.py:130-155) for B agents without
+ * leaving the device:   solve(x_cur, goal, warm start = previous X, U UNSHIFTED, agent.py:139-145) -> applied = U[:,0]
+ * (agent.py:154-155) -> x_cur <- X[:,1] (agent.py:70-72).  X, U are in/out (start values = the first warm start, e.g. the
+ * cold start X = tile(x_cur), U = 0 of agent.py:59-60; on return the last solution), x_cur is in/out.  Optional per-step
+ * records (NULL to skip): applied_log[steps][B][2] (handle layout per step), iters_log[steps][B], status_log[steps][B].
+ * active (int32 [B], in/out, or NULL): agents with active[b] == 0 are not solved (status_log = 1000, iters_log = 0) and
+ * keep their state -- the reference stops stepping an agent once its final goal is reached (environment.py:31-33);
+ * with goal_radius > 0 the mask is refreshed after every step with Agent.at_goal (agent.py:78-80):
+ * ||(goal_xy - p_xy) - agent_radius||_2 - goal_radius <= 0, the literal formula of geometry.py:44 (agent_radius = 0 gives
+ * the Euclidean distance).  Asynchronous on `cuda_stream`; device pointers.  No obstacle rows in this entry point. */
+int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur, const double *goal, double *X, double *U,
+                     double *applied_log, int32_t *iters_log, int32_t *status_log, int32_t *active, double goal_radius,
+                     double agent_radius, void *cuda_stream);
+
 /* Measurement helpers (no reference equivalent). */
 typedef struct kmpc_stats {
     double last_kernel_ms;    /* device time of the solver kernel of the last kmpc_solve on this handle (CUDA events on its stream) */

@@ -182,21 +182,34 @@ static cudaError_t launch_warp_kernel(int sm_count, int B, const Cfg &c, const I
 }
 
 // Batched EgoAgent.step hand-off (agent.py:139-155, :70-72): applied control = U[:,0]; next current state = X[:,1].
+// With a mask: agents already at their goal keep their state (the reference stops stepping an agent whose final goal is
+// reached, environment.py:31-33); after the hand-off the mask is refreshed with Agent.at_goal (agent.py:78-80):
+// || (goal_xy - p_xy) - agent_radius ||_2 - goal_radius <= 0  -- the literal formula of geometry.py:44 (the radius is
+// subtracted from both components); agent_radius = 0 gives the plain Euclidean goal distance.
 __global__ void kmpc_handoff_kernel(int B, int N, int layout, const double *__restrict__ X, const double *__restrict__ U,
-                                    double *__restrict__ x_cur, double *__restrict__ applied) {
+                                    double *__restrict__ x_cur, double *__restrict__ applied, const double *__restrict__ goal,
+                                    int32_t *__restrict__ active, double goal_radius, double agent_radius) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const bool was_active = !active || active[b];
+    double xn[3];
     for (int j = 0; j < 3; ++j) {
         const size_t src = layout ? ((size_t)j * (N + 1) + 1) * B + b : ((size_t)b * 3 + j) * (N + 1) + 1;
         const size_t dst = layout ? (size_t)j * B + b : (size_t)b * 3 + j;
-        x_cur[dst] = X[src];
+        xn[j] = was_active ? X[src] : x_cur[dst];
+        if (was_active) x_cur[dst] = xn[j];
     }
     if (applied)
         for (int j = 0; j < 2; ++j) {
             const size_t src = layout ? ((size_t)j * N) * B + b : ((size_t)b * 2 + j) * N;
             const size_t dst = layout ? (size_t)j * B + b : (size_t)b * 2 + j;
-            applied[dst] = U[src];
+            applied[dst] = was_active ? U[src] : 0.0;
         }
+    if (active && was_active && goal_radius > 0.0) {
+        const double gx = goal[layout ? (size_t)b : (size_t)b * 3], gy = goal[layout ? (size_t)B + b : (size_t)b * 3 + 1];
+        const double dx = (gx - xn[0]) - agent_radius, dy = (gy - xn[1]) - agent_radius;
+        if (sqrt(dx * dx + dy * dy) - goal_radius <= 0.0) active[b] = 0;
+    }
 }
 
 // FP64 FMA throughput micro-benchmark: 8 independent DFMA chains per thread.
@@ -348,9 +361,9 @@ static inline int nblocks(int n) { return (n + KMPC_TPB - 1) / KMPC_TPB; }
 // The trip loop is driven from the host: three launches per trip on `cuda_stream`, KMPC_LOOKAHEAD trips in flight; the
 // active-instance count of an older trip (async copy into pinned memory) sizes the grids and ends the loop.  On return
 // every instance has finished and the outputs are complete on `cuda_stream`.
-extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
-                          const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
-                          double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream) {
+static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
+                      const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
+                      double *obj_out, int32_t *status_out, int32_t *iters_out, const int32_t *active, void *cuda_stream) {
     if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_solve: NULL handle%s", "");
     if (B < 0 || B > h->cfg.B_max) return fail(h, KMPC_E_BADARG, "kmpc_solve: B outside [0, B_max]%s", "");
     if (O < 0 || O > h->cfg.O_max || (O > 0 && !obs_centers)) return fail(h, KMPC_E_BADARG, "kmpc_solve: bad obstacle arguments%s", "");
@@ -374,13 +387,14 @@ extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const doub
     c.r_mnb = 1.0 / (double)(c.m + c.nb); c.r_nb = c.nb ? 1.0 / (double)c.nb : 0.0;
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs_centers;
-    io.X_out = X_out; io.U_out = U_out; io.obj = obj_out; io.status = status_out; io.iters = iters_out;
+    io.X_out = X_out; io.U_out = U_out; io.obj = obj_out; io.status = status_out; io.iters = iters_out; io.active = active;
     const size_t S = (size_t)h->cols;
     Lists ls;
     ls.LA[0] = h->lists; ls.LA[1] = h->lists + S; ls.LT[0] = h->lists + 2 * S; ls.LT[1] = h->lists + 3 * S;
     ls.cnt = h->cnt; ls.trips = h->timing ? h->trips : NULL;
 
     if (h->timing) { CU(cudaMemsetAsync(h->trips, 0, sizeof(unsigned long long), st)); CU(cudaEventRecord(h->ev0, st)); }
+    if (active && !(O == 0 && cf->N + 1 <= 64)) return fail(h, KMPC_E_BADARG, "kmpc: the at-goal mask needs the warp solver (O = 0, N <= 63)%s", "");
     const bool use_warp = O == 0 && cf->N + 1 <= 64 && getenv("KMPC_FORCE_THREAD") == NULL;  // N + 1 <= 32 * SPL
     if (use_warp) {
         // warp-per-instance path: one persistent launch, instances pulled from a queue, no workspace traffic
@@ -467,6 +481,13 @@ extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const doub
     return 0;
 }
 
+extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
+                          const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
+                          double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream) {
+    return solve_impl(h, B, x_cur, goal, X0, U0, obs_centers, O, obs_radius, inflation, X_out, U_out, obj_out, status_out, iters_out, NULL,
+                      cuda_stream);
+}
+
 static int ensure_staging(kmpc_handle *h) {
     if (h->d_in) return 0;
     const kmpc_config *cf = &h->cfg;
@@ -541,7 +562,7 @@ extern "C" int kmpc_agent_handoff(kmpc_handle *h, int B, const double *X, const 
     if (B < 0 || !X || !U || !x_cur) return fail(h, KMPC_E_BADARG, "kmpc_agent_handoff: bad arguments%s", "");
     if (B == 0) return 0;
     CU(cudaSetDevice(h->device));
-    kmpc_handoff_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(B, h->cfg.N, h->cfg.layout, X, U, x_cur, applied_out);
+    kmpc_handoff_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(B, h->cfg.N, h->cfg.layout, X, U, x_cur, applied_out, NULL, NULL, 0.0, 0.0);
     CU(cudaGetLastError());
     h->launches++;
     return 0;
@@ -557,6 +578,28 @@ extern "C" int kmpc_debug_phase_cycles(double *out) {
     return KMPC_NPHASE;
 }
 #endif
+
+extern "C" int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur, const double *goal, double *X, double *U,
+                                double *applied_log, int32_t *iters_log, int32_t *status_log, int32_t *active, double goal_radius,
+                                double agent_radius, void *cuda_stream) {
+    if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_closed_loop: NULL handle%s", "");
+    if (B < 0 || B > h->cfg.B_max || steps < 0) return fail(h, KMPC_E_BADARG, "kmpc_closed_loop: bad B or steps%s", "");
+    if (B == 0 || steps == 0) return 0;
+    if (!x_cur || !goal || !X || !U) return fail(h, KMPC_E_BADARG, "kmpc_closed_loop: NULL required pointer%s", "");
+    if (getenv("KMPC_FORCE_THREAD")) active = NULL;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    for (int s = 0; s < steps; ++s) {
+        // in place: every instance reads its own warm-start rows before it writes its result rows
+        int rc = solve_impl(h, B, x_cur, goal, X, U, NULL, 0, 0.0, 0.0, X, U, NULL, status_log ? status_log + (size_t)s * B : NULL,
+                            iters_log ? iters_log + (size_t)s * B : NULL, active, cuda_stream);
+        if (rc) return rc;
+        kmpc_handoff_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, h->cfg.N, h->cfg.layout, X, U, x_cur,
+                                                            applied_log ? applied_log + (size_t)s * B * 2 : NULL, goal, active, goal_radius, agent_radius);
+        CU(cudaGetLastError());
+        h->launches++;
+    }
+    return 0;
+}
 
 extern "C" int kmpc_set_timing(kmpc_handle *h, int enable) {
     if (!h) return KMPC_E_BADARG;

@@ -597,6 +597,15 @@ __device__ unsigned long long g_phase_cycles[KMPC_NPHASE];
 #define PT_FLUSH
 #endif
 
+// next instance of the queue that is to be solved (masked-out instances only get their status / iteration records)
+KMPC_WN inline int w_fetch_active(const Cfg &c, const IO &io, int *queue) {
+    for (;;) {
+        const int b = w_fetch(queue);
+        if (b >= c.B || !io.active || io.active[b]) return b;
+        if (w_lane() == 0) { if (io.status) io.status[b] = KMPC_STATUS_SKIPPED; if (io.iters) io.iters[b] = 0; }
+    }
+}
+
 // ---- persistent worker: one warp pulls instances from a queue and solves each start to finish; the warps of a block
 // walk through the phases of a trip in step (block barriers) so that warp 0 can run every instance's serial recursions.
 // smem: WLay<SPL>::bytes(warps per block) bytes of block-shared scratch.
@@ -622,7 +631,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         // warp 0 is busy in the serial window below, so it takes its next instance here; the other warps take theirs
         // in that window (the global-memory round trip then costs the block nothing)
         if (!have && !drained && wid == 0) {
-            b = w_fetch(queue);
+            b = w_fetch_active(c, io, queue);
             if (b < c.B) { w_init<SPL>(c, sc, io, b, cur); have = true; } else drained = true;
         }
         PT(0)
@@ -645,7 +654,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 if (so->flag) so->ok = w_serial(c, smem + (size_t)lane * LY::COOP, LY::NSTG, so->d0) ? 1 : 0;
             }
         } else if (!have && !drained) {
-            b = w_fetch(queue);
+            b = w_fetch_active(c, io, queue);
             if (b < c.B) { w_init<SPL>(c, sc, io, b, cur); fresh = true; } else drained = true;
         }
         PT(4)

@@ -235,6 +235,41 @@ class BatchedMotionPlanner:
         rc = self._L.kmpc_agent_handoff(self._h, B, p(states), p(controls), p(current_state), p(applied), C.c_void_p(stream))
         _lib.check(rc, self._h, "kmpc_agent_handoff")
 
+    def closed_loop(self, current_state, goal_state, steps: int, states_matrix=None, controls_matrix=None,
+                    log_applied: bool = True, log_iters: bool = True, goal_radius: float = 0.0, agent_radius: float = 0.0,
+                    active=None):
+        """`steps` receding-horizon steps of EgoAgent.step (agent.py:130-155) for all B agents on the device
+        (kmpc_closed_loop): warm start = previous solution unshifted, x <- X[:,1], applied = U[:,0].
+        current_state [B,3] is advanced in place.  Returns (states, controls, applied_log [steps,B,2] | None,
+        iters_log [steps,B] | None, status_log [steps,B]).
+        goal_radius > 0: an agent that satisfies Agent.at_goal (agent.py:78-80, literal distance of geometry.py:44 with
+        agent_radius; 0 = Euclidean) after a step is not solved again (status 1000 in the log), as the reference's
+        environment stops stepping it (environment.py:31-33); `active` (int32 [B]) carries that mask in and out."""
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        B = self._batch_of(current_state)
+        sx, sX, sU, _, sA = self._shapes(B, 0)
+        N = self.config.N
+        if states_matrix is None:            # agent.py:59-60
+            if self.layout == _lib.LAYOUT_INSTANCE_MAJOR:
+                states_matrix = current_state[:, :, None].repeat(1, 1, N + 1).contiguous()
+            else:
+                states_matrix = current_state[:, None, :].repeat(1, N + 1, 1).contiguous()
+            controls_matrix = torch.zeros(sU, dtype=torch.float64, device=dev)
+        X, U = states_matrix.contiguous(), controls_matrix.contiguous()
+        applied = torch.empty((steps,) + sA, dtype=torch.float64, device=dev) if log_applied else None
+        iters = torch.empty((steps, B), dtype=torch.int32, device=dev) if log_iters else None
+        status = torch.empty((steps, B), dtype=torch.int32, device=dev)
+        if active is None and goal_radius > 0:
+            active = torch.ones(B, dtype=torch.int32, device=dev)
+        self.last_active = active
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        rc = self._L.kmpc_closed_loop(self._h, B, int(steps), p(current_state), p(goal_state.contiguous()), p(X), p(U), p(applied),
+                                      p(iters), p(status), p(active), float(goal_radius), float(agent_radius), C.c_void_p(stream))
+        _lib.check(rc, self._h, "kmpc_closed_loop")
+        return X, U, applied, iters, status
+
     # -- measurement --------------------------------------------------------------------------------
     def set_timing(self, enable: bool):
         self._L.kmpc_set_timing(self._h, 1 if enable else 0)

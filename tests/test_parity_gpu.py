@@ -140,6 +140,31 @@ def test_warm_start_and_handoff(oracle_mod):
     assert r1.iters.float().mean() < r0.iters.float().mean()
 
 
+def test_closed_loop_matches_stepwise_oracle(oracle_mod):
+    """BASELINE configs[4] semantics at test size: a few receding-horizon steps on the device (kmpc_closed_loop) against
+    the oracle driven step by step with the reference's hand-off (agent.py:139-155, :70-72)."""
+    from kiss_mpc_b200 import BatchedMotionPlanner
+    torch = _torch()
+    ocfg, pcfg = _pair(oracle_mod)
+    B, steps, N = 96, 6, 30
+    b = make_batch(B, seed=1005)
+    pl = BatchedMotionPlanner(pcfg, max_batch=B)
+    x, g = _dev(b["x_cur"]), _dev(b["goal"])
+    X, U, applied, iters, status = pl.closed_loop(x, g, steps)
+    torch.cuda.synchronize()
+    xr = b["x_cur"].copy()
+    Xr = np.repeat(xr[:, :, None], N + 1, axis=2); Ur = np.zeros((B, 2, N))
+    for s in range(steps):
+        ref = oracle_mod.solve(ocfg, xr, b["goal"], X0=Xr, U0=Ur)
+        assert (status[s].cpu().numpy() == ref.status).all()
+        assert np.abs(applied[s].cpu().numpy() - ref.U[:, :, 0]).max() <= CTRL_ATOL
+        Xr, Ur, xr = ref.X, ref.U, ref.X[:, :, 1].copy()
+    assert np.abs(x.cpu().numpy() - xr).max() <= 1e-5
+    assert np.abs(U.cpu().numpy() - Ur).max() <= CTRL_ATOL
+    # warm-started steps need far fewer iterations than the cold first one
+    assert iters[1:].float().mean().item() < 0.6 * iters[0].float().mean().item()
+
+
 def test_status_parity_infeasible(oracle_mod):
     """Status-parity batch: x_cur.x = +-25 violates the x bound -> the equality X_0 = x_cur is infeasible."""
     from kiss_mpc_b200 import BatchedMotionPlanner
