@@ -79,6 +79,7 @@ class ClockSampler:
 def cpu_oracle_rate(batch, nthreads=0, sample=CPU_SAMPLE):
     from oracle import oracle as ok
     ok.build()
+    nthreads = nthreads or os.cpu_count()      # explicit: torchrun exports OMP_NUM_THREADS=1
     cfg = ok.OracleConfig(N=HORIZON, T=TIME_STEP, linsolve="riccati")
     x, g = batch["x_cur"][:sample], batch["goal"][:sample]
     ok.solve(cfg, x[:64], g[:64], nthreads=nthreads)  # warm the thread pool
@@ -126,7 +127,14 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL may print its version banner on stdout; keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     B, N = B_PER_GPU, HORIZON
     batch = make_batch(B, seed=SEED + rank)          # every rank owns its own slice of the global batch
     planner = BatchedMotionPlanner(PlannerConfig(N=N, T=TIME_STEP), max_batch=B, device=local_rank)
@@ -200,12 +208,14 @@ def run_ours(args, rank, local_rank, world):
         ach_gbs = ALG_BYTES_PER_SOLVE * B / kernel_s / 1e9
         mean_it = float(stat[0].item())
         ach_tf = FLOPS_PER_ITER * mean_it * B / kernel_s / 1e12
-        cpu_rate, cpu_dt, cpu_res = cpu_oracle_rate(batch)
-        Ug = rh.controls[:CPU_SAMPLE]
-        conv_both = (rh.status[:CPU_SAMPLE] == 0) & (cpu_res.status == 0)
-        parity = {"status_equal": float((rh.status[:CPU_SAMPLE] == cpu_res.status).mean()),
+        # CPU arm beside it: the whole batch at N = 1 GPU, a 4,096-instance parity sample otherwise
+        cpu_n = CPU_SAMPLE if world == 1 else 4096
+        cpu_rate, cpu_dt, cpu_res = cpu_oracle_rate(batch, sample=cpu_n)
+        Ug = rh.controls[:cpu_n]
+        conv_both = (rh.status[:cpu_n] == 0) & (cpu_res.status == 0)
+        parity = {"status_equal": float((rh.status[:cpu_n] == cpu_res.status).mean()),
                   "max_abs_control_diff": float(np.abs(Ug - cpu_res.U)[conv_both].max()),
-                  "max_rel_objective_diff": float((np.abs(rh.objective[:CPU_SAMPLE] - cpu_res.obj) / np.abs(cpu_res.obj))[conv_both].max())}
+                  "max_rel_objective_diff": float((np.abs(rh.objective[:cpu_n] - cpu_res.obj) / np.abs(cpu_res.obj))[conv_both].max())}
         traffic = None
         tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tp):
@@ -226,7 +236,7 @@ def run_ours(args, rank, local_rank, world):
             "roofline_fp64": {"bound": "fp64_fma_pipe", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
                               "flops_per_iteration": FLOPS_PER_ITER, "peak_source": "DFMA micro-benchmark in this run (kmpc_measure_fp64_peak)"},
             "cpu_baseline": {"value": cpu_rate, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": f"first {CPU_SAMPLE} instances of rank 0's batch, oracle (IPOPT-restatement, not IPOPT), OpenMP all cores, {cpu_dt:.2f} s"},
+                             "sample": f"first {cpu_n} instances of rank 0's batch, oracle (IPOPT-restatement, not IPOPT), OpenMP all cores, {cpu_dt:.2f} s"},
             "parity_vs_oracle_on_sample": parity,
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks,

@@ -158,26 +158,35 @@ kmpc_trial_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_
 #define KMPC_MINB2 1
 #endif
 // FULL: every bound of x, y, v, omega exists (the default problem), so the per-side tests are compiled away.
-template <int SPL, bool FULL, int WPB, int MINB>
+// OBS: obstacle-distance rows present (their per-row state lives in shared memory; the block shrinks to what fits).
+template <int SPL, bool FULL, bool OBS, int WPB, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB)
 kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned long long *__restrict__ trips_total) {
-    extern __shared__ double s_dyn[];  // WLay<SPL>::bytes(WPB)
-    w_worker<SPL, FULL>(c, io, s_dyn, queue, trips_total);
+    extern __shared__ double s_dyn[];  // WLay<SPL>::bytes(warps per block, O)
+    w_worker<SPL, FULL, OBS>(c, io, s_dyn, queue, trips_total);
 }
 
-template <int SPL, bool FULL, int WPB, int MINB>
-static cudaError_t launch_warp_kernel(int sm_count, int B, const Cfg &c, const IO &io, int *queue, unsigned long long *trips, cudaStream_t st) {
-    const size_t smem = WLay<SPL>::bytes(WPB);
-    auto kern = kmpc_warp_kernel<SPL, FULL, WPB, MINB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// returns cudaErrorInvalidConfiguration if not even one instance fits into shared memory (caller falls back)
+template <int SPL, bool FULL, bool OBS, int WPB, int MINB>
+static cudaError_t launch_warp_kernel(int device, int sm_count, int B, const Cfg &c, const IO &io, int *queue, unsigned long long *trips,
+                                      cudaStream_t st) {
+    int max_smem = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e != cudaSuccess) return e;
+    int wpb = WPB;
+    while (wpb > 0 && WLay<SPL>::bytes(wpb, c.O) > (size_t)max_smem) --wpb;
+    if (wpb < 1) return cudaErrorInvalidConfiguration;
+    const size_t smem = WLay<SPL>::bytes(wpb, c.O);
+    auto kern = kmpc_warp_kernel<SPL, FULL, OBS, WPB, MINB>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int bpsm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsm, kern, 32 * WPB, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsm, kern, 32 * wpb, smem);
     if (e != cudaSuccess) return e;
     int grid = sm_count * (bpsm > 0 ? bpsm : 1);
-    const int need = (B + WPB - 1) / WPB;
+    const int need = (B + wpb - 1) / wpb;
     if (grid > need) grid = need;
-    kern<<<grid, 32 * WPB, smem, st>>>(c, io, queue, trips);
+    kern<<<grid, 32 * wpb, smem, st>>>(c, io, queue, trips);
     return cudaGetLastError();
 }
 
@@ -395,19 +404,29 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
 
     if (h->timing) { CU(cudaMemsetAsync(h->trips, 0, sizeof(unsigned long long), st)); CU(cudaEventRecord(h->ev0, st)); }
     if (active && !(O == 0 && cf->N + 1 <= 64)) return fail(h, KMPC_E_BADARG, "kmpc: the at-goal mask needs the warp solver (O = 0, N <= 63)%s", "");
-    const bool use_warp = O == 0 && cf->N + 1 <= 64 && getenv("KMPC_FORCE_THREAD") == NULL;  // N + 1 <= 32 * SPL
+    const bool use_warp = cf->N + 1 <= 64 && getenv("KMPC_FORCE_THREAD") == NULL;  // N + 1 <= 32 * SPL
+    bool use_warp_fits = true;
     if (use_warp) {
         // warp-per-instance path: one persistent launch, instances pulled from a queue, no workspace traffic
         CU(cudaMemsetAsync(h->cnt, 0, sizeof(int), st));
         bool full = true;
         for (int i = 0; i < 4; ++i) full = full && c.hasL[i] && c.hasU[i];
+        cudaError_t le;
+        const int dv = h->device, sms = h->sm_count;
         if (cf->N + 1 <= 32) {
-            if (full) { CU((launch_warp_kernel<1, true, KMPC_WPB1, KMPC_MINB1>(h->sm_count, B, c, io, h->cnt, ls.trips, st))); }
-            else { CU((launch_warp_kernel<1, false, KMPC_WPB1, KMPC_MINB1>(h->sm_count, B, c, io, h->cnt, ls.trips, st))); }
+            if (O > 0) le = full ? launch_warp_kernel<1, true, true, 8, 1>(dv, sms, B, c, io, h->cnt, ls.trips, st)
+                                 : launch_warp_kernel<1, false, true, 8, 1>(dv, sms, B, c, io, h->cnt, ls.trips, st);
+            else le = full ? launch_warp_kernel<1, true, false, KMPC_WPB1, KMPC_MINB1>(dv, sms, B, c, io, h->cnt, ls.trips, st)
+                           : launch_warp_kernel<1, false, false, KMPC_WPB1, KMPC_MINB1>(dv, sms, B, c, io, h->cnt, ls.trips, st);
         } else {
-            if (full) { CU((launch_warp_kernel<2, true, KMPC_WPB2, KMPC_MINB2>(h->sm_count, B, c, io, h->cnt, ls.trips, st))); }
-            else { CU((launch_warp_kernel<2, false, KMPC_WPB2, KMPC_MINB2>(h->sm_count, B, c, io, h->cnt, ls.trips, st))); }
+            if (O > 0) le = full ? launch_warp_kernel<2, true, true, 6, 1>(dv, sms, B, c, io, h->cnt, ls.trips, st)
+                                 : launch_warp_kernel<2, false, true, 6, 1>(dv, sms, B, c, io, h->cnt, ls.trips, st);
+            else le = full ? launch_warp_kernel<2, true, false, KMPC_WPB2, KMPC_MINB2>(dv, sms, B, c, io, h->cnt, ls.trips, st)
+                           : launch_warp_kernel<2, false, false, KMPC_WPB2, KMPC_MINB2>(dv, sms, B, c, io, h->cnt, ls.trips, st);
         }
+        if (le == cudaErrorInvalidConfiguration && O > 0) use_warp_fits = false;  // too many obstacle rows for shared memory
+        else { CU(le); }
+        if (use_warp_fits) {
         CU(cudaGetLastError());
         h->launches++;
         h->last_host_trips = 0;
@@ -422,6 +441,7 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
             h->last_trips = (long long)tr;
         }
         return 0;
+        }
     }
     const int cnt0[4] = {B, 0, 0, 0};
     CU(cudaMemcpyAsync(h->cnt, cnt0, sizeof cnt0, cudaMemcpyHostToDevice, st));

@@ -19,6 +19,7 @@
 // the product library contains only the CUDA path).
 #pragma once
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <float.h>
 

@@ -36,7 +36,7 @@ struct WStep { double dx0[SPL], dx1[SPL], dx2[SPL], du0[SPL], du1[SPL], dy0[SPL]
 // the forward roll-out overwrites K with (dx, du).
 enum { C_A13 = 0, C_A23, C_B11, C_B21, C_E0, C_E1, C_E2,
        C_Q00 = 7, C_Q11, C_Q22, C_Q0, C_Q1, C_Q2, C_QV, C_QW, C_DV, C_DW, C_HTV,
-       C_P00 = 18, C_P10, C_P11, C_P20, C_P21, C_P22, C_NF = 24 };
+       C_P00 = 18, C_P10, C_P11, C_P20, C_P21, C_P22, C_Q01 = 24, C_NF = 25 };  // Q01: x-y coupling of the obstacle rows
 enum { C_K00 = C_Q00, C_K01 = C_Q11, C_K02 = C_Q22, C_K10 = C_DV, C_K11 = C_DW, C_K12 = C_HTV,
        C_PV0 = C_Q0, C_PV1 = C_Q1, C_PV2 = C_Q2, C_KF0 = C_QV, C_KF1 = C_QW };
 enum { C_DX0 = C_K00, C_DX1 = C_K01, C_DX2 = C_K02, C_DU0 = C_K10, C_DU1 = C_K11 };
@@ -45,6 +45,11 @@ enum { C_DX0 = C_K00, C_DX1 = C_K01, C_DX2 = C_K02, C_DU0 = C_K10, C_DU1 = C_K11
 // + the reciprocal slacks 1/(x - l), 1/(u - x) of the current iterate's four bounded variables (x, y, v, omega)
 enum { V_DX0 = 0, V_DX1, V_DX2, V_DU0, V_DU1, V_DY0, V_DY1, V_DY2, V_CS0, V_CS1, V_CS2, V_CT0, V_CT1, V_CT2,
        V_RL0, V_RL1, V_RL2, V_RL3, V_RU0, V_RU1, V_RU2, V_RU3, V_NF };
+
+// obstacle area of one instance (owner warp only; circular obstacle-distance rows of optimizer.py:198-258, README.md:78-81):
+// per (field, obstacle, stage) the slack s of the row d(x_k) - s = 0, its multiplier yd, the multiplier vL of s >= I, the
+// second-order-correction rhs, the row residual at the last trial point; then the O circle centres (x, y).
+enum { B_S = 0, B_YD, B_VL, B_DSOC, B_DM, B_NF };
 
 struct WScal {  // warp-uniform per-instance scalars
     Ctx t;
@@ -58,7 +63,8 @@ struct WLay {
     static constexpr int NSTG = 32 * SPL;
     static constexpr int COOP = C_NF * NSTG + 1;
     static constexpr int PRIV = V_NF * NSTG;
-    static size_t bytes(int warps) { return (size_t)warps * ((COOP + PRIV) * sizeof(double) + sizeof(WScal)); }
+    KMPC_HD static int obs_doubles(int O) { return O > 0 ? B_NF * O * NSTG + 2 * O : 0; }
+    static size_t bytes(int warps, int O = 0) { return (size_t)warps * ((COOP + PRIV + obs_doubles(O)) * sizeof(double) + sizeof(WScal)); }
 };
 
 // value of the next / previous stage (neighbouring slot, or the neighbouring lane's edge slot)
@@ -145,10 +151,52 @@ KMPC_W bool wb_trial(double d, double vt, double lb, double ub, bool hL, bool hU
     return ok;
 }
 
+
+// ---- obstacle rows (stage-parallel: each lane loops over the O obstacles of its stage(s), s = 1..N) ----
+struct WObsT { double nx, ny, ir, rr, Ds, bd, bs, rsl; };  // unit normal, 1/|p-c|, |p-c|, condensed slack block, rhs terms, 1/(s - I)
+// terms of one (stage, obstacle) row at the current iterate (cf. obs_terms of kmpc_core.cuh); kind: lsq / soc / Newton
+KMPC_W WObsT w_obs_terms(const Cfg &c, double px, double py, double cx, double cy, double s, double yd, double vL, double mu,
+                         double delta, bool lsq, bool soc, double dsoc) {
+    WObsT r;
+    const double ex = px - cx, ey = py - cy;
+    r.rr = sqrt(ex * ex + ey * ey);
+    r.ir = KRCPF(r.rr);
+    r.nx = ex * r.ir; r.ny = ey * r.ir;
+    r.rsl = KRCPF(s - c.dL);
+    if (lsq) { r.Ds = 1.0; r.bd = 0.0; r.bs = -yd - vL; }
+    else {
+        r.Ds = fma(vL, r.rsl, delta);
+        r.bs = yd + mu * r.rsl - K_KAPPA_D * mu;
+        r.bd = soc ? -dsoc : -((r.rr - c.obs_radius) - s);
+    }
+    return r;
+}
+// slack / multiplier values of one row at the trial point (used by the trial pass and, again, to commit an accepted point)
+struct WObsV { double s, yd, z, sln; };
+KMPC_W WObsV w_obs_vals(const Cfg &c, const WObsT &ot, double s, double yd, double vL, double dxn, double mu, double alpha,
+                        double ay, double adu, bool clamp) {
+    WObsV v;
+    const double ds = dxn - ot.bd;                 // n^T dx - bd
+    const double dyd = fma(ot.Ds, ds, -ot.bs);
+    v.s = fma(alpha, ds, s);
+    v.sln = v.s - c.dL;
+    v.yd = fma(ay, dyd, yd);
+    double z = fma(adu, fma(ot.rsl, fma(-vL, ds, mu), -vL), vL);   // vL + adu (mu/sl - vL - vL ds/sl)
+    if (clamp) { const double mr = mu * KRCPF(v.sln); z = kmax(kmin(z, K_KAPPA_SIGMA * mr), mr * (1.0 / K_KAPPA_SIGMA)); }
+    v.z = z;
+    return v;
+}
+
 // ---- starting point: optimizer.py:375-385 (warm start) / agent.py:59-60 (cold start); IPOPT initialisation ----
-template <int SPL>
-KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<SPL> &w) {
-    const int N = c.N, lane = w_lane();
+template <int SPL, bool OBS>
+KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<SPL> &w, double *ob) {
+    constexpr int NSTG = WLay<SPL>::NSTG;
+    const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
+    if (OBS) {  // circle centres -> shared memory (optimizer.py:217-221)
+        double *cxy = ob + B_NF * O * NSTG;
+        for (int i = lane; i < 2 * O; i += 32) cxy[i] = io.obs[io_obs(c, b, i >> 1, i & 1)];
+        w_sync();
+    }
     double xc[3], gl[3];
     for (int j = 0; j < 3; ++j) { xc[j] = io.x_cur[io_vec3(c, b, j)]; gl[j] = io.goal[io_vec3(c, b, j)]; }
     double gm = 0.0;
@@ -179,6 +227,16 @@ KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<
         w.zLv[j] = (hasu && c.hasL[2]) ? 1.0 : 0.0; w.zUv[j] = (hasu && c.hasU[2]) ? 1.0 : 0.0;
         w.zLw[j] = (hasu && c.hasL[3]) ? 1.0 : 0.0; w.zUw[j] = (hasu && c.hasU[3]) ? 1.0 : 0.0;
         w.cs[j] = cs; w.sn[j] = sn;
+        if (OBS && s >= 1 && s <= N) {  // slacks pushed inside their bound, yd = 0, vL = 1
+            const double *cxy = ob + B_NF * O * NSTG;
+            const double dLpush = c.dL + K_BOUND_PUSH * fmax(1.0, fabs(c.dL));
+            for (int o = 0; o < O; ++o) {
+                const double ex = x[0] - cxy[2 * o], ey = x[1] - cxy[2 * o + 1];
+                const double d = sqrt(ex * ex + ey * ey) - c.obs_radius;
+                double *po = ob + o * NSTG + s;
+                po[B_S * O * NSTG] = fmax(d, dLpush); po[B_YD * O * NSTG] = 0.0; po[B_VL * O * NSTG] = 1.0;
+            }
+        }
     }
     gm = w_max_nn(gm);
     if (lane == 0) {
@@ -199,10 +257,10 @@ KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<
 // ---- phase 1a, ASSEMBLE: stage blocks of the KKT system -> coop area (all stages at once) ----
 // Stages without a control (the terminal stage N) become pass-through steps of the recursion: zero dynamics, unit Q_uu,
 // zero rhs -> P_out = P_in + Q, p_out = p_in + q.  Also leaves the reciprocal slacks of the iterate in the private area.
-template <int SPL, bool FULL>
-KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, double *priv, double *coop) {
+template <int SPL, bool FULL, bool OBS>
+KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, double *priv, double *coop, const double *ob) {
     constexpr int NSTG = WLay<SPL>::NSTG;
-    const int N = c.N, lane = w_lane();
+    const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     const int mode = sc->t.mode;
     const bool lsq = mode == M_LSQ, soc = mode == M_SOC;
     const double mu = sc->t.mu, delta = sc->t.delta, df = sc->t.df, T = c.T;
@@ -240,6 +298,24 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
             q0 = gx0 + w.y0[j] + rb0; q1 = gx1 + w.y1[j] + rb1; q2 = gx2 + w.y2[j];
             Q00 = h0 + sg0 + delta; Q11 = h1 + sg1 + delta; Q22 = h2 + delta;
         }
+        double Q01 = 0.0;
+        if (OBS && s >= 1) {  // slacks of the obstacle rows condensed into the x-y block
+            const double *cxy = ob + B_NF * O * NSTG;
+            for (int o = 0; o < O; ++o) {
+                const double *po = ob + o * NSTG + s;
+                const double yd = po[B_YD * O * NSTG];
+                const WObsT ot = w_obs_terms(c, x0, x1, cxy[2 * o], cxy[2 * o + 1], po[B_S * O * NSTG], yd, po[B_VL * O * NSTG], mu, delta,
+                                             lsq, soc, soc ? po[B_DSOC * O * NSTG] : 0.0);
+                if (!lsq) {
+                    const double h = yd * ot.ir;
+                    Q00 += h * (1.0 - ot.nx * ot.nx); Q01 += h * (-ot.nx * ot.ny); Q11 += h * (1.0 - ot.ny * ot.ny);
+                    q0 += ot.nx * yd; q1 += ot.ny * yd;
+                }
+                Q00 += ot.Ds * ot.nx * ot.nx; Q01 += ot.Ds * ot.nx * ot.ny; Q11 += ot.Ds * ot.ny * ot.ny;
+                const double tt = ot.Ds * ot.bd + ot.bs;
+                q0 -= ot.nx * tt; q1 -= ot.ny * tt;
+            }
+        }
         double a13 = -T * v * sn, a23 = T * v * cs, b11 = T * cs, b21 = T * sn;
         double gv, hvv;
         vcost(c, df, v, &gv, &hvv);
@@ -273,6 +349,7 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
         q[C_A13 * NSTG] = a13; q[C_A23 * NSTG] = a23; q[C_B11 * NSTG] = b11; q[C_B21 * NSTG] = b21;
         q[C_E0 * NSTG] = e0; q[C_E1 * NSTG] = e1; q[C_E2 * NSTG] = e2;
         q[C_Q00 * NSTG] = Q00; q[C_Q11 * NSTG] = Q11; q[C_Q22 * NSTG] = Q22;
+        if (OBS) q[C_Q01 * NSTG] = Q01;
         q[C_Q0 * NSTG] = q0; q[C_Q1 * NSTG] = q1; q[C_Q2 * NSTG] = q2;
         q[C_QV * NSTG] = qv; q[C_QW * NSTG] = qw; q[C_DV * NSTG] = dv; q[C_DW * NSTG] = dw; q[C_HTV * NSTG] = htv;
         if (s == 0) {  // dx of stage 0 (the rhs of the initial-state row)
@@ -305,16 +382,17 @@ KMPC_W void w_ric_vec(const WRicCarry &cy, double *q, const int NSTG, const doub
     q[C_PV0 * NSTG] = p0; q[C_PV1 * NSTG] = p1; q[C_PV2 * NSTG] = p2;
 }
 // matrix part of stage k: (P of stage k+1 in P..) -> K, M = -Quu^-1, P of stage k; leaves what the vector part needs in cy
+template <bool OBS>
 KMPC_W bool w_ric_mat(WRicCarry &cy, double *q, const int NSTG, const double T, const double TT, double &P00, double &P10,
                       double &P11, double &P20, double &P21, double &P22) {
     const double a13 = q[C_A13 * NSTG], a23 = q[C_A23 * NSTG], b11 = q[C_B11 * NSTG], b21 = q[C_B21 * NSTG];
-    const double Q00 = q[C_Q00 * NSTG], Q11 = q[C_Q11 * NSTG], Q22 = q[C_Q22 * NSTG];
+    const double Q00 = q[C_Q00 * NSTG], Q11 = q[C_Q11 * NSTG], Q22 = q[C_Q22 * NSTG], Q01 = OBS ? q[C_Q01 * NSTG] : 0.0;
     const double dv = q[C_DV * NSTG], dw = q[C_DW * NSTG], htv = q[C_HTV * NSTG];
     cy.P00 = P00; cy.P10 = P10; cy.P11 = P11; cy.P20 = P20; cy.P21 = P21; cy.P22 = P22;
     cy.a13 = a13; cy.a23 = a23; cy.b11 = b11; cy.b21 = b21;
     // P A (third column), symmetric Qxx = A^T P A + Q
     const double PA02 = fma(P00, a13, fma(P10, a23, P20)), PA12 = fma(P10, a13, fma(P11, a23, P21)), PA22 = fma(P20, a13, fma(P21, a23, P22));
-    const double X00 = P00 + Q00, X10 = P10, X11 = P11 + Q11, X20 = PA02, X21 = PA12;
+    const double X00 = P00 + Q00, X10 = P10 + Q01, X11 = P11 + Q11, X20 = PA02, X21 = PA12;
     const double X22 = fma(a13, PA02, fma(a23, PA12, PA22)) + Q22;
     // Qux = B^T P A (+ W_v,theta)
     const double U00 = fma(b11, P00, b21 * P10), U01 = fma(b11, P10, b21 * P11), U02 = fma(b11, PA02, fma(b21, PA12, htv));
@@ -345,17 +423,18 @@ KMPC_W void w_fwd_load(WFwdIn &r, const double *q, const int NSTG) {
     r.a13 = q[C_A13 * NSTG]; r.a23 = q[C_A23 * NSTG]; r.b11 = q[C_B11 * NSTG]; r.b21 = q[C_B21 * NSTG];
     r.e0 = q[C_E0 * NSTG]; r.e1 = q[C_E1 * NSTG]; r.e2 = q[C_E2 * NSTG];
 }
+template <bool OBS>
 KMPC_WN inline bool w_serial(const Cfg &c, double *coop, const int NSTG, const double *d0) {
     const int N = c.N;
     const double T = c.T, TT = T * T;
     double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0, p0 = 0, p1 = 0, p2 = 0;
     WRicCarry cy;
-    bool pd = w_ric_mat(cy, coop + N, NSTG, T, TT, P00, P10, P11, P20, P21, P22);
+    bool pd = w_ric_mat<OBS>(cy, coop + N, NSTG, T, TT, P00, P10, P11, P20, P21, P22);
 #pragma unroll 1
     for (int s = N - 1; s >= 0; --s) {
         double *q = coop + s;
         const WRicCarry cp = cy;
-        pd = w_ric_mat(cy, q, NSTG, T, TT, P00, P10, P11, P20, P21, P22) && pd;
+        pd = w_ric_mat<OBS>(cy, q, NSTG, T, TT, P00, P10, P11, P20, P21, P22) && pd;
         w_ric_vec(cp, q + 1, NSTG, T, p0, p1, p2);
     }
     w_ric_vec(cy, coop, NSTG, T, p0, p1, p2);
@@ -380,13 +459,13 @@ KMPC_WN inline bool w_serial(const Cfg &c, double *coop, const int NSTG, const d
 }
 
 // ---- phase 2, STEP: multiplier step dy = -(P dx + p), step-size limits, directional derivative (all stages at once) ----
-template <int SPL, bool FULL>
+template <int SPL, bool FULL, bool OBS>
 KMPC_WN inline void w_step(const Cfg &c, const WScal *sc, const WState<SPL> &w, const double *coop, const double *priv,
-                           WStep<SPL> &d, double *alpha_pr, double *alpha_du, double *gBD, double *ymax) {
+                           const double *ob, WStep<SPL> &d, double *alpha_pr, double *alpha_du, double *gBD, double *ymax) {
     constexpr int NSTG = WLay<SPL>::NSTG;
-    const int N = c.N, lane = w_lane();
-    const bool lsq = sc->t.mode == M_LSQ;
-    const double mu = sc->t.mu, df = sc->t.df, tau = sc->t.tau;
+    const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
+    const bool lsq = sc->t.mode == M_LSQ, soc = sc->t.mode == M_SOC;
+    const double mu = sc->t.mu, df = sc->t.df, tau = sc->t.tau, delta = sc->t.delta;
     const double gl0 = sc->gl[0], gl1 = sc->gl[1], gl2 = sc->gl[2];
     const bool hL0 = c.hasL[0], hU0 = c.hasU[0], hL1 = c.hasL[1], hU1 = c.hasU[1], hL2 = c.hasL[2], hU2 = c.hasU[2], hL3 = c.hasL[3], hU3 = c.hasU[3];
     double rpr = 0.0, rdu = 0.0, gbd = 0.0, ym = 0.0;
@@ -405,6 +484,23 @@ KMPC_WN inline void w_step(const Cfg &c, const WScal *sc, const WState<SPL> &w, 
         d.dx0[j] = d0; d.dx1[j] = d1; d.dx2[j] = d2; d.du0[j] = du0; d.du1[j] = du1;
         d.dy0[j] = dy0; d.dy1[j] = dy1; d.dy2[j] = dy2;
         ym = maxabs_nan(maxabs_nan(maxabs_nan(ym, dy0), dy1), dy2);
+        if (OBS && s >= 1) {  // slack steps ds = n^T dx - bd, multiplier steps dyd = Ds ds - bs of the obstacle rows
+            const double *cxy = ob + B_NF * O * NSTG;
+            for (int o = 0; o < O; ++o) {
+                const double *po = ob + o * NSTG + s;
+                const double vL = po[B_VL * O * NSTG];
+                const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], cxy[2 * o], cxy[2 * o + 1], po[B_S * O * NSTG], po[B_YD * O * NSTG], vL, mu,
+                                             delta, lsq, soc, soc ? po[B_DSOC * O * NSTG] : 0.0);
+                const double ds = fma(ot.nx, d0, ot.ny * d1) - ot.bd;
+                ym = maxabs_nan(ym, fma(ot.Ds, ds, -ot.bs));
+                if (!lsq) {
+                    rpr = kmax(-ds * ot.rsl, rpr);
+                    const double dvl = fma(ot.rsl, fma(-vL, ds, mu), -vL);
+                    rdu = kmax(-dvl * KRCPF(vL), rdu);
+                    gbd += (K_KAPPA_D * mu - mu * ot.rsl) * ds;
+                }
+            }
+        }
         if (lsq) continue;
         const double *pv = priv + s;
         const double x0 = w.x0[j], x1 = w.x1[j], x2 = w.x2[j];
@@ -453,12 +549,13 @@ KMPC_W void w_step_load(WStep<SPL> &d, const double *priv) {
 }
 
 // ---- phase 3, TRIAL: trial point + speculative multiplier update + residual norms (all stages at once) ----
-template <int SPL, bool FULL>
+template <int SPL, bool FULL, bool OBS>
 KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w, const WStep<SPL> &d, double alpha, double ay,
-                            double adu, bool clamp, WState<SPL> &n, double *priv, double *scr, Stats *out) {
+                            double adu, bool clamp, WState<SPL> &n, double *priv, double *scr, double *ob, Stats *out) {
     constexpr int NSTG = WLay<SPL>::NSTG;
-    const int N = c.N, lane = w_lane();
-    const double mu = sc->t.mu, df = sc->t.df, T = c.T;
+    const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
+    const double mu = sc->t.mu, df = sc->t.df, T = c.T, delta = sc->t.delta;
+    const bool lsq = sc->t.mode == M_LSQ, soc = sc->t.mode == M_SOC;
     const double xc0 = sc->xc[0], xc1 = sc->xc[1], xc2 = sc->xc[2], gl0 = sc->gl[0], gl1 = sc->gl[1], gl2 = sc->gl[2];
     const bool hL0 = c.hasL[0], hU0 = c.hasU[0], hL1 = c.hasL[1], hU1 = c.hasU[1], hL2 = c.hasL[2], hU2 = c.hasU[2], hL3 = c.hasL[3], hU3 = c.hasU[3];
     Stats st;
@@ -506,6 +603,26 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
         valid &= wb_trial<FULL>(d.dx1[j], x1, c.lb[1], c.ub[1], hL1, hU1, w.zLy[j], w.zUy[j], pv[V_RL1 * NSTG], pv[V_RU1 * NSTG], mu, adu,
                                 clamp, zLn, zUn, prod, st);
         n.zLy[j] = zLn; n.zUy[j] = zUn; r1 += zUn - zLn;
+        if (OBS && s >= 1) {  // obstacle rows at the trial point
+            const double *cxy = ob + B_NF * O * NSTG;
+            for (int o = 0; o < O; ++o) {
+                double *po = ob + o * NSTG + s;
+                const double so = po[B_S * O * NSTG], ydo = po[B_YD * O * NSTG], vL = po[B_VL * O * NSTG];
+                const double cx = cxy[2 * o], cy = cxy[2 * o + 1];
+                const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], cx, cy, so, ydo, vL, mu, delta, lsq, soc, soc ? po[B_DSOC * O * NSTG] : 0.0);
+                const WObsV tv = w_obs_vals(c, ot, so, ydo, vL, fma(ot.nx, d.dx0[j], ot.ny * d.dx1[j]), mu, alpha, ay, adu, clamp);
+                const double ex = x0 - cx, ey = x1 - cy, rr = sqrt(ex * ex + ey * ey), ir = KRCPF(rr);
+                const double dm = (rr - c.obs_radius) - tv.s;
+                po[B_DM * O * NSTG] = dm;
+                st.theta += fabs(dm); st.pinf = maxabs_nan(st.pinf, dm);
+                valid &= tv.sln > 0;
+                prod *= tv.sln; st.damp += tv.sln;
+                r0 += ex * ir * tv.yd; r1 += ey * ir * tv.yd;
+                st.dinf = maxabs_nan(st.dinf, -tv.yd - tv.z);
+                const double p = tv.sln * tv.z;
+                st.mn = kmin(p, st.mn); st.mx = kmax(p, st.mx); st.sumz += fabs(tv.z); st.sumy += fabs(tv.yd);
+            }
+        }
         if (s < N) {
             const double v = n.v[j], om = n.om[j], cs = n.cs[j], sn = n.sn[j];
             st.wmax = kmax(fabs(v), kmax(fabs(om), st.wmax));
@@ -534,10 +651,10 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
     // rows: conflict-free); max / min: two CREDUX each.  One barrier pair instead of eleven shuffle butterflies.
     Stats g;
     {
-        constexpr int NS = FULL ? 5 : 6;
+        constexpr int NS = (FULL && !OBS) ? 5 : 6;
         scr[0 * 33 + lane] = st.f; scr[1 * 33 + lane] = st.bar; scr[2 * 33 + lane] = st.theta; scr[3 * 33 + lane] = st.sumy;
         scr[4 * 33 + lane] = st.sumz;
-        if (!FULL) scr[5 * 33 + lane] = st.damp;
+        if (NS == 6) scr[5 * 33 + lane] = st.damp;
         w_sync();
         if (lane < NS) {
             const double *r = scr + lane * 33;
@@ -548,7 +665,7 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
         }
         w_sync();
         g.f = scr[6 * 33 + 0] * df; g.bar = scr[6 * 33 + 1]; g.theta = scr[6 * 33 + 2]; g.sumy = scr[6 * 33 + 3];
-        g.sumz = scr[6 * 33 + 4]; g.damp = FULL ? 0.0 : scr[6 * 33 + 5];
+        g.sumz = scr[6 * 33 + 4]; g.damp = NS == 6 ? scr[6 * 33 + 5] : 0.0;
     }
     g.dinf = w_max_nn(st.dinf); g.pinf = w_max_nn(st.pinf); g.mn = w_min_nn(st.mn); g.mx = w_max_nn(st.mx); g.wmax = w_max_nn(st.wmax);
     if (c.nb == 0) g.mn = 0.0;
@@ -557,11 +674,34 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
     return w_all(valid) && isfinite(phi) && isfinite(g.theta);
 }
 
-// c_soc <- al * base + c(trial); base = c(current) for the first correction, else the previous c_soc
+// accepted trial point: the slack / multiplier values of the obstacle rows are recomputed (same formulas, same inputs as
+// in the trial pass, hence the same bits) and become current.  Must run before `cur` is overwritten.
 template <int SPL>
-KMPC_WN inline void w_soc_rhs(const Cfg &c, const WScal *sc, const WState<SPL> &w, double al, bool first, double *priv) {
+KMPC_WN inline void w_obs_commit(const Cfg &c, const WState<SPL> &w, const WStep<SPL> &d, double mu, double delta, double alpha,
+                                 double ay, double adu, bool clamp, bool lsq, bool soc, double *ob) {
     constexpr int NSTG = WLay<SPL>::NSTG;
-    const int N = c.N, lane = w_lane();
+    const int N = c.N, lane = w_lane(), O = c.O;
+    const double *cxy = ob + B_NF * O * NSTG;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int s = lane * SPL + j;
+        if (s < 1 || s > N) continue;
+        for (int o = 0; o < O; ++o) {
+            double *po = ob + o * NSTG + s;
+            const double so = po[B_S * O * NSTG], ydo = po[B_YD * O * NSTG], vL = po[B_VL * O * NSTG];
+            const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], cxy[2 * o], cxy[2 * o + 1], so, ydo, vL, mu, delta, lsq, soc,
+                                         soc ? po[B_DSOC * O * NSTG] : 0.0);
+            const WObsV tv = w_obs_vals(c, ot, so, ydo, vL, fma(ot.nx, d.dx0[j], ot.ny * d.dx1[j]), mu, alpha, ay, adu, clamp);
+            po[B_S * O * NSTG] = tv.s; po[B_YD * O * NSTG] = tv.yd; po[B_VL * O * NSTG] = tv.z;
+        }
+    }
+}
+
+// c_soc <- al * base + c(trial); base = c(current) for the first correction, else the previous c_soc
+template <int SPL, bool OBS>
+KMPC_WN inline void w_soc_rhs(const Cfg &c, const WScal *sc, const WState<SPL> &w, double al, bool first, double *priv, double *ob) {
+    constexpr int NSTG = WLay<SPL>::NSTG;
+    const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     const double T = c.T;
     double xp0[SPL], xp1[SPL], xp2[SPL], pp0[SPL], pp1[SPL], pp2[SPL];
 #pragma unroll
@@ -578,6 +718,16 @@ KMPC_WN inline void w_soc_rhs(const Cfg &c, const WScal *sc, const WState<SPL> &
         if (first) { b0 = w.x0[j] - (s == 0 ? sc->xc[0] : pp0[j]); b1 = w.x1[j] - (s == 0 ? sc->xc[1] : pp1[j]); b2 = w.x2[j] - (s == 0 ? sc->xc[2] : pp2[j]); }
         else { b0 = pv[V_CS0 * NSTG]; b1 = pv[V_CS1 * NSTG]; b2 = pv[V_CS2 * NSTG]; }
         pv[V_CS0 * NSTG] = al * b0 + pv[V_CT0 * NSTG]; pv[V_CS1 * NSTG] = al * b1 + pv[V_CT1 * NSTG]; pv[V_CS2 * NSTG] = al * b2 + pv[V_CT2 * NSTG];
+        if (OBS && s >= 1) {
+            const double *cxy = ob + B_NF * O * NSTG;
+            for (int o = 0; o < O; ++o) {
+                double *po = ob + o * NSTG + s;
+                double base;
+                if (first) { const double ex = w.x0[j] - cxy[2 * o], ey = w.x1[j] - cxy[2 * o + 1]; base = (sqrt(ex * ex + ey * ey) - c.obs_radius) - po[B_S * O * NSTG]; }
+                else base = po[B_DSOC * O * NSTG];
+                po[B_DSOC * O * NSTG] = al * base + po[B_DM * O * NSTG];
+            }
+        }
     }
     w_sync();
 }
@@ -609,13 +759,15 @@ KMPC_WN inline int w_fetch_active(const Cfg &c, const IO &io, int *queue) {
 // ---- persistent worker: one warp pulls instances from a queue and solves each start to finish; the warps of a block
 // walk through the phases of a trip in step (block barriers) so that warp 0 can run every instance's serial recursions.
 // smem: WLay<SPL>::bytes(warps per block) bytes of block-shared scratch.
-template <int SPL, bool FULL>
+template <int SPL, bool FULL, bool OBS>
 KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queue, unsigned long long *trips_total) {
     typedef WLay<SPL> LY;
     const int N = c.N, lane = w_lane(), wid = w_warp(), W = w_warps();
     double *coop = smem + (size_t)wid * LY::COOP;
     double *priv = smem + (size_t)W * LY::COOP + (size_t)wid * LY::PRIV;
-    WScal *scal0 = (WScal *)(smem + (size_t)W * (LY::COOP + LY::PRIV));
+    const int OBD = LY::obs_doubles(OBS ? c.O : 0);
+    double *ob = smem + (size_t)W * (LY::COOP + LY::PRIV) + (size_t)wid * OBD;
+    WScal *scal0 = (WScal *)(smem + (size_t)W * (LY::COOP + LY::PRIV + OBD));
     WScal *sc = scal0 + wid;
     Ctx &t = sc->t;
     WState<SPL> cur;
@@ -632,7 +784,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         // in that window (the global-memory round trip then costs the block nothing)
         if (!have && !drained && wid == 0) {
             b = w_fetch_active(c, io, queue);
-            if (b < c.B) { w_init<SPL>(c, sc, io, b, cur); have = true; } else drained = true;
+            if (b < c.B) { w_init<SPL, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
         }
         PT(0)
         if (!w_block_any(have)) break;
@@ -641,7 +793,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         // ---- phase 1a: assemble the stage blocks ----
         const int mode = t.mode;
         const bool do_sweep = have && mode != M_TRIAL;
-        if (do_sweep) w_assemble<SPL, FULL>(c, sc, cur, priv, coop);
+        if (do_sweep) w_assemble<SPL, FULL, OBS>(c, sc, cur, priv, coop, ob);
         if (lane == 0) { sc->flag = do_sweep ? 1 : 0; if (do_sweep) t.trips++; }
         PT(2)
         w_block_sync();
@@ -651,11 +803,11 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         if (wid == 0) {
             if (lane < W) {
                 WScal *so = scal0 + lane;
-                if (so->flag) so->ok = w_serial(c, smem + (size_t)lane * LY::COOP, LY::NSTG, so->d0) ? 1 : 0;
+                if (so->flag) so->ok = w_serial<OBS>(c, smem + (size_t)lane * LY::COOP, LY::NSTG, so->d0) ? 1 : 0;
             }
         } else if (!have && !drained) {
             b = w_fetch_active(c, io, queue);
-            if (b < c.B) { w_init<SPL>(c, sc, io, b, cur); fresh = true; } else drained = true;
+            if (b < c.B) { w_init<SPL, OBS>(c, sc, io, b, cur, ob); fresh = true; } else drained = true;
         }
         PT(4)
         w_block_sync();
@@ -670,7 +822,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 status = sc->status;
             } else {
                 double apr, adu, gbd, ym;
-                w_step<SPL, FULL>(c, sc, cur, coop, priv, act, &apr, &adu, &gbd, &ym);
+                w_step<SPL, FULL, OBS>(c, sc, cur, coop, priv, ob, act, &apr, &adu, &gbd, &ym);
                 if (lane == 0) rollout_logic(t, apr, adu, gbd, ym);
                 w_sync();
                 if (t.sel == 0) w_step_store<SPL>(act, priv);
@@ -686,7 +838,10 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         if (go_trial) {
             Stats ts;
             WState<SPL> tri;
-            const bool evok = w_trial<SPL, FULL>(c, sc, cur, act, t.a_pr, t.a_y, t.a_du, t.tu == TU_STEP, tri, priv, coop, &ts);
+            // step sizes / barrier parameters of THIS trial, read before lane 0 moves the context on (begin_iteration)
+            const double ta_pr = t.a_pr, ta_y = t.a_y, ta_du = t.a_du, ta_mu = t.mu, ta_delta = t.delta;
+            const bool tclamp = t.tu == TU_STEP, tlsq = t.mode == M_LSQ, tsoc = t.mode == M_SOC;
+            const bool evok = w_trial<SPL, FULL, OBS>(c, sc, cur, act, ta_pr, ta_y, ta_du, tclamp, tri, priv, coop, ob, &ts);
             PT(7)
             if (lane == 0) {
                 bool aug; double ath, aph;
@@ -696,10 +851,11 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             }
             w_sync();
             const int r = sc->r;
-            if (r == R_SOC1 || r == R_SOC2) { PT_COUNT(11) w_soc_rhs<SPL>(c, sc, cur, t.alpha_soc, r == R_SOC1, priv); }
+            if (r == R_SOC1 || r == R_SOC2) { PT_COUNT(11) w_soc_rhs<SPL, OBS>(c, sc, cur, t.alpha_soc, r == R_SOC1, priv, ob); }
             else if (r == R_ACCEPT) {
                 PT_COUNT(12)
                 if (mode == M_SOC) { PT_COUNT(14) }
+                if (OBS) w_obs_commit<SPL>(c, cur, act, ta_mu, ta_delta, ta_pr, ta_y, ta_du, tclamp, tlsq, tsoc, ob);
                 cur = tri;
                 if (lane == 0) { t.c = ts; sc->status = begin_iteration(c, t); }
                 w_sync();

@@ -36,16 +36,16 @@ __global__ void bench(Cfg c, int lanes, int reps, long long *cyc, double *sink, 
             __syncwarp();
             long long a = clock64();
             if (lane < lanes) {
-                if (mode == 0) ok = w_serial(c, sm + lane * COOP, NSTG, d0) && ok;
+                if (mode == 0) ok = w_serial<false>(c, sm + lane * COOP, NSTG, d0) && ok;
                 else if (mode == 1) {  // backward sweep only
                     double *coop = sm + lane * COOP; const double T = c.T, TT = T * T;
                     double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0, p0 = 0, p1 = 0, p2 = 0;
                     WRicCarry cy;
-                    bool pd = w_ric_mat(cy, coop + c.N, NSTG, T, TT, P00, P10, P11, P20, P21, P22);
+                    bool pd = w_ric_mat<false>(cy, coop + c.N, NSTG, T, TT, P00, P10, P11, P20, P21, P22);
 #pragma unroll 1
                     for (int s = c.N - 1; s >= 0; --s) {
                         double *q = coop + s; const WRicCarry cp = cy;
-                        pd = w_ric_mat(cy, q, NSTG, T, TT, P00, P10, P11, P20, P21, P22) && pd;
+                        pd = w_ric_mat<false>(cy, q, NSTG, T, TT, P00, P10, P11, P20, P21, P22) && pd;
                         w_ric_vec(cp, q + 1, NSTG, T, p0, p1, p2);
                     }
                     w_ric_vec(cy, coop, NSTG, T, p0, p1, p2);
@@ -55,7 +55,7 @@ __global__ void bench(Cfg c, int lanes, int reps, long long *cyc, double *sink, 
                     double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0;
                     WRicCarry cy; bool pd = true;
 #pragma unroll 1
-                    for (int s = c.N; s >= 0; --s) pd = w_ric_mat(cy, coop + s, NSTG, T, TT, P00, P10, P11, P20, P21, P22) && pd;
+                    for (int s = c.N; s >= 0; --s) pd = w_ric_mat<false>(cy, coop + s, NSTG, T, TT, P00, P10, P11, P20, P21, P22) && pd;
                     ok = ok && pd;
                 }
             }

@@ -66,11 +66,11 @@ def solve(ocfg, x_cur, goal, X0=None, U0=None, obs=None, layout=0, warp=False):
     obj = np.empty(B); st = np.empty(B, np.int32); it = np.empty(B, np.int32); tp = np.empty(B, np.int32)
     p = lambda a, t=C.c_double: None if a is None else a.ctypes.data_as(C.POINTER(t))
     if warp:
-        assert O == 0
         L.emul_solve_warp.restype = C.c_int
-        L.emul_solve_warp.argtypes = [C.POINTER(KmpcConfig), C.c_int, dp, dp, dp, dp, dp, dp, dp, ip, ip, ip]
-        rc = L.emul_solve_warp(C.byref(c), B, p(xi), p(gi), p(X0i), p(U0i), p(Xo), p(Uo), p(obj), p(st, C.c_int32),
-                               p(it, C.c_int32), p(tp, C.c_int32))
+        L.emul_solve_warp.argtypes = [C.POINTER(KmpcConfig), C.c_int, dp, dp, dp, dp, dp, C.c_int, C.c_double, C.c_double, dp, dp,
+                                      dp, ip, ip, ip]
+        rc = L.emul_solve_warp(C.byref(c), B, p(xi), p(gi), p(X0i), p(U0i), p(obi), O, ocfg.obs_radius, ocfg.inflation, p(Xo), p(Uo),
+                               p(obj), p(st, C.c_int32), p(it, C.c_int32), p(tp, C.c_int32))
     else:
         rc = L.emul_solve(C.byref(c), B, p(xi), p(gi), p(X0i), p(U0i), p(obi), O, ocfg.obs_radius, ocfg.inflation, p(Xo), p(Uo),
                           p(obj), p(st, C.c_int32), p(it, C.c_int32), p(tp, C.c_int32))

@@ -126,27 +126,32 @@ extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, con
     return 0;
 }
 
-// warp-per-instance solver (kmpc_warp.cuh) on the fibre emulator; O must be 0 and N + 1 <= 64
+// warp-per-instance solver (kmpc_warp.cuh) on the fibre emulator; N + 1 <= 64
 extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur, const double *goal, const double *X0,
-                               const double *U0, double *X_out, double *U_out, double *obj, int32_t *status, int32_t *iters,
-                               int32_t *trips) {
+                               const double *U0, const double *obs, int O, double obs_radius, double inflation, double *X_out,
+                               double *U_out, double *obj, int32_t *status, int32_t *iters, int32_t *trips) {
     if (cf->N + 1 > 64) return -1;
-    Cfg c = make_cfg(cf, B, 0, 0.0, 0.0);
+    Cfg c = make_cfg(cf, B, O, obs_radius, inflation);
     IO io;
-    io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = NULL;
+    io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs;
     io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL;
     const int spl = cf->N + 1 <= 32 ? 1 : 2;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int b = 0; b < B; ++b) {
-        std::vector<double> smem((spl == 1 ? WLay<1>::bytes(1) : WLay<2>::bytes(1)) / sizeof(double), NAN);  // one emulated warp = one block
+        std::vector<double> smem((spl == 1 ? WLay<1>::bytes(1, O) : WLay<2>::bytes(1, O)) / sizeof(double), NAN);  // one emulated warp = one block
         unsigned long long tr = 0;
         int queue = b;          // this emulated warp is handed exactly instance b
         Cfg cb = c; cb.B = b + 1;
         bool full = true;
         for (int i = 0; i < 4; ++i) full = full && c.hasL[i] && c.hasU[i];
         simt_run([&]() {
-            if (spl == 1) { if (full) w_worker<1, true>(cb, io, smem.data(), &queue, &tr); else w_worker<1, false>(cb, io, smem.data(), &queue, &tr); }
-            else { if (full) w_worker<2, true>(cb, io, smem.data(), &queue, &tr); else w_worker<2, false>(cb, io, smem.data(), &queue, &tr); }
+            if (O > 0) {
+                if (spl == 1) { if (full) w_worker<1, true, true>(cb, io, smem.data(), &queue, &tr); else w_worker<1, false, true>(cb, io, smem.data(), &queue, &tr); }
+                else { if (full) w_worker<2, true, true>(cb, io, smem.data(), &queue, &tr); else w_worker<2, false, true>(cb, io, smem.data(), &queue, &tr); }
+            } else {
+                if (spl == 1) { if (full) w_worker<1, true, false>(cb, io, smem.data(), &queue, &tr); else w_worker<1, false, false>(cb, io, smem.data(), &queue, &tr); }
+                else { if (full) w_worker<2, true, false>(cb, io, smem.data(), &queue, &tr); else w_worker<2, false, false>(cb, io, smem.data(), &queue, &tr); }
+            }
         });
         if (trips) trips[b] = (int)tr;
     }

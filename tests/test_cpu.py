@@ -78,6 +78,38 @@ def test_solver_source_matches_oracle(oracle_mod, case):
     assert (it == ref.iters).mean() >= 0.95
 
 
+@pytest.mark.parametrize("case", ["box", "N50", "literal", "obs", "infeasible", "warm"])
+def test_warp_solver_source_matches_oracle(oracle_mod, case):
+    """The warp-per-instance kernel source (kmpc_warp.cuh: what the GPU runs for N <= 63) on the 32-fibre warp emulator
+    (tests/host_emul/simt.h, one emulated warp = one block) against the oracle."""
+    import emul
+    kw, B, seed, O = {}, 24, 1002, 0
+    if case == "N50":
+        kw, seed, B = dict(N=50), 1003, 12
+    elif case == "literal":
+        kw = dict(cost_mode="code_literal", goal_range="code", y_bounds=(-oracle_mod.INF, oracle_mod.INF))
+    elif case == "obs":
+        kw, seed, O = dict(O=10), 1004, 10
+    elif case == "infeasible":
+        kw = dict(max_iter=300)
+    cfg = oracle_mod.OracleConfig(linsolve="riccati", **kw)
+    b = make_batch(B, seed=seed, O=O)
+    X0 = U0 = None
+    x = b["x_cur"]
+    if case == "infeasible":
+        x[::4, 0] = 25.0
+    if case == "warm":
+        r0 = oracle_mod.solve(cfg, x, b["goal"])
+        X0, U0, x = r0.X, r0.U, r0.X[:, :, 1].copy()
+    ref = oracle_mod.solve(cfg, x, b["goal"], X0=X0, U0=U0, obs=b["obs"])
+    X, U, obj, st, it, tp = emul.solve(cfg, x, b["goal"], X0=X0, U0=U0, obs=b["obs"], warp=True)
+    assert (st == ref.status).all()
+    conv = st == 0
+    assert np.abs(U - ref.U)[conv].max() <= (1e-9 if O == 0 else 1e-6)
+    assert (np.abs(obj - ref.obj) / np.abs(ref.obj))[conv].max() <= 1e-9
+    assert (it == ref.iters).mean() >= (0.95 if O == 0 else 0.5)
+
+
 def test_solver_source_warm_start(oracle_mod):
     import emul
     cfg = oracle_mod.OracleConfig(linsolve="riccati")

@@ -102,19 +102,25 @@ def test_obstacles_O10(oracle_mod):
     ref = oracle_mod.solve(ocfg, b["x_cur"], b["goal"], obs=b["obs"])
     res = BatchedMotionPlanner(pcfg, max_batch=512).solve(_dev(b["x_cur"]), _dev(b["goal"]), obstacles=_dev(b["obs"]),
                                                            obstacle_radius=ocfg.obs_radius, inflation_radius=ocfg.inflation)
-    # Known gap (DESIGN.md "obstacle rows: end-game accuracy"): the slack-condensed Riccati solve has no iterative refinement
-    # yet, so once Sigma_s = v/s reaches ~1e12 a rare instance stalls at dual infeasibility ~1e-2 and runs into max_iter
-    # although its objective already equals the oracle's.  Tolerated here: <= 0.5 % of the batch.
-    conv = _check(res, ref, require_all_converged=False, max_status_mismatch=0.005)
-    assert conv.mean() > 0.9
-    stalled = (res.status.cpu().numpy() != ref.status)
-    if stalled.any():
-        og = res.objective.cpu().numpy()[stalled]
-        assert (np.abs(og - ref.obj[stalled]) <= 1e-6 * np.abs(ref.obj[stalled])).all()
+    conv = _check(res, ref, require_all_converged=False, max_status_mismatch=0.002)
+    assert conv.mean() > 0.99
+    assert (res.iters.cpu().numpy() == ref.iters).mean() > 0.9
     # constraint actually holds: distance >= inflation (up to IPOPT's bound relaxation)
     X = res.states.cpu().numpy()[conv]
     d = np.linalg.norm(X[:, None, :2, 1:] - b["obs"][conv][:, :, :, None], axis=2) - ocfg.obs_radius
     assert d.min() >= ocfg.inflation - 1e-6
+
+
+def test_cfg4_obstacles_4096(oracle_mod):
+    """BASELINE configs[3] at its full batch: 4,096 instances, O=10 static circles, N=30 (warp solver, obstacle rows in shared memory)."""
+    from kiss_mpc_b200 import BatchedMotionPlanner
+    ocfg, pcfg = _pair(oracle_mod, O=10)
+    b = make_batch(4096, seed=1004, O=10)
+    ref = oracle_mod.solve(ocfg, b["x_cur"], b["goal"], obs=b["obs"])
+    res = BatchedMotionPlanner(pcfg, max_batch=4096).solve(_dev(b["x_cur"]), _dev(b["goal"]), obstacles=_dev(b["obs"]),
+                                                            obstacle_radius=ocfg.obs_radius, inflation_radius=ocfg.inflation)
+    conv = _check(res, ref, require_all_converged=False, max_status_mismatch=0.001)
+    assert conv.mean() > 0.995
 
 
 def test_warm_start_and_handoff(oracle_mod):
