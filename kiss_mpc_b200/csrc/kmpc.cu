@@ -152,32 +152,38 @@ kmpc_trial_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_
 #define KMPC_MINB1 2
 #endif
 #ifndef KMPC_WPB2
-#define KMPC_WPB2 9
+#define KMPC_WPB2 8
 #endif
 #ifndef KMPC_MINB2
 #define KMPC_MINB2 1
 #endif
+#ifndef KMPC_WPB3
+#define KMPC_WPB3 9
+#endif
+#ifndef KMPC_MINB3
+#define KMPC_MINB3 1
+#endif
 // FULL: every bound of x, y, v, omega exists (the default problem), so the per-side tests are compiled away.
 // OBS: obstacle-distance rows present (their per-row state lives in shared memory; the block shrinks to what fits).
-template <int SPL, bool FULL, bool OBS, int WPB, int MINB>
+template <int SPL, int NST, bool FULL, bool OBS, int WPB, int MINB>
 __global__ void __launch_bounds__(32 * WPB, MINB)
 kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned long long *__restrict__ trips_total) {
-    extern __shared__ double s_dyn[];  // WLay<SPL>::bytes(warps per block, O)
-    w_worker<SPL, FULL, OBS>(c, io, s_dyn, queue, trips_total);
+    extern __shared__ double s_dyn[];  // WLay<SPL, NST>::bytes(warps per block, O)
+    w_worker<SPL, NST, FULL, OBS>(c, io, s_dyn, queue, trips_total);
 }
 
 // returns cudaErrorInvalidConfiguration if not even one instance fits into shared memory (caller falls back)
-template <int SPL, bool FULL, bool OBS, int WPB, int MINB>
+template <int SPL, int NST, bool FULL, bool OBS, int WPB, int MINB>
 static cudaError_t launch_warp_kernel(int device, int sm_count, int B, const Cfg &c, const IO &io, int *queue, unsigned long long *trips,
                                       cudaStream_t st) {
     int max_smem = 0;
     cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) return e;
     int wpb = WPB;
-    while (wpb > 0 && WLay<SPL>::bytes(wpb, c.O) > (size_t)max_smem) --wpb;
+    while (wpb > 0 && WLay<SPL, NST>::bytes(wpb, c.O) > (size_t)max_smem) --wpb;
     if (wpb < 1) return cudaErrorInvalidConfiguration;
-    const size_t smem = WLay<SPL>::bytes(wpb, c.O);
-    auto kern = kmpc_warp_kernel<SPL, FULL, OBS, WPB, MINB>;
+    const size_t smem = WLay<SPL, NST>::bytes(wpb, c.O);
+    auto kern = kmpc_warp_kernel<SPL, NST, FULL, OBS, WPB, MINB>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int bpsm = 0;
@@ -413,17 +419,14 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
         for (int i = 0; i < 4; ++i) full = full && c.hasL[i] && c.hasU[i];
         cudaError_t le;
         const int dv = h->device, sms = h->sm_count;
-        if (cf->N + 1 <= 32) {
-            if (O > 0) le = full ? launch_warp_kernel<1, true, true, 8, 1>(dv, sms, B, c, io, h->cnt, ls.trips, st)
-                                 : launch_warp_kernel<1, false, true, 8, 1>(dv, sms, B, c, io, h->cnt, ls.trips, st);
-            else le = full ? launch_warp_kernel<1, true, false, KMPC_WPB1, KMPC_MINB1>(dv, sms, B, c, io, h->cnt, ls.trips, st)
-                           : launch_warp_kernel<1, false, false, KMPC_WPB1, KMPC_MINB1>(dv, sms, B, c, io, h->cnt, ls.trips, st);
-        } else {
-            if (O > 0) le = full ? launch_warp_kernel<2, true, true, 6, 1>(dv, sms, B, c, io, h->cnt, ls.trips, st)
-                                 : launch_warp_kernel<2, false, true, 6, 1>(dv, sms, B, c, io, h->cnt, ls.trips, st);
-            else le = full ? launch_warp_kernel<2, true, false, KMPC_WPB2, KMPC_MINB2>(dv, sms, B, c, io, h->cnt, ls.trips, st)
-                           : launch_warp_kernel<2, false, false, KMPC_WPB2, KMPC_MINB2>(dv, sms, B, c, io, h->cnt, ls.trips, st);
-        }
+#define KMPC_LAUNCH(SPL, NST, OBS, WPB, MINB)                                                                          \
+    (full ? launch_warp_kernel<SPL, NST, true, OBS, WPB, MINB>(dv, sms, B, c, io, h->cnt, ls.trips, st)                 \
+          : launch_warp_kernel<SPL, NST, false, OBS, WPB, MINB>(dv, sms, B, c, io, h->cnt, ls.trips, st))
+        // stage slots per field: 32 (N <= 31), 52 (N <= 51, e.g. the N = 50 configuration), 64 (N <= 63)
+        if (cf->N + 1 <= 32) le = O > 0 ? KMPC_LAUNCH(1, 32, true, 8, 1) : KMPC_LAUNCH(1, 32, false, KMPC_WPB1, KMPC_MINB1);
+        else if (cf->N + 1 <= 52) le = O > 0 ? KMPC_LAUNCH(2, 52, true, 6, 1) : KMPC_LAUNCH(2, 52, false, KMPC_WPB2, KMPC_MINB2);
+        else le = O > 0 ? KMPC_LAUNCH(2, 64, true, 6, 1) : KMPC_LAUNCH(2, 64, false, KMPC_WPB3, KMPC_MINB3);
+#undef KMPC_LAUNCH
         if (le == cudaErrorInvalidConfiguration && O > 0) use_warp_fits = false;  // too many obstacle rows for shared memory
         else { CU(le); }
         if (use_warp_fits) {

@@ -58,9 +58,10 @@ struct WScal {  // warp-uniform per-instance scalars
     int flag, ok, r, status;
 };
 
-template <int SPL>
+// NST = stage slots allocated per field (>= N + 1, <= 32 * SPL): a smaller NST than 32 * SPL lets more instances fit
+template <int SPL, int NST = 32 * SPL>
 struct WLay {
-    static constexpr int NSTG = 32 * SPL;
+    static constexpr int NSTG = NST;
     static constexpr int COOP = C_NF * NSTG + 1;
     static constexpr int PRIV = V_NF * NSTG;
     KMPC_HD static int obs_doubles(int O) { return O > 0 ? B_NF * O * NSTG + 2 * O : 0; }
@@ -188,9 +189,9 @@ KMPC_W WObsV w_obs_vals(const Cfg &c, const WObsT &ot, double s, double yd, doub
 }
 
 // ---- starting point: optimizer.py:375-385 (warm start) / agent.py:59-60 (cold start); IPOPT initialisation ----
-template <int SPL, bool OBS>
+template <int SPL, int NST, bool OBS>
 KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<SPL> &w, double *ob) {
-    constexpr int NSTG = WLay<SPL>::NSTG;
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
     const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     if (OBS) {  // circle centres -> shared memory (optimizer.py:217-221)
         double *cxy = ob + B_NF * O * NSTG;
@@ -257,9 +258,9 @@ KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<
 // ---- phase 1a, ASSEMBLE: stage blocks of the KKT system -> coop area (all stages at once) ----
 // Stages without a control (the terminal stage N) become pass-through steps of the recursion: zero dynamics, unit Q_uu,
 // zero rhs -> P_out = P_in + Q, p_out = p_in + q.  Also leaves the reciprocal slacks of the iterate in the private area.
-template <int SPL, bool FULL, bool OBS>
+template <int SPL, int NST, bool FULL, bool OBS>
 KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, double *priv, double *coop, const double *ob) {
-    constexpr int NSTG = WLay<SPL>::NSTG;
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
     const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     const int mode = sc->t.mode;
     const bool lsq = mode == M_LSQ, soc = mode == M_SOC;
@@ -459,10 +460,10 @@ KMPC_WN inline bool w_serial(const Cfg &c, double *coop, const int NSTG, const d
 }
 
 // ---- phase 2, STEP: multiplier step dy = -(P dx + p), step-size limits, directional derivative (all stages at once) ----
-template <int SPL, bool FULL, bool OBS>
+template <int SPL, int NST, bool FULL, bool OBS>
 KMPC_WN inline void w_step(const Cfg &c, const WScal *sc, const WState<SPL> &w, const double *coop, const double *priv,
                            const double *ob, WStep<SPL> &d, double *alpha_pr, double *alpha_du, double *gBD, double *ymax) {
-    constexpr int NSTG = WLay<SPL>::NSTG;
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
     const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     const bool lsq = sc->t.mode == M_LSQ, soc = sc->t.mode == M_SOC;
     const double mu = sc->t.mu, df = sc->t.df, tau = sc->t.tau, delta = sc->t.delta;
@@ -527,21 +528,23 @@ KMPC_WN inline void w_step(const Cfg &c, const WScal *sc, const WState<SPL> &w, 
 }
 
 // kept Newton step <-> private area
-template <int SPL>
+template <int SPL, int NST>
 KMPC_W void w_step_store(const WStep<SPL> &d, double *priv) {
-    constexpr int NSTG = WLay<SPL>::NSTG;
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
+        if (w_lane() * SPL + j >= NSTG) continue;
         double *p = priv + w_lane() * SPL + j;
         p[V_DX0 * NSTG] = d.dx0[j]; p[V_DX1 * NSTG] = d.dx1[j]; p[V_DX2 * NSTG] = d.dx2[j]; p[V_DU0 * NSTG] = d.du0[j];
         p[V_DU1 * NSTG] = d.du1[j]; p[V_DY0 * NSTG] = d.dy0[j]; p[V_DY1 * NSTG] = d.dy1[j]; p[V_DY2 * NSTG] = d.dy2[j];
     }
 }
-template <int SPL>
+template <int SPL, int NST>
 KMPC_W void w_step_load(WStep<SPL> &d, const double *priv) {
-    constexpr int NSTG = WLay<SPL>::NSTG;
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
+        if (w_lane() * SPL + j >= NSTG) { d.dx0[j] = d.dx1[j] = d.dx2[j] = d.du0[j] = d.du1[j] = d.dy0[j] = d.dy1[j] = d.dy2[j] = 0.0; continue; }
         const double *p = priv + w_lane() * SPL + j;
         d.dx0[j] = p[V_DX0 * NSTG]; d.dx1[j] = p[V_DX1 * NSTG]; d.dx2[j] = p[V_DX2 * NSTG]; d.du0[j] = p[V_DU0 * NSTG];
         d.du1[j] = p[V_DU1 * NSTG]; d.dy0[j] = p[V_DY0 * NSTG]; d.dy1[j] = p[V_DY1 * NSTG]; d.dy2[j] = p[V_DY2 * NSTG];
@@ -549,10 +552,10 @@ KMPC_W void w_step_load(WStep<SPL> &d, const double *priv) {
 }
 
 // ---- phase 3, TRIAL: trial point + speculative multiplier update + residual norms (all stages at once) ----
-template <int SPL, bool FULL, bool OBS>
+template <int SPL, int NST, bool FULL, bool OBS>
 KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w, const WStep<SPL> &d, double alpha, double ay,
                             double adu, bool clamp, WState<SPL> &n, double *priv, double *scr, double *ob, Stats *out) {
-    constexpr int NSTG = WLay<SPL>::NSTG;
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
     const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     const double mu = sc->t.mu, df = sc->t.df, T = c.T, delta = sc->t.delta;
     const bool lsq = sc->t.mode == M_LSQ, soc = sc->t.mode == M_SOC;
@@ -676,10 +679,10 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
 
 // accepted trial point: the slack / multiplier values of the obstacle rows are recomputed (same formulas, same inputs as
 // in the trial pass, hence the same bits) and become current.  Must run before `cur` is overwritten.
-template <int SPL>
+template <int SPL, int NST>
 KMPC_WN inline void w_obs_commit(const Cfg &c, const WState<SPL> &w, const WStep<SPL> &d, double mu, double delta, double alpha,
                                  double ay, double adu, bool clamp, bool lsq, bool soc, double *ob) {
-    constexpr int NSTG = WLay<SPL>::NSTG;
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
     const int N = c.N, lane = w_lane(), O = c.O;
     const double *cxy = ob + B_NF * O * NSTG;
 #pragma unroll
@@ -698,9 +701,9 @@ KMPC_WN inline void w_obs_commit(const Cfg &c, const WState<SPL> &w, const WStep
 }
 
 // c_soc <- al * base + c(trial); base = c(current) for the first correction, else the previous c_soc
-template <int SPL, bool OBS>
+template <int SPL, int NST, bool OBS>
 KMPC_WN inline void w_soc_rhs(const Cfg &c, const WScal *sc, const WState<SPL> &w, double al, bool first, double *priv, double *ob) {
-    constexpr int NSTG = WLay<SPL>::NSTG;
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
     const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     const double T = c.T;
     double xp0[SPL], xp1[SPL], xp2[SPL], pp0[SPL], pp1[SPL], pp2[SPL];
@@ -758,10 +761,10 @@ KMPC_WN inline int w_fetch_active(const Cfg &c, const IO &io, int *queue) {
 
 // ---- persistent worker: one warp pulls instances from a queue and solves each start to finish; the warps of a block
 // walk through the phases of a trip in step (block barriers) so that warp 0 can run every instance's serial recursions.
-// smem: WLay<SPL>::bytes(warps per block) bytes of block-shared scratch.
-template <int SPL, bool FULL, bool OBS>
+// smem: WLay<SPL, NST>::bytes(warps per block, O) bytes of block-shared scratch.
+template <int SPL, int NST, bool FULL, bool OBS>
 KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queue, unsigned long long *trips_total) {
-    typedef WLay<SPL> LY;
+    typedef WLay<SPL, NST> LY;
     const int N = c.N, lane = w_lane(), wid = w_warp(), W = w_warps();
     double *coop = smem + (size_t)wid * LY::COOP;
     double *priv = smem + (size_t)W * LY::COOP + (size_t)wid * LY::PRIV;
@@ -784,7 +787,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         // in that window (the global-memory round trip then costs the block nothing)
         if (!have && !drained && wid == 0) {
             b = w_fetch_active(c, io, queue);
-            if (b < c.B) { w_init<SPL, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
+            if (b < c.B) { w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
         }
         PT(0)
         if (!w_block_any(have)) break;
@@ -793,7 +796,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         // ---- phase 1a: assemble the stage blocks ----
         const int mode = t.mode;
         const bool do_sweep = have && mode != M_TRIAL;
-        if (do_sweep) w_assemble<SPL, FULL, OBS>(c, sc, cur, priv, coop, ob);
+        if (do_sweep) w_assemble<SPL, NST, FULL, OBS>(c, sc, cur, priv, coop, ob);
         if (lane == 0) { sc->flag = do_sweep ? 1 : 0; if (do_sweep) t.trips++; }
         PT(2)
         w_block_sync();
@@ -807,7 +810,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             }
         } else if (!have && !drained) {
             b = w_fetch_active(c, io, queue);
-            if (b < c.B) { w_init<SPL, OBS>(c, sc, io, b, cur, ob); fresh = true; } else drained = true;
+            if (b < c.B) { w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); fresh = true; } else drained = true;
         }
         PT(4)
         w_block_sync();
@@ -822,16 +825,16 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 status = sc->status;
             } else {
                 double apr, adu, gbd, ym;
-                w_step<SPL, FULL, OBS>(c, sc, cur, coop, priv, ob, act, &apr, &adu, &gbd, &ym);
+                w_step<SPL, NST, FULL, OBS>(c, sc, cur, coop, priv, ob, act, &apr, &adu, &gbd, &ym);
                 if (lane == 0) rollout_logic(t, apr, adu, gbd, ym);
                 w_sync();
-                if (t.sel == 0) w_step_store<SPL>(act, priv);
+                if (t.sel == 0) w_step_store<SPL, NST>(act, priv);
                 go_trial = true;
             }
         } else if (have) {
             if (lane == 0) trial_setup(t);
             w_sync();
-            w_step_load<SPL>(act, priv);
+            w_step_load<SPL, NST>(act, priv);
         }
         PT(6)
         // ---- phase 3: trial point + acceptance logic ----
@@ -841,7 +844,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             // step sizes / barrier parameters of THIS trial, read before lane 0 moves the context on (begin_iteration)
             const double ta_pr = t.a_pr, ta_y = t.a_y, ta_du = t.a_du, ta_mu = t.mu, ta_delta = t.delta;
             const bool tclamp = t.tu == TU_STEP, tlsq = t.mode == M_LSQ, tsoc = t.mode == M_SOC;
-            const bool evok = w_trial<SPL, FULL, OBS>(c, sc, cur, act, ta_pr, ta_y, ta_du, tclamp, tri, priv, coop, ob, &ts);
+            const bool evok = w_trial<SPL, NST, FULL, OBS>(c, sc, cur, act, ta_pr, ta_y, ta_du, tclamp, tri, priv, coop, ob, &ts);
             PT(7)
             if (lane == 0) {
                 bool aug; double ath, aph;
@@ -851,11 +854,11 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             }
             w_sync();
             const int r = sc->r;
-            if (r == R_SOC1 || r == R_SOC2) { PT_COUNT(11) w_soc_rhs<SPL, OBS>(c, sc, cur, t.alpha_soc, r == R_SOC1, priv, ob); }
+            if (r == R_SOC1 || r == R_SOC2) { PT_COUNT(11) w_soc_rhs<SPL, NST, OBS>(c, sc, cur, t.alpha_soc, r == R_SOC1, priv, ob); }
             else if (r == R_ACCEPT) {
                 PT_COUNT(12)
                 if (mode == M_SOC) { PT_COUNT(14) }
-                if (OBS) w_obs_commit<SPL>(c, cur, act, ta_mu, ta_delta, ta_pr, ta_y, ta_du, tclamp, tlsq, tsoc, ob);
+                if (OBS) w_obs_commit<SPL, NST>(c, cur, act, ta_mu, ta_delta, ta_pr, ta_y, ta_du, tclamp, tlsq, tsoc, ob);
                 cur = tri;
                 if (lane == 0) { t.c = ts; sc->status = begin_iteration(c, t); }
                 w_sync();

@@ -138,21 +138,20 @@ extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur
     const int spl = cf->N + 1 <= 32 ? 1 : 2;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int b = 0; b < B; ++b) {
-        std::vector<double> smem((spl == 1 ? WLay<1>::bytes(1, O) : WLay<2>::bytes(1, O)) / sizeof(double), NAN);  // one emulated warp = one block
+        std::vector<double> smem((spl == 1 ? WLay<1, 32>::bytes(1, O) : cf->N + 1 <= 52 ? WLay<2, 52>::bytes(1, O) : WLay<2, 64>::bytes(1, O)) / sizeof(double), NAN);  // one emulated warp = one block
         unsigned long long tr = 0;
         int queue = b;          // this emulated warp is handed exactly instance b
         Cfg cb = c; cb.B = b + 1;
         bool full = true;
         for (int i = 0; i < 4; ++i) full = full && c.hasL[i] && c.hasU[i];
+        const int nst = spl == 1 ? 32 : cf->N + 1 <= 52 ? 52 : 64;
+#define EMUL_RUN(SPL, NST) do { \
+            if (O > 0) { if (full) w_worker<SPL, NST, true, true>(cb, io, smem.data(), &queue, &tr); else w_worker<SPL, NST, false, true>(cb, io, smem.data(), &queue, &tr); } \
+            else { if (full) w_worker<SPL, NST, true, false>(cb, io, smem.data(), &queue, &tr); else w_worker<SPL, NST, false, false>(cb, io, smem.data(), &queue, &tr); } } while (0)
         simt_run([&]() {
-            if (O > 0) {
-                if (spl == 1) { if (full) w_worker<1, true, true>(cb, io, smem.data(), &queue, &tr); else w_worker<1, false, true>(cb, io, smem.data(), &queue, &tr); }
-                else { if (full) w_worker<2, true, true>(cb, io, smem.data(), &queue, &tr); else w_worker<2, false, true>(cb, io, smem.data(), &queue, &tr); }
-            } else {
-                if (spl == 1) { if (full) w_worker<1, true, false>(cb, io, smem.data(), &queue, &tr); else w_worker<1, false, false>(cb, io, smem.data(), &queue, &tr); }
-                else { if (full) w_worker<2, true, false>(cb, io, smem.data(), &queue, &tr); else w_worker<2, false, false>(cb, io, smem.data(), &queue, &tr); }
-            }
+            if (nst == 32) EMUL_RUN(1, 32); else if (nst == 52) EMUL_RUN(2, 52); else EMUL_RUN(2, 64);
         });
+#undef EMUL_RUN
         if (trips) trips[b] = (int)tr;
     }
     return 0;
