@@ -549,12 +549,19 @@ extern "C" int kmpc_solve_host(kmpc_handle *h, int B, const double *x_cur, const
     if (O) { oO = o; memcpy(h->h_in + o, obs_centers, b * 2 * O * sizeof(double)); o += b * 2 * O; }
     (void)hx; (void)hg;
     CU(cudaMemcpyAsync(h->d_in, h->h_in, o * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    double *dX = h->d_out, *dU = h->d_out + nX, *dobj = h->d_out + nX + nU;
+    // Results: the warp solver writes each finished instance straight into the pinned host buffers (device-visible under
+    // unified addressing), so the 81 MB of D2H traffic at B = 65,536 rides over PCIe while later instances are still being
+    // solved; the thread solver (piecemeal writes) goes through device staging and a copy.
+    const bool direct = h->cfg.N + 1 <= 64 && getenv("KMPC_FORCE_THREAD") == NULL && getenv("KMPC_STAGED_D2H") == NULL;
+    double *dX = direct ? h->h_out : h->d_out, *dU = dX + nX, *dobj = dX + nX + nU;
+    int32_t *dst = direct ? h->h_iout : h->d_iout;
     rc = kmpc_solve(h, B, h->d_in, h->d_in + b * 3, X0 ? h->d_in + oX : NULL, X0 ? h->d_in + oU : NULL, O ? h->d_in + oO : NULL, O,
-                    obs_radius, inflation, dX, dU, dobj, h->d_iout, h->d_iout + b, h->stream);
+                    obs_radius, inflation, dX, dU, dobj, dst, dst + b, h->stream);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(h->h_out, h->d_out, (nX + nU + b) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(h->h_iout, h->d_iout, b * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (!direct) {
+        CU(cudaMemcpyAsync(h->h_out, h->d_out, (nX + nU + b) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->h_iout, h->d_iout, b * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
     CU(cudaStreamSynchronize(h->stream));
     h->host_B = B;
     if (!X_out) return 0;  // zero-copy: the caller reads the pinned buffers through kmpc_host_result

@@ -272,6 +272,9 @@ KMPC_HD bool bound_trial(double val, double d, double vt, double lb, double ub, 
 // A NaN in the FIRST argument is ignored (as fmin / fmax would), so candidates go first, accumulators second.
 KMPC_HD double kmin(double cand, double acc) { return cand < acc ? cand : acc; }
 KMPC_HD double kmax(double cand, double acc) { return cand > acc ? cand : acc; }
+// fmax / fmin with their exact NaN semantics (a NaN operand is dropped) in 4 instructions instead of ~9
+KMPC_HD double kfmax(double a, double b) { return (a > b || b != b) ? a : b; }
+KMPC_HD double kfmin(double a, double b) { return (a < b || b != b) ? a : b; }
 KMPC_HD double maxabs_nan(double m, double v) { double t = fabs(v); return (t > m || t != t) ? t : m; }
 
 // ------------------------------------------------------------------------------------------------
@@ -818,14 +821,14 @@ KMPC_HDN inline void pass_output(const Cfg &c, const Ctx &t, double *wsp, size_t
 
 // ---- scalar logic -------------------------------------------------------------------------------
 KMPC_HD double compl_inf(const Cfg &c, const Stats &s, double mu) {
-    return c.nb ? fmax(fabs(s.mx - mu), fabs(s.mn - mu)) : 0.0;
+    return c.nb ? kfmax(fabs(s.mx - mu), fabs(s.mn - mu)) : 0.0;
 }
 KMPC_HD double opt_error(const Cfg &c, const Stats &s, double mu) {
     // s_d = max(s_max, (|y|_1 + |z|_1) / (m + n_b)) / s_max, s_c likewise; both are >= 1 and almost always exactly 1
-    const double sd = fmax(K_S_MAX, (s.sumy + s.sumz) * c.r_mnb) * (1.0 / K_S_MAX);
-    const double sc = c.nb ? fmax(K_S_MAX, s.sumz * c.r_nb) * (1.0 / K_S_MAX) : 1.0;
+    const double sd = kfmax(K_S_MAX, (s.sumy + s.sumz) * c.r_mnb) * (1.0 / K_S_MAX);
+    const double sc = c.nb ? kfmax(K_S_MAX, s.sumz * c.r_nb) * (1.0 / K_S_MAX) : 1.0;
     const double di = sd > 1.0 ? s.dinf / sd : s.dinf, ci = compl_inf(c, s, mu);
-    return fmax(di, fmax(s.pinf, sc > 1.0 ? ci / sc : ci));
+    return kfmax(di, kfmax(s.pinf, sc > 1.0 ? ci / sc : ci));
 }
 KMPC_HD double phi_of(const Stats &s, double mu) { return s.f - mu * s.bar + K_KAPPA_D * mu * s.damp; }
 
@@ -846,7 +849,28 @@ KMPC_HD void filter_add(Ctx &t, double *filt, size_t FS, double theta, double ph
 }
 
 // FilterLSAcceptor::CheckAcceptabilityOfTrialPoint
-KMPC_HD bool is_ftype(const Ctx &t, double a) { return t.gBD < 0 && a * t.pw_g > K_DELTA_LS * t.pw_t; }
+// switching condition  gBD < 0  and  a (-gBD)^s_phi > delta theta^s_theta  (theta, gBD of the current iterate).
+// On the device the comparison is screened in single precision in the log2 domain (three MUFU.LG2); only a near-tie
+// (|log2 ratio| < 2^-6, far above the float error of ~1e-5) or an out-of-range operand takes the double-precision pow path.
+KMPC_HD bool is_ftype(const Ctx &t, double a) {
+    if (!(t.gBD < 0)) return false;
+#ifdef __CUDA_ARCH__
+    const float L = __log2f((float)a) + (float)K_S_PHI * __log2f((float)(-t.gBD)) - (float)K_S_THETA * __log2f((float)t.c.theta)
+                    - __log2f((float)K_DELTA_LS);
+    if (fabsf(L) > 0.015625f && fabsf(L) < 1e30f) return L > 0.0f;
+#endif
+    return a * pow(-t.gBD, K_S_PHI) > K_DELTA_LS * pow(t.c.theta, K_S_THETA);
+}
+// smallest step size of the back-tracking line search before IPOPT would switch to the restoration phase
+// (FilterLSAcceptor::CalculateAlphaMin); evaluated only when a trial point has been rejected
+KMPC_HD double alpha_min_of(const Ctx &t) {
+    double amin = K_GAMMA_THETA;
+    if (t.gBD < 0) {
+        amin = fmin(K_GAMMA_THETA, K_GAMMA_PHI * t.c.theta / (-t.gBD));
+        if (t.c.theta <= t.theta_min) amin = fmin(amin, K_DELTA_LS * pow(t.c.theta, K_S_THETA) / pow(-t.gBD, K_S_PHI));
+    }
+    return amin * K_ALPHA_MIN_FRAC;
+}
 KMPC_HD bool armijo(const Ctx &t, double a, double tphi, double cphi) { return cmp_le(tphi - cphi, K_ETA_PHI * a * t.gBD, cphi); }
 KMPC_HD bool acceptable(const Ctx &t, const double *filt, size_t FS, const Stats &tri) {
     const double cphi = phi_of(t.c, t.mu), tphi = phi_of(tri, t.mu), cth = t.c.theta;
@@ -877,9 +901,9 @@ KMPC_HD int begin_iteration(const Cfg &c, Ctx &t) {
     if (t.c.wmax > K_DIVERGING) return ST_DIVERGING;
     bool done = false;
     while (!done && opt_error(c, t.c, t.mu) <= K_KAPPA_EPS * t.mu) {
-        const double nm = fmax(fmin(K_MU_LIN * t.mu, t.mu * sqrt(t.mu)), fmin(c.tol, K_COMPL_INF_TOL) / (K_KAPPA_EPS + 1.0));  // mu^1.5 (mu_superlinear_decrease_power)
+        const double nm = kfmax(kfmin(K_MU_LIN * t.mu, t.mu * sqrt(t.mu)), kfmin(c.tol, K_COMPL_INF_TOL) / (K_KAPPA_EPS + 1.0));  // mu^1.5 (mu_superlinear_decrease_power)
         const bool changed = nm != t.mu;
-        t.mu = nm; t.tau = fmax(K_TAU_MIN, 1.0 - t.mu);
+        t.mu = nm; t.tau = kfmax(K_TAU_MIN, 1.0 - t.mu);
         if (changed) t.fn = 0; else done = true;
     }
     t.delta = 0.0;
@@ -922,16 +946,6 @@ KMPC_HD void rollout_logic(Ctx &t, double apr, double adu, double gbd, double ym
         if (t.delta > 0.0) t.delta_last = t.delta;
         t.gBD = gbd;
         if (t.theta_max < 0) { t.theta_max = K_THETA_MAX_FACT * fmax(1.0, t.c.theta); t.theta_min = K_THETA_MIN_FACT * fmax(1.0, t.c.theta); }
-        double amin = K_GAMMA_THETA;
-        t.pw_g = 0.0; t.pw_t = 0.0;
-        if (gbd < 0) {
-            // switching condition a (-gBD)^s_phi > delta theta^s_theta, kept as a > delta * ratio with
-            // ratio = theta^s_theta / (-gBD)^s_phi = exp(s_theta log theta - s_phi log(-gBD))  (pw_g = 1, pw_t = ratio)
-            t.pw_g = 1.0; t.pw_t = exp(K_S_THETA * log(t.c.theta) - K_S_PHI * log(-gbd));
-            amin = fmin(K_GAMMA_THETA, K_GAMMA_PHI * t.c.theta / (-gbd));
-            if (t.c.theta <= t.theta_min) amin = fmin(amin, K_DELTA_LS * t.pw_t / t.pw_g);
-        }
-        t.alpha_min = amin * K_ALPHA_MIN_FRAC;
         t.alpha = apr; t.alpha_test = apr; t.alpha_du0 = adu; t.nsteps = 0; t.soc_count = 0;
         t.a_pr = apr; t.a_y = apr; t.a_du = adu;
     } else {  // M_SOC
@@ -986,7 +1000,7 @@ KMPC_HD int trial_decide(Ctx &t, const double *filt, size_t FS, const Stats &tri
     if (!accept) {
         // back-track on the original step (also after a failed correction)
         t.alpha *= K_ALPHA_RED; t.nsteps++;
-        if (!(t.alpha > t.alpha_min)) return ST_RESTORATION;  // IPOPT would enter the restoration phase here
+        if (!(t.alpha > alpha_min_of(t))) return ST_RESTORATION;  // IPOPT would enter the restoration phase here
         t.mode = M_TRIAL;
         return R_BACKTRACK;
     }

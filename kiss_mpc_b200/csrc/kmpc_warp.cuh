@@ -781,11 +781,14 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     w_sync();
     PT_DECL
     bool drained = false;  // the queue has no more instances for this warp
+    // the block's Riccati warp: co-resident blocks (b and b + gridDim/2 under round-robin placement) pick different warp
+    // slots, hence different schedulers, so that two serial phases that coincide do not share one FP64 issue port
+    const int swid = w_serial_warp(W);
 #pragma unroll 1
     for (;;) {
         // warp 0 is busy in the serial window below, so it takes its next instance here; the other warps take theirs
         // in that window (the global-memory round trip then costs the block nothing)
-        if (!have && !drained && wid == 0) {
+        if (!have && !drained && wid == swid) {
             b = w_fetch_active(c, io, queue);
             if (b < c.B) { w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
         }
@@ -803,7 +806,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         PT(3)
         // ---- phase 1b: the serial recursions of all the block's instances, one lane each ----
         bool fresh = false;  // an instance taken in this window joins the next trip
-        if (wid == 0) {
+        if (wid == swid) {
             if (lane < W) {
                 WScal *so = scal0 + lane;
                 if (so->flag) so->ok = w_serial<OBS>(c, smem + (size_t)lane * LY::COOP, LY::NSTG, so->d0) ? 1 : 0;

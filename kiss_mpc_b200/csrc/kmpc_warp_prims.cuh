@@ -20,6 +20,10 @@ KMPC_W bool w_any(bool p) { return __any_sync(0xffffffffu, p); }
 KMPC_W void w_sync() { __syncwarp(); }
 KMPC_W void w_block_sync() { __syncthreads(); }
 KMPC_W bool w_block_any(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
+#ifndef KMPC_SERIAL_WARP_B
+#define KMPC_SERIAL_WARP_B 2
+#endif
+KMPC_W int w_serial_warp(int W) { return (blockIdx.x >= (gridDim.x + 1) / 2 && W > KMPC_SERIAL_WARP_B) ? KMPC_SERIAL_WARP_B : 0; }
 KMPC_W int w_fetch(int *queue) {  // next instance index for this warp
     int b = 0;
     if ((threadIdx.x & 31u) == 0) b = atomicAdd(queue, 1);
