@@ -217,9 +217,10 @@ def run_ours(args, rank, local_rank, world):
                   "max_abs_control_diff": float(np.abs(Ug - cpu_res.U)[conv_both].max()),
                   "max_rel_objective_diff": float((np.abs(rh.objective[:cpu_n] - cpu_res.obj) / np.abs(cpu_res.obj))[conv_both].max())}
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        import glob
+        tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))   # newest round's ncu --set full capture
+        if tps:
+            traffic = json.load(open(tps[-1])).get("dram_bytes_per_launch")
         print(json.dumps({
             "metric": "mpc_solves_per_sec", "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
