@@ -144,6 +144,34 @@ kmpc_trial_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_
 // queue and solving it start to finish with the whole iterate in registers.  Used for problems without obstacle rows
 // and N + 1 <= 32 * SPL.
 // ------------------------------------------------------------------------------------------------
+#define KMPC_LOOKAHEAD 4 /* trips enqueued before the host looks at the active-instance count of an older trip */
+
+struct kmpc_handle {
+    kmpc_config cfg;
+    Rows rows;
+    int device, sm_count, cols;  // cols = workspace columns (B_max rounded up to a multiple of 32)
+    double *ws;
+    int *lists;  // 4 x cols ints
+    int *cnt;    // 4 counters
+    unsigned long long *trips;
+    int *h_cnt;  // pinned: KMPC_LOOKAHEAD x 4 counters
+    cudaEvent_t ev0, ev1, evq[KMPC_LOOKAHEAD];
+    int timing;
+    double last_ms;
+    long long launches, last_trips;
+    int last_host_trips;
+    // staging for kmpc_solve_host
+    double *d_in, *d_out, *h_in, *h_out;
+    int32_t *d_iout, *h_iout;
+    size_t in_doubles, out_doubles;
+    double *wscratch;      // warp solver: global scratch slots (WLay::GPRIV doubles per resident warp)
+    size_t wscratch_doubles;
+    int host_B;  // batch of the last kmpc_solve_host (addresses kmpc_host_result hands out)
+    cudaStream_t stream;
+    char err[256];
+};
+
+
 // launch shape per stage-slot count: warps (= instances) per block, resident blocks per SM the register budget is cut for
 #ifndef KMPC_WPB1
 #define KMPC_WPB1 8
@@ -156,6 +184,12 @@ kmpc_trial_kernel(const Cfg c, const IO io, double *__restrict__ ws, const size_
 #endif
 #ifndef KMPC_MINB2
 #define KMPC_MINB2 1
+#endif
+#ifndef KMPC_WPBO   /* obstacle-row kernels, N <= 31 */
+#define KMPC_WPBO 12
+#endif
+#ifndef KMPC_MINBO
+#define KMPC_MINBO 1
 #endif
 #ifndef KMPC_WPB3
 #define KMPC_WPB3 9
@@ -174,8 +208,8 @@ kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned lon
 
 // returns cudaErrorInvalidConfiguration if not even one instance fits into shared memory (caller falls back)
 template <int SPL, int NST, bool FULL, bool OBS, int WPB, int MINB>
-static cudaError_t launch_warp_kernel(int device, int sm_count, int B, const Cfg &c, const IO &io, int *queue, unsigned long long *trips,
-                                      cudaStream_t st) {
+static cudaError_t launch_warp_kernel(kmpc_handle *h, int device, int sm_count, int B, const Cfg &c, const IO &io_in, int *queue,
+                                      unsigned long long *trips, cudaStream_t st) {
     int max_smem = 0;
     cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) return e;
@@ -192,6 +226,16 @@ static cudaError_t launch_warp_kernel(int device, int sm_count, int B, const Cfg
     int grid = sm_count * (bpsm > 0 ? bpsm : 1);
     const int need = (B + wpb - 1) / wpb;
     if (grid > need) grid = need;
+    // global scratch: one slot per resident warp (grown on demand; a solve on the handle is never concurrent with another)
+    const size_t want = (size_t)grid * wpb * WLay<SPL, NST>::GPRIV;
+    if (want > h->wscratch_doubles) {
+        if (h->wscratch) { e = cudaStreamSynchronize(st); if (e != cudaSuccess) return e; cudaFree(h->wscratch); h->wscratch = NULL; h->wscratch_doubles = 0; }
+        e = cudaMalloc(&h->wscratch, want * sizeof(double));
+        if (e != cudaSuccess) return e;
+        h->wscratch_doubles = want;
+    }
+    IO io = io_in;
+    io.wscratch = h->wscratch;
     kern<<<grid, 32 * wpb, smem, st>>>(c, io, queue, trips);
     return cudaGetLastError();
 }
@@ -244,31 +288,6 @@ __global__ void kmpc_dfma_kernel(double *out, int iters, double a, double b) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-#define KMPC_LOOKAHEAD 4 /* trips enqueued before the host looks at the active-instance count of an older trip */
-
-struct kmpc_handle {
-    kmpc_config cfg;
-    Rows rows;
-    int device, sm_count, cols;  // cols = workspace columns (B_max rounded up to a multiple of 32)
-    double *ws;
-    int *lists;  // 4 x cols ints
-    int *cnt;    // 4 counters
-    unsigned long long *trips;
-    int *h_cnt;  // pinned: KMPC_LOOKAHEAD x 4 counters
-    cudaEvent_t ev0, ev1, evq[KMPC_LOOKAHEAD];
-    int timing;
-    double last_ms;
-    long long launches, last_trips;
-    int last_host_trips;
-    // staging for kmpc_solve_host
-    double *d_in, *d_out, *h_in, *h_out;
-    int32_t *d_iout, *h_iout;
-    size_t in_doubles, out_doubles;
-    int host_B;  // batch of the last kmpc_solve_host (addresses kmpc_host_result hands out)
-    cudaStream_t stream;
-    char err[256];
-};
-
 static char g_err[256] = "";
 
 static int fail(kmpc_handle *h, int code, const char *fmt, const char *detail) {
@@ -314,6 +333,7 @@ extern "C" void kmpc_destroy(kmpc_handle *h) {
     if (h->cnt) cudaFree(h->cnt);
     if (h->trips) cudaFree(h->trips);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
+    if (h->wscratch) cudaFree(h->wscratch);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_iout) cudaFree(h->d_iout);
@@ -402,7 +422,7 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
     c.r_mnb = 1.0 / (double)(c.m + c.nb); c.r_nb = c.nb ? 1.0 / (double)c.nb : 0.0;
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs_centers;
-    io.X_out = X_out; io.U_out = U_out; io.obj = obj_out; io.status = status_out; io.iters = iters_out; io.active = active;
+    io.X_out = X_out; io.U_out = U_out; io.obj = obj_out; io.status = status_out; io.iters = iters_out; io.active = active; io.wscratch = NULL;
     const size_t S = (size_t)h->cols;
     Lists ls;
     ls.LA[0] = h->lists; ls.LA[1] = h->lists + S; ls.LT[0] = h->lists + 2 * S; ls.LT[1] = h->lists + 3 * S;
@@ -420,10 +440,10 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
         cudaError_t le;
         const int dv = h->device, sms = h->sm_count;
 #define KMPC_LAUNCH(SPL, NST, OBS, WPB, MINB)                                                                          \
-    (full ? launch_warp_kernel<SPL, NST, true, OBS, WPB, MINB>(dv, sms, B, c, io, h->cnt, ls.trips, st)                 \
-          : launch_warp_kernel<SPL, NST, false, OBS, WPB, MINB>(dv, sms, B, c, io, h->cnt, ls.trips, st))
+    (full ? launch_warp_kernel<SPL, NST, true, OBS, WPB, MINB>(h, dv, sms, B, c, io, h->cnt, ls.trips, st)                 \
+          : launch_warp_kernel<SPL, NST, false, OBS, WPB, MINB>(h, dv, sms, B, c, io, h->cnt, ls.trips, st))
         // stage slots per field: 32 (N <= 31), 52 (N <= 51, e.g. the N = 50 configuration), 64 (N <= 63)
-        if (cf->N + 1 <= 32) le = O > 0 ? KMPC_LAUNCH(1, 32, true, 8, 1) : KMPC_LAUNCH(1, 32, false, KMPC_WPB1, KMPC_MINB1);
+        if (cf->N + 1 <= 32) le = O > 0 ? KMPC_LAUNCH(1, 32, true, KMPC_WPBO, KMPC_MINBO) : KMPC_LAUNCH(1, 32, false, KMPC_WPB1, KMPC_MINB1);
         else if (cf->N + 1 <= 52) le = O > 0 ? KMPC_LAUNCH(2, 52, true, 6, 1) : KMPC_LAUNCH(2, 52, false, KMPC_WPB2, KMPC_MINB2);
         else le = O > 0 ? KMPC_LAUNCH(2, 64, true, 6, 1) : KMPC_LAUNCH(2, 64, false, KMPC_WPB3, KMPC_MINB3);
 #undef KMPC_LAUNCH

@@ -135,6 +135,7 @@ struct IO {
     const double *x_cur, *goal, *X0, *U0, *obs;
     double *X_out, *U_out, *obj;
     int32_t *status, *iters;
+    double *wscratch;       // warp solver: global scratch, WLay::GPRIV doubles per resident warp (owned by the handle)
     const int32_t *active;  // optional per-instance mask (closed loop: agents that reached their goal are not solved again)
 };
 #define KMPC_STATUS_SKIPPED 1000  /* status_log value of an agent that was not solved in a closed-loop step */

@@ -43,8 +43,11 @@ enum { C_DX0 = C_K00, C_DX1 = C_K01, C_DX2 = C_K02, C_DU0 = C_K10, C_DU1 = C_K11
 // private area of one instance (owner warp only): the kept Newton step (back-tracking / failed corrections return to
 // it), the second-order-correction rhs, the constraint values of the last trial point
 // + the reciprocal slacks 1/(x - l), 1/(u - x) of the current iterate's four bounded variables (x, y, v, omega)
-enum { V_DX0 = 0, V_DX1, V_DX2, V_DU0, V_DU1, V_DY0, V_DY1, V_DY2, V_CS0, V_CS1, V_CS2, V_CT0, V_CT1, V_CT2,
-       V_RL0, V_RL1, V_RL2, V_RL3, V_RU0, V_RU1, V_RU2, V_RU3, V_NF };
+enum { V_RL0 = 0, V_RL1, V_RL2, V_RL3, V_RU0, V_RU1, V_RU2, V_RU3, V_NF };
+// ... and its rarely-read part in GLOBAL memory (one slot per resident warp, L2-resident; written with fire-and-forget
+// stores, read only by back-tracking trials and second-order corrections): the kept Newton step, the correction rhs, the
+// constraint values of the last trial point.  Keeping it out of shared memory is what lets more instances fit per SM.
+enum { G_DX0 = 0, G_DX1, G_DX2, G_DU0, G_DU1, G_DY0, G_DY1, G_DY2, G_CS0, G_CS1, G_CS2, G_CT0, G_CT1, G_CT2, G_NF };
 
 // obstacle area of one instance (owner warp only; circular obstacle-distance rows of optimizer.py:198-258, README.md:78-81):
 // per (field, obstacle, stage) the slack s of the row d(x_k) - s = 0, its multiplier yd, the multiplier vL of s >= I, the
@@ -64,6 +67,7 @@ struct WLay {
     static constexpr int NSTG = NST;
     static constexpr int COOP = C_NF * NSTG + 1;
     static constexpr int PRIV = V_NF * NSTG;
+    static constexpr int GPRIV = G_NF * NSTG;   // doubles of global scratch per resident warp
     KMPC_HD static int obs_doubles(int O) { return O > 0 ? B_NF * O * NSTG + 2 * O : 0; }
     static size_t bytes(int warps, int O = 0) { return (size_t)warps * ((COOP + PRIV + obs_doubles(O)) * sizeof(double) + sizeof(WScal)); }
 };
@@ -259,7 +263,7 @@ KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<
 // Stages without a control (the terminal stage N) become pass-through steps of the recursion: zero dynamics, unit Q_uu,
 // zero rhs -> P_out = P_in + Q, p_out = p_in + q.  Also leaves the reciprocal slacks of the iterate in the private area.
 template <int SPL, int NST, bool FULL, bool OBS>
-KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, double *priv, double *coop, const double *ob) {
+KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, double *priv, const double *gp, double *coop, const double *ob) {
     constexpr int NSTG = WLay<SPL, NST>::NSTG;
     const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     const int mode = sc->t.mode;
@@ -338,8 +342,8 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
             qw = gw - T * yn2[j] + rbw;
             dv = hvv + (sgv + delta); dw = hww + (sgw + delta);
             if (soc) {  // rhs of the dynamics row s+1 = -c_soc of stage s+1
-                const double *pn = priv + (s + 1 < NSTG ? s + 1 : s);
-                e0 = -pn[V_CS0 * NSTG]; e1 = -pn[V_CS1 * NSTG]; e2 = -pn[V_CS2 * NSTG];
+                const double *pn = gp + (s + 1 < NSTG ? s + 1 : s);
+                e0 = -pn[G_CS0 * NSTG]; e1 = -pn[G_CS1 * NSTG]; e2 = -pn[G_CS2 * NSTG];
             } else { e0 = -(xn0[j] - (x0 + T * v * cs)); e1 = -(xn1[j] - (x1 + T * v * sn)); e2 = -(xn2[j] - (x2 + T * om)); }
         }
         if (s >= N) {
@@ -355,7 +359,7 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
         q[C_QV * NSTG] = qv; q[C_QW * NSTG] = qw; q[C_DV * NSTG] = dv; q[C_DW * NSTG] = dw; q[C_HTV * NSTG] = htv;
         if (s == 0) {  // dx of stage 0 (the rhs of the initial-state row)
             if (lsq) { sc->d0[0] = sc->d0[1] = sc->d0[2] = 0.0; }
-            else if (soc) { sc->d0[0] = -priv[V_CS0 * NSTG]; sc->d0[1] = -priv[V_CS1 * NSTG]; sc->d0[2] = -priv[V_CS2 * NSTG]; }
+            else if (soc) { sc->d0[0] = -gp[G_CS0 * NSTG]; sc->d0[1] = -gp[G_CS1 * NSTG]; sc->d0[2] = -gp[G_CS2 * NSTG]; }
             else { sc->d0[0] = -(x0 - sc->xc[0]); sc->d0[1] = -(x1 - sc->xc[1]); sc->d0[2] = -(x2 - sc->xc[2]); }
         }
     }
@@ -527,34 +531,34 @@ KMPC_WN inline void w_step(const Cfg &c, const WScal *sc, const WState<SPL> &w, 
     *gBD = w_sum(gbd); *ymax = w_max_nn(ym);
 }
 
-// kept Newton step <-> private area
+// kept Newton step <-> global private area
 template <int SPL, int NST>
-KMPC_W void w_step_store(const WStep<SPL> &d, double *priv) {
+KMPC_W void w_step_store(const WStep<SPL> &d, double *gp) {
     constexpr int NSTG = WLay<SPL, NST>::NSTG;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
         if (w_lane() * SPL + j >= NSTG) continue;
-        double *p = priv + w_lane() * SPL + j;
-        p[V_DX0 * NSTG] = d.dx0[j]; p[V_DX1 * NSTG] = d.dx1[j]; p[V_DX2 * NSTG] = d.dx2[j]; p[V_DU0 * NSTG] = d.du0[j];
-        p[V_DU1 * NSTG] = d.du1[j]; p[V_DY0 * NSTG] = d.dy0[j]; p[V_DY1 * NSTG] = d.dy1[j]; p[V_DY2 * NSTG] = d.dy2[j];
+        double *p = gp + w_lane() * SPL + j;
+        p[G_DX0 * NSTG] = d.dx0[j]; p[G_DX1 * NSTG] = d.dx1[j]; p[G_DX2 * NSTG] = d.dx2[j]; p[G_DU0 * NSTG] = d.du0[j];
+        p[G_DU1 * NSTG] = d.du1[j]; p[G_DY0 * NSTG] = d.dy0[j]; p[G_DY1 * NSTG] = d.dy1[j]; p[G_DY2 * NSTG] = d.dy2[j];
     }
 }
 template <int SPL, int NST>
-KMPC_W void w_step_load(WStep<SPL> &d, const double *priv) {
+KMPC_W void w_step_load(WStep<SPL> &d, const double *gp) {
     constexpr int NSTG = WLay<SPL, NST>::NSTG;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
         if (w_lane() * SPL + j >= NSTG) { d.dx0[j] = d.dx1[j] = d.dx2[j] = d.du0[j] = d.du1[j] = d.dy0[j] = d.dy1[j] = d.dy2[j] = 0.0; continue; }
-        const double *p = priv + w_lane() * SPL + j;
-        d.dx0[j] = p[V_DX0 * NSTG]; d.dx1[j] = p[V_DX1 * NSTG]; d.dx2[j] = p[V_DX2 * NSTG]; d.du0[j] = p[V_DU0 * NSTG];
-        d.du1[j] = p[V_DU1 * NSTG]; d.dy0[j] = p[V_DY0 * NSTG]; d.dy1[j] = p[V_DY1 * NSTG]; d.dy2[j] = p[V_DY2 * NSTG];
+        const double *p = gp + w_lane() * SPL + j;
+        d.dx0[j] = p[G_DX0 * NSTG]; d.dx1[j] = p[G_DX1 * NSTG]; d.dx2[j] = p[G_DX2 * NSTG]; d.du0[j] = p[G_DU0 * NSTG];
+        d.du1[j] = p[G_DU1 * NSTG]; d.dy0[j] = p[G_DY0 * NSTG]; d.dy1[j] = p[G_DY1 * NSTG]; d.dy2[j] = p[G_DY2 * NSTG];
     }
 }
 
 // ---- phase 3, TRIAL: trial point + speculative multiplier update + residual norms (all stages at once) ----
 template <int SPL, int NST, bool FULL, bool OBS>
 KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w, const WStep<SPL> &d, double alpha, double ay,
-                            double adu, bool clamp, WState<SPL> &n, double *priv, double *scr, double *ob, Stats *out) {
+                            double adu, bool clamp, WState<SPL> &n, const double *priv, double *gp, double *scr, double *ob, Stats *out) {
     constexpr int NSTG = WLay<SPL, NST>::NSTG;
     const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     const double mu = sc->t.mu, df = sc->t.df, T = c.T, delta = sc->t.delta;
@@ -587,8 +591,9 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
         if (s > N) continue;
         const double x0 = n.x0[j], x1 = n.x1[j], x2 = n.x2[j];
         const double c0 = x0 - (s == 0 ? xc0 : pp0[j]), c1 = x1 - (s == 0 ? xc1 : pp1[j]), c2 = x2 - (s == 0 ? xc2 : pp2[j]);
-        double *pv = priv + s;
-        pv[V_CT0 * NSTG] = c0; pv[V_CT1 * NSTG] = c1; pv[V_CT2 * NSTG] = c2;
+        const double *pv = priv + s;
+        double *pg = gp + s;
+        pg[G_CT0 * NSTG] = c0; pg[G_CT1 * NSTG] = c1; pg[G_CT2 * NSTG] = c2;
         st.theta += fabs(c0) + fabs(c1) + fabs(c2);
         st.pinf = maxabs_nan(maxabs_nan(maxabs_nan(st.pinf, c0), c1), c2);
         st.sumy += fabs(n.y0[j]) + fabs(n.y1[j]) + fabs(n.y2[j]);
@@ -702,7 +707,7 @@ KMPC_WN inline void w_obs_commit(const Cfg &c, const WState<SPL> &w, const WStep
 
 // c_soc <- al * base + c(trial); base = c(current) for the first correction, else the previous c_soc
 template <int SPL, int NST, bool OBS>
-KMPC_WN inline void w_soc_rhs(const Cfg &c, const WScal *sc, const WState<SPL> &w, double al, bool first, double *priv, double *ob) {
+KMPC_WN inline void w_soc_rhs(const Cfg &c, const WScal *sc, const WState<SPL> &w, double al, bool first, double *gp, double *ob) {
     constexpr int NSTG = WLay<SPL, NST>::NSTG;
     const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     const double T = c.T;
@@ -716,11 +721,11 @@ KMPC_WN inline void w_soc_rhs(const Cfg &c, const WScal *sc, const WState<SPL> &
     for (int j = 0; j < SPL; ++j) {
         const int s = lane * SPL + j;
         if (s > N) continue;
-        double *pv = priv + s;
+        double *pv = gp + s;
         double b0, b1, b2;
         if (first) { b0 = w.x0[j] - (s == 0 ? sc->xc[0] : pp0[j]); b1 = w.x1[j] - (s == 0 ? sc->xc[1] : pp1[j]); b2 = w.x2[j] - (s == 0 ? sc->xc[2] : pp2[j]); }
-        else { b0 = pv[V_CS0 * NSTG]; b1 = pv[V_CS1 * NSTG]; b2 = pv[V_CS2 * NSTG]; }
-        pv[V_CS0 * NSTG] = al * b0 + pv[V_CT0 * NSTG]; pv[V_CS1 * NSTG] = al * b1 + pv[V_CT1 * NSTG]; pv[V_CS2 * NSTG] = al * b2 + pv[V_CT2 * NSTG];
+        else { b0 = pv[G_CS0 * NSTG]; b1 = pv[G_CS1 * NSTG]; b2 = pv[G_CS2 * NSTG]; }
+        pv[G_CS0 * NSTG] = al * b0 + pv[G_CT0 * NSTG]; pv[G_CS1 * NSTG] = al * b1 + pv[G_CT1 * NSTG]; pv[G_CS2 * NSTG] = al * b2 + pv[G_CT2 * NSTG];
         if (OBS && s >= 1) {
             const double *cxy = ob + B_NF * O * NSTG;
             for (int o = 0; o < O; ++o) {
@@ -768,6 +773,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     const int N = c.N, lane = w_lane(), wid = w_warp(), W = w_warps();
     double *coop = smem + (size_t)wid * LY::COOP;
     double *priv = smem + (size_t)W * LY::COOP + (size_t)wid * LY::PRIV;
+    double *gp = io.wscratch + ((size_t)w_block() * W + wid) * LY::GPRIV;
     const int OBD = LY::obs_doubles(OBS ? c.O : 0);
     double *ob = smem + (size_t)W * (LY::COOP + LY::PRIV) + (size_t)wid * OBD;
     WScal *scal0 = (WScal *)(smem + (size_t)W * (LY::COOP + LY::PRIV + OBD));
@@ -799,7 +805,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         // ---- phase 1a: assemble the stage blocks ----
         const int mode = t.mode;
         const bool do_sweep = have && mode != M_TRIAL;
-        if (do_sweep) w_assemble<SPL, NST, FULL, OBS>(c, sc, cur, priv, coop, ob);
+        if (do_sweep) w_assemble<SPL, NST, FULL, OBS>(c, sc, cur, priv, gp, coop, ob);
         if (lane == 0) { sc->flag = do_sweep ? 1 : 0; if (do_sweep) t.trips++; }
         PT(2)
         w_block_sync();
@@ -831,13 +837,13 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 w_step<SPL, NST, FULL, OBS>(c, sc, cur, coop, priv, ob, act, &apr, &adu, &gbd, &ym);
                 if (lane == 0) rollout_logic(t, apr, adu, gbd, ym);
                 w_sync();
-                if (t.sel == 0) w_step_store<SPL, NST>(act, priv);
+                if (t.sel == 0) w_step_store<SPL, NST>(act, gp);
                 go_trial = true;
             }
         } else if (have) {
             if (lane == 0) trial_setup(t);
             w_sync();
-            w_step_load<SPL, NST>(act, priv);
+            w_step_load<SPL, NST>(act, gp);
         }
         PT(6)
         // ---- phase 3: trial point + acceptance logic ----
@@ -847,7 +853,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             // step sizes / barrier parameters of THIS trial, read before lane 0 moves the context on (begin_iteration)
             const double ta_pr = t.a_pr, ta_y = t.a_y, ta_du = t.a_du, ta_mu = t.mu, ta_delta = t.delta;
             const bool tclamp = t.tu == TU_STEP, tlsq = t.mode == M_LSQ, tsoc = t.mode == M_SOC;
-            const bool evok = w_trial<SPL, NST, FULL, OBS>(c, sc, cur, act, ta_pr, ta_y, ta_du, tclamp, tri, priv, coop, ob, &ts);
+            const bool evok = w_trial<SPL, NST, FULL, OBS>(c, sc, cur, act, ta_pr, ta_y, ta_du, tclamp, tri, priv, gp, coop, ob, &ts);
             PT(7)
             if (lane == 0) {
                 bool aug; double ath, aph;
@@ -857,7 +863,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             }
             w_sync();
             const int r = sc->r;
-            if (r == R_SOC1 || r == R_SOC2) { PT_COUNT(11) w_soc_rhs<SPL, NST, OBS>(c, sc, cur, t.alpha_soc, r == R_SOC1, priv, ob); }
+            if (r == R_SOC1 || r == R_SOC2) { PT_COUNT(11) w_soc_rhs<SPL, NST, OBS>(c, sc, cur, t.alpha_soc, r == R_SOC1, gp, ob); }
             else if (r == R_ACCEPT) {
                 PT_COUNT(12)
                 if (mode == M_SOC) { PT_COUNT(14) }

@@ -10,6 +10,7 @@ namespace kmpc {
 KMPC_W int w_lane() { return (int)(threadIdx.x & 31u); }
 KMPC_W int w_warp() { return (int)(threadIdx.x >> 5); }   // warp index inside the block
 KMPC_W int w_warps() { return (int)(blockDim.x >> 5); }  // warps per block
+KMPC_W int w_block() { return (int)blockIdx.x; }
 KMPC_W double w_down(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
 KMPC_W double w_up(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
 KMPC_W double w_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }

@@ -68,7 +68,7 @@ extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, con
     Cfg c = make_cfg(cf, B, O, obs_radius, inflation);
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs;
-    io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL;
+    io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL; io.wscratch = NULL;
     // Mirrors the launch structure of kmpc.cu on the host: per trip, sweep(LA[p]) -> rollout(LT[p]) -> trial(LT[p]), with the
     // solver context stored in / reloaded from the workspace between the phases exactly as the kernels do.
     const size_t S = (size_t)((B + 31) / 32 * 32);
@@ -134,7 +134,7 @@ extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur
     Cfg c = make_cfg(cf, B, O, obs_radius, inflation);
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs;
-    io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL;
+    io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL; io.wscratch = NULL;
     const int spl = cf->N + 1 <= 32 ? 1 : 2;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int b = 0; b < B; ++b) {
@@ -142,12 +142,14 @@ extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur
         unsigned long long tr = 0;
         int queue = b;          // this emulated warp is handed exactly instance b
         Cfg cb = c; cb.B = b + 1;
+        std::vector<double> gscr(G_NF * 64, NAN);   // the warp's global scratch slot
+        IO iob = io; iob.wscratch = gscr.data();
         bool full = true;
         for (int i = 0; i < 4; ++i) full = full && c.hasL[i] && c.hasU[i];
         const int nst = spl == 1 ? 32 : cf->N + 1 <= 52 ? 52 : 64;
 #define EMUL_RUN(SPL, NST) do { \
-            if (O > 0) { if (full) w_worker<SPL, NST, true, true>(cb, io, smem.data(), &queue, &tr); else w_worker<SPL, NST, false, true>(cb, io, smem.data(), &queue, &tr); } \
-            else { if (full) w_worker<SPL, NST, true, false>(cb, io, smem.data(), &queue, &tr); else w_worker<SPL, NST, false, false>(cb, io, smem.data(), &queue, &tr); } } while (0)
+            if (O > 0) { if (full) w_worker<SPL, NST, true, true>(cb, iob, smem.data(), &queue, &tr); else w_worker<SPL, NST, false, true>(cb, iob, smem.data(), &queue, &tr); } \
+            else { if (full) w_worker<SPL, NST, true, false>(cb, iob, smem.data(), &queue, &tr); else w_worker<SPL, NST, false, false>(cb, iob, smem.data(), &queue, &tr); } } while (0)
         simt_run([&]() {
             if (nst == 32) EMUL_RUN(1, 32); else if (nst == 52) EMUL_RUN(2, 52); else EMUL_RUN(2, 64);
         });

@@ -36,6 +36,7 @@ inline const double *simt_rendezvous(double v) {
 inline int w_lane() { return g_simt->cur; }
 inline int w_warp() { return 0; }   // one emulated warp = one block
 inline int w_warps() { return 1; }
+inline int w_block() { return 0; }
 inline int w_serial_warp(int) { return 0; }
 inline double w_down(double v, int d) { const int me = w_lane(); const double *b = simt_rendezvous(v); return me + d < 32 ? b[me + d] : v; }
 inline double w_up(double v, int d) { const int me = w_lane(); const double *b = simt_rendezvous(v); return me - d >= 0 ? b[me - d] : v; }
