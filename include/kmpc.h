@@ -116,6 +116,18 @@ int kmpc_host_result(kmpc_handle *h, const double **X, const double **U, const d
 int kmpc_agent_handoff(kmpc_handle *h, int B, const double *X, const double *U, double *x_cur, double *applied_out,
                        void *cuda_stream);
 
+/* Replaces the sensor filter of ROSEnvironment.step (environment.py:48-65) for B agents at once: of M candidate circles
+ * (cand_centers[M][2], cand_radius[M], shared by all agents) every agent keeps those whose distance to its state is
+ * <= sensor_radius (agent.py:101 default 5), nearest first, at most O of them.  Distance = Obstacle.calculate_distance
+ * (obstacle.py:22-23 -> geometry.py:44): literal != 0 gives the formula as written, ||(p - c) - r||_2 (the radius is subtracted
+ * from both components); literal == 0 the intended ||p - c||_2 - r.  Candidates at exactly equal distance
+ * collapse to the LAST one (the reference keys a dict by distance, environment.py:48-51).  obs_out has the handle's obstacle
+ * layout ([B][O][2] / [O][2][B]); unused slots get (pad_x, pad_y) -- pick a point far outside the workspace, its rows stay
+ * inactive; count_out[B] (may be NULL) is the number of real obstacles per agent.  Device pointers, asynchronous. */
+int kmpc_select_obstacles(kmpc_handle *h, int B, int M, const double *x_cur, const double *cand_centers, const double *cand_radius,
+                          double sensor_radius, int literal, int O, double pad_x, double pad_y, double *obs_out, int32_t *count_out,
+                          void *cuda_stream);
+
 /* Device-resident receding-horizon loop: `steps` repetitions of EgoAgent.step (agent.py:130-155) for B agents without
  * leaving the device:   solve(x_cur, goal, warm start = previous X, U UNSHIFTED, agent.py:139-145) -> applied = U[:,0]
  * (agent.py:154-155) -> x_cur <- X[:,1] (agent.py:70-72).  X, U are in/out (start values = the first warm start, e.g. the

@@ -15,7 +15,7 @@ NO_BOUND = 1e19
 
 # symbols include/kmpc.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["kmpc_version", "kmpc_workspace_bytes", "kmpc_create", "kmpc_destroy", "kmpc_last_error", "kmpc_solve",
-           "kmpc_solve_host", "kmpc_host_result", "kmpc_agent_handoff", "kmpc_closed_loop", "kmpc_set_timing", "kmpc_get_stats", "kmpc_measure_fp64_peak"]
+           "kmpc_solve_host", "kmpc_host_result", "kmpc_agent_handoff", "kmpc_closed_loop", "kmpc_select_obstacles", "kmpc_set_timing", "kmpc_get_stats", "kmpc_measure_fp64_peak"]
 
 
 class KmpcConfig(C.Structure):
@@ -68,6 +68,8 @@ def load():
     L.kmpc_agent_handoff.argtypes = [vp, C.c_int, dp, dp, dp, dp, vp]
     L.kmpc_closed_loop.restype = C.c_int
     L.kmpc_closed_loop.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, dp, ip, ip, ip, C.c_double, C.c_double, vp]
+    L.kmpc_select_obstacles.restype = C.c_int
+    L.kmpc_select_obstacles.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, dp, ip, vp]
     L.kmpc_set_timing.restype = C.c_int
     L.kmpc_set_timing.argtypes = [vp, C.c_int]
     L.kmpc_get_stats.restype = C.c_int

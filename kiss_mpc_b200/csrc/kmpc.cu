@@ -271,6 +271,42 @@ __global__ void kmpc_handoff_kernel(int B, int N, int layout, const double *__re
     }
 }
 
+// Sensor filter of ROSEnvironment.step (environment.py:48-65): one thread per agent keeps the (at most O <= 32) nearest
+// candidates within the sensor radius in a sorted list (insertion; M * O compares per agent, candidates are broadcast loads).
+#define KMPC_SEL_MAX_O 32
+__global__ void kmpc_select_kernel(int B, int M, int layout, const double *__restrict__ x_cur, const double *__restrict__ cc,
+                                   const double *__restrict__ cr, double sensor_radius, int literal, int O, double pad_x, double pad_y,
+                                   double *__restrict__ obs_out, int32_t *__restrict__ count_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double px = x_cur[layout ? (size_t)b : (size_t)b * 3], py = x_cur[layout ? (size_t)B + b : (size_t)b * 3 + 1];
+    double dist[KMPC_SEL_MAX_O];
+    int idx[KMPC_SEL_MAX_O];
+    int n = 0;
+    for (int m = 0; m < M; ++m) {
+        const double cx = cc[2 * m], cy = cc[2 * m + 1], r = cr[m];
+        double d;
+        if (literal) { const double ex = (px - cx) - r, ey = (py - cy) - r; d = sqrt(ex * ex + ey * ey); }   // geometry.py:44 as written
+        else { const double ex = px - cx, ey = py - cy; d = sqrt(ex * ex + ey * ey) - r; }
+        if (!(d <= sensor_radius)) continue;
+        // position of d in the ascending list
+        int pos = 0;
+        while (pos < n && dist[pos] < d) ++pos;
+        if (pos < n && dist[pos] == d) { idx[pos] = m; continue; }   // equal key: the later obstacle replaces the earlier one
+        if (pos >= O) continue;                                        // farther than the O nearest kept so far
+        const int last = n < O ? n : O - 1;
+        for (int j = last; j > pos; --j) { dist[j] = dist[j - 1]; idx[j] = idx[j - 1]; }
+        dist[pos] = d; idx[pos] = m;
+        if (n < O) ++n;
+    }
+    for (int o = 0; o < O; ++o) {
+        const double ox = o < n ? cc[2 * idx[o]] : pad_x, oy = o < n ? cc[2 * idx[o] + 1] : pad_y;
+        if (layout) { obs_out[((size_t)o * 2) * B + b] = ox; obs_out[((size_t)o * 2 + 1) * B + b] = oy; }
+        else { obs_out[((size_t)b * O + o) * 2] = ox; obs_out[((size_t)b * O + o) * 2 + 1] = oy; }
+    }
+    if (count_out) count_out[b] = n;
+}
+
 // FP64 FMA throughput micro-benchmark: 8 independent DFMA chains per thread.
 __global__ void kmpc_dfma_kernel(double *out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -628,6 +664,21 @@ extern "C" int kmpc_debug_phase_cycles(double *out) {
     return KMPC_NPHASE;
 }
 #endif
+
+extern "C" int kmpc_select_obstacles(kmpc_handle *h, int B, int M, const double *x_cur, const double *cand_centers,
+                                     const double *cand_radius, double sensor_radius, int literal, int O, double pad_x, double pad_y,
+                                     double *obs_out, int32_t *count_out, void *cuda_stream) {
+    if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_select_obstacles: NULL handle%s", "");
+    if (B < 0 || M < 0 || O < 1 || O > KMPC_SEL_MAX_O) return fail(h, KMPC_E_BADARG, "kmpc_select_obstacles: need B, M >= 0 and 1 <= O <= 32%s", "");
+    if (B == 0) return 0;
+    if (!x_cur || !obs_out || (M > 0 && (!cand_centers || !cand_radius))) return fail(h, KMPC_E_BADARG, "kmpc_select_obstacles: NULL required pointer%s", "");
+    CU(cudaSetDevice(h->device));
+    kmpc_select_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(B, M, h->cfg.layout, x_cur, cand_centers, cand_radius, sensor_radius,
+                                                                               literal, O, pad_x, pad_y, obs_out, count_out);
+    CU(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
 
 extern "C" int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur, const double *goal, double *X, double *U,
                                 double *applied_log, int32_t *iters_log, int32_t *status_log, int32_t *active, double goal_radius,

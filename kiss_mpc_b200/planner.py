@@ -235,6 +235,28 @@ class BatchedMotionPlanner:
         rc = self._L.kmpc_agent_handoff(self._h, B, p(states), p(controls), p(current_state), p(applied), C.c_void_p(stream))
         _lib.check(rc, self._h, "kmpc_agent_handoff")
 
+    def select_obstacles(self, current_state, centers, radii, sensor_radius: float = 5.0, slots: Optional[int] = None,
+                         literal_distance: bool = True, pad_center=(1.0e6, 1.0e6)):
+        """Batched sensor filter of ROSEnvironment.step (environment.py:48-65): per agent the candidate circles
+        (centers [M,2], radii [M], CUDA tensors) within `sensor_radius` (agent.py:101), nearest first, at most `slots`
+        (default O_max).  Returns (obstacles [B,slots,2] ready for ``solve(obstacles=...)``, count [B]); unused slots hold
+        `pad_center`, whose rows stay inactive.  literal_distance: geometry.py:44 as written (True) or ||p-c|| - r."""
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        B = self._batch_of(current_state)
+        O = int(slots if slots is not None else self.config.O_max)
+        M = int(centers.shape[0])
+        _, _, _, sO, _ = self._shapes(B, O)
+        out = torch.empty(sO, dtype=torch.float64, device=dev)
+        cnt = torch.empty(B, dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        rc = self._L.kmpc_select_obstacles(self._h, B, M, p(current_state.contiguous()), p(centers.contiguous()), p(radii.contiguous()),
+                                           float(sensor_radius), 1 if literal_distance else 0, O, float(pad_center[0]), float(pad_center[1]),
+                                           p(out), p(cnt), C.c_void_p(stream))
+        _lib.check(rc, self._h, "kmpc_select_obstacles")
+        return out, cnt
+
     def closed_loop(self, current_state, goal_state, steps: int, states_matrix=None, controls_matrix=None,
                     log_applied: bool = True, log_iters: bool = True, goal_radius: float = 0.0, agent_radius: float = 0.0,
                     active=None):

@@ -163,6 +163,18 @@ def test_product_never_imports_oracle():
                 assert "import oracle" not in src and "from oracle" not in src and "kmpc_oracle" not in src, f
 
 
+def test_sensor_filter_restatement():
+    """oracle/sensor_filter.py against the reference's semantics (environment.py:48-65): sorted by distance, within the
+    sensor radius, dict-keyed ties keep the later obstacle, literal distance of geometry.py:44."""
+    from oracle.sensor_filter import circle_distance, sensor_filter
+    st = np.array([0.0, 0.0, 0.3])
+    cen = np.array([[3.0, 0.0], [1.0, 1.0], [1.0, 1.0], [10.0, 0.0], [0.0, -2.0]]); rad = np.array([0.5, 0.3, 0.3, 0.5, 0.2])
+    assert abs(circle_distance(st, cen[0], 0.5) - np.hypot(-3.5, -0.5)) < 1e-15          # radius subtracted from both components
+    assert abs(circle_distance(st, cen[0], 0.5, literal=False) - 2.5) < 1e-15
+    assert sensor_filter(st, cen, rad, 5.0) == [2, 4, 0]                                 # tie 1/2 -> 2; 3 is out of range
+    assert sensor_filter(st, cen, rad, 5.0, literal=False) == [2, 4, 0]
+
+
 # ---------------- host logic ----------------
 def test_shard_range_partitions():
     from kiss_mpc_b200 import shard_range

@@ -265,3 +265,33 @@ def test_full_size_properties():
     lo, hi = shard_range(B, 3, 8)
     rs = pl.solve(x[lo:hi].contiguous(), g[lo:hi].contiguous())
     assert torch.equal(rs.controls, U[lo:hi]) and torch.equal(rs.status, r.status[lo:hi])
+
+
+def test_sensor_filter_matches_reference_loop():
+    """the batched sensor filter (kmpc_select_obstacles) against the reference's per-agent loop
+    (environment.py:48-65 restated in oracle/sensor_filter.py), literal and intended distance, incl. ties and O truncation."""
+    from kiss_mpc_b200 import BatchedMotionPlanner, PlannerConfig
+    from oracle.sensor_filter import sensor_filter
+    torch = _torch()
+    rng = np.random.default_rng(7)
+    B, M, O = 257, 40, 6
+    x = rng.uniform(-6, 6, size=(B, 3))
+    cen = rng.uniform(-8, 8, size=(M, 2)); rad = rng.uniform(0.2, 0.6, size=M)
+    cen[5] = cen[4]; rad[5] = rad[4]                  # exact tie: the reference's dict keeps the later obstacle
+    pl = BatchedMotionPlanner(PlannerConfig(O_max=O), max_batch=B)
+    for literal in (True, False):
+        obs, cnt = pl.select_obstacles(_dev(x), _dev(cen), _dev(rad), sensor_radius=5.0, literal_distance=literal)
+        obs = obs.cpu().numpy(); cnt = cnt.cpu().numpy()
+        for b in range(B):
+            want = sensor_filter(x[b], cen, rad, 5.0, literal)[:O]
+            assert cnt[b] == len(want)
+            np.testing.assert_array_equal(obs[b, :len(want)], cen[want])
+            assert (obs[b, len(want):] == 1.0e6).all()
+    # the padded slots are inactive rows: solving with them gives the solution of the rows that are really there
+    b2 = make_batch(64, seed=1004, O=2)
+    far = np.full((64, 4, 2), 1.0e6); far[:, :2] = b2["obs"]
+    pl4 = BatchedMotionPlanner(PlannerConfig(O_max=4), max_batch=64)
+    r2 = pl4.solve(_dev(b2["x_cur"]), _dev(b2["goal"]), obstacles=_dev(b2["obs"]), obstacle_radius=0.3, inflation_radius=0.5)
+    r4 = pl4.solve(_dev(b2["x_cur"]), _dev(b2["goal"]), obstacles=_dev(far), obstacle_radius=0.3, inflation_radius=0.5)
+    assert (r2.status == 0).all() and (r4.status == 0).all()
+    assert (r2.controls - r4.controls).abs().max().item() <= CTRL_ATOL
