@@ -171,7 +171,7 @@ def test_sensor_filter_restatement():
     cen = np.array([[3.0, 0.0], [1.0, 1.0], [1.0, 1.0], [10.0, 0.0], [0.0, -2.0]]); rad = np.array([0.5, 0.3, 0.3, 0.5, 0.2])
     assert abs(circle_distance(st, cen[0], 0.5) - np.hypot(-3.5, -0.5)) < 1e-15          # radius subtracted from both components
     assert abs(circle_distance(st, cen[0], 0.5, literal=False) - 2.5) < 1e-15
-    assert sensor_filter(st, cen, rad, 5.0) == [2, 4, 0]                                 # tie 1/2 -> 2; 3 is out of range
+    assert sensor_filter(st, cen, rad, 5.0) == [4, 2, 0]                                 # tie 1/2 -> 2; 3 is out of range; literal: 1.81 < 1.84
     assert sensor_filter(st, cen, rad, 5.0, literal=False) == [2, 4, 0]
 
 
