@@ -714,6 +714,8 @@ KMPC_HDN inline bool pass_trial(const Cfg &c, const Ctx &t, double *wsp, size_t 
                 const double slo = so - c.dL, sln = s - c.dL;
                 if (!(sln > 0)) valid = false;
                 prod *= sln; st.damp += sln;
+                // many obstacle rows: take the logarithm before the running product of slacks leaves the double range
+                if (!(prod < 1e250 && prod > 1e-250)) { st.bar += log(prod); prod = 1.0; }
                 const double yd = FD(po, 1) + ay * FD(pdo, 1);
                 double z = vL + adu * (mu / slo - vL - vL / slo * ds);
                 if (clamp) z = fmax(fmin(z, K_KAPPA_SIGMA * mu / sln), mu / (K_KAPPA_SIGMA * sln));

@@ -625,6 +625,7 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
                 st.theta += fabs(dm); st.pinf = maxabs_nan(st.pinf, dm);
                 valid &= tv.sln > 0;
                 prod *= tv.sln; st.damp += tv.sln;
+                if (!(prod < 1e250 && prod > 1e-250)) { st.bar += log(prod); prod = 1.0; }   // keep the product in range
                 r0 += ex * ir * tv.yd; r1 += ey * ir * tv.yd;
                 st.dinf = maxabs_nan(st.dinf, -tv.yd - tv.z);
                 const double p = tv.sln * tv.z;

@@ -145,6 +145,26 @@ def test_abi_struct_and_workspace_size():
     assert L.kmpc_workspace_bytes(C.byref(bad)) == 0
 
 
+def test_abi_argument_errors_without_gpu():
+    """Error behaviour of the C ABI that needs no device: bad configurations are rejected before any CUDA call, a missing
+    device is reported as KMPC_E_NODEVICE, nothing throws across the boundary."""
+    import torch
+    from kiss_mpc_b200 import PlannerConfig, _lib
+    L = _lib.load()
+    h = C.c_void_p()
+    bad = PlannerConfig(N=0).to_c(4, 0, 0)
+    assert L.kmpc_create(C.byref(bad), C.byref(h)) == -1 and not h.value            # KMPC_E_BADARG
+    assert b"invalid configuration" in L.kmpc_last_error(None)
+    bad2 = PlannerConfig(v_bounds=(0.5, -0.2)).to_c(4, 0, 0)                         # lo >= hi
+    assert L.kmpc_create(C.byref(bad2), C.byref(h)) == -1
+    assert L.kmpc_create(C.byref(bad2), None) == -1
+    if not torch.cuda.is_available():
+        ok = PlannerConfig().to_c(4, 0, 0)
+        assert L.kmpc_create(C.byref(ok), C.byref(h)) == -4 and not h.value         # KMPC_E_NODEVICE: no CPU path
+    assert L.kmpc_solve(None, 1, None, None, None, None, None, 0, 0.0, 0.0, None, None, None, None, None, None) == -1
+    L.kmpc_destroy(None)                                                              # no-op
+
+
 def test_no_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():

@@ -295,3 +295,33 @@ def test_sensor_filter_matches_reference_loop():
     r4 = pl4.solve(_dev(b2["x_cur"]), _dev(b2["goal"]), obstacles=_dev(far), obstacle_radius=0.3, inflation_radius=0.5)
     assert (r2.status == 0).all() and (r4.status == 0).all()
     assert (r2.controls - r4.controls).abs().max().item() <= CTRL_ATOL
+
+
+def test_edge_sizes_and_fallbacks(oracle_mod):
+    """Edge cases: empty batch, N = 1, N = 31 / 63 (the largest horizons of the one- / two-slot warp kernels), N = 70
+    (thread-solver fall-back), more obstacle rows than shared memory holds (fall-back), ragged batch sizes."""
+    from kiss_mpc_b200 import BatchedMotionPlanner, KmpcError
+    torch = _torch()
+    ocfg, pcfg = _pair(oracle_mod)
+    pl = BatchedMotionPlanner(pcfg, max_batch=64)
+    e = pl.solve(torch.empty(0, 3, dtype=torch.float64, device="cuda:0"), torch.empty(0, 3, dtype=torch.float64, device="cuda:0"))
+    assert e.states.shape == (0, 3, 31) and e.status.numel() == 0
+    with pytest.raises(KmpcError):
+        pl.solve(_dev(np.zeros((65, 3))), _dev(np.zeros((65, 3))))            # B > B_max
+    with pytest.raises(ValueError):
+        pl.solve(_dev(np.zeros((4, 3))), _dev(np.zeros((4, 2))))              # wrong shape
+    for N, B in ((1, 40), (31, 37), (63, 19), (70, 9)):
+        oc, pc = _pair(oracle_mod, N=N)
+        b = make_batch(B, seed=100 + N)
+        ref = oracle_mod.solve(oc, b["x_cur"], b["goal"])
+        res = BatchedMotionPlanner(pc, max_batch=B).solve(_dev(b["x_cur"]), _dev(b["goal"]))
+        _check(res, ref)
+    # 200 obstacle rows per stage do not fit into shared memory -> thread solver; all far away, so the plain solution
+    oc, pc = _pair(oracle_mod, O=200)
+    b = make_batch(6, seed=3)
+    far = np.tile(np.array([[[500.0, 500.0]]]), (6, 200, 1)) + np.arange(200)[None, :, None]
+    res = BatchedMotionPlanner(pc, max_batch=6).solve(_dev(b["x_cur"]), _dev(b["goal"]), obstacles=_dev(far), obstacle_radius=0.3,
+                                                       inflation_radius=0.5)
+    ref = oracle_mod.solve(ocfg, b["x_cur"], b["goal"])
+    assert (res.status.cpu().numpy() == 0).all()
+    assert np.abs(res.controls.cpu().numpy() - ref.U).max() <= CTRL_ATOL
