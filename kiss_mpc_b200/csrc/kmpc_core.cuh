@@ -922,9 +922,13 @@ KMPC_HD int begin_iteration(const Cfg &c, Ctx &t) {
 //   phase_trial   -> trial point + acceptance logic; 100: continue (t.mode tells which phase is next), else final status
 // ------------------------------------------------------------------------------------------------
 // inertia correction (IPOPT PDPerturbationHandler): raise delta_w; 101 = factorise again, else a final status
+// the perturbation IPOPT tries after `delta` has failed (delta_last = the last one that worked, 0 if none yet)
+KMPC_HD double inertia_next_delta(double delta, double delta_last) {
+    if (delta == 0.0) return delta_last == 0.0 ? K_DW_INIT : fmax(K_DW_MIN, delta_last * K_DW_DEC);
+    return (delta_last == 0.0 || 1e5 * delta_last < delta) ? K_DW_INC_FIRST * delta : K_DW_INC * delta;
+}
 KMPC_HD int inertia_update(Ctx &t) {
-    if (t.delta == 0.0) t.delta = t.delta_last == 0.0 ? K_DW_INIT : fmax(K_DW_MIN, t.delta_last * K_DW_DEC);
-    else t.delta = (t.delta_last == 0.0 || 1e5 * t.delta_last < t.delta) ? K_DW_INC_FIRST * t.delta : K_DW_INC * t.delta;
+    t.delta = inertia_next_delta(t.delta, t.delta_last);
     if (t.delta > K_DW_MAX) return ST_STEP_ERROR;
     return 101;
 }

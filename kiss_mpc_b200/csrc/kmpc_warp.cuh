@@ -31,14 +31,17 @@ struct WStep { double dx0[SPL], dx1[SPL], dx2[SPL], du0[SPL], du1[SPL], dy0[SPL]
 // ---- shared-memory layout ----------------------------------------------------------------------------------------
 // coop area of one instance: C_NF fields x NSTG stages (field-major: the owner lanes touch consecutive stages, the
 // Riccati lanes -- one per instance -- are COOP doubles apart, COOP odd => both patterns are bank-conflict free).
-// Fields 7..17 are the stage blocks going in.  The backward sweep overwrites the blocks its matrix part has consumed
-// (Q00 Q11 Q22 dv dw htv) with K, the ones its vector part has consumed (q, qv, qw) with p and k_ff, and adds P;
-// the forward roll-out overwrites K with (dx, du).
+// Fields 7..17 (+ Q01) are the stage blocks going in.  The backward sweep adds K and P and overwrites the blocks its vector
+// part has consumed (q, qv, qw) with p and k_ff; the forward roll-out overwrites K with (dx, du).  The matrix blocks
+// (Q00 Q11 Q22 Q01 dv dw htv) are never overwritten: the speculative inertia candidates read them at their own pace.
 enum { C_A13 = 0, C_A23, C_B11, C_B21, C_E0, C_E1, C_E2,
        C_Q00 = 7, C_Q11, C_Q22, C_Q0, C_Q1, C_Q2, C_QV, C_QW, C_DV, C_DW, C_HTV,
-       C_P00 = 18, C_P10, C_P11, C_P20, C_P21, C_P22, C_Q01 = 24, C_NF = 25 };  // Q01: x-y coupling of the obstacle rows
-enum { C_K00 = C_Q00, C_K01 = C_Q11, C_K02 = C_Q22, C_K10 = C_DV, C_K11 = C_DW, C_K12 = C_HTV,
-       C_PV0 = C_Q0, C_PV1 = C_Q1, C_PV2 = C_Q2, C_KF0 = C_QV, C_KF1 = C_QW };
+       C_P00 = 18, C_P10, C_P11, C_P20, C_P21, C_P22, C_Q01 = 24,   // Q01: x-y coupling of the obstacle rows
+       C_K00 = 25, C_K01, C_K02, C_K10, C_K11, C_K12, C_NF = 31 };
+enum { C_PV0 = C_Q0, C_PV1 = C_Q1, C_PV2 = C_Q2, C_KF0 = C_QV, C_KF1 = C_QW };
+#ifndef KMPC_NCAND
+#define KMPC_NCAND 4  /* inertia candidates tried at once: the current delta_w and the next ones of IPOPT's sequence */
+#endif
 enum { C_DX0 = C_K00, C_DX1 = C_K01, C_DX2 = C_K02, C_DU0 = C_K10, C_DU1 = C_K11 };
 // private area of one instance (owner warp only): the kept Newton step (back-tracking / failed corrections return to
 // it), the second-order-correction rhs, the constraint values of the last trial point
@@ -58,6 +61,8 @@ struct WScal {  // warp-uniform per-instance scalars
     Ctx t;
     double filt[2 * K_FILTER_CAP];
     double xc[3], gl[3], d0[3];
+    double dshift[KMPC_NCAND];  // delta_w of candidate k minus the delta_w the stage blocks were assembled with (NaN: none)
+    int pdc[KMPC_NCAND];        // candidate k has the right inertia
     int flag, ok, r, status;
 };
 
@@ -374,7 +379,7 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
 // left on either chain.
 struct WRicCarry { double P00, P10, P11, P20, P21, P22, K00, K01, K02, K10, K11, K12, m00, m01, m11, a13, a23, b11, b21; };
 // vector part of stage k (q = coop + k): uses the cost-to-go P of stage k+1 (in cy) and p of stage k+1 (p0..p2, updated)
-KMPC_W void w_ric_vec(const WRicCarry &cy, double *q, const int NSTG, const double T, double &p0, double &p1, double &p2) {
+KMPC_W void w_ric_vec(const WRicCarry &cy, const double *q, double *qs, const int NSTG, const double T, double &p0, double &p1, double &p2) {
     const double e0 = q[C_E0 * NSTG], e1 = q[C_E1 * NSTG], e2 = q[C_E2 * NSTG];
     const double q0 = q[C_Q0 * NSTG], q1 = q[C_Q1 * NSTG], q2 = q[C_Q2 * NSTG], qv = q[C_QV * NSTG], qw = q[C_QW * NSTG];
     const double Pe0 = fma(cy.P00, e0, fma(cy.P10, e1, cy.P20 * e2)) + p0, Pe1 = fma(cy.P10, e0, fma(cy.P11, e1, cy.P21 * e2)) + p1,
@@ -383,16 +388,17 @@ KMPC_W void w_ric_vec(const WRicCarry &cy, double *q, const int NSTG, const doub
     p0 = fma(cy.K00, qu0, fma(cy.K10, qu1, q0 + Pe0));
     p1 = fma(cy.K01, qu0, fma(cy.K11, qu1, q1 + Pe1));
     p2 = fma(cy.K02, qu0, fma(cy.K12, qu1, fma(cy.a13, Pe0, fma(cy.a23, Pe1, q2 + Pe2))));
-    q[C_KF0 * NSTG] = fma(cy.m00, qu0, cy.m01 * qu1); q[C_KF1 * NSTG] = fma(cy.m01, qu0, cy.m11 * qu1);
-    q[C_PV0 * NSTG] = p0; q[C_PV1 * NSTG] = p1; q[C_PV2 * NSTG] = p2;
+    const double kf0 = fma(cy.m00, qu0, cy.m01 * qu1), kf1 = fma(cy.m01, qu0, cy.m11 * qu1);
+    qs[C_KF0 * NSTG] = kf0; qs[C_KF1 * NSTG] = kf1; qs[C_PV0 * NSTG] = p0; qs[C_PV1 * NSTG] = p1; qs[C_PV2 * NSTG] = p2;
 }
 // matrix part of stage k: (P of stage k+1 in P..) -> K, M = -Quu^-1, P of stage k; leaves what the vector part needs in cy
+// dshift / dshift_u: extra delta_w on the x-x / u-u diagonal (0 here; the candidates have their own loop); qs: where K, P go
 template <bool OBS>
 KMPC_W bool w_ric_mat(WRicCarry &cy, double *q, const int NSTG, const double T, const double TT, double &P00, double &P10,
-                      double &P11, double &P20, double &P21, double &P22) {
+                      double &P11, double &P20, double &P21, double &P22, const double dshift, const double dshift_u, double *qs) {
     const double a13 = q[C_A13 * NSTG], a23 = q[C_A23 * NSTG], b11 = q[C_B11 * NSTG], b21 = q[C_B21 * NSTG];
-    const double Q00 = q[C_Q00 * NSTG], Q11 = q[C_Q11 * NSTG], Q22 = q[C_Q22 * NSTG], Q01 = OBS ? q[C_Q01 * NSTG] : 0.0;
-    const double dv = q[C_DV * NSTG], dw = q[C_DW * NSTG], htv = q[C_HTV * NSTG];
+    const double Q00 = q[C_Q00 * NSTG] + dshift, Q11 = q[C_Q11 * NSTG] + dshift, Q22 = q[C_Q22 * NSTG] + dshift, Q01 = OBS ? q[C_Q01 * NSTG] : 0.0;
+    const double dv = q[C_DV * NSTG] + dshift_u, dw = q[C_DW * NSTG] + dshift_u, htv = q[C_HTV * NSTG];
     cy.P00 = P00; cy.P10 = P10; cy.P11 = P11; cy.P20 = P20; cy.P21 = P21; cy.P22 = P22;
     cy.a13 = a13; cy.a23 = a23; cy.b11 = b11; cy.b21 = b21;
     // P A (third column), symmetric Qxx = A^T P A + Q
@@ -414,11 +420,44 @@ KMPC_W bool w_ric_mat(WRicCarry &cy, double *q, const int NSTG, const double T, 
     P00 = fma(U00, K00, fma(U10, K10, X00)); P10 = fma(U01, K00, fma(U11, K10, X10)); P11 = fma(U01, K01, fma(U11, K11, X11));
     P20 = fma(U02, K00, fma(U12, K10, X20)); P21 = fma(U02, K01, fma(U12, K11, X21)); P22 = fma(U02, K02, fma(U12, K12, X22));
     cy.K00 = K00; cy.K01 = K01; cy.K02 = K02; cy.K10 = K10; cy.K11 = K11; cy.K12 = K12; cy.m00 = m00; cy.m01 = m01; cy.m11 = m11;
-    q[C_K00 * NSTG] = K00; q[C_K01 * NSTG] = K01; q[C_K02 * NSTG] = K02;
-    q[C_K10 * NSTG] = K10; q[C_K11 * NSTG] = K11; q[C_K12 * NSTG] = K12;
-    q[C_P00 * NSTG] = P00; q[C_P10 * NSTG] = P10; q[C_P11 * NSTG] = P11;
-    q[C_P20 * NSTG] = P20; q[C_P21 * NSTG] = P21; q[C_P22 * NSTG] = P22;
+    // (plain unconditional stores: the whole stage stays in one basic block, so the compiler interleaves the vector part of
+    //  the stage behind with this chain)
+    qs[C_K00 * NSTG] = K00; qs[C_K01 * NSTG] = K01; qs[C_K02 * NSTG] = K02;
+    qs[C_K10 * NSTG] = K10; qs[C_K11 * NSTG] = K11; qs[C_K12 * NSTG] = K12;
+    qs[C_P00 * NSTG] = P00; qs[C_P10 * NSTG] = P10; qs[C_P11 * NSTG] = P11;
+    qs[C_P20 * NSTG] = P20; qs[C_P21 * NSTG] = P21; qs[C_P22 * NSTG] = P22;
     return d1 > 0.0 && ndet < 0.0;
+}
+// inertia test only: the matrix recursion of one instance with delta_w raised by dshift (a speculative candidate of IPOPT's
+// perturbation sequence); reads the assembled blocks, stores nothing.  Runs on a second warp next to the solving sweep.
+template <bool OBS>
+KMPC_WN inline bool w_serial_candidate(const Cfg &c, const double *coop, const int NSTG, const double dshift) {
+    const int N = c.N;
+    const double T = c.T, TT = T * T;
+    double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0;
+    bool pd = true;
+#pragma unroll 1
+    for (int s = N; s >= 0; --s) {
+        const double *q = coop + s;
+        const double a13 = q[C_A13 * NSTG], a23 = q[C_A23 * NSTG], b11 = q[C_B11 * NSTG], b21 = q[C_B21 * NSTG];
+        const double du = s < N ? dshift : 0.0;   // the terminal stage is a pass-through with unit Quu
+        const double Q00 = q[C_Q00 * NSTG] + dshift, Q11 = q[C_Q11 * NSTG] + dshift, Q22 = q[C_Q22 * NSTG] + dshift;
+        const double Q01 = OBS ? q[C_Q01 * NSTG] : 0.0, dv = q[C_DV * NSTG] + du, dw = q[C_DW * NSTG] + du, htv = q[C_HTV * NSTG];
+        const double PA02 = fma(P00, a13, fma(P10, a23, P20)), PA12 = fma(P10, a13, fma(P11, a23, P21)), PA22 = fma(P20, a13, fma(P21, a23, P22));
+        const double X00 = P00 + Q00, X10 = P10 + Q01, X11 = P11 + Q11, X20 = PA02, X21 = PA12;
+        const double X22 = fma(a13, PA02, fma(a23, PA12, PA22)) + Q22;
+        const double U00 = fma(b11, P00, b21 * P10), U01 = fma(b11, P10, b21 * P11), U02 = fma(b11, PA02, fma(b21, PA12, htv));
+        const double U10 = T * P20, U11 = T * P21, U12 = T * PA22;
+        const double d1 = fma(b11, U00, fma(b21, U01, dv)), qb = fma(b11, U10, b21 * U11), qc = fma(TT, P22, dw);
+        const double ndet = fma(qb, qb, -(d1 * qc));
+        pd = pd && d1 > 0.0 && ndet < 0.0;
+        const double rn = KRCPF(ndet), m00 = qc * rn, m01 = qb * -rn, m11 = d1 * rn;
+        const double K00 = fma(m00, U00, m01 * U10), K01 = fma(m00, U01, m01 * U11), K02 = fma(m00, U02, m01 * U12);
+        const double K10 = fma(m01, U00, m11 * U10), K11 = fma(m01, U01, m11 * U11), K12 = fma(m01, U02, m11 * U12);
+        P00 = fma(U00, K00, fma(U10, K10, X00)); P10 = fma(U01, K00, fma(U11, K10, X10)); P11 = fma(U01, K01, fma(U11, K11, X11));
+        P20 = fma(U02, K00, fma(U12, K10, X20)); P21 = fma(U02, K01, fma(U12, K11, X21)); P22 = fma(U02, K02, fma(U12, K12, X22));
+    }
+    return pd;
 }
 struct WFwdIn { double K00, K01, K02, K10, K11, K12, kf0, kf1, a13, a23, b11, b21, e0, e1, e2; };
 KMPC_W void w_fwd_load(WFwdIn &r, const double *q, const int NSTG) {
@@ -428,21 +467,33 @@ KMPC_W void w_fwd_load(WFwdIn &r, const double *q, const int NSTG) {
     r.a13 = q[C_A13 * NSTG]; r.a23 = q[C_A23 * NSTG]; r.b11 = q[C_B11 * NSTG]; r.b21 = q[C_B21 * NSTG];
     r.e0 = q[C_E0 * NSTG]; r.e1 = q[C_E1 * NSTG]; r.e2 = q[C_E2 * NSTG];
 }
+// the solving sweep of one instance: factors, vector part and roll-out of the system as assembled (the speculative inertia
+// candidates run w_serial_candidate on another warp)
 template <bool OBS>
 KMPC_WN inline bool w_serial(const Cfg &c, double *coop, const int NSTG, const double *d0) {
     const int N = c.N;
     const double T = c.T, TT = T * T;
     double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0, p0 = 0, p1 = 0, p2 = 0;
     WRicCarry cy;
-    bool pd = w_ric_mat<OBS>(cy, coop + N, NSTG, T, TT, P00, P10, P11, P20, P21, P22);
+    double *const st = coop;      // loads and stores through ONE base: the compiler can tell the fields apart and keeps hoisting
+    const double dshift = 0.0;    // the next stage's loads above this stage's stores (a second base pointer cost 15 %)
+    bool pd = w_ric_mat<OBS>(cy, coop + N, NSTG, T, TT, P00, P10, P11, P20, P21, P22, dshift, 0.0, st + N);
+    // two stages per trip of the loop with the carry structs swapping roles (no register copies between iterations)
+    WRicCarry cz;
+    int s = N - 1;
 #pragma unroll 1
-    for (int s = N - 1; s >= 0; --s) {
-        double *q = coop + s;
-        const WRicCarry cp = cy;
-        pd = w_ric_mat<OBS>(cy, q, NSTG, T, TT, P00, P10, P11, P20, P21, P22) && pd;
-        w_ric_vec(cp, q + 1, NSTG, T, p0, p1, p2);
+    for (; s >= 1; s -= 2) {
+        pd = w_ric_mat<OBS>(cz, coop + s, NSTG, T, TT, P00, P10, P11, P20, P21, P22, dshift, dshift, st + s) && pd;
+        w_ric_vec(cy, coop + s + 1, st + s + 1, NSTG, T, p0, p1, p2);
+        pd = w_ric_mat<OBS>(cy, coop + s - 1, NSTG, T, TT, P00, P10, P11, P20, P21, P22, dshift, dshift, st + s - 1) && pd;
+        w_ric_vec(cz, coop + s, st + s, NSTG, T, p0, p1, p2);
     }
-    w_ric_vec(cy, coop, NSTG, T, p0, p1, p2);
+    if (s == 0) {  // (only when the pair loop did not end on stage 0)
+        pd = w_ric_mat<OBS>(cz, coop, NSTG, T, TT, P00, P10, P11, P20, P21, P22, dshift, dshift, st) && pd;
+        w_ric_vec(cy, coop + 1, st + 1, NSTG, T, p0, p1, p2);
+        cy = cz;
+    }
+    w_ric_vec(cy, coop, coop, NSTG, T, p0, p1, p2);
     if (!pd) return false;
     double x0 = d0[0], x1 = d0[1], x2 = d0[2];
     WFwdIn fn;
@@ -791,11 +842,12 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     // the block's Riccati warp: co-resident blocks (b and b + gridDim/2 under round-robin placement) pick different warp
     // slots, hence different schedulers, so that two serial phases that coincide do not share one FP64 issue port
     const int swid = w_serial_warp(W);
+    const int cwid = W >= 2 ? (swid + 1) % W : -1;   // the warp that tests the speculative inertia candidates
 #pragma unroll 1
     for (;;) {
         // warp 0 is busy in the serial window below, so it takes its next instance here; the other warps take theirs
         // in that window (the global-memory round trip then costs the block nothing)
-        if (!have && !drained && wid == swid) {
+        if (!have && !drained && (wid == swid || wid == cwid)) {
             b = w_fetch_active(c, io, queue);
             if (b < c.B) { w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
         }
@@ -807,7 +859,21 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         const int mode = t.mode;
         const bool do_sweep = have && mode != M_TRIAL;
         if (do_sweep) w_assemble<SPL, NST, FULL, OBS>(c, sc, cur, priv, gp, coop, ob);
-        if (lane == 0) { sc->flag = do_sweep ? 1 : 0; if (do_sweep) t.trips++; }
+        if (lane == 0) {
+            sc->flag = do_sweep ? 1 : 0;
+            if (do_sweep) {
+                t.trips++;
+                // speculative inertia candidates (Newton systems without obstacle rows, where delta_w is a plain diagonal
+                // shift of the assembled blocks): the next perturbations IPOPT would try if this factorisation has the wrong inertia
+                double dk = t.delta;
+                sc->dshift[0] = 0.0;
+                for (int k = 1; k < KMPC_NCAND; ++k) {
+                    dk = inertia_next_delta(dk, t.delta_last);
+                    sc->dshift[k] = (!OBS && W >= 2 && mode == M_NEWTON && dk <= K_DW_MAX && k * W <= 32) ? dk - t.delta : NAN;
+                    sc->pdc[k] = 0;
+                }
+            }
+        }
         PT(2)
         w_block_sync();
         PT(3)
@@ -818,6 +884,12 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 WScal *so = scal0 + lane;
                 if (so->flag) so->ok = w_serial<OBS>(c, smem + (size_t)lane * LY::COOP, LY::NSTG, so->d0) ? 1 : 0;
             }
+        } else if (wid == cwid && KMPC_NCAND > 1) {
+            // speculative inertia candidates on a second warp: lane = (candidate - 1) * W + instance
+            const int inst = lane % W, cand = 1 + lane / W;
+            WScal *so = scal0 + inst;
+            const double ds = cand < KMPC_NCAND ? so->dshift[cand] : NAN;
+            if (so->flag && ds == ds) so->pdc[cand] = w_serial_candidate<OBS>(c, smem + (size_t)inst * LY::COOP, LY::NSTG, ds) ? 1 : 0;
         } else if (!have && !drained) {
             b = w_fetch_active(c, io, queue);
             if (b < c.B) { w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); fresh = true; } else drained = true;
@@ -830,7 +902,12 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         if (do_sweep) {
             if (!sc->ok) {
                 PT_COUNT(10)
-                if (lane == 0) sc->status = mode != M_NEWTON ? (int)ST_STEP_ERROR : inertia_update(t);  // R_RETRY: sweep again next trip
+                if (lane == 0) {
+                    // wrong inertia: raise delta_w (IPOPT's sequence) past the candidates already known to fail, sweep again next trip
+                    int st = mode != M_NEWTON ? (int)ST_STEP_ERROR : inertia_update(t);
+                    for (int k = 1; k < KMPC_NCAND && st == R_RETRY && sc->dshift[k] == sc->dshift[k] && !sc->pdc[k]; ++k) st = inertia_update(t);
+                    sc->status = st;
+                }
                 w_sync();
                 status = sc->status;
             } else {

@@ -19,6 +19,8 @@ KMPC_W int w_bcast_i(int v, int src) { return __shfl_sync(0xffffffffu, v, src); 
 KMPC_W bool w_all(bool p) { return __all_sync(0xffffffffu, p); }
 KMPC_W bool w_any(bool p) { return __any_sync(0xffffffffu, p); }
 KMPC_W void w_sync() { __syncwarp(); }
+KMPC_W unsigned w_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+KMPC_W void w_reconverge(unsigned mask) { __syncwarp(mask); }  // re-join the lanes of `mask` after a divergent region
 KMPC_W void w_block_sync() { __syncthreads(); }
 KMPC_W bool w_block_any(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
 #ifndef KMPC_SERIAL_WARP_B

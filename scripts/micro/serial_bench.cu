@@ -37,27 +37,6 @@ __global__ void bench(Cfg c, int lanes, int reps, long long *cyc, double *sink, 
             long long a = clock64();
             if (lane < lanes) {
                 if (mode == 0) ok = w_serial<false>(c, sm + lane * COOP, NSTG, d0) && ok;
-                else if (mode == 1) {  // backward sweep only
-                    double *coop = sm + lane * COOP; const double T = c.T, TT = T * T;
-                    double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0, p0 = 0, p1 = 0, p2 = 0;
-                    WRicCarry cy;
-                    bool pd = w_ric_mat<false>(cy, coop + c.N, NSTG, T, TT, P00, P10, P11, P20, P21, P22);
-#pragma unroll 1
-                    for (int s = c.N - 1; s >= 0; --s) {
-                        double *q = coop + s; const WRicCarry cp = cy;
-                        pd = w_ric_mat<false>(cy, q, NSTG, T, TT, P00, P10, P11, P20, P21, P22) && pd;
-                        w_ric_vec(cp, q + 1, NSTG, T, p0, p1, p2);
-                    }
-                    w_ric_vec(cy, coop, NSTG, T, p0, p1, p2);
-                    ok = ok && pd;
-                } else {  // matrix part only
-                    double *coop = sm + lane * COOP; const double T = c.T, TT = T * T;
-                    double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0;
-                    WRicCarry cy; bool pd = true;
-#pragma unroll 1
-                    for (int s = c.N; s >= 0; --s) pd = w_ric_mat<false>(cy, coop + s, NSTG, T, TT, P00, P10, P11, P20, P21, P22) && pd;
-                    ok = ok && pd;
-                }
             }
             __syncwarp();
             long long b = clock64();
@@ -76,7 +55,7 @@ int main() {
     long long *cyc; double *sink; cudaMalloc(&cyc, 8 * 64); cudaMalloc(&sink, 8 * 2048);
     const size_t smem = 8 * WLay<1>::COOP * 8;
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int mode : {0, 1, 2}) for (int nbg : {0, 15}) for (int lanes : {8}) {
+    for (int mode : {0}) for (int nbg : {0, 15}) for (int lanes : {8}) {
         const int reps = 8; long long h[8];
         bench<<<1, 32 * (1 + nbg), smem>>>(c, lanes, reps, cyc, sink, mode);
         cudaError_t e = cudaDeviceSynchronize();

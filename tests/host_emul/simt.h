@@ -46,6 +46,8 @@ inline int w_bcast_i(int v, int src) { const double *b = simt_rendezvous((double
 inline bool w_all(bool p) { const double *b = simt_rendezvous(p ? 1.0 : 0.0); bool r = true; for (int i = 0; i < 32; ++i) r = r && b[i] != 0.0; return r; }
 inline bool w_any(bool p) { const double *b = simt_rendezvous(p ? 1.0 : 0.0); bool r = false; for (int i = 0; i < 32; ++i) r = r || b[i] != 0.0; return r; }
 inline void w_sync() { simt_rendezvous(0.0); }
+inline unsigned w_ballot(bool p) { const double *b = simt_rendezvous(p ? 1.0 : 0.0); unsigned m = 0; for (int i = 0; i < 32; ++i) if (b[i] != 0.0) m |= 1u << i; return m; }
+inline void w_reconverge(unsigned) {}  // fibres run one after the other: nothing to re-join
 // emulation of the CREDUX-based reductions: max with NaN propagation / min, of sign-bit-clear doubles
 inline double w_max_nn(double v) { const double *b = simt_rendezvous(v); double r = b[0]; for (int i = 1; i < 32; ++i) r = (b[i] > r || b[i] != b[i]) ? b[i] : r; return r; }
 inline double w_min_nn(double v) { const double *b = simt_rendezvous(v); double r = INFINITY; bool any = false; for (int i = 0; i < 32; ++i) if (b[i] == b[i]) { any = true; r = b[i] < r ? b[i] : r; } return any ? r : NAN; }
