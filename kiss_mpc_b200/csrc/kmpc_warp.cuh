@@ -37,7 +37,8 @@ struct WStep { double dx0[SPL], dx1[SPL], dx2[SPL], du0[SPL], du1[SPL], dy0[SPL]
 enum { C_A13 = 0, C_A23, C_B11, C_B21, C_E0, C_E1, C_E2,
        C_Q00 = 7, C_Q11, C_Q22, C_Q0, C_Q1, C_Q2, C_QV, C_QW, C_DV, C_DW, C_HTV,
        C_P00 = 18, C_P10, C_P11, C_P20, C_P21, C_P22, C_Q01 = 24,   // Q01: x-y coupling of the obstacle rows
-       C_K00 = 25, C_K01, C_K02, C_K10, C_K11, C_K12, C_NF = 31 };
+       C_K00 = 25, C_K01, C_K02, C_K10, C_K11, C_K12,
+       C_S00 = 31, C_S01, C_S11, C_NF = 34 };   // sum of n n^T over the obstacle rows of a stage: d(x-y block) / d(delta_w) - I
 enum { C_PV0 = C_Q0, C_PV1 = C_Q1, C_PV2 = C_Q2, C_KF0 = C_QV, C_KF1 = C_QW };
 #ifndef KMPC_NCAND
 #define KMPC_NCAND 4  /* inertia candidates tried at once: the current delta_w and the next ones of IPOPT's sequence */
@@ -308,7 +309,7 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
             q0 = gx0 + w.y0[j] + rb0; q1 = gx1 + w.y1[j] + rb1; q2 = gx2 + w.y2[j];
             Q00 = h0 + sg0 + delta; Q11 = h1 + sg1 + delta; Q22 = h2 + delta;
         }
-        double Q01 = 0.0;
+        double Q01 = 0.0, S00 = 0.0, S01 = 0.0, S11 = 0.0;
         if (OBS && s >= 1) {  // slacks of the obstacle rows condensed into the x-y block
             const double *cxy = ob + B_NF * O * NSTG;
             for (int o = 0; o < O; ++o) {
@@ -322,6 +323,7 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
                     q0 += ot.nx * yd; q1 += ot.ny * yd;
                 }
                 Q00 += ot.Ds * ot.nx * ot.nx; Q01 += ot.Ds * ot.nx * ot.ny; Q11 += ot.Ds * ot.ny * ot.ny;
+                S00 += ot.nx * ot.nx; S01 += ot.nx * ot.ny; S11 += ot.ny * ot.ny;   // delta_w enters every Ds
                 const double tt = ot.Ds * ot.bd + ot.bs;
                 q0 -= ot.nx * tt; q1 -= ot.ny * tt;
             }
@@ -359,7 +361,7 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
         q[C_A13 * NSTG] = a13; q[C_A23 * NSTG] = a23; q[C_B11 * NSTG] = b11; q[C_B21 * NSTG] = b21;
         q[C_E0 * NSTG] = e0; q[C_E1 * NSTG] = e1; q[C_E2 * NSTG] = e2;
         q[C_Q00 * NSTG] = Q00; q[C_Q11 * NSTG] = Q11; q[C_Q22 * NSTG] = Q22;
-        if (OBS) q[C_Q01 * NSTG] = Q01;
+        if (OBS) { q[C_Q01 * NSTG] = Q01; q[C_S00 * NSTG] = S00; q[C_S01 * NSTG] = S01; q[C_S11 * NSTG] = S11; }
         q[C_Q0 * NSTG] = q0; q[C_Q1 * NSTG] = q1; q[C_Q2 * NSTG] = q2;
         q[C_QV * NSTG] = qv; q[C_QW * NSTG] = qw; q[C_DV * NSTG] = dv; q[C_DW * NSTG] = dw; q[C_HTV * NSTG] = htv;
         if (s == 0) {  // dx of stage 0 (the rhs of the initial-state row)
@@ -441,8 +443,10 @@ KMPC_WN inline bool w_serial_candidate(const Cfg &c, const double *coop, const i
         const double *q = coop + s;
         const double a13 = q[C_A13 * NSTG], a23 = q[C_A23 * NSTG], b11 = q[C_B11 * NSTG], b21 = q[C_B21 * NSTG];
         const double du = s < N ? dshift : 0.0;   // the terminal stage is a pass-through with unit Quu
-        const double Q00 = q[C_Q00 * NSTG] + dshift, Q11 = q[C_Q11 * NSTG] + dshift, Q22 = q[C_Q22 * NSTG] + dshift;
-        const double Q01 = OBS ? q[C_Q01 * NSTG] : 0.0, dv = q[C_DV * NSTG] + du, dw = q[C_DW * NSTG] + du, htv = q[C_HTV * NSTG];
+        // delta_w sits on the diagonal and, with obstacle rows, in every condensed slack block Ds n n^T
+        const double Q00 = fma(dshift, OBS ? 1.0 + q[C_S00 * NSTG] : 1.0, q[C_Q00 * NSTG]), Q11 = fma(dshift, OBS ? 1.0 + q[C_S11 * NSTG] : 1.0, q[C_Q11 * NSTG]);
+        const double Q22 = q[C_Q22 * NSTG] + dshift, Q01 = OBS ? fma(dshift, q[C_S01 * NSTG], q[C_Q01 * NSTG]) : 0.0;
+        const double dv = q[C_DV * NSTG] + du, dw = q[C_DW * NSTG] + du, htv = q[C_HTV * NSTG];
         const double PA02 = fma(P00, a13, fma(P10, a23, P20)), PA12 = fma(P10, a13, fma(P11, a23, P21)), PA22 = fma(P20, a13, fma(P21, a23, P22));
         const double X00 = P00 + Q00, X10 = P10 + Q01, X11 = P11 + Q11, X20 = PA02, X21 = PA12;
         const double X22 = fma(a13, PA02, fma(a23, PA12, PA22)) + Q22;
@@ -863,13 +867,13 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             sc->flag = do_sweep ? 1 : 0;
             if (do_sweep) {
                 t.trips++;
-                // speculative inertia candidates (Newton systems without obstacle rows, where delta_w is a plain diagonal
-                // shift of the assembled blocks): the next perturbations IPOPT would try if this factorisation has the wrong inertia
+                // speculative inertia candidates (Newton systems; delta_w is a diagonal shift of the assembled blocks plus, with
+                // obstacle rows, delta_w * sum n n^T): the next perturbations IPOPT would try if this factorisation has the wrong inertia
                 double dk = t.delta;
                 sc->dshift[0] = 0.0;
                 for (int k = 1; k < KMPC_NCAND; ++k) {
                     dk = inertia_next_delta(dk, t.delta_last);
-                    sc->dshift[k] = (!OBS && W >= 2 && mode == M_NEWTON && dk <= K_DW_MAX && k * W <= 32) ? dk - t.delta : NAN;
+                    sc->dshift[k] = (W >= 2 && mode == M_NEWTON && dk <= K_DW_MAX && k * W <= 32) ? dk - t.delta : NAN;
                     sc->pdc[k] = 0;
                 }
             }
