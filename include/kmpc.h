@@ -10,7 +10,8 @@
  *
  * Conventions
  *   - float64 everywhere (the reference computes in float64 through CasADi/IPOPT).
- *   - B independent problem instances ("agents") per call; one CUDA thread solves one instance.
+ *   - B independent problem instances ("agents") per call; one warp solves one instance, the serial Riccati recursions of a
+ *     block's instances run side by side on one warp; a thread-per-instance solver is the fall-back for N > 63.
  *   - I/O layouts, selected per handle by kmpc_config.layout:
  *       KMPC_LAYOUT_INSTANCE_MAJOR (0): x_cur[B][3], goal[B][3], X[B][3][N+1], U[B][2][N], obs[B][O][2]
  *            == what B stacked reference calls hold: states_matrix (3,N+1), controls_matrix (2,N) (optimizer.py:392-400)
