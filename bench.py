@@ -65,15 +65,24 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        """Index of the next sample (nvidia-smi is started before the warm-up so that it is already streaming)."""
+        return len(self.rows)
+
+    def stop(self, i0=0, i1=None):
+        """Stats over the samples taken between two marks (the timed region); if the region was shorter than one sampling
+        period, the samples next to it are used and `window` says so."""
         if self.proc is not None:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows, window = self.rows[i0:i1], "timed region"
+        if not rows:
+            rows, window = self.rows[max(0, i0 - 2):(i1 or 0) + 2], "timed region shorter than the sampling period: adjacent samples"
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def cpu_oracle_rate(batch, nthreads=0, sample=CPU_SAMPLE):
@@ -146,6 +155,9 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     res = None
     for _ in range(max(args.warmup, 3)):
         res = planner.solve(x, g)
@@ -153,12 +165,10 @@ def run_ours(args, rank, local_rank, world):
     fp64_peak = planner.measure_fp64_peak() if rank == 0 else 0.0
 
     # ---- device-resident throughput: CUDA events around each solve on its stream, L2 flushed between steps ----
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     l0 = planner.stats()["launches"]
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    m0 = sampler.mark()
     w0 = time.perf_counter()
     for s, e in evs:
         flush.fill_(1)
@@ -167,9 +177,10 @@ def run_ours(args, rank, local_rank, world):
         e.record()
     barrier()
     wall = time.perf_counter() - w0
+    m1 = sampler.mark()
     dev_ms = sum(s.elapsed_time(e) for s, e in evs)
     launches = planner.stats()["launches"] - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(m0, m1) if rank == 0 else None
     t = torch.tensor([dev_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
