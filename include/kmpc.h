@@ -79,7 +79,8 @@ int kmpc_version(void);
 size_t kmpc_workspace_bytes(const kmpc_config *cfg);
 
 /* Replaces MotionPlanner(time_step, horizon) (optimizer.py:40; called once per agent at agent.py:62):
- * binds a device, allocates the device workspace for B_max instances.  One handle = one device = one host thread at a time. */
+ * binds a device and sizes the solver for B_max instances (the thread-per-instance fall-back solver allocates its HBM workspace,
+ * kmpc_workspace_bytes, on first use; the warp solver needs a few MB of scratch).  One handle = one device = one host thread at a time. */
 int kmpc_create(const kmpc_config *cfg, kmpc_handle **out);
 void kmpc_destroy(kmpc_handle *h);
 const char *kmpc_last_error(const kmpc_handle *h);

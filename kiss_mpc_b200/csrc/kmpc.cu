@@ -400,8 +400,8 @@ extern "C" int kmpc_create(const kmpc_config *cfg, kmpc_handle **out) {
     h->cols = cols_for(cfg);
     cudaError_t e = cudaSetDevice(h->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
-    if (e == cudaSuccess) e = cudaMalloc(&h->ws, (size_t)h->rows.total * h->cols * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&h->lists, (size_t)4 * h->cols * sizeof(int));
+    // (the thread solver's HBM workspace -- 1.2 GB at B_max = 65,536, N = 30 -- is allocated on its first use: the warp solver
+    //  that serves N <= 63 keeps its state on chip and never touches it)
     if (e == cudaSuccess) e = cudaMalloc(&h->cnt, 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&h->trips, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_cnt, KMPC_LOOKAHEAD * 4 * sizeof(int));
@@ -502,6 +502,11 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
         return 0;
         }
     }
+    if (!h->ws) {   // first thread-solver solve on this handle
+        CU(cudaMalloc(&h->ws, (size_t)h->rows.total * h->cols * sizeof(double)));
+        CU(cudaMalloc(&h->lists, (size_t)4 * h->cols * sizeof(int)));
+    }
+    ls.LA[0] = h->lists; ls.LA[1] = h->lists + S; ls.LT[0] = h->lists + 2 * S; ls.LT[1] = h->lists + 3 * S;
     const int cnt0[4] = {B, 0, 0, 0};
     CU(cudaMemcpyAsync(h->cnt, cnt0, sizeof cnt0, cudaMemcpyHostToDevice, st));
     kmpc_init_kernel<<<nblocks(B), KMPC_TPB, 0, st>>>(c, io, h->ws, S, ls.LA[0]);
