@@ -99,6 +99,15 @@ int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const double *goal, c
                const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
                double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream);
 
+/* The same solve with circle centres that move with the stage: obs_tracks holds, per instance and obstacle, a track of N
+ * centres ([B][O][N][2]; SoA layout [O][N][2][B]); column t is the centre paired with X_{t+1}.  This is what the reference's
+ * per-obstacle constraint path builds from DynamicObstacle.states_matrix (dynamic_obstacle.py:47-56 called from
+ * optimizer.py:207-215; the vectorised path optimizer.py:217-250 keeps only the current centre).  A static obstacle is a track
+ * of N equal columns.  Everything else as kmpc_solve. */
+int kmpc_solve_tracks(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
+                      const double *obs_tracks, int O, double obs_radius, double inflation, double *X_out, double *U_out,
+                      double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream);
+
 /* Same call with HOST pointers (what a ctypes/NumPy caller such as the reference's agent.py holds): stages through the
  * handle's pinned buffers, copies host->device, solves, copies device->host and synchronises before returning. */
 int kmpc_solve_host(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
@@ -125,10 +134,22 @@ int kmpc_agent_handoff(kmpc_handle *h, int B, const double *X, const double *U, 
  * from both components); literal == 0 the intended ||p - c||_2 - r.  Candidates at exactly equal distance
  * collapse to the LAST one (the reference keys a dict by distance, environment.py:48-51).  obs_out has the handle's obstacle
  * layout ([B][O][2] / [O][2][B]); unused slots get (pad_x, pad_y) -- pick a point far outside the workspace, its rows stay
- * inactive; count_out[B] (may be NULL) is the number of real obstacles per agent.  Device pointers, asynchronous. */
+ * inactive; count_out[B] (may be NULL) is the number of real obstacles per agent; index_out[B][O] (may be NULL) the
+ * candidate index kept in every slot, -1 for padding.  Device pointers, asynchronous. */
 int kmpc_select_obstacles(kmpc_handle *h, int B, int M, const double *x_cur, const double *cand_centers, const double *cand_radius,
                           double sensor_radius, int literal, int O, double pad_x, double pad_y, double *obs_out, int32_t *count_out,
-                          void *cuda_stream);
+                          int32_t *index_out, void *cuda_stream);
+
+/* Replaces DynamicObstacle._get_predicted_states_matrix (dynamic_obstacle.py:20-37) for the obstacles every agent kept:
+ * M moving obstacles (state[M][3] = x, y, heading; lin_vel[M]; ang_vel[M]), index[B][O] = which obstacle sits in each
+ * agent's slot (kmpc_select_obstacles' index_out; -1 = empty slot -> the padding point in every column; NULL = slot o is
+ * obstacle o for every agent).  Column 0 of a track is the current position, column t = column t-1 advanced by
+ * [v cos(a) dt, v sin(a) dt, omega dt] (dt = 0.1 in the reference, :21); literal != 0 keeps a = deg2rad(heading) on a heading
+ * that is already in radians (:24-25), literal == 0 uses the heading itself.  tracks_out: N columns per slot in the
+ * obs_tracks layout of kmpc_solve_tracks (N = the handle's horizon).  Device pointers, asynchronous. */
+int kmpc_predict_tracks(kmpc_handle *h, int B, int O, int M, const int32_t *index, const double *state, const double *lin_vel,
+                        const double *ang_vel, double dt, int literal, double pad_x, double pad_y, double *tracks_out,
+                        void *cuda_stream);
 
 /* Device-resident receding-horizon loop: `steps` repetitions of EgoAgent.step (agent.py:130-155) for B agents without
  * leaving the device:   solve(x_cur, goal, warm start = previous X, U UNSHIFTED, agent.py:139-145) -> applied = U[:,0]

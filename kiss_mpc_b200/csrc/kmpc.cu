@@ -214,9 +214,9 @@ static cudaError_t launch_warp_kernel(kmpc_handle *h, int device, int sm_count, 
     cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     if (e != cudaSuccess) return e;
     int wpb = WPB;
-    while (wpb > 0 && WLay<SPL, NST>::bytes(wpb, c.O) > (size_t)max_smem) --wpb;
+    while (wpb > 0 && WLay<SPL, NST>::bytes(wpb, c.O, c.obs_sw) > (size_t)max_smem) --wpb;
     if (wpb < 1) return cudaErrorInvalidConfiguration;
-    const size_t smem = WLay<SPL, NST>::bytes(wpb, c.O);
+    const size_t smem = WLay<SPL, NST>::bytes(wpb, c.O, c.obs_sw);
     auto kern = kmpc_warp_kernel<SPL, NST, FULL, OBS, WPB, MINB>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -276,7 +276,7 @@ __global__ void kmpc_handoff_kernel(int B, int N, int layout, const double *__re
 #define KMPC_SEL_MAX_O 32
 __global__ void kmpc_select_kernel(int B, int M, int layout, const double *__restrict__ x_cur, const double *__restrict__ cc,
                                    const double *__restrict__ cr, double sensor_radius, int literal, int O, double pad_x, double pad_y,
-                                   double *__restrict__ obs_out, int32_t *__restrict__ count_out) {
+                                   double *__restrict__ obs_out, int32_t *__restrict__ count_out, int32_t *__restrict__ index_out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const double px = x_cur[layout ? (size_t)b : (size_t)b * 3], py = x_cur[layout ? (size_t)B + b : (size_t)b * 3 + 1];
@@ -303,8 +303,35 @@ __global__ void kmpc_select_kernel(int B, int M, int layout, const double *__res
         const double ox = o < n ? cc[2 * idx[o]] : pad_x, oy = o < n ? cc[2 * idx[o] + 1] : pad_y;
         if (layout) { obs_out[((size_t)o * 2) * B + b] = ox; obs_out[((size_t)o * 2 + 1) * B + b] = oy; }
         else { obs_out[((size_t)b * O + o) * 2] = ox; obs_out[((size_t)b * O + o) * 2 + 1] = oy; }
+        if (index_out) index_out[(size_t)b * O + o] = o < n ? idx[o] : -1;
     }
     if (count_out) count_out[b] = n;
+}
+
+// Constant-velocity predictor of DynamicObstacle (dynamic_obstacle.py:20-37) for the obstacles each agent selected: one thread
+// per (agent, slot) runs the N-column recursion  column 0 = current state, column t = column t-1 + [v cos(a) dt, v sin(a) dt,
+// omega dt]  with a = deg2rad(heading) as the reference writes it (:24-25; literal == 0: the heading taken as radians) and
+// stores the x, y of every column.  Slots without an obstacle (index < 0) get the padding point in every column.
+__global__ void kmpc_predict_kernel(int B, int O, int M, int N, int layout, const int32_t *__restrict__ index, const double *__restrict__ state,
+                                    const double *__restrict__ lin_vel, const double *__restrict__ ang_vel, double dt, int literal,
+                                    double pad_x, double pad_y, double *__restrict__ tracks) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * O) return;
+    const int b = (int)(i / O), o = (int)(i % O);
+    const int m = index ? index[i] : o;
+    const bool real = m >= 0 && m < M;
+    double x = real ? state[3 * m] : pad_x, y = real ? state[3 * m + 1] : pad_y, th = real ? state[3 * m + 2] : 0.0;
+    const double v = real ? lin_vel[m] : 0.0, w = real ? ang_vel[m] : 0.0;
+    for (int t = 0; t < N; ++t) {
+        const size_t ox = layout ? (((size_t)o * N + t) * 2) * B + b : (((size_t)b * O + o) * N + t) * 2;
+        tracks[ox] = x; tracks[layout ? ox + B : ox + 1] = y;
+        if (real) {
+            const double a = literal ? th * 0.017453292519943295 : th;   // np.deg2rad = multiplication by pi / 180
+            double sn, cs;
+            sincos(a, &sn, &cs);
+            x = x + v * cs * dt; y = y + v * sn * dt; th = th + w * dt;
+        }
+    }
 }
 
 // FP64 FMA throughput micro-benchmark: 8 independent DFMA chains per thread.
@@ -355,7 +382,7 @@ extern "C" int kmpc_version(void) { return KMPC_VERSION; }
 
 extern "C" size_t kmpc_workspace_bytes(const kmpc_config *cfg) {
     if (!check_cfg(cfg)) return 0;
-    Rows r = make_rows(cfg->N, cfg->O_max);
+    Rows r = make_rows(cfg->N, cfg->O_max, 1);
     return (size_t)r.total * cols_for(cfg) * sizeof(double) + (size_t)4 * cols_for(cfg) * sizeof(int);
 }
 
@@ -396,7 +423,7 @@ extern "C" int kmpc_create(const kmpc_config *cfg, kmpc_handle **out) {
     if (!h) return fail(NULL, KMPC_E_NOMEM, "kmpc_create: out of host memory%s", "");
     h->cfg = *cfg;
     h->device = cfg->device;
-    h->rows = make_rows(cfg->N, cfg->O_max);
+    h->rows = make_rows(cfg->N, cfg->O_max, 1);   // sized for stage-wise obstacle centres
     h->cols = cols_for(cfg);
     cudaError_t e = cudaSetDevice(h->device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
@@ -433,7 +460,7 @@ static inline int nblocks(int n) { return (n + KMPC_TPB - 1) / KMPC_TPB; }
 // active-instance count of an older trip (async copy into pinned memory) sizes the grids and ends the loop.  On return
 // every instance has finished and the outputs are complete on `cuda_stream`.
 static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
-                      const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
+                      const double *obs_centers, int O, int stagewise, double obs_radius, double inflation, double *X_out, double *U_out,
                       double *obj_out, int32_t *status_out, int32_t *iters_out, const int32_t *active, void *cuda_stream) {
     if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_solve: NULL handle%s", "");
     if (B < 0 || B > h->cfg.B_max) return fail(h, KMPC_E_BADARG, "kmpc_solve: B outside [0, B_max]%s", "");
@@ -447,12 +474,12 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
     memset(&c, 0, sizeof c);
     const kmpc_config *cf = &h->cfg;
     c.N = cf->N; c.O = O; c.cost_mode = cf->cost_mode; c.gk_lo = cf->goal_k_lo; c.gk_hi = cf->goal_k_hi;
-    c.max_iter = cf->max_iter; c.layout = cf->layout; c.B = B;
+    c.max_iter = cf->max_iter; c.layout = cf->layout; c.B = B; c.obs_sw = (stagewise && O > 0) ? 1 : 0;
     relax_bounds(cf, &c);
     c.T = cf->T; c.W[0] = cf->W[0]; c.W[1] = cf->W[1]; c.W[2] = cf->W[2];
     c.Wvn = cf->Wv_neg; c.Wvp = cf->Wv_pos; c.Ww = cf->Ww; c.tol = cf->tol;
     c.obs_radius = obs_radius; c.dL = inflation - K_BOUND_RELAX * fmax(1.0, fabs(inflation));
-    c.L = make_rows(cf->N, O);
+    c.L = make_rows(cf->N, O, c.obs_sw);
     c.nb = (cf->N + 1) * (c.hasL[0] + c.hasU[0] + c.hasL[1] + c.hasU[1]) + cf->N * (c.hasL[2] + c.hasU[2] + c.hasL[3] + c.hasU[3]) + cf->N * O;
     c.m = 3 * (cf->N + 1) + cf->N * O;
     c.r_mnb = 1.0 / (double)(c.m + c.nb); c.r_nb = c.nb ? 1.0 / (double)c.nb : 0.0;
@@ -568,7 +595,14 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
 extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
                           const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
                           double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream) {
-    return solve_impl(h, B, x_cur, goal, X0, U0, obs_centers, O, obs_radius, inflation, X_out, U_out, obj_out, status_out, iters_out, NULL,
+    return solve_impl(h, B, x_cur, goal, X0, U0, obs_centers, O, 0, obs_radius, inflation, X_out, U_out, obj_out, status_out, iters_out, NULL,
+                      cuda_stream);
+}
+
+extern "C" int kmpc_solve_tracks(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
+                                 const double *obs_tracks, int O, double obs_radius, double inflation, double *X_out, double *U_out,
+                                 double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream) {
+    return solve_impl(h, B, x_cur, goal, X0, U0, obs_tracks, O, 1, obs_radius, inflation, X_out, U_out, obj_out, status_out, iters_out, NULL,
                       cuda_stream);
 }
 
@@ -672,14 +706,30 @@ extern "C" int kmpc_debug_phase_cycles(double *out) {
 
 extern "C" int kmpc_select_obstacles(kmpc_handle *h, int B, int M, const double *x_cur, const double *cand_centers,
                                      const double *cand_radius, double sensor_radius, int literal, int O, double pad_x, double pad_y,
-                                     double *obs_out, int32_t *count_out, void *cuda_stream) {
+                                     double *obs_out, int32_t *count_out, int32_t *index_out, void *cuda_stream) {
     if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_select_obstacles: NULL handle%s", "");
     if (B < 0 || M < 0 || O < 1 || O > KMPC_SEL_MAX_O) return fail(h, KMPC_E_BADARG, "kmpc_select_obstacles: need B, M >= 0 and 1 <= O <= 32%s", "");
     if (B == 0) return 0;
     if (!x_cur || !obs_out || (M > 0 && (!cand_centers || !cand_radius))) return fail(h, KMPC_E_BADARG, "kmpc_select_obstacles: NULL required pointer%s", "");
     CU(cudaSetDevice(h->device));
     kmpc_select_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(B, M, h->cfg.layout, x_cur, cand_centers, cand_radius, sensor_radius,
-                                                                               literal, O, pad_x, pad_y, obs_out, count_out);
+                                                                               literal, O, pad_x, pad_y, obs_out, count_out, index_out);
+    CU(cudaGetLastError());
+    h->launches++;
+    return 0;
+}
+
+extern "C" int kmpc_predict_tracks(kmpc_handle *h, int B, int O, int M, const int32_t *index, const double *state, const double *lin_vel,
+                                  const double *ang_vel, double dt, int literal, double pad_x, double pad_y, double *tracks_out,
+                                  void *cuda_stream) {
+    if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_predict_tracks: NULL handle%s", "");
+    if (B < 0 || O < 1 || M < 0 || (!index && O > M)) return fail(h, KMPC_E_BADARG, "kmpc_predict_tracks: need B, M >= 0, O >= 1 (and O <= M without an index)%s", "");
+    if (B == 0) return 0;
+    if (!tracks_out || (M > 0 && (!state || !lin_vel || !ang_vel))) return fail(h, KMPC_E_BADARG, "kmpc_predict_tracks: NULL required pointer%s", "");
+    CU(cudaSetDevice(h->device));
+    const size_t n = (size_t)B * O;
+    kmpc_predict_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(B, O, M, h->cfg.N, h->cfg.layout, index, state, lin_vel,
+                                                                                          ang_vel, dt, literal, pad_x, pad_y, tracks_out);
     CU(cudaGetLastError());
     h->launches++;
     return 0;
@@ -696,7 +746,7 @@ extern "C" int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur,
     cudaStream_t st = (cudaStream_t)cuda_stream;
     for (int s = 0; s < steps; ++s) {
         // in place: every instance reads its own warm-start rows before it writes its result rows
-        int rc = solve_impl(h, B, x_cur, goal, X, U, NULL, 0, 0.0, 0.0, X, U, NULL, status_log ? status_log + (size_t)s * B : NULL,
+        int rc = solve_impl(h, B, x_cur, goal, X, U, NULL, 0, 0, 0.0, 0.0, X, U, NULL, status_log ? status_log + (size_t)s * B : NULL,
                             iters_log ? iters_log + (size_t)s * B : NULL, active, cuda_stream);
         if (rc) return rc;
         kmpc_handoff_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, h->cfg.N, h->cfg.layout, X, U, x_cur,

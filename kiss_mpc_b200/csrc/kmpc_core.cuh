@@ -95,7 +95,7 @@ struct Rows {
     int rCsoc, rDsoc, rFilt, rSc, rCtx, total;
 };
 
-KMPC_HD Rows make_rows(int N, int O) {
+KMPC_HD Rows make_rows(int N, int O, int stagewise = 0) {
     Rows L;
     L.N = N; L.O = O;
     const int NO = N * O;
@@ -112,7 +112,7 @@ KMPC_HD Rows make_rows(int N, int O) {
     L.rCsoc = r; r += 3 * (N + 1);
     L.rDsoc = r; r += NO;
     L.rFilt = r; r += 2 * K_FILTER_CAP;
-    L.rSc = r; r += 6 + 2 * O;
+    L.rSc = r; r += 6 + 2 * O * (stagewise ? N : 1);   // x_cur, goal, circle centres (per obstacle, or per obstacle and stage)
     L.rCtx = r; r += KMPC_NCTX;
     L.total = r;
     return L;
@@ -121,6 +121,7 @@ KMPC_HD Rows make_rows(int N, int O) {
 // Per-solve constants (kernel parameter, by value).
 struct Cfg {
     int N, O, cost_mode, gk_lo, gk_hi, max_iter, layout, B;
+    int obs_sw;            // circle centres given per obstacle AND stage (dynamic_obstacle.py:47-56) instead of per obstacle
     int hasL[4], hasU[4];  // x, y, v, omega
     int nb, m;             // number of bound sides incl. obstacle slacks; number of constraint rows
     double r_mnb, r_nb;    // 1 / (m + nb), 1 / nb (0 if nb == 0): the averaging factors of IPOPT's s_d, s_c
@@ -177,6 +178,12 @@ KMPC_HD size_t io_U(const Cfg &c, int b, int j, int k) {
 KMPC_HD size_t io_obs(const Cfg &c, int b, int o, int j) {
     return c.layout ? ((size_t)o * 2 + j) * c.B + b : ((size_t)b * c.O + o) * 2 + j;
 }
+// stage-wise centres: column t of obstacle o's track is paired with X_{t+1} (dynamic_obstacle.py:47-56)
+KMPC_HD size_t io_obs_sw(const Cfg &c, int b, int o, int t, int j) {
+    return c.layout ? (((size_t)o * c.N + t) * 2 + j) * c.B + b : (((size_t)b * c.O + o) * c.N + t) * 2 + j;
+}
+// row (within the scalar rows of the thread solver's workspace) of coordinate j of obstacle o's centre at stage k >= 1
+#define CEN_ROW(o, k, j) (6 + 2 * (c.obs_sw ? (o) * c.N + ((k) - 1) : (o)) + (j))
 
 // cost gradient of v (scaled) and its second derivative; optimizer.py:91-96 (literal) / README.md:23-24
 KMPC_HD void vcost(const Cfg &c, double df, double v, double *g, double *h) {
@@ -361,7 +368,12 @@ KMPC_HDN inline void pass_init(const Cfg &c, Ctx &t, double *wsp, size_t S, cons
         xc[j] = io.x_cur[io_vec3(c, b, j)]; gl[j] = io.goal[io_vec3(c, b, j)];
         FD(sc, j) = xc[j]; FD(sc, 3 + j) = gl[j];
     }
-    for (int o = 0; o < O; ++o) for (int j = 0; j < 2; ++j) FD(sc, 6 + 2 * o + j) = io.obs[io_obs(c, b, o, j)];
+    if (c.obs_sw) {
+        for (int o = 0; o < O; ++o) for (int t = 0; t < N; ++t) for (int j = 0; j < 2; ++j)
+            FD(sc, CEN_ROW(o, t + 1, j)) = io.obs[io_obs_sw(c, b, o, t, j)];
+    } else {
+        for (int o = 0; o < O; ++o) for (int j = 0; j < 2; ++j) FD(sc, 6 + 2 * o + j) = io.obs[io_obs(c, b, o, j)];
+    }
     double gm = 0.0;
     const double dLpush = c.dL + K_BOUND_PUSH * fmax(1.0, fabs(c.dL));
     double *ps = wsp + (size_t)L.rState[0] * S;
@@ -395,7 +407,7 @@ KMPC_HDN inline void pass_init(const Cfg &c, Ctx &t, double *wsp, size_t S, cons
         FD(ps, F_CS) = cs; FD(ps, F_SN) = sn;
         if (k >= 1)
             for (int o = 0; o < O; ++o, po += (size_t)3 * S) {
-                const double ex = x[0] - FD(sc, 6 + 2 * o), ey = x[1] - FD(sc, 7 + 2 * o);
+                const double ex = x[0] - FD(sc, CEN_ROW(o, k, 0)), ey = x[1] - FD(sc, CEN_ROW(o, k, 1));
                 const double d = sqrt(ex * ex + ey * ey) - c.obs_radius;
                 FD(po, 0) = fmax(d, dLpush); FD(po, 1) = 0.0; FD(po, 2) = 1.0;
             }
@@ -483,7 +495,7 @@ KMPC_HDN inline bool pass_sweep(const Cfg &c, const Ctx &t, double *wsp, size_t 
             for (int o = O - 1; o >= 0; --o) {
                 po -= (size_t)3 * S; pds -= S;
                 const double yd = FD(po, 1);
-                ObsT ot = obs_terms(c, x0, x1, FD(sc, 6 + 2 * o), FD(sc, 7 + 2 * o), FD(po, 0), yd, FD(po, 2), mu, delta, lsq,
+                ObsT ot = obs_terms(c, x0, x1, FD(sc, CEN_ROW(o, k, 0)), FD(sc, CEN_ROW(o, k, 1)), FD(po, 0), yd, FD(po, 2), mu, delta, lsq,
                                     soc, soc ? FD(pds, 0) : 0.0);
                 if (!lsq) {
                     const double h = yd / ot.rr;
@@ -597,7 +609,7 @@ KMPC_HDN inline void pass_rollout(const Cfg &c, const Ctx &t, double *wsp, size_
 #pragma unroll 1
             for (int o = 0; o < O; ++o, po += (size_t)3 * S, pdo += (size_t)2 * S, pds += S) {
                 const double s = FD(po, 0), yd = FD(po, 1), vL = FD(po, 2);
-                ObsT ot = obs_terms(c, x0, x1, FD(sc, 6 + 2 * o), FD(sc, 7 + 2 * o), s, yd, vL, mu, delta, lsq, soc,
+                ObsT ot = obs_terms(c, x0, x1, FD(sc, CEN_ROW(o, k, 0)), FD(sc, CEN_ROW(o, k, 1)), s, yd, vL, mu, delta, lsq, soc,
                                     soc ? FD(pds, 0) : 0.0);
                 const double ds = ot.nx * d0 + ot.ny * d1 - ot.bd;
                 const double dyd = ot.Ds * ds - ot.bs;
@@ -707,7 +719,7 @@ KMPC_HDN inline bool pass_trial(const Cfg &c, const Ctx &t, double *wsp, size_t 
             for (int o = 0; o < O; ++o, po += (size_t)3 * S, pdo += (size_t)2 * S, pno += (size_t)3 * S) {
                 const double so = FD(po, 0), ds = FD(pdo, 0), vL = FD(po, 2);
                 const double s = so + alpha * ds;
-                const double ex = x0 - FD(sc, 6 + 2 * o), ey = x1 - FD(sc, 7 + 2 * o);
+                const double ex = x0 - FD(sc, CEN_ROW(o, k, 0)), ey = x1 - FD(sc, CEN_ROW(o, k, 1));
                 const double rr = sqrt(ex * ex + ey * ey), nx = ex / rr, ny = ey / rr;
                 const double dm = (rr - c.obs_radius) - s;
                 st.theta += fabs(dm); st.pinf = maxabs_nan(st.pinf, dm);
@@ -792,7 +804,7 @@ KMPC_HDN inline void pass_soc_rhs(const Cfg &c, const Ctx &t, double *wsp, size_
         FD(pcs, 0) = al * b0 + (t0 - tp0); FD(pcs, 1) = al * b1 + (t1 - tp1); FD(pcs, 2) = al * b2 + (t2 - tp2);
         if (O > 0 && k >= 1)
             for (int o = 0; o < O; ++o, po += (size_t)3 * S, pto += (size_t)3 * S, pds += S) {
-                const double cx = FD(sc, 6 + 2 * o), cy = FD(sc, 7 + 2 * o);
+                const double cx = FD(sc, CEN_ROW(o, k, 0)), cy = FD(sc, CEN_ROW(o, k, 1));
                 double base;
                 if (first) { const double ex = x0 - cx, ey = x1 - cy; base = (sqrt(ex * ex + ey * ey) - c.obs_radius) - FD(po, 0); }
                 else base = FD(pds, 0);

@@ -55,7 +55,8 @@ enum { G_DX0 = 0, G_DX1, G_DX2, G_DU0, G_DU1, G_DY0, G_DY1, G_DY2, G_CS0, G_CS1,
 
 // obstacle area of one instance (owner warp only; circular obstacle-distance rows of optimizer.py:198-258, README.md:78-81):
 // per (field, obstacle, stage) the slack s of the row d(x_k) - s = 0, its multiplier yd, the multiplier vL of s >= I, the
-// second-order-correction rhs, the row residual at the last trial point; then the O circle centres (x, y).
+// second-order-correction rhs, the row residual at the last trial point; then the circle centres: (x, y) per obstacle
+// (optimizer.py:217-221), or -- stage-wise centres, dynamic_obstacle.py:47-56 -- an x plane and a y plane of O * NSTG.
 enum { B_S = 0, B_YD, B_VL, B_DSOC, B_DM, B_NF };
 
 struct WScal {  // warp-uniform per-instance scalars
@@ -74,8 +75,8 @@ struct WLay {
     static constexpr int COOP = C_NF * NSTG + 1;
     static constexpr int PRIV = V_NF * NSTG;
     static constexpr int GPRIV = G_NF * NSTG;   // doubles of global scratch per resident warp
-    KMPC_HD static int obs_doubles(int O) { return O > 0 ? B_NF * O * NSTG + 2 * O : 0; }
-    static size_t bytes(int warps, int O = 0) { return (size_t)warps * ((COOP + PRIV + obs_doubles(O)) * sizeof(double) + sizeof(WScal)); }
+    KMPC_HD static int obs_doubles(int O, int sw = 0) { return O > 0 ? B_NF * O * NSTG + 2 * O * (sw ? NSTG : 1) : 0; }
+    static size_t bytes(int warps, int O = 0, int sw = 0) { return (size_t)warps * ((COOP + PRIV + obs_doubles(O, sw)) * sizeof(double) + sizeof(WScal)); }
 };
 
 // value of the next / previous stage (neighbouring slot, or the neighbouring lane's edge slot)
@@ -166,6 +167,17 @@ KMPC_W bool wb_trial(double d, double vt, double lb, double ub, bool hL, bool hU
 // ---- obstacle rows (stage-parallel: each lane loops over the O obstacles of its stage(s), s = 1..N) ----
 struct WObsT { double nx, ny, ir, rr, Ds, bd, bs, rsl; };  // unit normal, 1/|p-c|, |p-c|, condensed slack block, rhs terms, 1/(s - I)
 // terms of one (stage, obstacle) row at the current iterate (cf. obs_terms of kmpc_core.cuh); kind: lsq / soc / Newton
+// circle centres seen from stage s of this lane: one (x, y) per obstacle, or the obstacle's own track at that stage
+struct WCen { const double *p; int so, yo; };
+KMPC_W WCen w_cen(const Cfg &c, const double *ob, int O, int NSTG, int s) {
+    const double *base = ob + B_NF * O * NSTG;
+    WCen r;
+    r.p = c.obs_sw ? base + s : base; r.so = c.obs_sw ? NSTG : 2; r.yo = c.obs_sw ? O * NSTG : 1;
+    return r;
+}
+KMPC_W double w_cx(const WCen &cn, int o) { return cn.p[o * cn.so]; }
+KMPC_W double w_cy(const WCen &cn, int o) { return cn.p[o * cn.so + cn.yo]; }
+
 KMPC_W WObsT w_obs_terms(const Cfg &c, double px, double py, double cx, double cy, double s, double yd, double vL, double mu,
                          double delta, bool lsq, bool soc, double dsoc) {
     WObsT r;
@@ -205,7 +217,15 @@ KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<
     const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     if (OBS) {  // circle centres -> shared memory (optimizer.py:217-221)
         double *cxy = ob + B_NF * O * NSTG;
-        for (int i = lane; i < 2 * O; i += 32) cxy[i] = io.obs[io_obs(c, b, i >> 1, i & 1)];
+        if (c.obs_sw) {  // track of every obstacle, column t for stage t + 1 (dynamic_obstacle.py:47-56)
+            for (int o = 0; o < O; ++o)
+                for (int t = lane; t < N; t += 32) {
+                    cxy[o * NSTG + t + 1] = io.obs[io_obs_sw(c, b, o, t, 0)];
+                    cxy[(O + o) * NSTG + t + 1] = io.obs[io_obs_sw(c, b, o, t, 1)];
+                }
+        } else {
+            for (int i = lane; i < 2 * O; i += 32) cxy[i] = io.obs[io_obs(c, b, i >> 1, i & 1)];
+        }
         w_sync();
     }
     double xc[3], gl[3];
@@ -239,10 +259,10 @@ KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<
         w.zLw[j] = (hasu && c.hasL[3]) ? 1.0 : 0.0; w.zUw[j] = (hasu && c.hasU[3]) ? 1.0 : 0.0;
         w.cs[j] = cs; w.sn[j] = sn;
         if (OBS && s >= 1 && s <= N) {  // slacks pushed inside their bound, yd = 0, vL = 1
-            const double *cxy = ob + B_NF * O * NSTG;
+            const WCen cen = w_cen(c, ob, O, NSTG, s);
             const double dLpush = c.dL + K_BOUND_PUSH * fmax(1.0, fabs(c.dL));
             for (int o = 0; o < O; ++o) {
-                const double ex = x[0] - cxy[2 * o], ey = x[1] - cxy[2 * o + 1];
+                const double ex = x[0] - w_cx(cen, o), ey = x[1] - w_cy(cen, o);
                 const double d = sqrt(ex * ex + ey * ey) - c.obs_radius;
                 double *po = ob + o * NSTG + s;
                 po[B_S * O * NSTG] = fmax(d, dLpush); po[B_YD * O * NSTG] = 0.0; po[B_VL * O * NSTG] = 1.0;
@@ -311,11 +331,11 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
         }
         double Q01 = 0.0, S00 = 0.0, S01 = 0.0, S11 = 0.0;
         if (OBS && s >= 1) {  // slacks of the obstacle rows condensed into the x-y block
-            const double *cxy = ob + B_NF * O * NSTG;
+            const WCen cen = w_cen(c, ob, O, NSTG, s);
             for (int o = 0; o < O; ++o) {
                 const double *po = ob + o * NSTG + s;
                 const double yd = po[B_YD * O * NSTG];
-                const WObsT ot = w_obs_terms(c, x0, x1, cxy[2 * o], cxy[2 * o + 1], po[B_S * O * NSTG], yd, po[B_VL * O * NSTG], mu, delta,
+                const WObsT ot = w_obs_terms(c, x0, x1, w_cx(cen, o), w_cy(cen, o), po[B_S * O * NSTG], yd, po[B_VL * O * NSTG], mu, delta,
                                              lsq, soc, soc ? po[B_DSOC * O * NSTG] : 0.0);
                 if (!lsq) {
                     const double h = yd * ot.ir;
@@ -545,11 +565,11 @@ KMPC_WN inline void w_step(const Cfg &c, const WScal *sc, const WState<SPL> &w, 
         d.dy0[j] = dy0; d.dy1[j] = dy1; d.dy2[j] = dy2;
         ym = maxabs_nan(maxabs_nan(maxabs_nan(ym, dy0), dy1), dy2);
         if (OBS && s >= 1) {  // slack steps ds = n^T dx - bd, multiplier steps dyd = Ds ds - bs of the obstacle rows
-            const double *cxy = ob + B_NF * O * NSTG;
+            const WCen cen = w_cen(c, ob, O, NSTG, s);
             for (int o = 0; o < O; ++o) {
                 const double *po = ob + o * NSTG + s;
                 const double vL = po[B_VL * O * NSTG];
-                const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], cxy[2 * o], cxy[2 * o + 1], po[B_S * O * NSTG], po[B_YD * O * NSTG], vL, mu,
+                const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], w_cx(cen, o), w_cy(cen, o), po[B_S * O * NSTG], po[B_YD * O * NSTG], vL, mu,
                                              delta, lsq, soc, soc ? po[B_DSOC * O * NSTG] : 0.0);
                 const double ds = fma(ot.nx, d0, ot.ny * d1) - ot.bd;
                 ym = maxabs_nan(ym, fma(ot.Ds, ds, -ot.bs));
@@ -667,11 +687,11 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
                                 clamp, zLn, zUn, prod, st);
         n.zLy[j] = zLn; n.zUy[j] = zUn; r1 += zUn - zLn;
         if (OBS && s >= 1) {  // obstacle rows at the trial point
-            const double *cxy = ob + B_NF * O * NSTG;
+            const WCen cen = w_cen(c, ob, O, NSTG, s);
             for (int o = 0; o < O; ++o) {
                 double *po = ob + o * NSTG + s;
                 const double so = po[B_S * O * NSTG], ydo = po[B_YD * O * NSTG], vL = po[B_VL * O * NSTG];
-                const double cx = cxy[2 * o], cy = cxy[2 * o + 1];
+                const double cx = w_cx(cen, o), cy = w_cy(cen, o);
                 const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], cx, cy, so, ydo, vL, mu, delta, lsq, soc, soc ? po[B_DSOC * O * NSTG] : 0.0);
                 const WObsV tv = w_obs_vals(c, ot, so, ydo, vL, fma(ot.nx, d.dx0[j], ot.ny * d.dx1[j]), mu, alpha, ay, adu, clamp);
                 const double ex = x0 - cx, ey = x1 - cy, rr = sqrt(ex * ex + ey * ey), ir = KRCPF(rr);
@@ -745,15 +765,15 @@ KMPC_WN inline void w_obs_commit(const Cfg &c, const WState<SPL> &w, const WStep
                                  double ay, double adu, bool clamp, bool lsq, bool soc, double *ob) {
     constexpr int NSTG = WLay<SPL, NST>::NSTG;
     const int N = c.N, lane = w_lane(), O = c.O;
-    const double *cxy = ob + B_NF * O * NSTG;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
         const int s = lane * SPL + j;
         if (s < 1 || s > N) continue;
+        const WCen cen = w_cen(c, ob, O, NSTG, s);
         for (int o = 0; o < O; ++o) {
             double *po = ob + o * NSTG + s;
             const double so = po[B_S * O * NSTG], ydo = po[B_YD * O * NSTG], vL = po[B_VL * O * NSTG];
-            const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], cxy[2 * o], cxy[2 * o + 1], so, ydo, vL, mu, delta, lsq, soc,
+            const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], w_cx(cen, o), w_cy(cen, o), so, ydo, vL, mu, delta, lsq, soc,
                                          soc ? po[B_DSOC * O * NSTG] : 0.0);
             const WObsV tv = w_obs_vals(c, ot, so, ydo, vL, fma(ot.nx, d.dx0[j], ot.ny * d.dx1[j]), mu, alpha, ay, adu, clamp);
             po[B_S * O * NSTG] = tv.s; po[B_YD * O * NSTG] = tv.yd; po[B_VL * O * NSTG] = tv.z;
@@ -783,11 +803,11 @@ KMPC_WN inline void w_soc_rhs(const Cfg &c, const WScal *sc, const WState<SPL> &
         else { b0 = pv[G_CS0 * NSTG]; b1 = pv[G_CS1 * NSTG]; b2 = pv[G_CS2 * NSTG]; }
         pv[G_CS0 * NSTG] = al * b0 + pv[G_CT0 * NSTG]; pv[G_CS1 * NSTG] = al * b1 + pv[G_CT1 * NSTG]; pv[G_CS2 * NSTG] = al * b2 + pv[G_CT2 * NSTG];
         if (OBS && s >= 1) {
-            const double *cxy = ob + B_NF * O * NSTG;
+            const WCen cen = w_cen(c, ob, O, NSTG, s);
             for (int o = 0; o < O; ++o) {
                 double *po = ob + o * NSTG + s;
                 double base;
-                if (first) { const double ex = w.x0[j] - cxy[2 * o], ey = w.x1[j] - cxy[2 * o + 1]; base = (sqrt(ex * ex + ey * ey) - c.obs_radius) - po[B_S * O * NSTG]; }
+                if (first) { const double ex = w.x0[j] - w_cx(cen, o), ey = w.x1[j] - w_cy(cen, o); base = (sqrt(ex * ex + ey * ey) - c.obs_radius) - po[B_S * O * NSTG]; }
                 else base = po[B_DSOC * O * NSTG];
                 po[B_DSOC * O * NSTG] = al * base + po[B_DM * O * NSTG];
             }
@@ -830,7 +850,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     double *coop = smem + (size_t)wid * LY::COOP;
     double *priv = smem + (size_t)W * LY::COOP + (size_t)wid * LY::PRIV;
     double *gp = io.wscratch + ((size_t)w_block() * W + wid) * LY::GPRIV;
-    const int OBD = LY::obs_doubles(OBS ? c.O : 0);
+    const int OBD = LY::obs_doubles(OBS ? c.O : 0, c.obs_sw);
     double *ob = smem + (size_t)W * (LY::COOP + LY::PRIV) + (size_t)wid * OBD;
     WScal *scal0 = (WScal *)(smem + (size_t)W * (LY::COOP + LY::PRIV + OBD));
     WScal *sc = scal0 + wid;

@@ -133,7 +133,8 @@ class BatchedMotionPlanner:
     def solve(self, current_state, goal_state, states_matrix=None, controls_matrix=None, obstacles=None,
               obstacle_radius: float = 0.3, inflation_radius: float = 0.0, copy: bool = True) -> SolveResult:
         """current_state/goal_state [B,3]; states_matrix [B,3,N+1] and controls_matrix [B,2,N] = primal warm start
-        (both None: the cold start of agent.py:59-60); obstacles [B,O,2] circle centres.  CUDA tensors stay on the
+        (both None: the cold start of agent.py:59-60); obstacles [B,O,2] circle centres, or [B,O,N,2] centre tracks (column t
+        paired with X_{t+1}, dynamic_obstacle.py:47-56; kmpc_solve_tracks).  CUDA tensors stay on the
         device (asynchronous on the current torch stream); NumPy arrays / CPU tensors go through kmpc_solve_host.
         Host path only: ``copy=False`` returns NumPy views of the planner's pinned result buffers (no 80 MB memcpy at
         B = 65,536); they are overwritten by the next solve on this planner."""
@@ -141,6 +142,12 @@ class BatchedMotionPlanner:
         if isinstance(current_state, torch.Tensor) and current_state.is_cuda:
             return self._solve_device(current_state, goal_state, states_matrix, controls_matrix, obstacles,
                                       obstacle_radius, inflation_radius)
+        if obstacles is not None and np.ndim(obstacles) == 4:   # tracks: staged through torch, solved by kmpc_solve_tracks
+            dev = torch.device("cuda", self.device)
+            up = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+            r = self._solve_device(up(current_state), up(goal_state), up(states_matrix), up(controls_matrix), up(obstacles),
+                                   obstacle_radius, inflation_radius)
+            return SolveResult(*[t.cpu().numpy() for t in r])
         return self._solve_host(current_state, goal_state, states_matrix, controls_matrix, obstacles, obstacle_radius,
                                 inflation_radius, copy)
 
@@ -148,6 +155,8 @@ class BatchedMotionPlanner:
         if obstacles is None:
             return 0
         O = int(obstacles.shape[1] if self.layout == _lib.LAYOUT_INSTANCE_MAJOR else obstacles.shape[0])
+        if O == 0:
+            return 0
         if O > self.config.O_max:
             raise ValueError(f"{O} obstacles > O_max={self.config.O_max} of this planner")
         return O
@@ -170,6 +179,9 @@ class BatchedMotionPlanner:
 
         x, goal = prep(x, sx, "current_state"), prep(goal, sx, "goal_state")
         X0, U0 = prep(X0, sX, "states_matrix"), prep(U0, sU, "controls_matrix")
+        tracks = O > 0 and obs.dim() == 4
+        if tracks:   # [B,O,N,2] / [O,N,2,B]
+            sO = (B, O, self.config.N, 2) if self.layout == _lib.LAYOUT_INSTANCE_MAJOR else (O, self.config.N, 2, B)
         obs = prep(obs, sO, "obstacles") if O else None
         if (X0 is None) != (U0 is None):
             raise ValueError("states_matrix and controls_matrix must both be given or both be None")
@@ -181,9 +193,10 @@ class BatchedMotionPlanner:
             it = torch.empty(B, dtype=torch.int32, device=dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
             p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
-            rc = self._L.kmpc_solve(self._h, B, p(x), p(goal), p(X0), p(U0), p(obs), O, float(obs_radius), float(inflation),
-                                    p(Xo), p(Uo), p(obj), p(st), p(it), C.c_void_p(stream))
-        _lib.check(rc, self._h, "kmpc_solve")
+            fn = self._L.kmpc_solve_tracks if tracks else self._L.kmpc_solve
+            rc = fn(self._h, B, p(x), p(goal), p(X0), p(U0), p(obs), O, float(obs_radius), float(inflation),
+                    p(Xo), p(Uo), p(obj), p(st), p(it), C.c_void_p(stream))
+        _lib.check(rc, self._h, "kmpc_solve_tracks" if tracks else "kmpc_solve")
         return SolveResult(Xo, Uo, obj, st, it)
 
     def _solve_host(self, x, goal, X0, U0, obs, obs_radius, inflation, copy=True) -> SolveResult:
@@ -236,11 +249,12 @@ class BatchedMotionPlanner:
         _lib.check(rc, self._h, "kmpc_agent_handoff")
 
     def select_obstacles(self, current_state, centers, radii, sensor_radius: float = 5.0, slots: Optional[int] = None,
-                         literal_distance: bool = True, pad_center=(1.0e6, 1.0e6)):
+                         literal_distance: bool = True, pad_center=(1.0e6, 1.0e6), return_index: bool = False):
         """Batched sensor filter of ROSEnvironment.step (environment.py:48-65): per agent the candidate circles
         (centers [M,2], radii [M], CUDA tensors) within `sensor_radius` (agent.py:101), nearest first, at most `slots`
         (default O_max).  Returns (obstacles [B,slots,2] ready for ``solve(obstacles=...)``, count [B]); unused slots hold
-        `pad_center`, whose rows stay inactive.  literal_distance: geometry.py:44 as written (True) or ||p-c|| - r."""
+        `pad_center`, whose rows stay inactive.  literal_distance: geometry.py:44 as written (True) or ||p-c|| - r.
+        return_index: also return index [B,slots] int32, the candidate kept in every slot (-1 = padding)."""
         torch = _torch()
         dev = torch.device("cuda", self.device)
         B = self._batch_of(current_state)
@@ -249,13 +263,36 @@ class BatchedMotionPlanner:
         _, _, _, sO, _ = self._shapes(B, O)
         out = torch.empty(sO, dtype=torch.float64, device=dev)
         cnt = torch.empty(B, dtype=torch.int32, device=dev)
+        idx = torch.empty((B, O), dtype=torch.int32, device=dev) if return_index else None
         stream = torch.cuda.current_stream(dev).cuda_stream
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
         rc = self._L.kmpc_select_obstacles(self._h, B, M, p(current_state.contiguous()), p(centers.contiguous()), p(radii.contiguous()),
                                            float(sensor_radius), 1 if literal_distance else 0, O, float(pad_center[0]), float(pad_center[1]),
-                                           p(out), p(cnt), C.c_void_p(stream))
+                                           p(out), p(cnt), p(idx), C.c_void_p(stream))
         _lib.check(rc, self._h, "kmpc_select_obstacles")
-        return out, cnt
+        return (out, cnt, idx) if return_index else (out, cnt)
+
+    def predict_tracks(self, batch: int, obstacle_state, linear_velocity, angular_velocity, index=None, slots: Optional[int] = None,
+                       dt: float = 0.1, literal_heading: bool = True, pad_center=(1.0e6, 1.0e6)):
+        """Batched DynamicObstacle._get_predicted_states_matrix (dynamic_obstacle.py:20-37): N-column constant-velocity tracks
+        of the moving obstacles every agent kept.  obstacle_state [M,3] (x, y, heading), linear_velocity [M], angular_velocity
+        [M] (CUDA float64); index [B,slots] int32 from ``select_obstacles(..., return_index=True)`` (None: slot o = obstacle o
+        for every agent).  literal_heading keeps the reference's deg2rad of a radian heading (:24-25).  Returns tracks
+        [B,slots,N,2] ready for ``solve(obstacles=...)``."""
+        torch = _torch()
+        dev = torch.device("cuda", self.device)
+        M = int(obstacle_state.shape[0])
+        O = int(slots if slots is not None else (index.shape[1] if index is not None else M))
+        N = self.config.N
+        shape = (batch, O, N, 2) if self.layout == _lib.LAYOUT_INSTANCE_MAJOR else (O, N, 2, batch)
+        out = torch.empty(shape, dtype=torch.float64, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        p = lambda t: None if t is None else C.c_void_p(t.contiguous().data_ptr())
+        rc = self._L.kmpc_predict_tracks(self._h, int(batch), O, M, p(index), p(obstacle_state), p(linear_velocity), p(angular_velocity),
+                                         float(dt), 1 if literal_heading else 0, float(pad_center[0]), float(pad_center[1]), p(out),
+                                         C.c_void_p(stream))
+        _lib.check(rc, self._h, "kmpc_predict_tracks")
+        return out
 
     def closed_loop(self, current_state, goal_state, steps: int, states_matrix=None, controls_matrix=None,
                     log_applied: bool = True, log_iters: bool = True, goal_radius: float = 0.0, agent_radius: float = 0.0,

@@ -34,6 +34,17 @@ def make_batch(B: int, seed: int = 1000, O: int = 0, obs_radius: float = 0.3, in
     return {"x_cur": x_cur, "goal": goal, "obs": obs}
 
 
+def make_tracks(obs, N: int, seed: int = 0, max_speed: float = 0.3, dt: float = 0.1):
+    """Moving-obstacle tracks [B,O,N,2] from the centres of ``make_batch``: every circle drifts with a constant velocity
+    (speed ~ U(0, max_speed) m/s, direction ~ U(-pi, pi)); column t = centre + t dt v is the centre paired with X_{t+1}
+    (the straight-line case of dynamic_obstacle.py:20-37)."""
+    rng = np.random.default_rng(seed)
+    B, O = obs.shape[:2]
+    sp = rng.uniform(0.0, max_speed, size=(B, O)); hd = rng.uniform(-np.pi, np.pi, size=(B, O))
+    vel = np.stack([sp * np.cos(hd), sp * np.sin(hd)], axis=2)
+    return np.ascontiguousarray(obs[:, :, None, :] + (np.arange(N) * dt)[None, None, :, None] * vel[:, :, None, :])
+
+
 def cfg1_instance():
     """BASELINE config 0: single agent, start (0,0,pi/2) (ros2interface.py:30-31), goal (2,3,0) (SURVEY 8d cfg 1)."""
     return np.array([[0.0, 0.0, np.pi / 2]]), np.array([[2.0, 3.0, 0.0]])

@@ -107,7 +107,8 @@ typedef struct {
     int32_t goal_k_hi;
     int32_t max_iter;
     int32_t linsolve; /* 0 dense Bunch-Kaufman on the full augmented system, 1 stage-wise Riccati */
-    int32_t reserved;
+    int32_t obs_stagewise; /* 0: one centre per obstacle, obs[O][2] (optimizer.py:217-221); 1: a centre per obstacle and stage,
+                            * obs[O][N][2], column t paired with X_{t+1} (dynamic_obstacle.py:47-56 over optimizer.py:201-215) */
     double T;
     double W[3];      /* optimizer.py:57 */
     double Wv_neg;    /* optimizer.py:59 */
@@ -138,7 +139,8 @@ typedef struct {
     int N, O, n, ns, mc, md, nk;
     /* problem data */
     double xcur[3], goal[3], df;
-    double *obs; /* [O][2] */
+    double *obs; /* [O][2], or [O][N][2] when the centres move with the stage */
+    int obs_sw;
     double *lb, *ub;
     int *hasL, *hasU;
     double dL; /* relaxed slack lower bound */
@@ -173,7 +175,7 @@ static work_t *work_new(const kmo_config *cf) {
     w->linsolve = cf->linsolve;
     int n = w->n, ns = w->ns, mc = w->mc;
 #define D(name, cnt) w->name = (double *)xcalloc((cnt), sizeof(double))
-    D(obs, 2 * O); D(lb, n); D(ub, n);
+    w->obs_sw = cf->obs_stagewise != 0; D(obs, 2 * O * (w->obs_sw ? N : 1)); D(lb, n); D(ub, n);
     w->hasL = (int *)xcalloc(n, sizeof(int)); w->hasU = (int *)xcalloc(n, sizeof(int));
     D(w, n); D(s, ns); D(yc, mc); D(yd, ns); D(zL, n); D(zU, n); D(vL, ns);
     D(g, n); D(c, mc); D(dms, ns); D(cs, N + 1); D(sn, N + 1); D(nrm, 2 * ns); D(dist, ns);
@@ -257,7 +259,8 @@ static void eval_d(const kmo_config *cf, const work_t *wk, const double *w, doub
     int N = wk->N, O = wk->O;
     for (int o = 0; o < O; ++o)
         for (int k = 1; k <= N; ++k) {
-            double ex = w[IX(k, 0)] - wk->obs[2 * o], ey = w[IX(k, 1)] - wk->obs[2 * o + 1];
+            const double *cc = wk->obs + (wk->obs_sw ? 2 * ((size_t)o * N + (k - 1)) : 2 * (size_t)o);
+            double ex = w[IX(k, 0)] - cc[0], ey = w[IX(k, 1)] - cc[1];
             double r = sqrt(ex * ex + ey * ey);
             d[IS(o, k)] = r - cf->obs_radius;
             if (nrm) { nrm[2 * IS(o, k)] = ex / r; nrm[2 * IS(o, k) + 1] = ey / r; dist[IS(o, k)] = r; }
@@ -728,7 +731,7 @@ static void solve_one(const kmo_config *cf, work_t *wk, const double *xcur, cons
                       double *obj, int32_t *status, int32_t *iters, kmo_diag *dg, trace_t *tr) {
     int N = wk->N, O = wk->O, n = wk->n, ns = wk->ns, mc = wk->mc;
     memcpy(wk->xcur, xcur, 3 * sizeof(double)); memcpy(wk->goal, goal, 3 * sizeof(double));
-    if (O) memcpy(wk->obs, obs, sizeof(double) * 2 * O);
+    if (O) memcpy(wk->obs, obs, sizeof(double) * 2 * O * (wk->obs_sw ? N : 1));
     kmo_diag dloc; memset(&dloc, 0, sizeof dloc);
 
     /* bounds, relaxed (optimizer.py:111-156 + IPOPT bound_relax_factor) */
@@ -960,7 +963,7 @@ int kmo_version(void) { return KMO_VERSION; }
 int kmo_duals_len(const kmo_config *cf) { int N = cf->N, O = cf->O; return 3 * (N + 1) + 2 * (5 * N + 3) + 3 * N * O; }
 
 /* Layouts (row-major, per-instance contiguous = numpy C order):
- *   x_cur[B][3], goal[B][3], X0[B][3][N+1] or NULL, U0[B][2][N] or NULL, obs[B][O][2] or NULL,
+ *   x_cur[B][3], goal[B][3], X0[B][3][N+1] or NULL, U0[B][2][N] or NULL, obs[B][O][2] (obs_stagewise: [B][O][N][2]) or NULL,
  *   X_out[B][3][N+1], U_out[B][2][N], obj[B], status[B], iters[B], duals[B][kmo_duals_len] or NULL, diag[B] or NULL */
 int kmo_solve(const kmo_config *cf, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
               const double *obs, double *X_out, double *U_out, double *obj, int32_t *status, int32_t *iters,
@@ -979,7 +982,7 @@ int kmo_solve(const kmo_config *cf, int B, const double *x_cur, const double *go
 #pragma omp for schedule(dynamic, 1)
         for (int b = 0; b < B; ++b) {
             solve_one(cf, wk, x_cur + 3 * (size_t)b, goal + 3 * (size_t)b, X0 ? X0 + (size_t)b * 3 * (N + 1) : NULL,
-                      U0 ? U0 + (size_t)b * 2 * N : NULL, O ? obs + (size_t)b * 2 * O : NULL,
+                      U0 ? U0 + (size_t)b * 2 * N : NULL, O ? obs + (size_t)b * 2 * O * (cf->obs_stagewise ? N : 1) : NULL,
                       X_out + (size_t)b * 3 * (N + 1), U_out + (size_t)b * 2 * N, duals ? duals + (size_t)b * dl : NULL,
                       obj + b, status + b, iters + b, diag ? diag + b : NULL, NULL);
         }

@@ -26,7 +26,12 @@ class NLP:
         self.W = np.asarray(cfg.W, float)
         self.x_cur = np.asarray(x_cur, float).reshape(3)
         self.goal = np.asarray(goal, float).reshape(3)
-        self.obs = None if not self.O else np.asarray(obs, float).reshape(self.O, 2)
+        # centre of obstacle o at stage k = self.cen[o, k - 1]: constant per obstacle (optimizer.py:217-221), or the obstacle's
+        # own track, column t paired with X_{t+1} (dynamic_obstacle.py:47-56), when obs has a stage axis
+        obs = None if not self.O else np.asarray(obs, float)
+        self.obs = obs
+        if obs is not None:
+            self.cen = obs.reshape(self.O, N, 2) if obs.ndim == 3 else np.repeat(obs.reshape(self.O, 1, 2), N, axis=1)
         self.n = 5 * N + 3
         self.k_lo = 1
         self.k_hi = N if cfg.goal_range == "readme" else N - 1
@@ -98,7 +103,7 @@ class NLP:
         if not self.O:
             return np.zeros(0)
         X, _ = self.unpack(z)
-        diff = X[None, :2, 1:] - self.obs[:, :, None]
+        diff = X[None, :2, 1:] - self.cen.transpose(0, 2, 1)
         return (np.sqrt((diff ** 2).sum(1)) - self.cfg.obs_radius).reshape(-1)
 
     def jac_d(self, z):
@@ -109,7 +114,7 @@ class NLP:
         X, _ = self.unpack(z)
         for o in range(O):
             for k in range(1, N + 1):
-                e = X[:2, k] - self.obs[o]
+                e = X[:2, k] - self.cen[o, k - 1]
                 r = np.linalg.norm(e)
                 J[o * N + k - 1, 3 * k:3 * k + 2] = e / r
         return J
@@ -136,7 +141,7 @@ class NLP:
         if self.O and yd is not None:
             for o in range(self.O):
                 for k in range(1, N + 1):
-                    e = X[:2, k] - self.obs[o]; r = np.linalg.norm(e); nn = e / r
+                    e = X[:2, k] - self.cen[o, k - 1]; r = np.linalg.norm(e); nn = e / r
                     H[3 * k:3 * k + 2, 3 * k:3 * k + 2] += yd[o * N + k - 1] * (np.eye(2) - np.outer(nn, nn)) / r
         return H
 

@@ -26,7 +26,7 @@ INF = 1e20  # IPOPT treats |b| >= 1e19 as "no bound"
 class _Cfg(C.Structure):
     _fields_ = [
         ("N", C.c_int32), ("O", C.c_int32), ("cost_mode", C.c_int32), ("goal_k_lo", C.c_int32),
-        ("goal_k_hi", C.c_int32), ("max_iter", C.c_int32), ("linsolve", C.c_int32), ("reserved", C.c_int32),
+        ("goal_k_hi", C.c_int32), ("max_iter", C.c_int32), ("linsolve", C.c_int32), ("obs_stagewise", C.c_int32),
         ("T", C.c_double), ("W", C.c_double * 3), ("Wv_neg", C.c_double), ("Wv_pos", C.c_double), ("Ww", C.c_double),
         ("lo", C.c_double * 5), ("hi", C.c_double * 5), ("obs_radius", C.c_double), ("inflation", C.c_double),
         ("tol", C.c_double),
@@ -65,6 +65,7 @@ class OracleConfig:
     tol: float = 1e-8
     max_iter: int = 2000                             # optimizer.py:346
     linsolve: str = "dense"                          # "dense" | "riccati"
+    obs_stagewise: bool = False                      # centres per obstacle AND stage, obs[B,O,N,2] (dynamic_obstacle.py:47-56)
 
     def to_c(self) -> _Cfg:
         c = _Cfg()
@@ -74,6 +75,7 @@ class OracleConfig:
         c.goal_k_hi = self.N if self.goal_range == "readme" else self.N - 1
         c.max_iter = int(self.max_iter)
         c.linsolve = {"dense": 0, "riccati": 1}[self.linsolve]
+        c.obs_stagewise = int(bool(self.obs_stagewise))
         c.T = float(self.T)
         c.W = (C.c_double * 3)(*[float(v) for v in self.W])
         c.Wv_neg, c.Wv_pos, c.Ww = float(self.Wv_neg), float(self.Wv_pos), float(self.Ww)
@@ -130,7 +132,8 @@ class OracleResult:
 
 
 def solve(cfg: OracleConfig, x_cur, goal, X0=None, U0=None, obs=None, want_duals=False, nthreads=0) -> OracleResult:
-    """Solve B independent instances.  x_cur,goal: [B,3]; X0: [B,3,N+1]; U0: [B,2,N]; obs: [B,O,2]."""
+    """Solve B independent instances.  x_cur,goal: [B,3]; X0: [B,3,N+1]; U0: [B,2,N]; obs: [B,O,2], or [B,O,N,2] with
+    cfg.obs_stagewise (column t of an obstacle's track is paired with X_{t+1}, dynamic_obstacle.py:47-56)."""
     L = lib()
     c = cfg.to_c()
     x_cur = np.ascontiguousarray(np.atleast_2d(x_cur), dtype=np.float64)
@@ -140,7 +143,7 @@ def solve(cfg: OracleConfig, x_cur, goal, X0=None, U0=None, obs=None, want_duals
     X0 = None if X0 is None else np.ascontiguousarray(X0, dtype=np.float64).reshape(B, 3, N + 1)
     U0 = None if U0 is None else np.ascontiguousarray(U0, dtype=np.float64).reshape(B, 2, N)
     if O:
-        obs = np.ascontiguousarray(obs, dtype=np.float64).reshape(B, O, 2)
+        obs = np.ascontiguousarray(obs, dtype=np.float64).reshape((B, O, N, 2) if cfg.obs_stagewise else (B, O, 2))
     X = np.empty((B, 3, N + 1)); U = np.empty((B, 2, N)); obj = np.empty(B)
     status = np.empty(B, np.int32); iters = np.empty(B, np.int32)
     diag = np.zeros(B, DIAG_DTYPE)
@@ -159,7 +162,7 @@ def solve_trace(cfg: OracleConfig, x_cur, goal, X0=None, U0=None, obs=None, cap=
     x_cur = np.ascontiguousarray(x_cur, dtype=np.float64).reshape(3); goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(3)
     X0 = None if X0 is None else np.ascontiguousarray(X0, dtype=np.float64).reshape(3, N + 1)
     U0 = None if U0 is None else np.ascontiguousarray(U0, dtype=np.float64).reshape(2, N)
-    obs = None if not cfg.O else np.ascontiguousarray(obs, dtype=np.float64).reshape(cfg.O, 2)
+    obs = None if not cfg.O else np.ascontiguousarray(obs, dtype=np.float64).reshape((cfg.O, N, 2) if cfg.obs_stagewise else (cfg.O, 2))
     X = np.empty((3, N + 1)); U = np.empty((2, N)); obj = np.empty(1); st = np.empty(1, np.int32); it = np.empty(1, np.int32)
     rows = np.zeros((cap, 8)); ln = np.zeros(1, np.int32)
     rc = L.kmo_solve_trace(C.byref(c), _p(x_cur), _p(goal), _p(X0), _p(U0), _p(obs), _p(X), _p(U), _p(obj),

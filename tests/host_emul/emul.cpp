@@ -42,7 +42,7 @@ void simt_run(const std::function<void()> &fn) {
 }
 }  // namespace kmpc
 
-static Cfg make_cfg(const kmpc_config *cf, int B, int O, double obs_radius, double inflation) {
+static Cfg make_cfg(const kmpc_config *cf, int B, int O, int stagewise, double obs_radius, double inflation) {
     Cfg c;
     memset(&c, 0, sizeof c);
     c.N = cf->N; c.O = O; c.cost_mode = cf->cost_mode; c.gk_lo = cf->goal_k_lo; c.gk_hi = cf->goal_k_hi;
@@ -55,7 +55,8 @@ static Cfg make_cfg(const kmpc_config *cf, int B, int O, double obs_radius, doub
     c.T = cf->T; c.W[0] = cf->W[0]; c.W[1] = cf->W[1]; c.W[2] = cf->W[2];
     c.Wvn = cf->Wv_neg; c.Wvp = cf->Wv_pos; c.Ww = cf->Ww; c.tol = cf->tol;
     c.obs_radius = obs_radius; c.dL = inflation - K_BOUND_RELAX * fmax(1.0, fabs(inflation));
-    c.L = make_rows(cf->N, O);
+    c.obs_sw = (stagewise && O > 0) ? 1 : 0;
+    c.L = make_rows(cf->N, O, c.obs_sw);
     c.nb = (cf->N + 1) * (c.hasL[0] + c.hasU[0] + c.hasL[1] + c.hasU[1]) + cf->N * (c.hasL[2] + c.hasU[2] + c.hasL[3] + c.hasU[3]) + cf->N * O;
     c.m = 3 * (cf->N + 1) + cf->N * O;
     c.r_mnb = 1.0 / (double)(c.m + c.nb); c.r_nb = c.nb ? 1.0 / (double)c.nb : 0.0;
@@ -63,9 +64,9 @@ static Cfg make_cfg(const kmpc_config *cf, int B, int O, double obs_radius, doub
 }
 
 extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, const double *goal, const double *X0,
-                          const double *U0, const double *obs, int O, double obs_radius, double inflation, double *X_out,
+                          const double *U0, const double *obs, int O, int stagewise, double obs_radius, double inflation, double *X_out,
                           double *U_out, double *obj, int32_t *status, int32_t *iters, int32_t *trips) {
-    Cfg c = make_cfg(cf, B, O, obs_radius, inflation);
+    Cfg c = make_cfg(cf, B, O, stagewise, obs_radius, inflation);
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs;
     io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL; io.wscratch = NULL;
@@ -128,17 +129,17 @@ extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, con
 
 // warp-per-instance solver (kmpc_warp.cuh) on the fibre emulator; N + 1 <= 64
 extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur, const double *goal, const double *X0,
-                               const double *U0, const double *obs, int O, double obs_radius, double inflation, double *X_out,
+                               const double *U0, const double *obs, int O, int stagewise, double obs_radius, double inflation, double *X_out,
                                double *U_out, double *obj, int32_t *status, int32_t *iters, int32_t *trips) {
     if (cf->N + 1 > 64) return -1;
-    Cfg c = make_cfg(cf, B, O, obs_radius, inflation);
+    Cfg c = make_cfg(cf, B, O, stagewise, obs_radius, inflation);
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs;
     io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL; io.wscratch = NULL;
     const int spl = cf->N + 1 <= 32 ? 1 : 2;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int b = 0; b < B; ++b) {
-        std::vector<double> smem((spl == 1 ? WLay<1, 32>::bytes(1, O) : cf->N + 1 <= 52 ? WLay<2, 52>::bytes(1, O) : WLay<2, 64>::bytes(1, O)) / sizeof(double), NAN);  // one emulated warp = one block
+        std::vector<double> smem((spl == 1 ? WLay<1, 32>::bytes(1, O, c.obs_sw) : cf->N + 1 <= 52 ? WLay<2, 52>::bytes(1, O, c.obs_sw) : WLay<2, 64>::bytes(1, O, c.obs_sw)) / sizeof(double), NAN);  // one emulated warp = one block
         unsigned long long tr = 0;
         int queue = b;          // this emulated warp is handed exactly instance b
         Cfg cb = c; cb.B = b + 1;

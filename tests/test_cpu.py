@@ -7,7 +7,7 @@ import re
 import numpy as np
 import pytest
 
-from kiss_mpc_b200.synthetic import cfg1_instance, make_batch
+from kiss_mpc_b200.synthetic import cfg1_instance, make_batch, make_tracks
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -51,8 +51,49 @@ def test_oracle_golden(oracle_mod):
     assert (np.abs(r.obj - g["obj_slsqp"]) / np.abs(g["obj_slsqp"])).max() <= 1e-6
 
 
+def test_oracle_stagewise_obstacle_centres(oracle_mod):
+    """centres that move with the stage (dynamic_obstacle.py:47-56).  A track of N equal columns IS the static
+    problem (same bits); a moving track is checked with the solver-independent certificate of the NumPy NLP."""
+    from dataclasses import replace
+    from oracle.nlp_numpy import NLP, kkt_certificate
+    cfg = oracle_mod.OracleConfig(linsolve="dense", O=4)
+    cfs = replace(cfg, obs_stagewise=True)
+    b = make_batch(8, seed=1004, O=4)
+    still = np.ascontiguousarray(np.repeat(b["obs"][:, :, None, :], cfg.N, axis=2))
+    r0 = oracle_mod.solve(cfg, b["x_cur"], b["goal"], obs=b["obs"])
+    r1 = oracle_mod.solve(cfs, b["x_cur"], b["goal"], obs=still)
+    assert (r0.status == r1.status).all() and (r0.iters == r1.iters).all()
+    np.testing.assert_array_equal(r0.U, r1.U)
+    tr = make_tracks(b["obs"], cfg.N, seed=5)
+    r2 = oracle_mod.solve(cfs, b["x_cur"], b["goal"], obs=tr)
+    assert (r2.status == 0).all()
+    assert np.abs(r2.U - r0.U).max() > 1e-6          # the motion matters
+    for i in range(8):
+        nlp = NLP(cfs, b["x_cur"][i], b["goal"][i], obs=tr[i])
+        cert = kkt_certificate(nlp, r2.X[i], r2.U[i], inflation=cfg.inflation)
+        assert cert["primal"] < 1e-8 and cert["obstacle_violation"] < 1e-7 and cert["stationarity_rel"] < 1e-5
+        d = np.linalg.norm(r2.X[i][None, :2, 1:] - tr[i].transpose(0, 2, 1), axis=1) - cfg.obs_radius
+        assert d.min() >= cfg.inflation - 1e-7
+
+
+def test_obstacle_predictor_restatement():
+    """oracle/obstacle_predictor.py (dynamic_obstacle.py:20-37): straight line when omega = 0, heading through deg2rad as
+    the reference writes it, the current state in column 0."""
+    from oracle.obstacle_predictor import predict_track, predict_tracks
+    tr = predict_track((1.0, 2.0, np.deg2rad(90)), 1.0, 0.0, 6)           # the constructor defaults (:8)
+    a = np.deg2rad(np.deg2rad(90))                                          # radians fed to deg2rad (:24-25)
+    np.testing.assert_allclose(tr[0], 1.0 + 0.1 * np.cos(a) * np.arange(6), rtol=0, atol=1e-15)
+    np.testing.assert_allclose(tr[1], 2.0 + 0.1 * np.sin(a) * np.arange(6), rtol=0, atol=1e-15)
+    assert (tr[2] == np.deg2rad(90)).all()
+    tr = predict_track((0.0, 0.0, 0.5), 2.0, 1.0, 4, literal=False)
+    assert tr[:, 0].tolist() == [0.0, 0.0, 0.5]
+    np.testing.assert_allclose(tr[:, 1], [0.2 * np.cos(0.5), 0.2 * np.sin(0.5), 0.6])
+    np.testing.assert_allclose(tr[:, 2], [tr[0, 1] + 0.2 * np.cos(0.6), tr[1, 1] + 0.2 * np.sin(0.6), 0.7])
+    assert predict_tracks(np.zeros((3, 3)), np.ones(3), np.zeros(3), 5).shape == (3, 5, 2)
+
+
 # ---------------- per-thread solver source (g++ build) vs oracle ----------------
-@pytest.mark.parametrize("case", ["box", "N50", "literal", "obs", "layout1", "infeasible"])
+@pytest.mark.parametrize("case", ["box", "N50", "literal", "obs", "tracks", "layout1", "infeasible"])
 def test_solver_source_matches_oracle(oracle_mod, case):
     import emul
     kw, B, seed, O, layout = {}, 96, 1002, 0, 0
@@ -62,6 +103,8 @@ def test_solver_source_matches_oracle(oracle_mod, case):
         kw = dict(cost_mode="code_literal", goal_range="code", y_bounds=(-oracle_mod.INF, oracle_mod.INF))
     elif case == "obs":
         kw, seed, O = dict(O=10), 1004, 10
+    elif case == "tracks":
+        kw, seed, O = dict(O=6, obs_stagewise=True), 1004, 6
     elif case == "layout1":
         layout = 1
     elif case == "infeasible":
@@ -70,6 +113,8 @@ def test_solver_source_matches_oracle(oracle_mod, case):
     b = make_batch(B, seed=seed, O=O)
     if case == "infeasible":
         b["x_cur"][::4, 0] = 25.0
+    if case == "tracks":
+        b["obs"] = make_tracks(b["obs"], cfg.N, seed=9)
     ref = oracle_mod.solve(cfg, b["x_cur"], b["goal"], obs=b["obs"])
     X, U, obj, st, it, tp = emul.solve(cfg, b["x_cur"], b["goal"], obs=b["obs"], layout=layout)
     assert (st == ref.status).all()
@@ -78,7 +123,7 @@ def test_solver_source_matches_oracle(oracle_mod, case):
     assert (it == ref.iters).mean() >= 0.95
 
 
-@pytest.mark.parametrize("case", ["box", "N50", "literal", "obs", "infeasible", "warm"])
+@pytest.mark.parametrize("case", ["box", "N50", "literal", "obs", "tracks", "tracksN50", "infeasible", "warm"])
 def test_warp_solver_source_matches_oracle(oracle_mod, case):
     """The warp-per-instance kernel source (kmpc_warp.cuh: what the GPU runs for N <= 63) on the 32-fibre warp emulator
     (tests/host_emul/simt.h, one emulated warp = one block) against the oracle."""
@@ -90,10 +135,16 @@ def test_warp_solver_source_matches_oracle(oracle_mod, case):
         kw = dict(cost_mode="code_literal", goal_range="code", y_bounds=(-oracle_mod.INF, oracle_mod.INF))
     elif case == "obs":
         kw, seed, O = dict(O=10), 1004, 10
+    elif case == "tracks":
+        kw, seed, O = dict(O=6, obs_stagewise=True), 1004, 6
+    elif case == "tracksN50":
+        kw, seed, O, B = dict(N=50, O=3, obs_stagewise=True), 1004, 3, 8
     elif case == "infeasible":
         kw = dict(max_iter=300)
     cfg = oracle_mod.OracleConfig(linsolve="riccati", **kw)
     b = make_batch(B, seed=seed, O=O)
+    if case.startswith("tracks"):
+        b["obs"] = make_tracks(b["obs"], cfg.N, seed=9)
     X0 = U0 = None
     x = b["x_cur"]
     if case == "infeasible":

@@ -4,7 +4,7 @@ converged instances, identical status."""
 import numpy as np
 import pytest
 
-from kiss_mpc_b200.synthetic import cfg1_instance, make_batch
+from kiss_mpc_b200.synthetic import cfg1_instance, make_batch, make_tracks
 
 pytestmark = pytest.mark.gpu
 
@@ -295,6 +295,83 @@ def test_sensor_filter_matches_reference_loop():
     r4 = pl4.solve(_dev(b2["x_cur"]), _dev(b2["goal"]), obstacles=_dev(far), obstacle_radius=0.3, inflation_radius=0.5)
     assert (r2.status == 0).all() and (r4.status == 0).all()
     assert (r2.controls - r4.controls).abs().max().item() <= CTRL_ATOL
+
+
+def test_moving_obstacle_tracks(oracle_mod):
+    """circle centres that move with the stage (DynamicObstacle tracks, dynamic_obstacle.py:47-56) through
+    kmpc_solve_tracks -- warp solver (N = 30 and the two-slot N = 50 kernel), thread-solver fall-back (N = 70), host arrays."""
+    from dataclasses import replace
+    from kiss_mpc_b200 import BatchedMotionPlanner
+    ocfg, pcfg = _pair(oracle_mod, O=6)
+    ocs = replace(ocfg, obs_stagewise=True)
+    b = make_batch(512, seed=1004, O=6)
+    tr = make_tracks(b["obs"], ocfg.N, seed=9)
+    pl = BatchedMotionPlanner(pcfg, max_batch=512)
+    kw = dict(obstacle_radius=ocfg.obs_radius, inflation_radius=ocfg.inflation)
+    # a track of N equal columns is the static problem: same bits as kmpc_solve
+    still = np.ascontiguousarray(np.repeat(b["obs"][:, :, None, :], ocfg.N, axis=2))
+    r_static = pl.solve(_dev(b["x_cur"]), _dev(b["goal"]), obstacles=_dev(b["obs"]), **kw)
+    r_still = pl.solve(_dev(b["x_cur"]), _dev(b["goal"]), obstacles=_dev(still), **kw)
+    assert (r_static.status == r_still.status).all() and (r_static.controls == r_still.controls).all()
+    # moving circles against the oracle
+    ref = oracle_mod.solve(ocs, b["x_cur"], b["goal"], obs=tr)
+    res = pl.solve(_dev(b["x_cur"]), _dev(b["goal"]), obstacles=_dev(tr), **kw)
+    conv = _check(res, ref, require_all_converged=False, max_status_mismatch=0.004)
+    assert conv.mean() > 0.98
+    assert (res.iters.cpu().numpy() == ref.iters).mean() > 0.9
+    X = res.states.cpu().numpy()[conv]
+    d = np.linalg.norm(X[:, None, :2, 1:] - tr[conv].transpose(0, 1, 3, 2), axis=2) - ocfg.obs_radius
+    assert d.min() >= ocfg.inflation - 1e-6
+    assert (res.controls - r_static.controls).abs().max().item() > 1e-3      # the motion changes the plans
+    # NumPy in / NumPy out
+    rh = pl.solve(b["x_cur"][:40], b["goal"][:40], obstacles=tr[:40], **kw)
+    assert isinstance(rh.controls, np.ndarray) and np.array_equal(rh.controls, res.controls.cpu().numpy()[:40])
+    # other kernels: N = 50 (two stages per lane), N = 70 (thread solver)
+    for N, B, O in ((50, 96, 4), (70, 12, 2)):
+        oc, pc = _pair(oracle_mod, N=N, O=O)
+        oc = replace(oc, obs_stagewise=True)
+        bb = make_batch(B, seed=1004, O=O)
+        tt = make_tracks(bb["obs"], N, seed=N)
+        rf = oracle_mod.solve(oc, bb["x_cur"], bb["goal"], obs=tt)
+        rs = BatchedMotionPlanner(pc, max_batch=B).solve(_dev(bb["x_cur"]), _dev(bb["goal"]), obstacles=_dev(tt), **kw)
+        cv = _check(rs, rf, require_all_converged=False, max_status_mismatch=0.02)
+        assert cv.mean() > 0.95
+
+
+def test_track_predictor_matches_reference_loop():
+    """kmpc_predict_tracks against DynamicObstacle._get_predicted_states_matrix (dynamic_obstacle.py:20-37,
+    restated in oracle/obstacle_predictor.py) for the obstacles each agent's sensor filter kept (environment.py:57-65)."""
+    from kiss_mpc_b200 import BatchedMotionPlanner, PlannerConfig
+    from oracle.obstacle_predictor import predict_tracks
+    from oracle.sensor_filter import sensor_filter
+    torch = _torch()
+    rng = np.random.default_rng(11)
+    B, M, O, N = 129, 12, 4, 30
+    x = rng.uniform(-6, 6, size=(B, 3))
+    state = np.concatenate([rng.uniform(-8, 8, size=(M, 2)), rng.uniform(-np.pi, np.pi, size=(M, 1))], axis=1)
+    v = rng.uniform(0.0, 1.5, size=M); w = rng.uniform(-0.5, 0.5, size=M); rad = np.full(M, 0.3)
+    pl = BatchedMotionPlanner(PlannerConfig(N=N, O_max=O), max_batch=B)
+    obs, cnt, idx = pl.select_obstacles(_dev(x), _dev(state[:, :2]), _dev(rad), sensor_radius=5.0, slots=O, return_index=True)
+    idx_h = idx.cpu().numpy(); cnt_h = cnt.cpu().numpy()
+    for b in range(B):
+        want = sensor_filter(x[b], state[:, :2], rad, 5.0, True)[:O]
+        assert idx_h[b, :len(want)].tolist() == want and (idx_h[b, len(want):] == -1).all() and cnt_h[b] == len(want)
+    for literal in (True, False):
+        want = predict_tracks(state, v, w, N, 0.1, literal)                    # [M,N,2]
+        got = pl.predict_tracks(B, _dev(state), _dev(v), _dev(w), index=idx, literal_heading=literal).cpu().numpy()
+        assert got.shape == (B, O, N, 2)
+        real = idx_h >= 0
+        np.testing.assert_allclose(got[real], want[idx_h[real]], rtol=0, atol=1e-12)
+        assert (got[~real] == 1.0e6).all()
+        np.testing.assert_array_equal(got[:, :, 0, :][real], state[idx_h[real], :2])   # column 0 = the current position
+    # no index: slot o = obstacle o for every agent
+    got = pl.predict_tracks(3, _dev(state[:O]), _dev(v[:O]), _dev(w[:O])).cpu().numpy()
+    np.testing.assert_allclose(got[2], predict_tracks(state[:O], v[:O], w[:O], N), rtol=0, atol=1e-12)
+    # the tracks feed the solve
+    b2 = make_batch(B, seed=21)
+    r = pl.solve(_dev(b2["x_cur"]), _dev(b2["goal"]), obstacles=pl.predict_tracks(B, _dev(state), _dev(v), _dev(w), index=idx),
+                 obstacle_radius=0.3, inflation_radius=0.5)
+    assert r.states.shape == (B, 3, N + 1) and torch.isin(r.status, torch.tensor([0, -1, -2, 2], device="cuda:0", dtype=torch.int32)).all()
 
 
 def test_edge_sizes_and_fallbacks(oracle_mod):
