@@ -353,9 +353,14 @@ class MotionPlanner:
     ``state_bounds``) or "code_literal" (optimizer.py as written: k=1..N-1, 300*fmin(v,0), only x bounded).
     After each call ``last_status`` / ``last_iterations`` / ``last_objective`` hold what IPOPT's stats would (the reference
     never reads them, optimizer.py:375-400).
+    ``use_obstacle_tracks``: False (default) reads only the current centre of every obstacle, as the reference's vectorised
+    constraint path does (optimizer.py:217-221); True pairs X_{t+1} with column t of a dynamic obstacle's ``states_matrix``
+    (what DynamicObstacle.calculate_symbolic_matrix_distance builds, dynamic_obstacle.py:47-56) when it has >= N columns.
     """
 
-    def __init__(self, time_step: float, horizon: int, problem_form: str = "readme", device: int = 0):
+    def __init__(self, time_step: float, horizon: int, problem_form: str = "readme", device: int = 0,
+                 use_obstacle_tracks: bool = False):
+        self.use_obstacle_tracks = bool(use_obstacle_tracks)
         self.time_step = float(time_step)
         self.horizon = int(horizon)
         self.num_states, self.num_controls = 3, 2          # optimizer.py:44-55
@@ -400,6 +405,12 @@ class MotionPlanner:
         if (X0 is None) != (U0 is None):
             raise ValueError("states_matrix and controls_matrix must both be given")
         centers = np.array([c for c, _ in obs], dtype=np.float64).reshape(1, O, 2) if O else None
+        if O and self.use_obstacle_tracks:
+            centers = np.ascontiguousarray(np.repeat(centers[:, :, None, :], N, axis=2))          # static: N equal columns
+            for j, ob in enumerate(dynamic_obstacles, start=len(static_obstacles)):
+                sm = getattr(ob, "states_matrix", None)
+                if sm is not None and np.shape(sm)[1] >= N:
+                    centers[0, j] = np.asarray(sm, dtype=np.float64)[:2, :N].T
         radius = obs[0][1] if O else 0.0                      # optimizer.py:231-245: the first obstacle's radius for all
         infl = float(inflation_radius) if inflation_radius is not None else 0.0   # optimizer.py:362
         r = self._planner.solve(x, g, X0, U0, centers, radius, infl)

@@ -4,7 +4,7 @@ import json, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
 from kiss_mpc_b200 import BatchedMotionPlanner, MotionPlanner, PlannerConfig
-from kiss_mpc_b200.synthetic import cfg1_instance, make_batch
+from kiss_mpc_b200.synthetic import cfg1_instance, make_batch, make_tracks
 from oracle import oracle as ok
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
@@ -27,13 +27,15 @@ def cpu(cfg, b, n, **kw):
     return n / (time.perf_counter() - t0), r
 
 
-def batch_case(name, B, N, O, seed, cpu_n):
+def batch_case(name, B, N, O, seed, cpu_n, tracks=False):
     b = make_batch(B, seed=seed, O=O)
+    if tracks:   # every circle drifts along a constant-velocity track
+        b["obs"] = make_tracks(b["obs"], N, seed=seed)
     pl = BatchedMotionPlanner(PlannerConfig(N=N, O_max=O), max_batch=B)
     x = torch.tensor(b["x_cur"], device="cuda"); g = torch.tensor(b["goal"], device="cuda")
     ob = torch.tensor(b["obs"], device="cuda") if O else None
     ms, r = timed(lambda: pl.solve(x, g, obstacles=ob, obstacle_radius=0.3, inflation_radius=0.5 if O else 0.0))
-    rate, ref = cpu(ok.OracleConfig(N=N, O=O, linsolve="riccati"), b, cpu_n)
+    rate, ref = cpu(ok.OracleConfig(N=N, O=O, linsolve="riccati", obs_stagewise=tracks), b, cpu_n)
     st = r.status.cpu().numpy()[:cpu_n]; U = r.controls.cpu().numpy()[:cpu_n]; obj = r.objective.cpu().numpy()[:cpu_n]
     conv = (st == 0) & (ref.status == 0)
     out[name] = {"B": B, "N": N, "O": O, "ms": ms, "solves_per_sec": B / ms * 1e3, "mean_iters": r.iters.float().mean().item(),
@@ -62,6 +64,8 @@ batch_case("headline_65536_N30", 65536, 30, 0, 1000, 8192)
 batch_case("cfg3_65536_N50", 65536, 50, 0, 1003, 4096)
 batch_case("cfg4_4096_N30_O10", 4096, 30, 10, 1004, 4096)
 batch_case("cfg4_65536_N30_O10", 65536, 30, 10, 1004, 2048)
+batch_case("tracks_4096_N30_O10", 4096, 30, 10, 1004, 2048, tracks=True)
+batch_case("tracks_65536_N30_O10", 65536, 30, 10, 1004, 2048, tracks=True)
 # cfg 5: closed loop, 16,384 agents x 200 steps, warm-started, stop at goal (agent.py:65 goal radius 0.5)
 B, steps = 16384, 200
 b = make_batch(B, seed=1005)

@@ -235,6 +235,17 @@ def test_motion_planner_drop_in(oracle_mod):
     ref2 = oracle_mod.solve(oc, xc, gl, X0=X0[None], U0=U0[None], obs=np.array([[[1.0, 1.2], [1.6, 2.6]]]))
     assert mp.last_status == ref2.status[0]
     assert np.abs(U2 - ref2.U[0]).max() <= CTRL_ATOL
+    # use_obstacle_tracks: the dynamic obstacle's predicted states (dynamic_obstacle.py:30-37) instead of its current centre
+    from dataclasses import replace
+    from oracle.obstacle_predictor import predict_track
+    obs[1].states_matrix = predict_track((1.6, 2.6, np.deg2rad(250.0)), 1.0, 0.0, N, literal=False)   # crosses the path
+    mpt = MotionPlanner(time_step=0.1, horizon=N, use_obstacle_tracks=True)
+    X3, U3 = mpt.solve(current_state=xc[0], goal_state=gl[0], states_matrix=X0, controls_matrix=U0, state_bounds=(-20, 20),
+                       static_obstacles=obs[:1], dynamic_obstacles=obs[1:], inflation_radius=0.5)
+    tr = np.stack([np.tile([1.0, 1.2], (N, 1)), obs[1].states_matrix[:2].T])[None]
+    ref3 = oracle_mod.solve(replace(oc, obs_stagewise=True), xc, gl, X0=X0[None], U0=U0[None], obs=tr)
+    assert mpt.last_status == ref3.status[0] == 0
+    assert np.abs(U3 - ref3.U[0]).max() <= CTRL_ATOL and np.abs(U3 - U2).max() > 1e-4
 
 
 def test_full_size_properties():
