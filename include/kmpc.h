@@ -165,6 +165,15 @@ int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur, const doub
                      double *applied_log, int32_t *iters_log, int32_t *status_log, int32_t *active, double goal_radius,
                      double agent_radius, void *cuda_stream);
 
+/* Scheduling of the batch inside kmpc_solve (no reference equivalent; results never depend on it).  The solver kernel is
+ * persistent: warps pull instances from a queue, and interior-point iteration counts differ by more than 8x between instances,
+ * so an instance that is fetched late and runs long sets the end of the launch.  KMPC_ORDER_PRIOR (default) hands the
+ * instances out in descending order of a geometric prior of their iteration count (bearing of the goal from the start
+ * heading, heading change, goal distance; csrc/kmpc_order_prior.h); KMPC_ORDER_NATURAL in index order. */
+#define KMPC_ORDER_NATURAL 0
+#define KMPC_ORDER_PRIOR 1
+int kmpc_set_queue_order(kmpc_handle *h, int mode);
+
 /* Measurement helpers (no reference equivalent). */
 typedef struct kmpc_stats {
     double last_kernel_ms;    /* device time of the solver kernel of the last kmpc_solve on this handle (CUDA events on its stream) */

@@ -16,7 +16,7 @@ NO_BOUND = 1e19
 # symbols include/kmpc.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["kmpc_version", "kmpc_workspace_bytes", "kmpc_create", "kmpc_destroy", "kmpc_last_error", "kmpc_solve",
            "kmpc_solve_tracks", "kmpc_solve_host", "kmpc_host_result", "kmpc_agent_handoff", "kmpc_closed_loop", "kmpc_select_obstacles", "kmpc_predict_tracks",
-           "kmpc_set_timing", "kmpc_get_stats", "kmpc_measure_fp64_peak"]
+           "kmpc_set_queue_order", "kmpc_set_timing", "kmpc_get_stats", "kmpc_measure_fp64_peak"]
 
 
 class KmpcConfig(C.Structure):
@@ -75,6 +75,8 @@ def load():
     L.kmpc_select_obstacles.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, dp, ip, ip, vp]
     L.kmpc_predict_tracks.restype = C.c_int
     L.kmpc_predict_tracks.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, dp, dp, dp, C.c_double, C.c_int, C.c_double, C.c_double, dp, vp]
+    L.kmpc_set_queue_order.restype = C.c_int
+    L.kmpc_set_queue_order.argtypes = [vp, C.c_int]
     L.kmpc_set_timing.restype = C.c_int
     L.kmpc_set_timing.argtypes = [vp, C.c_int]
     L.kmpc_get_stats.restype = C.c_int

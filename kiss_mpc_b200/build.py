@@ -6,7 +6,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "kmpc.cu")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "kmpc_core.cuh"), os.path.join(_HERE, "csrc", "kmpc_warp.cuh"), os.path.join(_HERE, "csrc", "kmpc_warp_prims.cuh"), os.path.join(_HERE, "..", "include", "kmpc.h")]
+DEPS = [SRC, os.path.join(_HERE, "csrc", "kmpc_order_prior.h"), os.path.join(_HERE, "csrc", "kmpc_core.cuh"), os.path.join(_HERE, "csrc", "kmpc_warp.cuh"), os.path.join(_HERE, "csrc", "kmpc_warp_prims.cuh"), os.path.join(_HERE, "..", "include", "kmpc.h")]
 SO = os.path.join(_HERE, "libkmpc.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-cudart", "shared"]

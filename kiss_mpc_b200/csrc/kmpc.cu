@@ -10,9 +10,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../include/kmpc.h"
 #include "kmpc_core.cuh"
 #include "kmpc_warp.cuh"
+#include "kmpc_order_prior.h"
 
 using namespace kmpc;
 
@@ -167,6 +170,12 @@ struct kmpc_handle {
     double *wscratch;      // warp solver: global scratch slots (WLay::GPRIV doubles per resident warp)
     size_t wscratch_doubles;
     int host_B;  // batch of the last kmpc_solve_host (addresses kmpc_host_result hands out)
+    // queue order of the warp solver (likely-long instances first): keys / instance indices before and after the sort
+    int order_mode;
+    float *okey;           // 2 x cols
+    int32_t *oval;         // 2 x cols; the second half is the order the kernel reads
+    void *osort_tmp;
+    size_t osort_bytes;
     cudaStream_t stream;
     char err[256];
 };
@@ -206,6 +215,52 @@ kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned lon
     w_worker<SPL, NST, FULL, OBS>(c, io, s_dyn, queue, trips_total);
 }
 
+// Queue order of the persistent kernel.  Iteration counts differ by more than 8x between instances and a long instance that is
+// fetched late sets the end of the launch; how long an instance takes is largely a function of its geometry, so the instances
+// are handed out in descending order of a prior (kmpc_order_prior.h, fitted by scripts/fit_order_prior.py): expected iteration
+// count + 1 sd per bin of (|bearing of the goal from the start heading|, signed heading change, goal distance).  Scheduling
+// only -- every instance is solved by the same arithmetic whatever its queue position.
+__global__ void kmpc_order_key_kernel(int B, int layout, const double *__restrict__ x_cur, const double *__restrict__ goal,
+                                      float *__restrict__ key, int32_t *__restrict__ val) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const size_t s0 = layout ? (size_t)b : (size_t)b * 3, st = layout ? (size_t)B : 1;
+    const double dx = goal[s0] - x_cur[s0], dy = goal[s0 + st] - x_cur[s0 + st], th = x_cur[s0 + 2 * st], thg = goal[s0 + 2 * st];
+    const double kPi = 3.14159265358979323846;
+    double bs = atan2(dy, dx) - th;
+    bs -= 2.0 * kPi * rint(bs / (2.0 * kPi));
+    const double dt = (bs < 0 ? -1.0 : 1.0) * (thg - th);
+    const double fa = floor(fabs(bs) / kPi * KMPC_PRIOR_NB), fd = floor((dt + 2.0 * kPi) / (4.0 * kPi) * KMPC_PRIOR_ND),
+                 fr = floor(sqrt(dx * dx + dy * dy) / 6.0 * KMPC_PRIOR_NR);
+    // (comparisons written so that a NaN input lands in bin 0)
+    const int ia = fa >= 0 ? (fa < KMPC_PRIOR_NB ? (int)fa : KMPC_PRIOR_NB - 1) : 0;
+    const int id = fd >= 0 ? (fd < KMPC_PRIOR_ND ? (int)fd : KMPC_PRIOR_ND - 1) : 0;
+    const int ir = fr >= 0 ? (fr < KMPC_PRIOR_NR ? (int)fr : KMPC_PRIOR_NR - 1) : 0;
+    key[b] = kmpc_order_prior[(ia * KMPC_PRIOR_ND + id) * KMPC_PRIOR_NR + ir];
+    val[b] = b;
+}
+
+// fills h->oval[cols..] with the queue order of this batch; returns NULL in *order when the natural order is kept
+static cudaError_t queue_order(kmpc_handle *h, int B, int resident, const IO &io, int layout, cudaStream_t st, const int32_t **order) {
+    *order = NULL;
+    if (!h->order_mode || B <= resident) return cudaSuccess;   // a single wave: every instance starts at once
+    const size_t S = (size_t)h->cols;
+    cudaError_t e;
+    if (!h->okey) {
+        if ((e = cudaMalloc(&h->okey, 2 * S * sizeof(float))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&h->oval, 2 * S * sizeof(int32_t))) != cudaSuccess) return e;
+        h->osort_bytes = 0;
+        if ((e = cub::DeviceRadixSort::SortPairsDescending(NULL, h->osort_bytes, h->okey, h->okey + S, h->oval, h->oval + S, (int)S, 0, 32, st)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&h->osort_tmp, h->osort_bytes)) != cudaSuccess) return e;
+    }
+    kmpc_order_key_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, layout, io.x_cur, io.goal, h->okey, h->oval);
+    size_t bytes = h->osort_bytes;
+    if ((e = cub::DeviceRadixSort::SortPairsDescending(h->osort_tmp, bytes, h->okey, h->okey + S, h->oval, h->oval + S, B, 0, 32, st)) != cudaSuccess) return e;
+    h->launches += 2;
+    *order = h->oval + S;
+    return cudaGetLastError();
+}
+
 // returns cudaErrorInvalidConfiguration if not even one instance fits into shared memory (caller falls back)
 template <int SPL, int NST, bool FULL, bool OBS, int WPB, int MINB>
 static cudaError_t launch_warp_kernel(kmpc_handle *h, int device, int sm_count, int B, const Cfg &c, const IO &io_in, int *queue,
@@ -236,6 +291,8 @@ static cudaError_t launch_warp_kernel(kmpc_handle *h, int device, int sm_count, 
     }
     IO io = io_in;
     io.wscratch = h->wscratch;
+    e = queue_order(h, B, grid * wpb, io, c.layout, st, &io.order);
+    if (e != cudaSuccess) return e;
     kern<<<grid, 32 * wpb, smem, st>>>(c, io, queue, trips);
     return cudaGetLastError();
 }
@@ -397,6 +454,9 @@ extern "C" void kmpc_destroy(kmpc_handle *h) {
     if (h->trips) cudaFree(h->trips);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     if (h->wscratch) cudaFree(h->wscratch);
+    if (h->okey) cudaFree(h->okey);
+    if (h->oval) cudaFree(h->oval);
+    if (h->osort_tmp) cudaFree(h->osort_tmp);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_iout) cudaFree(h->d_iout);
@@ -422,6 +482,7 @@ extern "C" int kmpc_create(const kmpc_config *cfg, kmpc_handle **out) {
     h = (kmpc_handle *)calloc(1, sizeof(kmpc_handle));
     if (!h) return fail(NULL, KMPC_E_NOMEM, "kmpc_create: out of host memory%s", "");
     h->cfg = *cfg;
+    { const char *om = getenv("KMPC_ORDER"); h->order_mode = om ? (atoi(om) != 0) : KMPC_ORDER_PRIOR; }   // measurement override
     h->device = cfg->device;
     h->rows = make_rows(cfg->N, cfg->O_max, 1);   // sized for stage-wise obstacle centres
     h->cols = cols_for(cfg);
@@ -485,7 +546,7 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
     c.r_mnb = 1.0 / (double)(c.m + c.nb); c.r_nb = c.nb ? 1.0 / (double)c.nb : 0.0;
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs_centers;
-    io.X_out = X_out; io.U_out = U_out; io.obj = obj_out; io.status = status_out; io.iters = iters_out; io.active = active; io.wscratch = NULL;
+    io.X_out = X_out; io.U_out = U_out; io.obj = obj_out; io.status = status_out; io.iters = iters_out; io.active = active; io.wscratch = NULL; io.order = NULL;
     const size_t S = (size_t)h->cols;
     Lists ls;
     ls.LA[0] = h->lists; ls.LA[1] = h->lists + S; ls.LT[0] = h->lists + 2 * S; ls.LT[1] = h->lists + 3 * S;
@@ -693,6 +754,14 @@ extern "C" int kmpc_agent_handoff(kmpc_handle *h, int B, const double *X, const 
     return 0;
 }
 
+#ifdef KMPC_SCHED_TRACE
+// tuning builds only: device buffer (4 x u64 per instance) the warp kernel records its schedule in; NULL switches it off
+extern "C" int kmpc_debug_sched_trace(void *buf) {
+    unsigned long long *p = (unsigned long long *)buf;
+    return cudaMemcpyToSymbol(g_sched, &p, sizeof p) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 #ifdef KMPC_PHASE_TIMING
 // tuning builds only: read and reset the phase timers of kmpc_warp.cuh
 extern "C" int kmpc_debug_phase_cycles(double *out) {
@@ -754,6 +823,12 @@ extern "C" int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur,
         CU(cudaGetLastError());
         h->launches++;
     }
+    return 0;
+}
+
+extern "C" int kmpc_set_queue_order(kmpc_handle *h, int mode) {
+    if (!h || (mode != KMPC_ORDER_NATURAL && mode != KMPC_ORDER_PRIOR)) return KMPC_E_BADARG;
+    h->order_mode = mode;
     return 0;
 }
 

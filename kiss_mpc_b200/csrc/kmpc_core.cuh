@@ -138,6 +138,7 @@ struct IO {
     int32_t *status, *iters;
     double *wscratch;       // warp solver: global scratch, WLay::GPRIV doubles per resident warp (owned by the handle)
     const int32_t *active;  // optional per-instance mask (closed loop: agents that reached their goal are not solved again)
+    const int32_t *order;   // warp solver: instance handed out at queue position q (NULL: q itself); a permutation of 0..B-1
 };
 #define KMPC_STATUS_SKIPPED 1000  /* status_log value of an agent that was not solved in a closed-loop step */
 

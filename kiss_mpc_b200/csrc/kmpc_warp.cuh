@@ -831,11 +831,31 @@ __device__ unsigned long long g_phase_cycles[KMPC_NPHASE];
 #define PT_FLUSH
 #endif
 
+// rejected trial points re-evaluated within one trip before the instance goes round the block loop again (bounds what the
+// other warps of the block can be made to wait for)
+#ifndef KMPC_INLINE_BACKTRACKS
+#define KMPC_INLINE_BACKTRACKS 24
+#endif
+
+#if defined(KMPC_SCHED_TRACE) && defined(__CUDACC__)
+// tuning builds only: per instance the times (globaltimer, ns) at which a warp took it and finished it, its trips and its SM
+__device__ unsigned long long *g_sched;
+__device__ __forceinline__ unsigned long long kmpc_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned kmpc_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define SCHED_START(b) if (lane == 0 && g_sched) g_sched[4 * (size_t)(b)] = kmpc_gtime();
+#define SCHED_END(b, trips) if (g_sched) { g_sched[4 * (size_t)(b) + 1] = kmpc_gtime(); g_sched[4 * (size_t)(b) + 2] = (unsigned long long)(trips); g_sched[4 * (size_t)(b) + 3] = ((unsigned long long)kmpc_smid() << 32) | (blockIdx.x << 8) | wid; }
+#else
+#define SCHED_START(b)
+#define SCHED_END(b, trips)
+#endif
+
 // next instance of the queue that is to be solved (masked-out instances only get their status / iteration records)
 KMPC_WN inline int w_fetch_active(const Cfg &c, const IO &io, int *queue) {
     for (;;) {
-        const int b = w_fetch(queue);
-        if (b >= c.B || !io.active || io.active[b]) return b;
+        const int q = w_fetch(queue);
+        if (q >= c.B) return q;
+        const int b = io.order ? io.order[q] : q;   // likely-long instances first (kmpc_order_kernel)
+        if (!io.active || io.active[b]) return b;
         if (w_lane() == 0) { if (io.status) io.status[b] = KMPC_STATUS_SKIPPED; if (io.iters) io.iters[b] = 0; }
     }
 }
@@ -873,7 +893,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         // in that window (the global-memory round trip then costs the block nothing)
         if (!have && !drained && (wid == swid || wid == cwid)) {
             b = w_fetch_active(c, io, queue);
-            if (b < c.B) { w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
+            if (b < c.B) { SCHED_START(b) w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
         }
         PT(0)
         if (!w_block_any(have)) break;
@@ -916,7 +936,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             if (so->flag && ds == ds) so->pdc[cand] = w_serial_candidate<OBS>(c, smem + (size_t)inst * LY::COOP, LY::NSTG, ds) ? 1 : 0;
         } else if (!have && !drained) {
             b = w_fetch_active(c, io, queue);
-            if (b < c.B) { w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); fresh = true; } else drained = true;
+            if (b < c.B) { SCHED_START(b) w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); fresh = true; } else drained = true;
         }
         PT(4)
         w_block_sync();
@@ -949,7 +969,9 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         }
         PT(6)
         // ---- phase 3: trial point + acceptance logic ----
-        if (go_trial) {
+        // A rejected trial point is followed at once by the next, shorter one: back-tracking needs no new factorisation, and an
+        // instance with a difficult line search (hundreds of rejected points) would otherwise pay a whole block trip for each.
+        for (int nbt = 0; go_trial; ++nbt) {
             Stats ts;
             WState<SPL> tri;
             // step sizes / barrier parameters of THIS trial, read before lane 0 moves the context on (begin_iteration)
@@ -975,7 +997,12 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 w_sync();
                 status = sc->status;
             } else if (r != R_BACKTRACK) status = r;
-            else { PT_COUNT(13) }
+            else {
+                PT_COUNT(13)
+                // (after a failed second-order correction `act` holds the corrected step: the original one is re-read next trip)
+                if (nbt < KMPC_INLINE_BACKTRACKS && mode != M_SOC) { if (lane == 0) trial_setup(t); w_sync(); continue; }
+            }
+            break;
         }
         PT(8)
         if (have && status != 100 && status != R_RETRY) {
@@ -991,6 +1018,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 if (io.status) io.status[b] = status;
                 if (io.iters) io.iters[b] = t.iter;
                 w_count_trips(trips_total, t.trips);
+                SCHED_END(b, t.trips)
                 t.mode = M_DONE;
             }
             have = false;

@@ -119,6 +119,11 @@ class BatchedMotionPlanner:
         except Exception:
             pass
 
+    def set_queue_order(self, prior: bool = True):
+        """Order in which the persistent solver kernel takes the instances of a batch: likely-long instances first (a geometric
+        prior of the iteration count, default) or index order.  Scheduling only; results are identical."""
+        _lib.check(self._L.kmpc_set_queue_order(self._h, 1 if prior else 0), self._h, "kmpc_set_queue_order")
+
     # -- shapes ---------------------------------------------------------------------------------
     def _shapes(self, B: int, O: int):
         N = self.config.N

@@ -69,7 +69,7 @@ extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, con
     Cfg c = make_cfg(cf, B, O, stagewise, obs_radius, inflation);
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs;
-    io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL; io.wscratch = NULL;
+    io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL; io.wscratch = NULL; io.order = NULL;
     // Mirrors the launch structure of kmpc.cu on the host: per trip, sweep(LA[p]) -> rollout(LT[p]) -> trial(LT[p]), with the
     // solver context stored in / reloaded from the workspace between the phases exactly as the kernels do.
     const size_t S = (size_t)((B + 31) / 32 * 32);
@@ -135,7 +135,7 @@ extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur
     Cfg c = make_cfg(cf, B, O, stagewise, obs_radius, inflation);
     IO io;
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs;
-    io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL; io.wscratch = NULL;
+    io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL; io.wscratch = NULL; io.order = NULL;
     const int spl = cf->N + 1 <= 32 ? 1 : 2;
 #pragma omp parallel for schedule(dynamic, 1)
     for (int b = 0; b < B; ++b) {

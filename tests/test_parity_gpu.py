@@ -278,6 +278,37 @@ def test_full_size_properties():
     assert torch.equal(rs.controls, U[lo:hi]) and torch.equal(rs.status, r.status[lo:hi])
 
 
+def test_queue_order_does_not_change_results():
+    """The order in which the persistent kernel hands out instances (geometric prior, include/kmpc.h kmpc_set_queue_order) is
+    scheduling only: same bits as the index order -- box bounds, obstacle rows, batch-minor layout, an at-goal mask."""
+    from kiss_mpc_b200 import BatchedMotionPlanner, PlannerConfig
+    torch = _torch()
+    B = 20000                                               # several waves of the 148 x 16 resident instances
+    b = make_batch(B, seed=77, O=3)
+    x, g, ob = _dev(b["x_cur"]), _dev(b["goal"]), _dev(b["obs"])
+    pl = BatchedMotionPlanner(PlannerConfig(O_max=3), max_batch=B)
+    res = {}
+    for prior in (True, False):
+        pl.set_queue_order(prior)
+        res[prior] = (pl.solve(x, g), pl.solve(x, g, obstacles=ob, obstacle_radius=0.3, inflation_radius=0.5))
+    for a, c in zip(res[True], res[False]):
+        for ta, tc in zip(a, c):
+            assert torch.equal(ta, tc)
+    assert (res[True][0].status == 0).float().mean().item() > 0.999
+    plm = BatchedMotionPlanner(PlannerConfig(), max_batch=B, layout="batch_minor")
+    rm = plm.solve(x.t().contiguous(), g.t().contiguous())
+    assert torch.equal(rm.controls.permute(2, 0, 1), res[True][0].controls) and torch.equal(rm.status, res[True][0].status)
+    # closed loop with the at-goal mask: the skipped agents are skipped wherever they sit in the queue
+    out = {}
+    for prior in (True, False):
+        pl.set_queue_order(prior)
+        xc = x[:8192].clone()
+        out[prior] = pl.closed_loop(xc, g[:8192].contiguous(), 6, goal_radius=2.0) + (xc,)
+    for ta, tc in zip(out[True], out[False]):
+        assert torch.equal(ta, tc)
+    assert (out[True][4] == 1000).any()
+
+
 def test_sensor_filter_matches_reference_loop():
     """the batched sensor filter (kmpc_select_obstacles) against the reference's per-agent loop
     (environment.py:48-65 restated in oracle/sensor_filter.py), literal and intended distance, incl. ties and O truncation."""
