@@ -238,7 +238,7 @@ def run_ours(args, rank, local_rank, world):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{B}-instance batch per GPU, N={N}, T={TIME_STEP}, box bounds only, cold start, seed {SEED}+rank",
                        "global_batch": world * B, "timing": "CUDA events per step on the solve stream, L2 flushed (256 MB fill) between steps, max over ranks",
-                       "kernel": "kmpc_warp_kernel<SPL=1,FULL> (warp per instance + block-cooperative Riccati lane, 1 launch per step)",
+                       "kernel": "kmpc_warp_kernel<SPL=1,FULL> (warp per instance + block-cooperative Riccati lane; per step 1 solver launch + the queue-order key kernel and radix sort)",
                        "e2e_api": "BatchedMotionPlanner.solve(numpy, numpy, copy=False) -> kmpc_solve_host (pinned staging, H2D + D2H inside)", "parallelism": f"batch slices x{world}, no collective in the solve"},
             "p50_us_per_solve_amortised": ms_per_step * 1e3 / B, "wall_s_timed_region": wall,
             "mean_ipm_iterations": mean_it, "max_ipm_iterations": float(stat[1].item()), "converged_fraction": float(stat[2].item()),

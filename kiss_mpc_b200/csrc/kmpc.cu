@@ -172,7 +172,7 @@ struct kmpc_handle {
     int host_B;  // batch of the last kmpc_solve_host (addresses kmpc_host_result hands out)
     // queue order of the warp solver (likely-long instances first): keys / instance indices before and after the sort
     int order_mode;
-    float *okey;           // 2 x cols
+    unsigned *okey;        // 2 x cols
     int32_t *oval;         // 2 x cols; the second half is the order the kernel reads
     void *osort_tmp;
     size_t osort_bytes;
@@ -221,7 +221,7 @@ kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned lon
 // count + 1 sd per bin of (|bearing of the goal from the start heading|, signed heading change, goal distance).  Scheduling
 // only -- every instance is solved by the same arithmetic whatever its queue position.
 __global__ void kmpc_order_key_kernel(int B, int layout, const double *__restrict__ x_cur, const double *__restrict__ goal,
-                                      float *__restrict__ key, int32_t *__restrict__ val) {
+                                      unsigned *__restrict__ key, int32_t *__restrict__ val) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const size_t s0 = layout ? (size_t)b : (size_t)b * 3, st = layout ? (size_t)B : 1;
@@ -236,7 +236,8 @@ __global__ void kmpc_order_key_kernel(int B, int layout, const double *__restric
     const int ia = fa >= 0 ? (fa < KMPC_PRIOR_NB ? (int)fa : KMPC_PRIOR_NB - 1) : 0;
     const int id = fd >= 0 ? (fd < KMPC_PRIOR_ND ? (int)fd : KMPC_PRIOR_ND - 1) : 0;
     const int ir = fr >= 0 ? (fr < KMPC_PRIOR_NR ? (int)fr : KMPC_PRIOR_NR - 1) : 0;
-    key[b] = kmpc_order_prior[(ia * KMPC_PRIOR_ND + id) * KMPC_PRIOR_NR + ir];
+    // 1/32-trip resolution, 16 bits: two radix passes instead of four
+    key[b] = (unsigned)fminf(kmpc_order_prior[(ia * KMPC_PRIOR_ND + id) * KMPC_PRIOR_NR + ir] * 32.0f, 65535.0f);
     val[b] = b;
 }
 
@@ -247,15 +248,15 @@ static cudaError_t queue_order(kmpc_handle *h, int B, int resident, const IO &io
     const size_t S = (size_t)h->cols;
     cudaError_t e;
     if (!h->okey) {
-        if ((e = cudaMalloc(&h->okey, 2 * S * sizeof(float))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&h->okey, 2 * S * sizeof(unsigned))) != cudaSuccess) return e;
         if ((e = cudaMalloc(&h->oval, 2 * S * sizeof(int32_t))) != cudaSuccess) return e;
         h->osort_bytes = 0;
-        if ((e = cub::DeviceRadixSort::SortPairsDescending(NULL, h->osort_bytes, h->okey, h->okey + S, h->oval, h->oval + S, (int)S, 0, 32, st)) != cudaSuccess) return e;
+        if ((e = cub::DeviceRadixSort::SortPairsDescending(NULL, h->osort_bytes, h->okey, h->okey + S, h->oval, h->oval + S, (int)S, 0, 16, st)) != cudaSuccess) return e;
         if ((e = cudaMalloc(&h->osort_tmp, h->osort_bytes)) != cudaSuccess) return e;
     }
     kmpc_order_key_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, layout, io.x_cur, io.goal, h->okey, h->oval);
     size_t bytes = h->osort_bytes;
-    if ((e = cub::DeviceRadixSort::SortPairsDescending(h->osort_tmp, bytes, h->okey, h->okey + S, h->oval, h->oval + S, B, 0, 32, st)) != cudaSuccess) return e;
+    if ((e = cub::DeviceRadixSort::SortPairsDescending(h->osort_tmp, bytes, h->okey, h->okey + S, h->oval, h->oval + S, B, 0, 16, st)) != cudaSuccess) return e;
     h->launches += 2;
     *order = h->oval + S;
     return cudaGetLastError();

@@ -1016,7 +1016,11 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             if (lane == 0) {
                 if (io.obj) io.obj[b] = t.c.f / t.df;
                 if (io.status) io.status[b] = status;
+#ifdef KMPC_ITERS_OUT_TRIPS   /* tuning build for scripts/fit_order_prior.py: report trips (what an instance costs) as "iterations" */
+                if (io.iters) io.iters[b] = t.trips;
+#else
                 if (io.iters) io.iters[b] = t.iter;
+#endif
                 w_count_trips(trips_total, t.trips);
                 SCHED_END(b, t.trips)
                 t.mode = M_DONE;
