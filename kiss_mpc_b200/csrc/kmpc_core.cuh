@@ -909,7 +909,8 @@ KMPC_HD bool acceptable(const Ctx &t, const double *filt, size_t FS, const Stats
 // Returns a status < 100 to finish the instance, 100 to continue with a Newton step.
 KMPC_HD int begin_iteration(const Cfg &c, Ctx &t) {
     const double E0 = opt_error(c, t.c, 0.0);
-    if (!isfinite(E0)) return ST_INVALID;
+    // (IPOPT checks every evaluated quantity for non-finite numbers; the max-norms carry a NaN / inf through, the scaled max may lose it)
+    if (!isfinite(E0) || !isfinite(t.c.pinf) || !isfinite(t.c.dinf)) return ST_INVALID;
     if (E0 <= c.tol && t.c.dinf / t.df <= K_DUAL_INF_TOL && t.c.pinf <= K_CONSTR_VIOL_TOL &&
         compl_inf(c, t.c, 0.0) / t.df <= K_COMPL_INF_TOL)
         return ST_SUCCESS;
@@ -946,12 +947,17 @@ KMPC_HD int inertia_update(Ctx &t) {
     return 101;
 }
 
+// status of a factorisation that failed outside a Newton step.  The least-squares system of the multiplier estimate ([I J^T; J 0],
+// J of full row rank) always has the right inertia for finite data, so a failure there means non-finite numbers in the starting
+// point: IPOPT keeps y = 0 and stops at its first convergence check with Invalid_Number_Detected -- the same status, one trip earlier.
+KMPC_HD int sweep_failure_status(const Ctx &t) { return t.mode == M_LSQ ? (int)ST_INVALID : (int)ST_STEP_ERROR; }
+
 template <bool OBS>
 KMPC_HDN inline int phase_sweep(const Cfg &c, Ctx &t, double *wsp, size_t S) {
     t.trips++;
     const bool ok = pass_sweep<OBS>(c, t, wsp, S);
     if (ok) return 100;
-    if (t.mode != M_NEWTON) return ST_STEP_ERROR;
+    if (t.mode != M_NEWTON) return sweep_failure_status(t);
     return inertia_update(t);
 }
 

@@ -948,7 +948,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 PT_COUNT(10)
                 if (lane == 0) {
                     // wrong inertia: raise delta_w (IPOPT's sequence) past the candidates already known to fail, sweep again next trip
-                    int st = mode != M_NEWTON ? (int)ST_STEP_ERROR : inertia_update(t);
+                    int st = mode != M_NEWTON ? sweep_failure_status(t) : inertia_update(t);
                     for (int k = 1; k < KMPC_NCAND && st == R_RETRY && sc->dshift[k] == sc->dshift[k] && !sc->pdc[k]; ++k) st = inertia_update(t);
                     sc->status = st;
                 }

@@ -659,8 +659,9 @@ static void eval_errors(const kmo_config *cf, work_t *wk, errs_t *e, double *rx 
         rs[i] = -wk->yd[i] - wk->vL[i];
         double p = (wk->s[i] - wk->dL) * wk->vL[i]; mn = fmin(mn, p); mx = fmax(mx, p); sz += fabs(wk->vL[i]); nb++;
     }
-    e->dual_inf = fmax(vmaxabs(rx, n), ns ? vmaxabs(rs, ns) : 0.0);
-    e->primal_inf = fmax(vmaxabs(wk->c, wk->mc), ns ? vmaxabs(wk->dms, ns) : 0.0);
+    /* (fmax would drop a NaN; the invalid-number test of the main loop needs it) */
+    { double a = vmaxabs(rx, n), b = ns ? vmaxabs(rs, ns) : 0.0; e->dual_inf = (a != a || b != b) ? NAN : fmax(a, b); }
+    { double a = vmaxabs(wk->c, wk->mc), b = ns ? vmaxabs(wk->dms, ns) : 0.0; e->primal_inf = (a != a || b != b) ? NAN : fmax(a, b); }
     e->min_sz = nb ? mn : 0.0; e->max_sz = mx; e->sum_z = sz; e->nb = nb;
     e->sum_y = vsumabs(wk->yc, wk->mc) + (ns ? vsumabs(wk->yd, ns) : 0.0);
 }
@@ -803,7 +804,8 @@ static void solve_one(const kmo_config *cf, work_t *wk, const double *xcur, cons
             double *r = tr->rows + 8 * tr->len; r[0] = mu; r[6] = E0; r[7] = eval_f(cf, wk, wk->w) / wk->df;
             r[4] = vsumabs(wk->c, mc) + (ns ? vsumabs(wk->dms, ns) : 0.0);
         }
-        if (!isfinite(E0)) { st = ST_INVALID_NUMBER; break; }
+        /* IPOPT checks every evaluated quantity for non-finite numbers; the max-norms carry a NaN / inf through, the scaled max may lose it */
+        if (!isfinite(E0) || !isfinite(er.dual_inf) || !isfinite(er.primal_inf)) { st = ST_INVALID_NUMBER; break; }
         /* convergence: scaled E_0 <= tol and the unscaled safeguards (objective scaling undone) */
         if (E0 <= cf->tol && er.dual_inf / wk->df <= DUAL_INF_TOL && er.primal_inf <= CONSTR_VIOL_TOL &&
             compl_inf(&er, 0.0) / wk->df <= COMPL_INF_TOL) { st = ST_SUCCESS; break; }

@@ -161,6 +161,26 @@ def test_warp_solver_source_matches_oracle(oracle_mod, case):
     assert (it == ref.iters).mean() >= (0.95 if O == 0 else 0.5)
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(O=2), dict(cost_mode="code_literal", goal_range="code", y_bounds=(-1e20, 1e20))])
+def test_non_finite_inputs_give_invalid_number(oracle_mod, kw):
+    """NaN / inf in the current state, the goal or an obstacle centre: IPOPT's Invalid_Number_Detected (-13) for that instance
+    (1e300 diverges, 4), nothing hangs, the neighbours are solved as usual -- oracle, thread solver and warp solver alike."""
+    import emul
+    cfg = oracle_mod.OracleConfig(linsolve="riccati", max_iter=200, **kw)
+    O = kw.get("O", 0)
+    b = make_batch(8, seed=5, O=O)
+    b["x_cur"][1, 0] = np.nan; b["goal"][2, 1] = np.inf; b["x_cur"][3, 2] = 1e300; b["goal"][4, 0] = -np.inf
+    b["x_cur"][5, 2] = np.nan; b["goal"][6, 2] = np.nan
+    want = [0, -13, -13, 4, -13, -13, -13, 0]
+    if O:
+        b["obs"][7, 0, 0] = np.nan; want[7] = -13
+    ref = oracle_mod.solve(cfg, b["x_cur"], b["goal"], obs=b["obs"])
+    assert ref.status.tolist() == want
+    for warp in (False, True):
+        X, U, obj, st, it, tp = emul.solve(cfg, b["x_cur"], b["goal"], obs=b["obs"], warp=warp)
+        assert st.tolist() == want and np.abs(U[0] - ref.U[0]).max() <= 1e-9
+
+
 def test_solver_source_warm_start(oracle_mod):
     import emul
     cfg = oracle_mod.OracleConfig(linsolve="riccati")

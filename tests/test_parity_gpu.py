@@ -278,6 +278,32 @@ def test_full_size_properties():
     assert torch.equal(rs.controls, U[lo:hi]) and torch.equal(rs.status, r.status[lo:hi])
 
 
+def test_non_finite_inputs(oracle_mod):
+    """NaN / inf in the inputs of some instances: those return Invalid_Number_Detected (-13; 1e300 diverges: 4) exactly as the
+    oracle, nothing hangs, every other instance of the batch is solved as usual (also through the queue-order key kernel)."""
+    from kiss_mpc_b200 import BatchedMotionPlanner
+    for O in (0, 3):
+        ocfg, pcfg = _pair(oracle_mod, **({"O": O} if O else {}))
+        B = 6000
+        b = make_batch(B, seed=31, O=O)
+        bad = np.arange(7, B, 500)
+        b["x_cur"][bad[0], 0] = np.nan; b["goal"][bad[1], 1] = np.inf; b["x_cur"][bad[2], 2] = 1e300; b["goal"][bad[3], 0] = -np.inf
+        b["x_cur"][bad[4], 2] = np.nan; b["goal"][bad[5], 2] = np.nan; b["x_cur"][bad[6], 1] = -np.inf
+        if O:
+            b["obs"][bad[7], 1, 0] = np.nan
+        ref = oracle_mod.solve(ocfg, b["x_cur"], b["goal"], obs=b["obs"])
+        res = BatchedMotionPlanner(pcfg, max_batch=B).solve(_dev(b["x_cur"]), _dev(b["goal"]), obstacles=_dev(b["obs"]),
+                                                             obstacle_radius=ocfg.obs_radius, inflation_radius=ocfg.inflation if O else 0.0)
+        st = res.status.cpu().numpy()
+        assert (st[bad[:7]] == ref.status[bad[:7]]).all() and set(st[bad[:7]].tolist()) == {-13, 4}
+        if O:
+            assert st[bad[7]] == ref.status[bad[7]] == -13
+        good = np.ones(B, bool); good[bad[:8]] = False
+        assert (st[good] == ref.status[good]).mean() >= 0.998
+        conv = good & (st == 0) & (ref.status == 0)
+        assert conv.sum() > 0.99 * good.sum() and np.abs(res.controls.cpu().numpy() - ref.U)[conv].max() <= CTRL_ATOL
+
+
 def test_queue_order_does_not_change_results():
     """The order in which the persistent kernel hands out instances (geometric prior, include/kmpc.h kmpc_set_queue_order) is
     scheduling only: same bits as the index order -- box bounds, obstacle rows, batch-minor layout, an at-goal mask."""
