@@ -160,10 +160,23 @@ int kmpc_predict_tracks(kmpc_handle *h, int B, int O, int M, const int32_t *inde
  * keep their state -- the reference stops stepping an agent once its final goal is reached (environment.py:31-33);
  * with goal_radius > 0 the mask is refreshed after every step with Agent.at_goal (agent.py:78-80):
  * ||(goal_xy - p_xy) - agent_radius||_2 - goal_radius <= 0, the literal formula of geometry.py:44 (agent_radius = 0 gives
- * the Euclidean distance).  Asynchronous on `cuda_stream`; device pointers.  No obstacle rows in this entry point. */
+ * the Euclidean distance).  Asynchronous on `cuda_stream`; device pointers.  No obstacle rows in this entry point
+ * (kmpc_environment_loop has them). */
 int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur, const double *goal, double *X, double *U,
                      double *applied_log, int32_t *iters_log, int32_t *status_log, int32_t *active, double goal_radius,
                      double agent_radius, void *cuda_stream);
+
+/* kmpc_closed_loop with the environment's sensor filter in the loop -- `steps` repetitions of ROSEnvironment.step
+ * (environment.py:39-80) for B agents on the device: every step each agent keeps the (at most O) nearest of the M static
+ * candidate circles within its sensor radius (kmpc_select_obstacles' rules; environment.py:48-56), solves with them as obstacle
+ * rows (optimizer.py:198-258; uniform obs_radius as optimizer.py:231-245, inflation = agent radius + 0.1, agent.py:149; unused
+ * slots at (pad_x, pad_y)), hands off (agent.py:139-155) and refreshes the at-goal mask (agent.py:78-80).  count_log[steps][B]
+ * (may be NULL) records how many real obstacles each agent saw; the other arguments are kmpc_closed_loop's. */
+int kmpc_environment_loop(kmpc_handle *h, int B, int steps, double *x_cur, const double *goal, double *X, double *U, int M,
+                          const double *cand_centers, const double *cand_radius, double sensor_radius, int literal, int O,
+                          double obs_radius, double inflation, double pad_x, double pad_y, double *applied_log, int32_t *iters_log,
+                          int32_t *status_log, int32_t *count_log, int32_t *active, double goal_radius, double agent_radius,
+                          void *cuda_stream);
 
 /* Scheduling of the batch inside kmpc_solve (no reference equivalent; results never depend on it).  The solver kernel is
  * persistent: warps pull instances from a queue, and interior-point iteration counts differ by more than 8x between instances,

@@ -15,7 +15,7 @@ NO_BOUND = 1e19
 
 # symbols include/kmpc.h declares (checked by tests/test_abi.py)
 SYMBOLS = ["kmpc_version", "kmpc_workspace_bytes", "kmpc_create", "kmpc_destroy", "kmpc_last_error", "kmpc_solve",
-           "kmpc_solve_tracks", "kmpc_solve_host", "kmpc_host_result", "kmpc_agent_handoff", "kmpc_closed_loop", "kmpc_select_obstacles", "kmpc_predict_tracks",
+           "kmpc_solve_tracks", "kmpc_solve_host", "kmpc_host_result", "kmpc_agent_handoff", "kmpc_closed_loop", "kmpc_environment_loop", "kmpc_select_obstacles", "kmpc_predict_tracks",
            "kmpc_set_queue_order", "kmpc_set_timing", "kmpc_get_stats", "kmpc_measure_fp64_peak"]
 
 
@@ -71,6 +71,9 @@ def load():
     L.kmpc_agent_handoff.argtypes = [vp, C.c_int, dp, dp, dp, dp, vp]
     L.kmpc_closed_loop.restype = C.c_int
     L.kmpc_closed_loop.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, dp, ip, ip, ip, C.c_double, C.c_double, vp]
+    L.kmpc_environment_loop.restype = C.c_int
+    L.kmpc_environment_loop.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, dp, C.c_int, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
+                                        C.c_double, C.c_double, dp, ip, ip, ip, ip, C.c_double, C.c_double, vp]
     L.kmpc_select_obstacles.restype = C.c_int
     L.kmpc_select_obstacles.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, dp, ip, ip, vp]
     L.kmpc_predict_tracks.restype = C.c_int

@@ -176,6 +176,7 @@ struct kmpc_handle {
     int32_t *oval;         // 2 x cols; the second half is the order the kernel reads
     void *osort_tmp;
     size_t osort_bytes;
+    double *env_obs;       // kmpc_environment_loop: the obstacles each agent kept this step, cols x O_max x 2
     cudaStream_t stream;
     char err[256];
 };
@@ -456,6 +457,7 @@ extern "C" void kmpc_destroy(kmpc_handle *h) {
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
     if (h->wscratch) cudaFree(h->wscratch);
     if (h->okey) cudaFree(h->okey);
+    if (h->env_obs) cudaFree(h->env_obs);
     if (h->oval) cudaFree(h->oval);
     if (h->osort_tmp) cudaFree(h->osort_tmp);
     if (h->d_in) cudaFree(h->d_in);
@@ -554,7 +556,7 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
     ls.cnt = h->cnt; ls.trips = h->timing ? h->trips : NULL;
 
     if (h->timing) { CU(cudaMemsetAsync(h->trips, 0, sizeof(unsigned long long), st)); CU(cudaEventRecord(h->ev0, st)); }
-    if (active && !(O == 0 && cf->N + 1 <= 64)) return fail(h, KMPC_E_BADARG, "kmpc: the at-goal mask needs the warp solver (O = 0, N <= 63)%s", "");
+    if (active && cf->N + 1 > 64) return fail(h, KMPC_E_BADARG, "kmpc: the at-goal mask needs the warp solver (N <= 63)%s", "");
     const bool use_warp = cf->N + 1 <= 64 && getenv("KMPC_FORCE_THREAD") == NULL;  // N + 1 <= 32 * SPL
     bool use_warp_fits = true;
     if (use_warp) {
@@ -574,6 +576,7 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
 #undef KMPC_LAUNCH
         if (le == cudaErrorInvalidConfiguration && O > 0) use_warp_fits = false;  // too many obstacle rows for shared memory
         else { CU(le); }
+        if (!use_warp_fits && active) return fail(h, KMPC_E_BADARG, "kmpc: the at-goal mask needs the warp solver (obstacle rows must fit shared memory)%s", "");
         if (use_warp_fits) {
         CU(cudaGetLastError());
         h->launches++;
@@ -818,6 +821,36 @@ extern "C" int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur,
         // in place: every instance reads its own warm-start rows before it writes its result rows
         int rc = solve_impl(h, B, x_cur, goal, X, U, NULL, 0, 0, 0.0, 0.0, X, U, NULL, status_log ? status_log + (size_t)s * B : NULL,
                             iters_log ? iters_log + (size_t)s * B : NULL, active, cuda_stream);
+        if (rc) return rc;
+        kmpc_handoff_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, h->cfg.N, h->cfg.layout, X, U, x_cur,
+                                                            applied_log ? applied_log + (size_t)s * B * 2 : NULL, goal, active, goal_radius, agent_radius);
+        CU(cudaGetLastError());
+        h->launches++;
+    }
+    return 0;
+}
+
+extern "C" int kmpc_environment_loop(kmpc_handle *h, int B, int steps, double *x_cur, const double *goal, double *X, double *U, int M,
+                                     const double *cand_centers, const double *cand_radius, double sensor_radius, int literal, int O,
+                                     double obs_radius, double inflation, double pad_x, double pad_y, double *applied_log,
+                                     int32_t *iters_log, int32_t *status_log, int32_t *count_log, int32_t *active, double goal_radius,
+                                     double agent_radius, void *cuda_stream) {
+    if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_environment_loop: NULL handle%s", "");
+    if (B < 0 || B > h->cfg.B_max || steps < 0 || M < 0) return fail(h, KMPC_E_BADARG, "kmpc_environment_loop: bad B, steps or M%s", "");
+    if (O < 1 || O > h->cfg.O_max || O > KMPC_SEL_MAX_O) return fail(h, KMPC_E_BADARG, "kmpc_environment_loop: need 1 <= O <= min(O_max, 32)%s", "");
+    if (B == 0 || steps == 0) return 0;
+    if (!x_cur || !goal || !X || !U || (M > 0 && (!cand_centers || !cand_radius))) return fail(h, KMPC_E_BADARG, "kmpc_environment_loop: NULL required pointer%s", "");
+    CU(cudaSetDevice(h->device));
+    if (!h->env_obs) CU(cudaMalloc(&h->env_obs, (size_t)h->cols * h->cfg.O_max * 2 * sizeof(double)));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    for (int s = 0; s < steps; ++s) {
+        // ROSEnvironment.step (environment.py:39-80): sensor filter -> EgoAgent.step (solve + hand-off) -> at-goal test
+        kmpc_select_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, M, h->cfg.layout, x_cur, cand_centers, cand_radius, sensor_radius, literal, O,
+                                                           pad_x, pad_y, h->env_obs, count_log ? count_log + (size_t)s * B : NULL, NULL);
+        CU(cudaGetLastError());
+        h->launches++;
+        int rc = solve_impl(h, B, x_cur, goal, X, U, h->env_obs, O, 0, obs_radius, inflation, X, U, NULL,
+                            status_log ? status_log + (size_t)s * B : NULL, iters_log ? iters_log + (size_t)s * B : NULL, active, cuda_stream);
         if (rc) return rc;
         kmpc_handoff_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, h->cfg.N, h->cfg.layout, X, U, x_cur,
                                                             applied_log ? applied_log + (size_t)s * B * 2 : NULL, goal, active, goal_radius, agent_radius);

@@ -301,14 +301,19 @@ class BatchedMotionPlanner:
 
     def closed_loop(self, current_state, goal_state, steps: int, states_matrix=None, controls_matrix=None,
                     log_applied: bool = True, log_iters: bool = True, goal_radius: float = 0.0, agent_radius: float = 0.0,
-                    active=None):
+                    active=None, obstacle_centers=None, obstacle_radii=None, sensor_radius: float = 5.0, slots: Optional[int] = None,
+                    obstacle_radius: float = 0.3, inflation_radius: float = 0.5, literal_distance: bool = True,
+                    pad_center=(1.0e6, 1.0e6)):
         """`steps` receding-horizon steps of EgoAgent.step (agent.py:130-155) for all B agents on the device
         (kmpc_closed_loop): warm start = previous solution unshifted, x <- X[:,1], applied = U[:,0].
         current_state [B,3] is advanced in place.  Returns (states, controls, applied_log [steps,B,2] | None,
         iters_log [steps,B] | None, status_log [steps,B]).
         goal_radius > 0: an agent that satisfies Agent.at_goal (agent.py:78-80, literal distance of geometry.py:44 with
         agent_radius; 0 = Euclidean) after a step is not solved again (status 1000 in the log), as the reference's
-        environment stops stepping it (environment.py:31-33); `active` (int32 [B]) carries that mask in and out."""
+        environment stops stepping it (environment.py:31-33); `active` (int32 [B]) carries that mask in and out.
+        obstacle_centers [M,2] / obstacle_radii [M] (CUDA float64): the whole ROSEnvironment.step (environment.py:39-80,
+        kmpc_environment_loop) -- every step each agent keeps the `slots` nearest circles within `sensor_radius` and solves with
+        them as obstacle rows; the per-step obstacle counts are left in ``self.last_obstacle_counts`` [steps,B]."""
         torch = _torch()
         dev = torch.device("cuda", self.device)
         B = self._batch_of(current_state)
@@ -329,6 +334,18 @@ class BatchedMotionPlanner:
         self.last_active = active
         stream = torch.cuda.current_stream(dev).cuda_stream
         p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        if obstacle_centers is not None:
+            O = int(slots if slots is not None else self.config.O_max)
+            counts = torch.empty((steps, B), dtype=torch.int32, device=dev)
+            cen, rad = obstacle_centers.contiguous(), obstacle_radii.contiguous()
+            rc = self._L.kmpc_environment_loop(self._h, B, int(steps), p(current_state), p(goal_state.contiguous()), p(X), p(U),
+                                               int(cen.shape[0]), p(cen), p(rad), float(sensor_radius), 1 if literal_distance else 0, O,
+                                               float(obstacle_radius), float(inflation_radius), float(pad_center[0]), float(pad_center[1]),
+                                               p(applied), p(iters), p(status), p(counts), p(active), float(goal_radius),
+                                               float(agent_radius), C.c_void_p(stream))
+            _lib.check(rc, self._h, "kmpc_environment_loop")
+            self.last_obstacle_counts = counts
+            return X, U, applied, iters, status
         rc = self._L.kmpc_closed_loop(self._h, B, int(steps), p(current_state), p(goal_state.contiguous()), p(X), p(U), p(applied),
                                       p(iters), p(status), p(active), float(goal_radius), float(agent_radius), C.c_void_p(stream))
         _lib.check(rc, self._h, "kmpc_closed_loop")

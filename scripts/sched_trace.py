@@ -25,7 +25,7 @@ for prior in (False, True):
     st = (t[:, 0] - t0) * 1e-6; en = (t[:, 1] - t0) * 1e-6; trips = t[:, 2]
     dur = en - st
     name = "prior" if prior else "natural"
-    np.save(f"gpurun_out/sched_{name}.npy", np.stack([st, en, trips, t[:, 3] >> 32, r.iters.cpu().numpy()], 1))
+    np.save(f"gpurun_out/sched_{name}.npy", np.stack([st, en, trips, t[:, 3] >> 32, r.iters.cpu().numpy(), t[:, 3] & 0xffffffff], 1))
     edges = np.linspace(0, en.max(), 21)
     conc = [int(((st <= e) & (en > e)).sum()) for e in edges]
     late = np.argsort(-en)[:8]

@@ -171,6 +171,45 @@ def test_closed_loop_matches_stepwise_oracle(oracle_mod):
     assert iters[1:].float().mean().item() < 0.6 * iters[0].float().mean().item()
 
 
+def test_environment_loop_matches_stepwise_oracle(oracle_mod):
+    """ROSEnvironment.step on the device (kmpc_environment_loop: sensor filter -> solve with the kept circles -> hand-off ->
+    at-goal mask, environment.py:39-80) against the same loop run step by step with the reference's per-agent filter
+    (oracle/sensor_filter.py) and the oracle solve."""
+    from kiss_mpc_b200 import BatchedMotionPlanner, PlannerConfig
+    from oracle.sensor_filter import sensor_filter
+    torch = _torch()
+    B, O, M, steps = 96, 4, 30, 5
+    rng = np.random.default_rng(3)
+    b = make_batch(B, seed=41)
+    cen = rng.uniform(-9, 9, size=(M, 2)); rad = np.full(M, 0.3)
+    keep = np.min(np.linalg.norm(cen[None] - b["x_cur"][:, None, :2], axis=2), axis=0) > 1.3      # no agent starts inside a circle
+    cen, rad = cen[keep], rad[keep]; M = len(cen)
+    ocfg, pcfg = _pair(oracle_mod, O=O)
+    pl = BatchedMotionPlanner(pcfg, max_batch=B)
+    x = _dev(b["x_cur"]).clone()
+    X, U, applied, iters, status = pl.closed_loop(x, _dev(b["goal"]), steps, goal_radius=0.5, obstacle_centers=_dev(cen),
+                                                   obstacle_radii=_dev(rad), sensor_radius=3.0, slots=O, obstacle_radius=0.3,
+                                                   inflation_radius=0.5)
+    counts = pl.last_obstacle_counts.cpu().numpy(); status = status.cpu().numpy(); applied = applied.cpu().numpy()
+    # the reference loop
+    xc = b["x_cur"].copy(); Xw = np.repeat(xc[:, :, None], ocfg.N + 1, axis=2); Uw = np.zeros((B, 2, ocfg.N)); act = np.ones(B, bool)
+    for s in range(steps):
+        obs = np.full((B, O, 2), 1.0e6); cnt = np.zeros(B, int)
+        for i in range(B):
+            idx = sensor_filter(xc[i], cen, rad, 3.0, True)[:O]
+            obs[i, :len(idx)] = cen[idx]; cnt[i] = len(idx)
+        assert (counts[s] == cnt).all()
+        r = oracle_mod.solve(ocfg, xc, b["goal"], X0=Xw, U0=Uw, obs=obs)
+        assert (status[s][act] == r.status[act]).mean() >= 0.98 and (status[s][~act] == 1000).all()
+        same = act & (status[s] == 0) & (r.status == 0)
+        assert np.abs(applied[s][same] - r.U[same][:, :, 0]).max() <= CTRL_ATOL
+        # continue from the GPU trajectory: copy the device state so that both loops see the same warm start
+        Xw[act], Uw[act], xc[act] = r.X[act], r.U[act], r.X[act][:, :, 1]
+        d = (b["goal"][:, :2] - xc[:, :2]); act &= ~(np.linalg.norm(d, axis=1) - 0.5 <= 0)
+    assert (counts.max() >= 1) and (counts.min() == 0)
+    assert np.abs(x.cpu().numpy() - xc).max() <= 1e-4
+
+
 def test_status_parity_infeasible(oracle_mod):
     """Status-parity batch: x_cur.x = +-25 violates the x bound -> the equality X_0 = x_cur is infeasible."""
     from kiss_mpc_b200 import BatchedMotionPlanner
