@@ -886,12 +886,16 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     // the block's Riccati warp: co-resident blocks (b and b + gridDim/2 under round-robin placement) pick different warp
     // slots, hence different schedulers, so that two serial phases that coincide do not share one FP64 issue port
     const int swid = w_serial_warp(W);
-    const int cwid = W >= 2 ? (swid + 1) % W : -1;   // the warp that tests the speculative inertia candidates
+    // the warps that test the speculative inertia candidates: (KMPC_NCAND - 1) * W lanes, i.e. one warp for blocks of up to 10
+    // instances, two for 16; candidate-lane g = cj * 32 + lane serves instance g % W with candidate 1 + g / W
+    const int ncw = W >= 2 ? ((KMPC_NCAND - 1) * W + 31) / 32 < W - 1 ? ((KMPC_NCAND - 1) * W + 31) / 32 : W - 1 : 0;
+    const int cj = (wid - swid - 1 + W) % W;          // 0 .. ncw - 1: this warp is a candidate warp
+    const bool is_cand = W >= 2 && wid != swid && cj < ncw;
 #pragma unroll 1
     for (;;) {
         // warp 0 is busy in the serial window below, so it takes its next instance here; the other warps take theirs
         // in that window (the global-memory round trip then costs the block nothing)
-        if (!have && !drained && (wid == swid || wid == cwid)) {
+        if (!have && !drained && (wid == swid || is_cand)) {
             b = w_fetch_active(c, io, queue);
             if (b < c.B) { SCHED_START(b) w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
         }
@@ -913,7 +917,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 sc->dshift[0] = 0.0;
                 for (int k = 1; k < KMPC_NCAND; ++k) {
                     dk = inertia_next_delta(dk, t.delta_last);
-                    sc->dshift[k] = (W >= 2 && mode == M_NEWTON && dk <= K_DW_MAX && k * W <= 32) ? dk - t.delta : NAN;
+                    sc->dshift[k] = (W >= 2 && mode == M_NEWTON && dk <= K_DW_MAX && k * W <= 32 * ncw) ? dk - t.delta : NAN;
                     sc->pdc[k] = 0;
                 }
             }
@@ -928,9 +932,9 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 WScal *so = scal0 + lane;
                 if (so->flag) so->ok = w_serial<OBS>(c, smem + (size_t)lane * LY::COOP, LY::NSTG, so->d0) ? 1 : 0;
             }
-        } else if (wid == cwid && KMPC_NCAND > 1) {
-            // speculative inertia candidates on a second warp: lane = (candidate - 1) * W + instance
-            const int inst = lane % W, cand = 1 + lane / W;
+        } else if (is_cand && KMPC_NCAND > 1) {
+            // speculative inertia candidates: candidate-lane g = (candidate - 1) * W + instance
+            const int g = cj * 32 + lane, inst = g % W, cand = 1 + g / W;
             WScal *so = scal0 + inst;
             const double ds = cand < KMPC_NCAND ? so->dshift[cand] : NAN;
             if (so->flag && ds == ds) so->pdc[cand] = w_serial_candidate<OBS>(c, smem + (size_t)inst * LY::COOP, LY::NSTG, ds) ? 1 : 0;
