@@ -818,16 +818,20 @@ KMPC_WN inline void w_soc_rhs(const Cfg &c, const WScal *sc, const WState<SPL> &
 
 // Optional phase timers (tuning builds only, -DKMPC_PHASE_TIMING): cycles per phase summed over all owner warps.
 #if defined(KMPC_PHASE_TIMING) && defined(__CUDACC__)
-#define KMPC_NPHASE 16
+#define KMPC_NPHASE 18
 __device__ unsigned long long g_phase_cycles[KMPC_NPHASE];
 #define PT_DECL long long pt_acc[KMPC_NPHASE] = {0}; long long pt_last = clock64();
 #define PT(i) { const long long pt_now = clock64(); pt_acc[i] += pt_now - pt_last; pt_last = pt_now; }
 #define PT_COUNT(i) pt_acc[i] += 1;
+#define PT_SERIAL_BEGIN const long long pt_s0 = clock64();
+#define PT_SERIAL_END { w_sync(); pt_acc[17] += clock64() - pt_s0; pt_acc[16] += 1; }   /* whole serial window of the block, per trip */
 #define PT_FLUSH if (lane == 0) { for (int i = 0; i < KMPC_NPHASE; ++i) atomicAdd(&g_phase_cycles[i], (unsigned long long)pt_acc[i]); }
 #else
 #define PT_DECL
 #define PT(i)
 #define PT_COUNT(i)
+#define PT_SERIAL_BEGIN
+#define PT_SERIAL_END
 #define PT_FLUSH
 #endif
 
@@ -928,10 +932,12 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         // ---- phase 1b: the serial recursions of all the block's instances, one lane each ----
         bool fresh = false;  // an instance taken in this window joins the next trip
         if (wid == swid) {
+            PT_SERIAL_BEGIN
             if (lane < W) {
                 WScal *so = scal0 + lane;
                 if (so->flag) so->ok = w_serial<OBS>(c, smem + (size_t)lane * LY::COOP, LY::NSTG, so->d0) ? 1 : 0;
             }
+            PT_SERIAL_END
         } else if (is_cand && KMPC_NCAND > 1) {
             // speculative inertia candidates: candidate-lane g = (candidate - 1) * W + instance
             const int g = cj * 32 + lane, inst = g % W, cand = 1 + g / W;

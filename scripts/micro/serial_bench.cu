@@ -8,10 +8,10 @@ __global__ void bench(Cfg c, int lanes, int reps, long long *cyc, double *sink, 
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     constexpr int COOP = WLay<1>::COOP, NSTG = 32;
-    for (int i = threadIdx.x; i < 8 * COOP; i += blockDim.x) sm[i] = 0.0;
+    for (int i = threadIdx.x; i < 16 * COOP; i += blockDim.x) sm[i] = 0.0;
     __syncthreads();
     // plausible stage blocks: Q = 2, R = 1, small dynamics terms
-    if (wid == 0 && lane < 8)
+    if (wid == 0 && lane < 16)
         for (int s = 0; s <= c.N; ++s) {
             double *q = sm + lane * COOP + s;
             q[C_A13 * NSTG] = -0.01; q[C_A23 * NSTG] = 0.02; q[C_B11 * NSTG] = 0.08; q[C_B21 * NSTG] = 0.06;
@@ -53,9 +53,9 @@ __global__ void bench(Cfg c, int lanes, int reps, long long *cyc, double *sink, 
 int main() {
     Cfg c; memset(&c, 0, sizeof c); c.N = 30; c.T = 0.1;
     long long *cyc; double *sink; cudaMalloc(&cyc, 8 * 64); cudaMalloc(&sink, 8 * 2048);
-    const size_t smem = 8 * WLay<1>::COOP * 8;
+    const size_t smem = 16 * WLay<1>::COOP * 8;
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    for (int mode : {0}) for (int nbg : {0, 15}) for (int lanes : {8}) {
+    for (int mode : {0}) for (int nbg : {0, 2, 15}) for (int lanes : {1, 8, 16}) {
         const int reps = 8; long long h[8];
         bench<<<1, 32 * (1 + nbg), smem>>>(c, lanes, reps, cyc, sink, mode);
         cudaError_t e = cudaDeviceSynchronize();
