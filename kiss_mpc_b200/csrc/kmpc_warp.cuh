@@ -491,6 +491,42 @@ KMPC_W void w_fwd_load(WFwdIn &r, const double *q, const int NSTG) {
     r.a13 = q[C_A13 * NSTG]; r.a23 = q[C_A23 * NSTG]; r.b11 = q[C_B11 * NSTG]; r.b21 = q[C_B21 * NSTG];
     r.e0 = q[C_E0 * NSTG]; r.e1 = q[C_E1 * NSTG]; r.e2 = q[C_E2 * NSTG];
 }
+// one stage of the forward roll-out: stores (dx, du) of the stage over its K, returns dx of the next stage in x0..x2
+KMPC_W void w_fwd_stage(const WFwdIn &f, double *q, const int NSTG, const double T, double &x0, double &x1, double &x2) {
+    const double du0 = fma(f.K00, x0, fma(f.K01, x1, fma(f.K02, x2, f.kf0)));
+    const double du1 = fma(f.K10, x0, fma(f.K11, x1, fma(f.K12, x2, f.kf1)));
+    q[C_DX0 * NSTG] = x0; q[C_DX1 * NSTG] = x1; q[C_DX2 * NSTG] = x2; q[C_DU0 * NSTG] = du0; q[C_DU1 * NSTG] = du1;
+    const double n0 = x0 + f.a13 * x2 + f.b11 * du0 + f.e0;
+    const double n1 = x1 + f.a23 * x2 + f.b21 * du0 + f.e1;
+    const double n2 = x2 + T * du1 + f.e2;
+    x0 = n0; x1 = n1; x2 = n2;
+}
+// forward roll-out dx+ = A dx + B du + e, du = K dx + k_ff over all stages
+KMPC_WN inline void w_serial_fwd(const Cfg &c, double *coop, const int NSTG, const double *d0) {
+    const int N = c.N;
+    const double T = c.T;
+    double x0 = d0[0], x1 = d0[1], x2 = d0[2];
+    // two stages per trip, the two operand sets swapping roles (no register copies, no guarded load block -- the guarded
+    // block of a one-stage loop kept the shared-window address arithmetic, an S2R per stage, inside the loop: 255 cycles/stage)
+    WFwdIn fa, fb;
+    w_fwd_load(fa, coop, NSTG);
+    int s = 0;
+#pragma unroll 1
+    for (; s + 2 <= N; s += 2) {   // every address is the loop base plus a constant: loads move freely above the stores
+        double *q = coop + s;
+        w_fwd_load(fb, q + 1, NSTG);
+        w_fwd_stage(fa, q, NSTG, T, x0, x1, x2);
+        w_fwd_load(fa, q + 2, NSTG);
+        w_fwd_stage(fb, q + 1, NSTG, T, x0, x1, x2);
+    }
+    if (s + 1 <= N) {              // the last one or two stages
+        w_fwd_load(fb, coop + s + 1, NSTG);
+        w_fwd_stage(fa, coop + s, NSTG, T, x0, x1, x2);
+        w_fwd_stage(fb, coop + s + 1, NSTG, T, x0, x1, x2);
+    } else {
+        w_fwd_stage(fa, coop + s, NSTG, T, x0, x1, x2);
+    }
+}
 // the solving sweep of one instance: factors, vector part and roll-out of the system as assembled (the speculative inertia
 // candidates run w_serial_candidate on another warp)
 template <bool OBS>
@@ -519,22 +555,7 @@ KMPC_WN inline bool w_serial(const Cfg &c, double *coop, const int NSTG, const d
     }
     w_ric_vec(cy, coop, coop, NSTG, T, p0, p1, p2);
     if (!pd) return false;
-    double x0 = d0[0], x1 = d0[1], x2 = d0[2];
-    WFwdIn fn;
-    w_fwd_load(fn, coop, NSTG);
-#pragma unroll 1
-    for (int s = 0; s <= N; ++s) {
-        double *q = coop + s;
-        const WFwdIn f = fn;
-        if (s < N) w_fwd_load(fn, q + 1, NSTG);
-        const double du0 = fma(f.K00, x0, fma(f.K01, x1, fma(f.K02, x2, f.kf0)));
-        const double du1 = fma(f.K10, x0, fma(f.K11, x1, fma(f.K12, x2, f.kf1)));
-        q[C_DX0 * NSTG] = x0; q[C_DX1 * NSTG] = x1; q[C_DX2 * NSTG] = x2; q[C_DU0 * NSTG] = du0; q[C_DU1 * NSTG] = du1;
-        const double n0 = x0 + f.a13 * x2 + f.b11 * du0 + f.e0;
-        const double n1 = x1 + f.a23 * x2 + f.b21 * du0 + f.e1;
-        const double n2 = x2 + T * du1 + f.e2;
-        x0 = n0; x1 = n1; x2 = n2;
-    }
+    w_serial_fwd(c, coop, NSTG, d0);
     return true;
 }
 
