@@ -51,49 +51,7 @@ __global__ void bench(Cfg c, int lanes, int reps, long long *cyc, double *sink, 
         sink[threadIdx.x] = x;
     }
 }
-// the split version: warp 0 = matrix lanes (w_serial_mat), warp 1 = vector lanes (w_serial_vec); window = both done
-__global__ void bench2(Cfg c, int lanes, int reps, long long *cyc, double *sink, int nbg) {
-    extern __shared__ double sm[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr int COOP = WLay<1>::COOP, NSTG = 32;
-    for (int i = threadIdx.x; i < 16 * COOP; i += blockDim.x) sm[i] = 0.0;
-    __syncthreads();
-    double d0[3] = {0.1, 0.2, 0.3};
-    bool ok = true;
-    double x = threadIdx.x;
-    for (int r = 0; r < reps; ++r) {
-        if (wid == 0 && lane < 16)
-            for (int s = 0; s <= c.N; ++s) {
-                double *q = sm + lane * COOP + s;
-                q[C_A13 * NSTG] = -0.01; q[C_A23 * NSTG] = 0.02; q[C_B11 * NSTG] = 0.08; q[C_B21 * NSTG] = 0.06;
-                q[C_Q00 * NSTG] = 2; q[C_Q11 * NSTG] = 2; q[C_Q22 * NSTG] = 1; q[C_DV * NSTG] = 1; q[C_DW * NSTG] = 1; q[C_HTV * NSTG] = 0.01;
-                q[C_Q0 * NSTG] = 0.3; q[C_Q1 * NSTG] = -0.2; q[C_Q2 * NSTG] = 0.1; q[C_QV * NSTG] = 0.05; q[C_QW * NSTG] = 0.02;
-                q[C_E0 * NSTG] = 0.001; q[C_E1 * NSTG] = 0.002; q[C_E2 * NSTG] = 0.0;
-                q[C_M00 * NSTG] = w_not_ready();
-            }
-        __syncthreads();
-        const long long a = clk();
-        long long a2 = a;
-        if (nbg < 0) {   // one after the other: the vector lanes never wait
-            if (wid == 0 && lane < lanes) ok = w_serial_mat<false>(c, sm + lane * COOP, NSTG) && ok;
-            __syncthreads();
-            a2 = clk();
-            if (wid == 1 && lane < lanes) w_serial_vec(c, sm + lane * COOP, NSTG, d0);
-        } else {
-            if (wid == 0) { if (lane < lanes) ok = w_serial_mat<false>(c, sm + lane * COOP, NSTG) && ok; }
-            else if (wid == 1) { if (lane < lanes) w_serial_vec(c, sm + lane * COOP, NSTG, d0); }
-            else { for (int i = 0; i < 1500; ++i) x = fma(x, 0.999, 1e-9); }
-        }
-        const long long m = clk() - (a2 - a);
-        __syncthreads();
-        const long long b = clk();
-        if (threadIdx.x == 0) { cyc[r] = b - a; cyc[32 + r] = m - a; }
-        if (threadIdx.x == 32) cyc[64 + r] = m - a;
-    }
-    if (threadIdx.x == 0) sink[0] = ok ? sm[C_DX0 * NSTG + 5] + sm[C_PV0 * NSTG + 3] : -1.0;
-    if (wid >= 2) sink[threadIdx.x] = x;
-}
-// both parts on the same lanes, one after the other, timed separately (no hand-off wait, one clock domain)
+// the whole sweep (w_serial) and the forward roll-out alone (w_serial_fwd), timed on the same warp
 __global__ void bench3(Cfg c, int lanes, int reps, long long *cyc, double *sink) {
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31;
@@ -110,16 +68,13 @@ __global__ void bench3(Cfg c, int lanes, int reps, long long *cyc, double *sink)
                 q[C_Q00 * NSTG] = 2; q[C_Q11 * NSTG] = 2; q[C_Q22 * NSTG] = 1; q[C_DV * NSTG] = 1; q[C_DW * NSTG] = 1; q[C_HTV * NSTG] = 0.01;
                 q[C_Q0 * NSTG] = 0.3; q[C_Q1 * NSTG] = -0.2; q[C_Q2 * NSTG] = 0.1; q[C_QV * NSTG] = 0.05; q[C_QW * NSTG] = 0.02;
                 q[C_E0 * NSTG] = 0.001; q[C_E1 * NSTG] = 0.002; q[C_E2 * NSTG] = 0.0;
-                q[C_M00 * NSTG] = w_not_ready();
             }
         __syncwarp();
         const long long t0 = clk();
-        if (lane < lanes) ok = w_serial_mat<false>(c, sm + lane * COOP, NSTG) && ok;
+        if (lane < lanes) ok = w_serial<false>(c, sm + lane * COOP, NSTG, d0) && ok;
         __syncwarp();
         const long long t1 = clk();
-        if (lane < lanes) w_serial_vec(c, sm + lane * COOP, NSTG, d0);
-        __syncwarp();
-        const long long t2 = clk();
+        const long long t2 = t1;
         if (lane < lanes) w_serial_fwd(c, sm + lane * COOP, NSTG, d0);
         __syncwarp();
         const long long t3 = clk();
@@ -137,22 +92,9 @@ int main() {
         bench3<<<1, 32, smem>>>(c, 16, 8, cyc, sink);
         cudaError_t e = cudaDeviceSynchronize();
         cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
-        printf("sequential on one warp: matrix part %lld cycles, vector part + roll-out %lld cycles, roll-out alone (again) %lld [%s]\n", h[5], h[32 + 5], h[64 + 5], cudaGetErrorString(e));
+        printf("one warp, 16 lanes: whole sweep %lld cycles, forward roll-out alone %lld cycles [%s]\n", h[5], h[64 + 5], cudaGetErrorString(e));
     }
 
-    {
-        Cfg c; memset(&c, 0, sizeof c); c.N = 30; c.T = 0.1;
-        long long *cyc; double *sink; cudaMalloc(&cyc, 8 * 128); cudaMalloc(&sink, 8 * 2048);
-        const size_t smem = 16 * WLay<1>::COOP * 8;
-        cudaFuncSetAttribute(bench2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        for (int nbg : {-1, 0, 14}) for (int lanes : {16}) {
-            long long h[96];
-            bench2<<<1, 32 * (2 + (nbg < 0 ? 0 : nbg)), smem>>>(c, lanes, 8, cyc, sink, nbg);
-            cudaError_t e = cudaDeviceSynchronize();
-            cudaMemcpy(h, cyc, sizeof h, cudaMemcpyDeviceToHost);
-            double sk; cudaMemcpy(&sk, sink, 8, cudaMemcpyDeviceToHost);
-            printf("split: background warps %2d lanes %2d: window %lld cycles (matrix lane %lld, vector lane %lld)  check %.12g [%s]\n", nbg, lanes, h[5], h[32 + 5], h[64 + 5], sk, cudaGetErrorString(e));
-        }
     }
 
     Cfg c; memset(&c, 0, sizeof c); c.N = 30; c.T = 0.1;
