@@ -95,8 +95,6 @@ int main() {
         printf("one warp, 16 lanes: whole sweep %lld cycles, forward roll-out alone %lld cycles [%s]\n", h[5], h[64 + 5], cudaGetErrorString(e));
     }
 
-    }
-
     Cfg c; memset(&c, 0, sizeof c); c.N = 30; c.T = 0.1;
     long long *cyc; double *sink; cudaMalloc(&cyc, 8 * 64); cudaMalloc(&sink, 8 * 2048);
     const size_t smem = 16 * WLay<1>::COOP * 8;
