@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define KMPC_VERSION 100
+#define KMPC_VERSION 200
 
 #define KMPC_LAYOUT_INSTANCE_MAJOR 0
 #define KMPC_LAYOUT_BATCH_MINOR 1
@@ -91,13 +91,17 @@ const char *kmpc_last_error(const kmpc_handle *h);
  *   X0, U0                states_matrix / controls_matrix     (optimizer.py:376-385 primal warm start); both NULL = the
  *                         cold start of agent.py:59-60 (X = tile(x_cur), U = 0) synthesised on chip
  *   obs_centers, O        static/dynamic obstacle circle centres (optimizer.py:217-221), 0 <= O <= O_max; NULL iff O == 0
- *   obs_radius            uniform obstacle radius (optimizer.py:231-245 uses the first obstacle's radius for all)
+ *   obs_radius, obs_radii radius subtracted from the centre distance of every obstacle slot.  The reference keeps ONE radius per obstacle
+ *                         class: static_obstacles[0].radius for the static columns, dynamic_obstacles[0].radius for the dynamic
+ *                         ones (optimizer.py:231-250).  obs_radii ([B][O]; batch-minor [O][B]) carries a radius per instance and
+ *                         slot, so the caller writes the first static radius into the static slots and the first dynamic radius
+ *                         into the dynamic slots; obs_radii == NULL: every slot uses the scalar obs_radius.
  *   inflation             inflation_radius = lower bound of the distance rows (optimizer.py:254-258; agent.py:149)
  *   X_out, U_out          the returned (3,N+1) / (2,N) matrices (optimizer.py:392-400)
  *   obj_out, status_out, iters_out   new outputs (the reference never reads IPOPT's stats); each may be NULL. */
 int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
-               const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
-               double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream);
+               const double *obs_centers, int O, double obs_radius, const double *obs_radii, double inflation, double *X_out,
+               double *U_out, double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream);
 
 /* The same solve with circle centres that move with the stage: obs_tracks holds, per instance and obstacle, a track of N
  * centres ([B][O][N][2]; SoA layout [O][N][2][B]); column t is the centre paired with X_{t+1}.  This is what the reference's
@@ -105,14 +109,38 @@ int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const double *goal, c
  * optimizer.py:207-215; the vectorised path optimizer.py:217-250 keeps only the current centre).  A static obstacle is a track
  * of N equal columns.  Everything else as kmpc_solve. */
 int kmpc_solve_tracks(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
-                      const double *obs_tracks, int O, double obs_radius, double inflation, double *X_out, double *U_out,
-                      double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream);
+                      const double *obs_tracks, int O, double obs_radius, const double *obs_radii, double inflation, double *X_out,
+                      double *U_out, double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream);
 
 /* Same call with HOST pointers (what a ctypes/NumPy caller such as the reference's agent.py holds): stages through the
  * handle's pinned buffers, copies host->device, solves, copies device->host and synchronises before returning. */
 int kmpc_solve_host(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
-                    const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
-                    double *obj_out, int32_t *status_out, int32_t *iters_out);
+                    const double *obs_centers, int O, double obs_radius, const double *obs_radii, double inflation, double *X_out,
+                    double *U_out, double *obj_out, int32_t *status_out, int32_t *iters_out);
+
+/* The host path of ONE SHARD of a batch that is split over several devices (one handle per device): inputs are host
+ * pointers as in kmpc_solve_host, the result pointers are slices of ONE caller-owned pinned buffer (kmpc_pinned_alloc) shared by
+ * all the handles -- every device writes its finished instances straight into its slice, so the gather of the sharded batch costs
+ * no extra copy.  Returns once the work is queued on the handle's own stream; kmpc_host_sync(h) waits for it.  obj / status /
+ * iters may be NULL.  Needs the warp solver (N <= 63). */
+int kmpc_solve_host_into(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
+                         const double *obs_centers, int O, double obs_radius, const double *obs_radii, double inflation,
+                         double *X_pinned, double *U_pinned, double *obj_pinned, int32_t *status_pinned, int32_t *iters_pinned);
+int kmpc_host_sync(kmpc_handle *h);
+int kmpc_pinned_alloc(size_t bytes, void **out); /* portable, device-mapped pinned host memory (visible to every device of the box) */
+int kmpc_pinned_free(void *p);
+
+/* Gather buffer of a batch sharded over the GPUs of one box, one PROCESS per GPU (the final result gather of SURVEY 8e; the
+ * reference has no counterpart -- one NLP per agent, no coupling, optimizer.py:375-391).  The root rank creates the buffer on its
+ * device and hands the 64-byte handle to the other ranks (any transport: torch.distributed broadcast); they open it and pass
+ * pointers into it as the X_out / U_out / ... of kmpc_solve: every finished instance is then written over NVLink straight into
+ * the root's memory -- compute and gather are one kernel, no collective.  kmpc_enable_peer does the same for several handles of
+ * ONE process (peer access from h's device to peer_device). */
+#define KMPC_IPC_HANDLE_BYTES 64
+int kmpc_shared_buffer_create(kmpc_handle *h, size_t bytes, void **dptr, unsigned char *ipc_handle_out /* [64] or NULL */);
+int kmpc_shared_buffer_open(kmpc_handle *h, const unsigned char *ipc_handle /* [64] */, void **dptr);
+int kmpc_shared_buffer_close(kmpc_handle *h, void *dptr, int owner);
+int kmpc_enable_peer(kmpc_handle *h, int peer_device);
 
 /* Zero-copy variant of the host path: when kmpc_solve_host is called with X_out == U_out == NULL the results are left in
  * the handle's pinned staging buffers; this call returns their addresses (layout as kmpc_config.layout, sized for the
@@ -135,10 +163,12 @@ int kmpc_agent_handoff(kmpc_handle *h, int B, const double *X, const double *U, 
  * collapse to the LAST one (the reference keys a dict by distance, environment.py:48-51).  obs_out has the handle's obstacle
  * layout ([B][O][2] / [O][2][B]); unused slots get (pad_x, pad_y) -- pick a point far outside the workspace, its rows stay
  * inactive; count_out[B] (may be NULL) is the number of real obstacles per agent; index_out[B][O] (may be NULL) the
- * candidate index kept in every slot, -1 for padding.  Device pointers, asynchronous. */
+ * candidate index kept in every slot, -1 for padding; radius_out[B][O] (may be NULL; layout as obs_radii) gets, in every slot,
+ * the radius of the NEAREST kept circle -- the list handed to the planner is sorted nearest-first and the planner reads the
+ * radius of its first element for the whole class (optimizer.py:231-245).  Device pointers, asynchronous. */
 int kmpc_select_obstacles(kmpc_handle *h, int B, int M, const double *x_cur, const double *cand_centers, const double *cand_radius,
                           double sensor_radius, int literal, int O, double pad_x, double pad_y, double *obs_out, int32_t *count_out,
-                          int32_t *index_out, void *cuda_stream);
+                          int32_t *index_out, double *radius_out, void *cuda_stream);
 
 /* Replaces DynamicObstacle._get_predicted_states_matrix (dynamic_obstacle.py:20-37) for the obstacles every agent kept:
  * M moving obstacles (state[M][3] = x, y, heading; lin_vel[M]; ang_vel[M]), index[B][O] = which obstacle sits in each
@@ -166,17 +196,24 @@ int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur, const doub
                      double *applied_log, int32_t *iters_log, int32_t *status_log, int32_t *active, double goal_radius,
                      double agent_radius, void *cuda_stream);
 
-/* kmpc_closed_loop with the environment's sensor filter in the loop -- `steps` repetitions of ROSEnvironment.step
- * (environment.py:39-80) for B agents on the device: every step each agent keeps the (at most O) nearest of the M static
- * candidate circles within its sensor radius (kmpc_select_obstacles' rules; environment.py:48-56), solves with them as obstacle
- * rows (optimizer.py:198-258; uniform obs_radius as optimizer.py:231-245, inflation = agent radius + 0.1, agent.py:149; unused
- * slots at (pad_x, pad_y)), hands off (agent.py:139-155) and refreshes the at-goal mask (agent.py:78-80).  count_log[steps][B]
- * (may be NULL) records how many real obstacles each agent saw; the other arguments are kmpc_closed_loop's. */
+/* kmpc_closed_loop with the environment's sensor filters in the loop -- `steps` repetitions of ROSEnvironment.step
+ * (environment.py:39-80) for B agents on the device.  Every step each agent keeps the (at most O) nearest of the M static candidate
+ * circles within its sensor radius (environment.py:48-56) and the (at most Od) nearest of the Md dynamic obstacles
+ * (environment.py:57-65; dyn_state[Md][3] = x, y, heading, dyn_radius[Md]; they are filtered by their current centre), solves with
+ * the static slots followed by the dynamic slots as obstacle rows (optimizer.py:198-258; radius per class = the nearest kept
+ * circle's, optimizer.py:231-250; inflation = agent radius + 0.1, agent.py:149; unused slots at (pad_x, pad_y)), hands off
+ * (agent.py:139-155) and refreshes the at-goal mask (agent.py:78-80).  use_tracks == 0: every circle enters with its current centre,
+ * as the reference's vectorised constraint path reads it (optimizer.py:217-221); use_tracks != 0: a dynamic slot is paired stage by
+ * stage with the constant-velocity prediction of its obstacle (kmpc_predict_tracks: dyn_lin_vel / dyn_ang_vel [Md], track_dt,
+ * literal_heading; dynamic_obstacle.py:20-37, :47-56) and a static slot is a track of N equal columns.  Obstacles themselves do
+ * not move between steps (the reference never advances them).  count_log / dyn_count_log [steps][B] (may be NULL): how many real
+ * static / dynamic circles each agent saw; the other arguments are kmpc_closed_loop's. */
 int kmpc_environment_loop(kmpc_handle *h, int B, int steps, double *x_cur, const double *goal, double *X, double *U, int M,
-                          const double *cand_centers, const double *cand_radius, double sensor_radius, int literal, int O,
-                          double obs_radius, double inflation, double pad_x, double pad_y, double *applied_log, int32_t *iters_log,
-                          int32_t *status_log, int32_t *count_log, int32_t *active, double goal_radius, double agent_radius,
-                          void *cuda_stream);
+                          const double *cand_centers, const double *cand_radius, int O, int Md, const double *dyn_state,
+                          const double *dyn_radius, const double *dyn_lin_vel, const double *dyn_ang_vel, int Od, int use_tracks,
+                          double track_dt, int literal_heading, double sensor_radius, int literal, double inflation, double pad_x,
+                          double pad_y, double *applied_log, int32_t *iters_log, int32_t *status_log, int32_t *count_log,
+                          int32_t *dyn_count_log, int32_t *active, double goal_radius, double agent_radius, void *cuda_stream);
 
 /* Scheduling of the batch inside kmpc_solve (no reference equivalent; results never depend on it).  The solver kernel is
  * persistent: warps pull instances from a queue, and interior-point iteration counts differ by more than 8x between instances,
@@ -196,6 +233,8 @@ typedef struct kmpc_stats {
     int32_t threads_per_block;
     int32_t sm_count;
     int64_t trips;            /* total solver-loop trips of the last solve (sum over threads), if timing enabled */
+    int32_t warp_path;        /* 1: the last solve ran the warp kernel; 0: the thread-per-instance fall-back */
+    int32_t reserved;
 } kmpc_stats;
 int kmpc_set_timing(kmpc_handle *h, int enable); /* enable: kmpc_solve records events + syncs to fill last_kernel_ms */
 int kmpc_get_stats(kmpc_handle *h, kmpc_stats *out);

@@ -2,8 +2,8 @@
 (mpc/optimizer.py MotionPlanner.solve -> CasADi/IPOPT).  See DESIGN.md."""
 from ._lib import KmpcError  # noqa: F401
 from .model import Model  # noqa: F401
-from .planner import (BatchedMotionPlanner, MotionPlanner, PlannerConfig, SolveResult, STATUS_NAMES,  # noqa: F401
-                      gather_results, shard_range)
+from .planner import (BatchedMotionPlanner, MotionPlanner, PlannerConfig, RankGather, ShardedMotionPlanner, SolveResult,  # noqa: F401
+                      STATUS_NAMES, gather_results, shard_range)
 
-__all__ = ["BatchedMotionPlanner", "Model", "MotionPlanner", "PlannerConfig", "SolveResult", "STATUS_NAMES", "KmpcError",
-           "gather_results", "shard_range"]
+__all__ = ["BatchedMotionPlanner", "Model", "MotionPlanner", "PlannerConfig", "RankGather", "ShardedMotionPlanner", "SolveResult",
+           "STATUS_NAMES", "KmpcError", "gather_results", "shard_range"]

@@ -1,9 +1,11 @@
 // kmpc.cu -- CUDA kernels (sm_100a) and the C ABI of include/kmpc.h.
 //
 // Replaces the numerical core of mpc/optimizer.py:319-400 (MotionPlanner.solve -> CasADi/IPOPT) for B instances at
-// once.  One CUDA thread per problem instance and phase; per-instance state lives in a structure-of-arrays HBM
-// workspace (see kmpc_core.cuh); each launch works on a compacted list of the instances that still need that phase.
-// No tensor cores: the stage blocks are 3x3 / 2x2 / 2x3 and the work is FP64 FMA + HBM streaming.
+// once.  The solver proper is kmpc_warp_kernel (kmpc_warp.cuh): a persistent grid, one warp per problem instance, the
+// iterate in registers, the block's serial Riccati recursions side by side on one warp, nothing but the problem data and
+// the result in HBM.  The thread-per-instance kernels below (state in a structure-of-arrays HBM workspace, host-driven
+// trip loop) are the correctness fall-back for horizons above 63 stages or more obstacle rows than shared memory holds.
+// No tensor cores: the stage blocks are 3x3 / 2x2 / 2x3 with a data-dependent 2x2 inverse between them.
 // No CPU fallback exists in this library.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -176,7 +178,11 @@ struct kmpc_handle {
     int32_t *oval;         // 2 x cols; the second half is the order the kernel reads
     void *osort_tmp;
     size_t osort_bytes;
-    double *env_obs;       // kmpc_environment_loop: the obstacles each agent kept this step, cols x O_max x 2
+    double *env_obs;       // kmpc_environment_loop: the circles each agent kept this step: cols x O_max x 2 centres, then their N-column tracks
+    double *env_rad;       //   ... their per-slot radii, cols x O_max
+    int32_t *env_idx;      //   ... which dynamic candidate sits in every dynamic slot
+    int max_smem;          // opt-in shared memory per block of the device
+    int last_path;         // 1: the last solve ran the warp kernel, 0: the thread-per-instance fall-back
     cudaStream_t stream;
     char err[256];
 };
@@ -225,8 +231,8 @@ kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned lon
 // the part of the straight start-goal segment the horizon can reach (v_max T N) adds 10 trips to the key (4,096 x 65,536
 // instances, O = 10 and 4: tail 1.05-1.15 x ideal with the geometric prior alone, 1.015-1.03 x with this term).
 __global__ void kmpc_order_key_kernel(int B, int layout, const double *__restrict__ x_cur, const double *__restrict__ goal,
-                                      const double *__restrict__ obs, int O, int obs_sw, int N, double reach, double near,
-                                      unsigned *__restrict__ key, int32_t *__restrict__ val) {
+                                      const double *__restrict__ obs, const double *__restrict__ orad, int O, int obs_sw, int N,
+                                      double reach, double near_u, double near_add, unsigned *__restrict__ key, int32_t *__restrict__ val) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const size_t s0 = layout ? (size_t)b : (size_t)b * 3, st = layout ? (size_t)B : 1;
@@ -254,6 +260,7 @@ __global__ void kmpc_order_key_kernel(int B, int layout, const double *__restric
             double t = rx * ux + ry * uy;
             t = t < 0 ? 0 : (t > L ? L : t);
             const double ex = rx - t * ux, ey = ry - t * uy;
+            const double near = orad ? orad[layout ? (size_t)o * B + b : (size_t)b * O + o] + near_add : near_u;
             blocked += (ex * ex + ey * ey < near * near) ? 1 : 0;
         }
         k += 10.0f * (float)blocked;
@@ -269,16 +276,17 @@ static cudaError_t queue_order(kmpc_handle *h, int B, int resident, const Cfg &c
     if (!h->order_mode || B <= resident) return cudaSuccess;   // a single wave: every instance starts at once
     const size_t S = (size_t)h->cols;
     cudaError_t e;
-    if (!h->okey) {
-        if ((e = cudaMalloc(&h->okey, 2 * S * sizeof(unsigned))) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&h->oval, 2 * S * sizeof(int32_t))) != cudaSuccess) return e;
-        h->osort_bytes = 0;
-        if ((e = cub::DeviceRadixSort::SortPairsDescending(NULL, h->osort_bytes, h->okey, h->okey + S, h->oval, h->oval + S, (int)S, 0, 16, st)) != cudaSuccess) return e;
-        if ((e = cudaMalloc(&h->osort_tmp, h->osort_bytes)) != cudaSuccess) return e;
+    if (!h->osort_tmp) {   // (the three buffers are committed to the handle together: a failed allocation leaves none behind)
+        unsigned *k = NULL; int32_t *v = NULL; void *tmp = NULL; size_t nb = 0;
+        if ((e = cudaMalloc(&k, 2 * S * sizeof(unsigned))) == cudaSuccess && (e = cudaMalloc(&v, 2 * S * sizeof(int32_t))) == cudaSuccess &&
+            (e = cub::DeviceRadixSort::SortPairsDescending(NULL, nb, k, k + S, v, v + S, (int)S, 0, 16, st)) == cudaSuccess)
+            e = cudaMalloc(&tmp, nb ? nb : 16);
+        if (e != cudaSuccess) { cudaFree(k); cudaFree(v); cudaFree(tmp); return e; }
+        h->okey = k; h->oval = v; h->osort_tmp = tmp; h->osort_bytes = nb;
     }
     const double inflation = c.dL + K_BOUND_RELAX * fmax(1.0, fabs(c.dL));   // (c.dL is the relaxed bound; close enough for a heuristic)
-    kmpc_order_key_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, layout, io.x_cur, io.goal, io.obs, c.O, c.obs_sw, c.N, c.ub[2] * c.T * c.N,
-                                                          c.obs_radius + inflation + 0.4, h->okey, h->oval);
+    kmpc_order_key_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, layout, io.x_cur, io.goal, io.obs, io.orad, c.O, c.obs_sw, c.N, c.ub[2] * c.T * c.N,
+                                                          c.obs_radius + inflation + 0.4, inflation + 0.4, h->okey, h->oval);
     size_t bytes = h->osort_bytes;
     if ((e = cub::DeviceRadixSort::SortPairsDescending(h->osort_tmp, bytes, h->okey, h->okey + S, h->oval, h->oval + S, B, 0, 16, st)) != cudaSuccess) return e;
     h->launches += 2;
@@ -356,9 +364,13 @@ __global__ void kmpc_handoff_kernel(int B, int N, int layout, const double *__re
 // Sensor filter of ROSEnvironment.step (environment.py:48-65): one thread per agent keeps the (at most O <= 32) nearest
 // candidates within the sensor radius in a sorted list (insertion; M * O compares per agent, candidates are broadcast loads).
 #define KMPC_SEL_MAX_O 32
-__global__ void kmpc_select_kernel(int B, int M, int layout, const double *__restrict__ x_cur, const double *__restrict__ cc,
-                                   const double *__restrict__ cr, double sensor_radius, int literal, int O, double pad_x, double pad_y,
-                                   double *__restrict__ obs_out, int32_t *__restrict__ count_out, int32_t *__restrict__ index_out) {
+// cc: candidate centres, `cstride` doubles apart (2: [M][2] centres; 3: [M][3] states x, y, heading); the O kept circles go to
+// slots slot0 .. slot0 + O - 1 of an agent's Otot slots; rad_out: every slot of this class gets the radius of the nearest kept
+// candidate -- the reference builds one radius per obstacle class from its first element (optimizer.py:231-250).
+__global__ void kmpc_select_kernel(int B, int M, int layout, const double *__restrict__ x_cur, const double *__restrict__ cc, int cstride,
+                                   const double *__restrict__ cr, double sensor_radius, int literal, int O, int Otot, int slot0, double pad_x,
+                                   double pad_y, double *__restrict__ obs_out, int32_t *__restrict__ count_out, int32_t *__restrict__ index_out,
+                                   double *__restrict__ rad_out) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const double px = x_cur[layout ? (size_t)b : (size_t)b * 3], py = x_cur[layout ? (size_t)B + b : (size_t)b * 3 + 1];
@@ -366,7 +378,7 @@ __global__ void kmpc_select_kernel(int B, int M, int layout, const double *__res
     int idx[KMPC_SEL_MAX_O];
     int n = 0;
     for (int m = 0; m < M; ++m) {
-        const double cx = cc[2 * m], cy = cc[2 * m + 1], r = cr[m];
+        const double cx = cc[(size_t)cstride * m], cy = cc[(size_t)cstride * m + 1], r = cr[m];
         double d;
         if (literal) { const double ex = (px - cx) - r, ey = (py - cy) - r; d = sqrt(ex * ex + ey * ey); }   // geometry.py:44 as written
         else { const double ex = px - cx, ey = py - cy; d = sqrt(ex * ex + ey * ey) - r; }
@@ -381,20 +393,36 @@ __global__ void kmpc_select_kernel(int B, int M, int layout, const double *__res
         dist[pos] = d; idx[pos] = m;
         if (n < O) ++n;
     }
+    const double rad = n > 0 ? cr[idx[0]] : 0.0;
     for (int o = 0; o < O; ++o) {
-        const double ox = o < n ? cc[2 * idx[o]] : pad_x, oy = o < n ? cc[2 * idx[o] + 1] : pad_y;
-        if (layout) { obs_out[((size_t)o * 2) * B + b] = ox; obs_out[((size_t)o * 2 + 1) * B + b] = oy; }
-        else { obs_out[((size_t)b * O + o) * 2] = ox; obs_out[((size_t)b * O + o) * 2 + 1] = oy; }
+        const double ox = o < n ? cc[(size_t)cstride * idx[o]] : pad_x, oy = o < n ? cc[(size_t)cstride * idx[o] + 1] : pad_y;
+        const int so = slot0 + o;
+        if (layout) { obs_out[((size_t)so * 2) * B + b] = ox; obs_out[((size_t)so * 2 + 1) * B + b] = oy; }
+        else { obs_out[((size_t)b * Otot + so) * 2] = ox; obs_out[((size_t)b * Otot + so) * 2 + 1] = oy; }
         if (index_out) index_out[(size_t)b * O + o] = o < n ? idx[o] : -1;
+        if (rad_out) rad_out[layout ? (size_t)so * B + b : (size_t)b * Otot + so] = rad;
     }
     if (count_out) count_out[b] = n;
+}
+
+// a static circle as a track: its centre in every one of the N columns (slot o of Otot; the dynamic slots follow)
+__global__ void kmpc_repeat_kernel(int B, int O, int Otot, int N, int layout, const double *__restrict__ cen, double *__restrict__ tracks) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * O) return;
+    const int b = (int)(i / O), o = (int)(i % O);
+    const double x = cen[layout ? ((size_t)o * 2) * B + b : ((size_t)b * Otot + o) * 2];
+    const double y = cen[layout ? ((size_t)o * 2 + 1) * B + b : ((size_t)b * Otot + o) * 2 + 1];
+    for (int t = 0; t < N; ++t) {
+        const size_t ox = layout ? (((size_t)o * N + t) * 2) * B + b : (((size_t)b * Otot + o) * N + t) * 2;
+        tracks[ox] = x; tracks[layout ? ox + B : ox + 1] = y;
+    }
 }
 
 // Constant-velocity predictor of DynamicObstacle (dynamic_obstacle.py:20-37) for the obstacles each agent selected: one thread
 // per (agent, slot) runs the N-column recursion  column 0 = current state, column t = column t-1 + [v cos(a) dt, v sin(a) dt,
 // omega dt]  with a = deg2rad(heading) as the reference writes it (:24-25; literal == 0: the heading taken as radians) and
 // stores the x, y of every column.  Slots without an obstacle (index < 0) get the padding point in every column.
-__global__ void kmpc_predict_kernel(int B, int O, int M, int N, int layout, const int32_t *__restrict__ index, const double *__restrict__ state,
+__global__ void kmpc_predict_kernel(int B, int O, int Otot, int slot0, int M, int N, int layout, const int32_t *__restrict__ index, const double *__restrict__ state,
                                     const double *__restrict__ lin_vel, const double *__restrict__ ang_vel, double dt, int literal,
                                     double pad_x, double pad_y, double *__restrict__ tracks) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -405,7 +433,7 @@ __global__ void kmpc_predict_kernel(int B, int O, int M, int N, int layout, cons
     double x = real ? state[3 * m] : pad_x, y = real ? state[3 * m + 1] : pad_y, th = real ? state[3 * m + 2] : 0.0;
     const double v = real ? lin_vel[m] : 0.0, w = real ? ang_vel[m] : 0.0;
     for (int t = 0; t < N; ++t) {
-        const size_t ox = layout ? (((size_t)o * N + t) * 2) * B + b : (((size_t)b * O + o) * N + t) * 2;
+        const size_t ox = layout ? (((size_t)(slot0 + o) * N + t) * 2) * B + b : (((size_t)b * Otot + slot0 + o) * N + t) * 2;
         tracks[ox] = x; tracks[layout ? ox + B : ox + 1] = y;
         if (real) {
             const double a = literal ? th * 0.017453292519943295 : th;   // np.deg2rad = multiplication by pi / 180
@@ -447,6 +475,21 @@ static int fail(kmpc_handle *h, int code, const char *fmt, const char *detail) {
         if (e_ != cudaSuccess) return fail(h, KMPC_E_CUDA, #call ": %s", cudaGetErrorString(e_)); \
     } while (0)
 
+// The calling thread's current device is left as it was found (torch and other CUDA users of the thread keep theirs).
+struct DeviceGuard {
+    int prev;
+    cudaError_t err;
+    explicit DeviceGuard(int dev) : prev(-1) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        err = prev == dev ? cudaSuccess : cudaSetDevice(dev);
+        if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define KMPC_ON_DEVICE(h)                 \
+    DeviceGuard dev_guard_((h)->device);  \
+    CU(dev_guard_.err)
+
 static int check_cfg(const kmpc_config *cfg) {
     if (!cfg) return 0;
     if (cfg->N < 1 || cfg->N > 4096 || cfg->O_max < 0 || cfg->O_max > 256 || cfg->B_max < 1) return 0;
@@ -472,7 +515,7 @@ extern "C" const char *kmpc_last_error(const kmpc_handle *h) { return h ? h->err
 
 extern "C" void kmpc_destroy(kmpc_handle *h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard_(h->device);
     if (h->ws) cudaFree(h->ws);
     if (h->lists) cudaFree(h->lists);
     if (h->cnt) cudaFree(h->cnt);
@@ -481,6 +524,8 @@ extern "C" void kmpc_destroy(kmpc_handle *h) {
     if (h->wscratch) cudaFree(h->wscratch);
     if (h->okey) cudaFree(h->okey);
     if (h->env_obs) cudaFree(h->env_obs);
+    if (h->env_rad) cudaFree(h->env_rad);
+    if (h->env_idx) cudaFree(h->env_idx);
     if (h->oval) cudaFree(h->oval);
     if (h->osort_tmp) cudaFree(h->osort_tmp);
     if (h->d_in) cudaFree(h->d_in);
@@ -512,8 +557,10 @@ extern "C" int kmpc_create(const kmpc_config *cfg, kmpc_handle **out) {
     h->device = cfg->device;
     h->rows = make_rows(cfg->N, cfg->O_max, 1);   // sized for stage-wise obstacle centres
     h->cols = cols_for(cfg);
-    cudaError_t e = cudaSetDevice(h->device);
+    DeviceGuard dev_guard_(h->device);
+    cudaError_t e = dev_guard_.err;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
     // (the thread solver's HBM workspace -- 1.2 GB at B_max = 65,536, N = 30 -- is allocated on its first use: the warp solver
     //  that serves N <= 63 keeps its state on chip and never touches it)
     if (e == cudaSuccess) e = cudaMalloc(&h->cnt, 4 * sizeof(int));
@@ -543,45 +590,66 @@ static void relax_bounds(const kmpc_config *cfg, Cfg *c) {
 
 static inline int nblocks(int n) { return (n + KMPC_TPB - 1) / KMPC_TPB; }
 
-// The trip loop is driven from the host: three launches per trip on `cuda_stream`, KMPC_LOOKAHEAD trips in flight; the
-// active-instance count of an older trip (async copy into pinned memory) sizes the grids and ends the loop.  On return
-// every instance has finished and the outputs are complete on `cuda_stream`.
-static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
-                      const double *obs_centers, int O, int stagewise, double obs_radius, double inflation, double *X_out, double *U_out,
-                      double *obj_out, int32_t *status_out, int32_t *iters_out, const int32_t *active, void *cuda_stream) {
+// Which solver serves a problem on this handle: the warp kernel whenever the horizon fits its stage slots (N + 1 <= 64) and the
+// obstacle rows of one instance fit shared memory; otherwise the thread-per-instance fall-back.  Every entry point asks here,
+// so what is decided before the launch (zero-copy result writes, the at-goal mask) is what runs.
+static bool warp_path(const kmpc_handle *h, int O, int stagewise) {
+    const int N1 = h->cfg.N + 1;
+    if (N1 > 64 || getenv("KMPC_FORCE_THREAD") != NULL) return false;
+    const int sw = (stagewise && O > 0) ? 1 : 0;
+    const size_t one = N1 <= 32 ? WLay<1, 32>::bytes(1, O, sw) : N1 <= 52 ? WLay<2, 52>::bytes(1, O, sw) : WLay<2, 64>::bytes(1, O, sw);
+    return one <= (size_t)h->max_smem;
+}
+
+struct SolveArgs {
+    const double *x_cur, *goal, *X0, *U0, *obs, *orad;
+    int O, stagewise;
+    double obs_radius, inflation;
+    double *X_out, *U_out, *obj;
+    int32_t *status, *iters;
+    const int32_t *active;
+};
+
+// One batch solve, asynchronous on `cuda_stream`.  Warp path: one persistent launch (+ the queue-order kernels).  Thread path:
+// the trip loop is driven from the host, three launches per trip, KMPC_LOOKAHEAD trips in flight; the active-instance count
+// of an older trip (async copy into pinned memory) sizes the grids and ends the loop.
+static int solve_impl(kmpc_handle *h, int B, const SolveArgs &a, void *cuda_stream) {
     if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_solve: NULL handle%s", "");
+    const int O = a.O;
     if (B < 0 || B > h->cfg.B_max) return fail(h, KMPC_E_BADARG, "kmpc_solve: B outside [0, B_max]%s", "");
-    if (O < 0 || O > h->cfg.O_max || (O > 0 && !obs_centers)) return fail(h, KMPC_E_BADARG, "kmpc_solve: bad obstacle arguments%s", "");
-    if ((X0 == NULL) != (U0 == NULL)) return fail(h, KMPC_E_BADARG, "kmpc_solve: X0 and U0 must both be given or both be NULL%s", "");
+    if (O < 0 || O > h->cfg.O_max || (O > 0 && !a.obs)) return fail(h, KMPC_E_BADARG, "kmpc_solve: bad obstacle arguments%s", "");
+    if ((a.X0 == NULL) != (a.U0 == NULL)) return fail(h, KMPC_E_BADARG, "kmpc_solve: X0 and U0 must both be given or both be NULL%s", "");
     if (B == 0) return 0;
-    if (!x_cur || !goal || !X_out || !U_out) return fail(h, KMPC_E_BADARG, "kmpc_solve: NULL required pointer%s", "");
+    if (!a.x_cur || !a.goal || !a.X_out || !a.U_out) return fail(h, KMPC_E_BADARG, "kmpc_solve: NULL required pointer%s", "");
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    CU(cudaSetDevice(h->device));
+    KMPC_ON_DEVICE(h);
     Cfg c;
     memset(&c, 0, sizeof c);
     const kmpc_config *cf = &h->cfg;
     c.N = cf->N; c.O = O; c.cost_mode = cf->cost_mode; c.gk_lo = cf->goal_k_lo; c.gk_hi = cf->goal_k_hi;
-    c.max_iter = cf->max_iter; c.layout = cf->layout; c.B = B; c.obs_sw = (stagewise && O > 0) ? 1 : 0;
+    c.max_iter = cf->max_iter; c.layout = cf->layout; c.B = B; c.obs_sw = (a.stagewise && O > 0) ? 1 : 0;
     relax_bounds(cf, &c);
     c.T = cf->T; c.W[0] = cf->W[0]; c.W[1] = cf->W[1]; c.W[2] = cf->W[2];
     c.Wvn = cf->Wv_neg; c.Wvp = cf->Wv_pos; c.Ww = cf->Ww; c.tol = cf->tol;
-    c.obs_radius = obs_radius; c.dL = inflation - K_BOUND_RELAX * fmax(1.0, fabs(inflation));
+    c.obs_radius = a.obs_radius; c.dL = a.inflation - K_BOUND_RELAX * fmax(1.0, fabs(a.inflation));
     c.L = make_rows(cf->N, O, c.obs_sw);
     c.nb = (cf->N + 1) * (c.hasL[0] + c.hasU[0] + c.hasL[1] + c.hasU[1]) + cf->N * (c.hasL[2] + c.hasU[2] + c.hasL[3] + c.hasU[3]) + cf->N * O;
     c.m = 3 * (cf->N + 1) + cf->N * O;
     c.r_mnb = 1.0 / (double)(c.m + c.nb); c.r_nb = c.nb ? 1.0 / (double)c.nb : 0.0;
     IO io;
-    io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs_centers;
-    io.X_out = X_out; io.U_out = U_out; io.obj = obj_out; io.status = status_out; io.iters = iters_out; io.active = active; io.wscratch = NULL; io.order = NULL;
+    memset(&io, 0, sizeof io);
+    io.x_cur = a.x_cur; io.goal = a.goal; io.X0 = a.X0; io.U0 = a.U0; io.obs = a.obs; io.orad = O > 0 ? a.orad : NULL;
+    io.X_out = a.X_out; io.U_out = a.U_out; io.obj = a.obj; io.status = a.status; io.iters = a.iters; io.active = a.active;
     const size_t S = (size_t)h->cols;
     Lists ls;
     ls.LA[0] = h->lists; ls.LA[1] = h->lists + S; ls.LT[0] = h->lists + 2 * S; ls.LT[1] = h->lists + 3 * S;
     ls.cnt = h->cnt; ls.trips = h->timing ? h->trips : NULL;
 
+    const bool use_warp = warp_path(h, O, c.obs_sw);
+    if (a.active && !use_warp)
+        return fail(h, KMPC_E_BADARG, "kmpc: the at-goal mask needs the warp solver (N <= 63, obstacle rows within shared memory, no KMPC_FORCE_THREAD)%s", "");
     if (h->timing) { CU(cudaMemsetAsync(h->trips, 0, sizeof(unsigned long long), st)); CU(cudaEventRecord(h->ev0, st)); }
-    if (active && cf->N + 1 > 64) return fail(h, KMPC_E_BADARG, "kmpc: the at-goal mask needs the warp solver (N <= 63)%s", "");
-    const bool use_warp = cf->N + 1 <= 64 && getenv("KMPC_FORCE_THREAD") == NULL;  // N + 1 <= 32 * SPL
-    bool use_warp_fits = true;
+    h->last_path = use_warp ? 1 : 0;
     if (use_warp) {
         // warp-per-instance path: one persistent launch, instances pulled from a queue, no workspace traffic
         CU(cudaMemsetAsync(h->cnt, 0, sizeof(int), st));
@@ -597,10 +665,7 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
         else if (cf->N + 1 <= 52) le = O > 0 ? KMPC_LAUNCH(2, 52, true, 6, 1) : KMPC_LAUNCH(2, 52, false, KMPC_WPB2, KMPC_MINB2);
         else le = O > 0 ? KMPC_LAUNCH(2, 64, true, 6, 1) : KMPC_LAUNCH(2, 64, false, KMPC_WPB3, KMPC_MINB3);
 #undef KMPC_LAUNCH
-        if (le == cudaErrorInvalidConfiguration && O > 0) use_warp_fits = false;  // too many obstacle rows for shared memory
-        else { CU(le); }
-        if (!use_warp_fits && active) return fail(h, KMPC_E_BADARG, "kmpc: the at-goal mask needs the warp solver (obstacle rows must fit shared memory)%s", "");
-        if (use_warp_fits) {
+        CU(le);
         CU(cudaGetLastError());
         h->launches++;
         h->last_host_trips = 0;
@@ -615,11 +680,13 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
             h->last_trips = (long long)tr;
         }
         return 0;
-        }
     }
-    if (!h->ws) {   // first thread-solver solve on this handle
-        CU(cudaMalloc(&h->ws, (size_t)h->rows.total * h->cols * sizeof(double)));
-        CU(cudaMalloc(&h->lists, (size_t)4 * h->cols * sizeof(int)));
+    if (!h->lists) {   // first thread-solver solve on this handle (both buffers are committed together)
+        double *ws = NULL; int *li = NULL;
+        cudaError_t e = cudaMalloc(&ws, (size_t)h->rows.total * h->cols * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&li, (size_t)4 * h->cols * sizeof(int));
+        if (e != cudaSuccess) { cudaFree(ws); cudaFree(li); CU(e); }
+        h->ws = ws; h->lists = li;
     }
     ls.LA[0] = h->lists; ls.LA[1] = h->lists + S; ls.LT[0] = h->lists + 2 * S; ls.LT[1] = h->lists + 3 * S;
     const int cnt0[4] = {B, 0, 0, 0};
@@ -680,72 +747,101 @@ static int solve_impl(kmpc_handle *h, int B, const double *x_cur, const double *
     return 0;
 }
 
+static SolveArgs solve_args(const double *x_cur, const double *goal, const double *X0, const double *U0, const double *obs, int O, int stagewise,
+                            double obs_radius, const double *obs_radii, double inflation, double *X_out, double *U_out, double *obj_out,
+                            int32_t *status_out, int32_t *iters_out, const int32_t *active) {
+    SolveArgs a;
+    a.x_cur = x_cur; a.goal = goal; a.X0 = X0; a.U0 = U0; a.obs = obs; a.orad = obs_radii; a.O = O; a.stagewise = stagewise;
+    a.obs_radius = obs_radius; a.inflation = inflation; a.X_out = X_out; a.U_out = U_out; a.obj = obj_out; a.status = status_out;
+    a.iters = iters_out; a.active = active;
+    return a;
+}
+
 extern "C" int kmpc_solve(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
-                          const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
-                          double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream) {
-    return solve_impl(h, B, x_cur, goal, X0, U0, obs_centers, O, 0, obs_radius, inflation, X_out, U_out, obj_out, status_out, iters_out, NULL,
-                      cuda_stream);
+                          const double *obs_centers, int O, double obs_radius, const double *obs_radii, double inflation, double *X_out,
+                          double *U_out, double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream) {
+    return solve_impl(h, B, solve_args(x_cur, goal, X0, U0, obs_centers, O, 0, obs_radius, obs_radii, inflation, X_out, U_out, obj_out, status_out,
+                                       iters_out, NULL), cuda_stream);
 }
 
 extern "C" int kmpc_solve_tracks(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
-                                 const double *obs_tracks, int O, double obs_radius, double inflation, double *X_out, double *U_out,
-                                 double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream) {
-    return solve_impl(h, B, x_cur, goal, X0, U0, obs_tracks, O, 1, obs_radius, inflation, X_out, U_out, obj_out, status_out, iters_out, NULL,
-                      cuda_stream);
+                                 const double *obs_tracks, int O, double obs_radius, const double *obs_radii, double inflation, double *X_out,
+                                 double *U_out, double *obj_out, int32_t *status_out, int32_t *iters_out, void *cuda_stream) {
+    return solve_impl(h, B, solve_args(x_cur, goal, X0, U0, obs_tracks, O, 1, obs_radius, obs_radii, inflation, X_out, U_out, obj_out, status_out,
+                                       iters_out, NULL), cuda_stream);
 }
 
+// pinned + device staging of kmpc_solve_host; all six buffers are committed to the handle together or not at all
 static int ensure_staging(kmpc_handle *h) {
-    if (h->d_in) return 0;
+    if (h->h_iout) return 0;
     const kmpc_config *cf = &h->cfg;
     const size_t Bm = cf->B_max, N = cf->N, O = cf->O_max;
-    h->in_doubles = Bm * (6 + 5 * N + 3 + 2 * O);
-    h->out_doubles = Bm * (5 * N + 3 + 1);
-    CU(cudaMalloc(&h->d_in, h->in_doubles * sizeof(double)));
-    CU(cudaMalloc(&h->d_out, h->out_doubles * sizeof(double)));
-    CU(cudaMalloc(&h->d_iout, Bm * 2 * sizeof(int32_t)));
-    CU(cudaMallocHost(&h->h_in, h->in_doubles * sizeof(double)));
-    CU(cudaMallocHost(&h->h_out, h->out_doubles * sizeof(double)));
-    CU(cudaMallocHost(&h->h_iout, Bm * 2 * sizeof(int32_t)));
+    const size_t in_doubles = Bm * (6 + 5 * N + 3 + 3 * O), out_doubles = Bm * (5 * N + 3 + 1);
+    double *d_in = NULL, *d_out = NULL, *h_in = NULL, *h_out = NULL;
+    int32_t *d_iout = NULL, *h_iout = NULL;
+    cudaError_t e = cudaMalloc(&d_in, in_doubles * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, out_doubles * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_iout, Bm * 2 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaHostAlloc(&h_in, in_doubles * sizeof(double), cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostAlloc(&h_out, out_doubles * sizeof(double), cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostAlloc(&h_iout, Bm * 2 * sizeof(int32_t), cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e != cudaSuccess) {
+        cudaFree(d_in); cudaFree(d_out); cudaFree(d_iout);
+        if (h_in) cudaFreeHost(h_in);
+        if (h_out) cudaFreeHost(h_out);
+        if (h_iout) cudaFreeHost(h_iout);
+        CU(e);
+    }
+    h->in_doubles = in_doubles; h->out_doubles = out_doubles;
+    h->d_in = d_in; h->d_out = d_out; h->d_iout = d_iout; h->h_in = h_in; h->h_out = h_out; h->h_iout = h_iout;
     return 0;
 }
 
-extern "C" int kmpc_solve_host(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
-                               const double *obs_centers, int O, double obs_radius, double inflation, double *X_out, double *U_out,
-                               double *obj_out, int32_t *status_out, int32_t *iters_out) {
+// Host-pointer solve.  X_out == NULL: results stay in the handle's pinned buffers (kmpc_host_result).  When ext_* are given
+// (kmpc_solve_host_into) the solver writes into caller-owned pinned memory instead and nothing is copied afterwards.
+static int solve_host_impl(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
+                           const double *obs_centers, int O, double obs_radius, const double *obs_radii, double inflation, double *X_out,
+                           double *U_out, double *obj_out, int32_t *status_out, int32_t *iters_out, int pinned_out, int do_sync) {
     if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_solve_host: NULL handle%s", "");
     if (B < 0 || B > h->cfg.B_max) return fail(h, KMPC_E_BADARG, "kmpc_solve_host: B outside [0, B_max]%s", "");
     if (O < 0 || O > h->cfg.O_max || (O > 0 && !obs_centers)) return fail(h, KMPC_E_BADARG, "kmpc_solve_host: bad obstacle arguments%s", "");
     if ((X0 == NULL) != (U0 == NULL)) return fail(h, KMPC_E_BADARG, "kmpc_solve_host: X0 and U0 must both be given or both be NULL%s", "");
     if (B == 0) return 0;
     if (!x_cur || !goal || ((X_out == NULL) != (U_out == NULL))) return fail(h, KMPC_E_BADARG, "kmpc_solve_host: NULL required pointer%s", "");
-    CU(cudaSetDevice(h->device));
+    if (pinned_out && !X_out) return fail(h, KMPC_E_BADARG, "kmpc_solve_host_into: X_out and U_out are required%s", "");
+    KMPC_ON_DEVICE(h);
     int rc = ensure_staging(h);
     if (rc) return rc;
     const size_t N = h->cfg.N, b = B;
     const size_t nX = b * 3 * (N + 1), nU = b * 2 * N;
-    // pack inputs into the pinned buffer: [x_cur | goal | X0 | U0 | obs]
+    // pack inputs into the pinned buffer: [x_cur | goal | X0 | U0 | obs | radii]
     size_t o = 0;
-    double *hx = h->h_in + o; memcpy(hx, x_cur, b * 3 * sizeof(double)); o += b * 3;
-    double *hg = h->h_in + o; memcpy(hg, goal, b * 3 * sizeof(double)); o += b * 3;
-    size_t oX = 0, oU = 0, oO = 0;
+    memcpy(h->h_in + o, x_cur, b * 3 * sizeof(double)); o += b * 3;
+    memcpy(h->h_in + o, goal, b * 3 * sizeof(double)); o += b * 3;
+    size_t oX = 0, oU = 0, oO = 0, oR = 0;
     if (X0) { oX = o; memcpy(h->h_in + o, X0, nX * sizeof(double)); o += nX; oU = o; memcpy(h->h_in + o, U0, nU * sizeof(double)); o += nU; }
     if (O) { oO = o; memcpy(h->h_in + o, obs_centers, b * 2 * O * sizeof(double)); o += b * 2 * O; }
-    (void)hx; (void)hg;
+    if (O && obs_radii) { oR = o; memcpy(h->h_in + o, obs_radii, b * O * sizeof(double)); o += b * O; }
     CU(cudaMemcpyAsync(h->d_in, h->h_in, o * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    // Results: the warp solver writes each finished instance straight into the pinned host buffers (device-visible under
-    // unified addressing), so the 81 MB of D2H traffic at B = 65,536 rides over PCIe while later instances are still being
-    // solved; the thread solver (piecemeal writes) goes through device staging and a copy.
-    const bool direct = h->cfg.N + 1 <= 64 && getenv("KMPC_FORCE_THREAD") == NULL && getenv("KMPC_STAGED_D2H") == NULL;
-    double *dX = direct ? h->h_out : h->d_out, *dU = dX + nX, *dobj = dX + nX + nU;
-    int32_t *dst = direct ? h->h_iout : h->d_iout;
-    rc = kmpc_solve(h, B, h->d_in, h->d_in + b * 3, X0 ? h->d_in + oX : NULL, X0 ? h->d_in + oU : NULL, O ? h->d_in + oO : NULL, O,
-                    obs_radius, inflation, dX, dU, dobj, dst, dst + b, h->stream);
+    // Results: the warp solver writes each finished instance straight into pinned host memory (device-visible under unified
+    // addressing), so the 81 MB of D2H traffic at B = 65,536 rides over PCIe while later instances are still being solved; the
+    // thread solver (piecemeal 8-byte writes) goes through device staging and one copy.
+    const bool direct = warp_path(h, O, 0) && getenv("KMPC_STAGED_D2H") == NULL;
+    if (pinned_out && !direct) return fail(h, KMPC_E_BADARG, "kmpc_solve_host_into: needs the warp solver (N <= 63, obstacle rows within shared memory)%s", "");
+    double *dX, *dU, *dobj;
+    int32_t *dst, *dit;
+    if (pinned_out) { dX = X_out; dU = U_out; dobj = obj_out; dst = status_out; dit = iters_out; }
+    else { dX = direct ? h->h_out : h->d_out; dU = dX + nX; dobj = dX + nX + nU; dst = direct ? h->h_iout : h->d_iout; dit = dst + b; }
+    rc = solve_impl(h, B, solve_args(h->d_in, h->d_in + b * 3, X0 ? h->d_in + oX : NULL, X0 ? h->d_in + oU : NULL, O ? h->d_in + oO : NULL, O, 0,
+                                     obs_radius, (O && obs_radii) ? h->d_in + oR : NULL, inflation, dX, dU, dobj, dst, dit, NULL), h->stream);
     if (rc) return rc;
     if (!direct) {
         CU(cudaMemcpyAsync(h->h_out, h->d_out, (nX + nU + b) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaMemcpyAsync(h->h_iout, h->d_iout, b * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     }
+    if (!do_sync) return 0;
     CU(cudaStreamSynchronize(h->stream));
+    if (pinned_out) return 0;
     h->host_B = B;
     if (!X_out) return 0;  // zero-copy: the caller reads the pinned buffers through kmpc_host_result
     memcpy(X_out, h->h_out, nX * sizeof(double));
@@ -753,6 +849,27 @@ extern "C" int kmpc_solve_host(kmpc_handle *h, int B, const double *x_cur, const
     if (obj_out) memcpy(obj_out, h->h_out + nX + nU, b * sizeof(double));
     if (status_out) memcpy(status_out, h->h_iout, b * sizeof(int32_t));
     if (iters_out) memcpy(iters_out, h->h_iout + b, b * sizeof(int32_t));
+    return 0;
+}
+
+extern "C" int kmpc_solve_host(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
+                               const double *obs_centers, int O, double obs_radius, const double *obs_radii, double inflation, double *X_out,
+                               double *U_out, double *obj_out, int32_t *status_out, int32_t *iters_out) {
+    return solve_host_impl(h, B, x_cur, goal, X0, U0, obs_centers, O, obs_radius, obs_radii, inflation, X_out, U_out, obj_out, status_out,
+                           iters_out, 0, 1);
+}
+
+extern "C" int kmpc_solve_host_into(kmpc_handle *h, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
+                                    const double *obs_centers, int O, double obs_radius, const double *obs_radii, double inflation,
+                                    double *X_pinned, double *U_pinned, double *obj_pinned, int32_t *status_pinned, int32_t *iters_pinned) {
+    return solve_host_impl(h, B, x_cur, goal, X0, U0, obs_centers, O, obs_radius, obs_radii, inflation, X_pinned, U_pinned, obj_pinned,
+                           status_pinned, iters_pinned, 1, 0);
+}
+
+extern "C" int kmpc_host_sync(kmpc_handle *h) {
+    if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_host_sync: NULL handle%s", "");
+    KMPC_ON_DEVICE(h);
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
 
@@ -769,12 +886,68 @@ extern "C" int kmpc_host_result(kmpc_handle *h, const double **X, const double *
     return 0;
 }
 
+// ---- buffers shared between the devices / processes of one box (the gather of a sharded batch) ----
+extern "C" int kmpc_pinned_alloc(size_t bytes, void **out) {
+    if (!out || bytes == 0) return KMPC_E_BADARG;
+    *out = NULL;
+    return cudaHostAlloc(out, bytes, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess ? 0 : KMPC_E_NOMEM;
+}
+extern "C" int kmpc_pinned_free(void *p) { return (!p || cudaFreeHost(p) == cudaSuccess) ? 0 : KMPC_E_CUDA; }
+
+extern "C" int kmpc_shared_buffer_create(kmpc_handle *h, size_t bytes, void **dptr, unsigned char *ipc_handle_out) {
+    if (!h || !dptr || bytes == 0) return fail(h, KMPC_E_BADARG, "kmpc_shared_buffer_create: bad arguments%s", "");
+    KMPC_ON_DEVICE(h);
+    void *p = NULL;
+    CU(cudaMalloc(&p, bytes));
+    if (ipc_handle_out) {
+        cudaIpcMemHandle_t mh;
+        cudaError_t e = cudaIpcGetMemHandle(&mh, p);
+        if (e != cudaSuccess) { cudaFree(p); CU(e); }
+        static_assert(sizeof(cudaIpcMemHandle_t) == KMPC_IPC_HANDLE_BYTES, "ipc handle size");
+        memcpy(ipc_handle_out, &mh, sizeof mh);
+    }
+    *dptr = p;
+    return 0;
+}
+
+extern "C" int kmpc_shared_buffer_open(kmpc_handle *h, const unsigned char *ipc_handle, void **dptr) {
+    if (!h || !dptr || !ipc_handle) return fail(h, KMPC_E_BADARG, "kmpc_shared_buffer_open: bad arguments%s", "");
+    KMPC_ON_DEVICE(h);
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, ipc_handle, sizeof mh);
+    CU(cudaIpcOpenMemHandle(dptr, mh, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int kmpc_shared_buffer_close(kmpc_handle *h, void *dptr, int owner) {
+    if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_shared_buffer_close: NULL handle%s", "");
+    if (!dptr) return 0;
+    KMPC_ON_DEVICE(h);
+    if (owner) { CU(cudaFree(dptr)); } else { CU(cudaIpcCloseMemHandle(dptr)); }
+    return 0;
+}
+
+// peer access from this handle's device to `peer_device` (same process): afterwards kmpc_solve on this handle may be given
+// result pointers that live on the peer -- every finished instance is then written over NVLink straight into the gather buffer
+extern "C" int kmpc_enable_peer(kmpc_handle *h, int peer_device) {
+    if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_enable_peer: NULL handle%s", "");
+    if (peer_device == h->device) return 0;
+    KMPC_ON_DEVICE(h);
+    int can = 0;
+    CU(cudaDeviceCanAccessPeer(&can, h->device, peer_device));
+    if (!can) return fail(h, KMPC_E_CUDA, "kmpc_enable_peer: no peer access between the devices%s", "");
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+    CU(e);
+    return 0;
+}
+
 extern "C" int kmpc_agent_handoff(kmpc_handle *h, int B, const double *X, const double *U, double *x_cur, double *applied_out,
                                   void *cuda_stream) {
     if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_agent_handoff: NULL handle%s", "");
     if (B < 0 || !X || !U || !x_cur) return fail(h, KMPC_E_BADARG, "kmpc_agent_handoff: bad arguments%s", "");
     if (B == 0) return 0;
-    CU(cudaSetDevice(h->device));
+    KMPC_ON_DEVICE(h);
     kmpc_handoff_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(B, h->cfg.N, h->cfg.layout, X, U, x_cur, applied_out, NULL, NULL, 0.0, 0.0);
     CU(cudaGetLastError());
     h->launches++;
@@ -802,14 +975,14 @@ extern "C" int kmpc_debug_phase_cycles(double *out) {
 
 extern "C" int kmpc_select_obstacles(kmpc_handle *h, int B, int M, const double *x_cur, const double *cand_centers,
                                      const double *cand_radius, double sensor_radius, int literal, int O, double pad_x, double pad_y,
-                                     double *obs_out, int32_t *count_out, int32_t *index_out, void *cuda_stream) {
+                                     double *obs_out, int32_t *count_out, int32_t *index_out, double *radius_out, void *cuda_stream) {
     if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_select_obstacles: NULL handle%s", "");
     if (B < 0 || M < 0 || O < 1 || O > KMPC_SEL_MAX_O) return fail(h, KMPC_E_BADARG, "kmpc_select_obstacles: need B, M >= 0 and 1 <= O <= 32%s", "");
     if (B == 0) return 0;
     if (!x_cur || !obs_out || (M > 0 && (!cand_centers || !cand_radius))) return fail(h, KMPC_E_BADARG, "kmpc_select_obstacles: NULL required pointer%s", "");
-    CU(cudaSetDevice(h->device));
-    kmpc_select_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(B, M, h->cfg.layout, x_cur, cand_centers, cand_radius, sensor_radius,
-                                                                               literal, O, pad_x, pad_y, obs_out, count_out, index_out);
+    KMPC_ON_DEVICE(h);
+    kmpc_select_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)cuda_stream>>>(B, M, h->cfg.layout, x_cur, cand_centers, 2, cand_radius, sensor_radius,
+                                                                               literal, O, O, 0, pad_x, pad_y, obs_out, count_out, index_out, radius_out);
     CU(cudaGetLastError());
     h->launches++;
     return 0;
@@ -822,9 +995,9 @@ extern "C" int kmpc_predict_tracks(kmpc_handle *h, int B, int O, int M, const in
     if (B < 0 || O < 1 || M < 0 || (!index && O > M)) return fail(h, KMPC_E_BADARG, "kmpc_predict_tracks: need B, M >= 0, O >= 1 (and O <= M without an index)%s", "");
     if (B == 0) return 0;
     if (!tracks_out || (M > 0 && (!state || !lin_vel || !ang_vel))) return fail(h, KMPC_E_BADARG, "kmpc_predict_tracks: NULL required pointer%s", "");
-    CU(cudaSetDevice(h->device));
+    KMPC_ON_DEVICE(h);
     const size_t n = (size_t)B * O;
-    kmpc_predict_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(B, O, M, h->cfg.N, h->cfg.layout, index, state, lin_vel,
+    kmpc_predict_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)cuda_stream>>>(B, O, O, 0, M, h->cfg.N, h->cfg.layout, index, state, lin_vel,
                                                                                           ang_vel, dt, literal, pad_x, pad_y, tracks_out);
     CU(cudaGetLastError());
     h->launches++;
@@ -838,12 +1011,12 @@ extern "C" int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur,
     if (B < 0 || B > h->cfg.B_max || steps < 0) return fail(h, KMPC_E_BADARG, "kmpc_closed_loop: bad B or steps%s", "");
     if (B == 0 || steps == 0) return 0;
     if (!x_cur || !goal || !X || !U) return fail(h, KMPC_E_BADARG, "kmpc_closed_loop: NULL required pointer%s", "");
-    if (getenv("KMPC_FORCE_THREAD")) active = NULL;
+    KMPC_ON_DEVICE(h);
     cudaStream_t st = (cudaStream_t)cuda_stream;
     for (int s = 0; s < steps; ++s) {
         // in place: every instance reads its own warm-start rows before it writes its result rows
-        int rc = solve_impl(h, B, x_cur, goal, X, U, NULL, 0, 0, 0.0, 0.0, X, U, NULL, status_log ? status_log + (size_t)s * B : NULL,
-                            iters_log ? iters_log + (size_t)s * B : NULL, active, cuda_stream);
+        int rc = solve_impl(h, B, solve_args(x_cur, goal, X, U, NULL, 0, 0, 0.0, NULL, 0.0, X, U, NULL, status_log ? status_log + (size_t)s * B : NULL,
+                                             iters_log ? iters_log + (size_t)s * B : NULL, active), cuda_stream);
         if (rc) return rc;
         kmpc_handoff_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, h->cfg.N, h->cfg.layout, X, U, x_cur,
                                                             applied_log ? applied_log + (size_t)s * B * 2 : NULL, goal, active, goal_radius, agent_radius);
@@ -854,26 +1027,63 @@ extern "C" int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur,
 }
 
 extern "C" int kmpc_environment_loop(kmpc_handle *h, int B, int steps, double *x_cur, const double *goal, double *X, double *U, int M,
-                                     const double *cand_centers, const double *cand_radius, double sensor_radius, int literal, int O,
-                                     double obs_radius, double inflation, double pad_x, double pad_y, double *applied_log,
-                                     int32_t *iters_log, int32_t *status_log, int32_t *count_log, int32_t *active, double goal_radius,
-                                     double agent_radius, void *cuda_stream) {
+                                     const double *cand_centers, const double *cand_radius, int O, int Md, const double *dyn_state,
+                                     const double *dyn_radius, const double *dyn_lin_vel, const double *dyn_ang_vel, int Od, int use_tracks,
+                                     double track_dt, int literal_heading, double sensor_radius, int literal, double inflation, double pad_x,
+                                     double pad_y, double *applied_log, int32_t *iters_log, int32_t *status_log, int32_t *count_log,
+                                     int32_t *dyn_count_log, int32_t *active, double goal_radius, double agent_radius, void *cuda_stream) {
     if (!h) return fail(NULL, KMPC_E_BADARG, "kmpc_environment_loop: NULL handle%s", "");
-    if (B < 0 || B > h->cfg.B_max || steps < 0 || M < 0) return fail(h, KMPC_E_BADARG, "kmpc_environment_loop: bad B, steps or M%s", "");
-    if (O < 1 || O > h->cfg.O_max || O > KMPC_SEL_MAX_O) return fail(h, KMPC_E_BADARG, "kmpc_environment_loop: need 1 <= O <= min(O_max, 32)%s", "");
+    if (B < 0 || B > h->cfg.B_max || steps < 0 || M < 0 || Md < 0) return fail(h, KMPC_E_BADARG, "kmpc_environment_loop: bad B, steps, M or Md%s", "");
+    if (O < 0 || Od < 0 || O + Od < 1 || O + Od > h->cfg.O_max || O > KMPC_SEL_MAX_O || Od > KMPC_SEL_MAX_O)
+        return fail(h, KMPC_E_BADARG, "kmpc_environment_loop: need 1 <= O + Od <= O_max, each <= 32%s", "");
     if (B == 0 || steps == 0) return 0;
-    if (!x_cur || !goal || !X || !U || (M > 0 && (!cand_centers || !cand_radius))) return fail(h, KMPC_E_BADARG, "kmpc_environment_loop: NULL required pointer%s", "");
-    CU(cudaSetDevice(h->device));
-    if (!h->env_obs) CU(cudaMalloc(&h->env_obs, (size_t)h->cols * h->cfg.O_max * 2 * sizeof(double)));
+    if (!x_cur || !goal || !X || !U || (M > 0 && O > 0 && (!cand_centers || !cand_radius)) ||
+        (Md > 0 && Od > 0 && (!dyn_state || !dyn_radius)) || (use_tracks && Md > 0 && Od > 0 && (!dyn_lin_vel || !dyn_ang_vel)))
+        return fail(h, KMPC_E_BADARG, "kmpc_environment_loop: NULL required pointer%s", "");
+    KMPC_ON_DEVICE(h);
+    const int Ot = O + Od, N = h->cfg.N;
+    const bool tracks = use_tracks && Od > 0;
+    if (!h->env_rad) {   // kept circles of every agent: centres (or N-column tracks), radii, the dynamic candidates' indices
+        double *eo = NULL, *er = NULL; int32_t *ei = NULL;
+        cudaError_t e = cudaMalloc(&eo, (size_t)h->cols * h->cfg.O_max * 2 * sizeof(double) * (size_t)(N + 1));
+        if (e == cudaSuccess) e = cudaMalloc(&er, (size_t)h->cols * h->cfg.O_max * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&ei, (size_t)h->cols * h->cfg.O_max * sizeof(int32_t));
+        if (e != cudaSuccess) { cudaFree(eo); cudaFree(er); cudaFree(ei); CU(e); }
+        h->env_obs = eo; h->env_rad = er; h->env_idx = ei;
+    }
+    double *cen = h->env_obs;                                          // [B][Ot][2] current centres
+    double *trk = h->env_obs + (size_t)h->cols * h->cfg.O_max * 2;      // [B][Ot][N][2] tracks (use_tracks)
     cudaStream_t st = (cudaStream_t)cuda_stream;
     for (int s = 0; s < steps; ++s) {
-        // ROSEnvironment.step (environment.py:39-80): sensor filter -> EgoAgent.step (solve + hand-off) -> at-goal test
-        kmpc_select_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, M, h->cfg.layout, x_cur, cand_centers, cand_radius, sensor_radius, literal, O,
-                                                           pad_x, pad_y, h->env_obs, count_log ? count_log + (size_t)s * B : NULL, NULL);
-        CU(cudaGetLastError());
-        h->launches++;
-        int rc = solve_impl(h, B, x_cur, goal, X, U, h->env_obs, O, 0, obs_radius, inflation, X, U, NULL,
-                            status_log ? status_log + (size_t)s * B : NULL, iters_log ? iters_log + (size_t)s * B : NULL, active, cuda_stream);
+        // ROSEnvironment.step (environment.py:39-80): sensor filters (static, then dynamic) -> EgoAgent.step (solve + hand-off) -> at-goal test
+        if (O > 0) {
+            kmpc_select_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, M, h->cfg.layout, x_cur, cand_centers, 2, cand_radius, sensor_radius, literal, O, Ot, 0,
+                                                               pad_x, pad_y, cen, count_log ? count_log + (size_t)s * B : NULL, NULL, h->env_rad);
+            CU(cudaGetLastError());
+            h->launches++;
+        }
+        if (Od > 0) {   // dynamic obstacles are filtered by where they are now (dynamic_obstacle.py: the centre of their Circle)
+            kmpc_select_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, Md, h->cfg.layout, x_cur, dyn_state, 3, dyn_radius, sensor_radius, literal, Od, Ot, O,
+                                                               pad_x, pad_y, cen, dyn_count_log ? dyn_count_log + (size_t)s * B : NULL, h->env_idx, h->env_rad);
+            CU(cudaGetLastError());
+            h->launches++;
+        }
+        const double *obs = cen;
+        if (tracks) {
+            // static slots: N equal columns; dynamic slots: the constant-velocity prediction of the kept obstacle (dynamic_obstacle.py:20-37)
+            if (O > 0) {
+                kmpc_repeat_kernel<<<(unsigned)(((size_t)B * O + 127) / 128), 128, 0, st>>>(B, O, Ot, N, h->cfg.layout, cen, trk);
+                h->launches++;
+            }
+            kmpc_predict_kernel<<<(unsigned)(((size_t)B * Od + 127) / 128), 128, 0, st>>>(B, Od, Ot, O, Md, N, h->cfg.layout, h->env_idx, dyn_state,
+                                                                                         dyn_lin_vel, dyn_ang_vel, track_dt, literal_heading, pad_x, pad_y, trk);
+            CU(cudaGetLastError());
+            h->launches++;
+            obs = trk;
+        }
+        int rc = solve_impl(h, B, solve_args(x_cur, goal, X, U, obs, Ot, tracks ? 1 : 0, 0.0, h->env_rad, inflation, X, U, NULL,
+                                             status_log ? status_log + (size_t)s * B : NULL, iters_log ? iters_log + (size_t)s * B : NULL, active),
+                            cuda_stream);
         if (rc) return rc;
         kmpc_handoff_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, h->cfg.N, h->cfg.layout, X, U, x_cur,
                                                             applied_log ? applied_log + (size_t)s * B * 2 : NULL, goal, active, goal_radius, agent_radius);
@@ -898,13 +1108,13 @@ extern "C" int kmpc_set_timing(kmpc_handle *h, int enable) {
 extern "C" int kmpc_get_stats(kmpc_handle *h, kmpc_stats *out) {
     if (!h || !out) return KMPC_E_BADARG;
     out->last_kernel_ms = h->last_ms; out->launches = h->launches; out->slots = h->cols; out->blocks = h->last_host_trips;
-    out->threads_per_block = KMPC_TPB; out->sm_count = h->sm_count; out->trips = h->last_trips;
+    out->threads_per_block = KMPC_TPB; out->sm_count = h->sm_count; out->trips = h->last_trips; out->warp_path = h->last_path;
     return 0;
 }
 
 extern "C" int kmpc_measure_fp64_peak(kmpc_handle *h, double *tflops_out) {
     if (!h || !tflops_out) return KMPC_E_BADARG;
-    CU(cudaSetDevice(h->device));
+    KMPC_ON_DEVICE(h);
     const int blocks = h->sm_count * 8, tpb = 256, iters = 4096;
     double *buf = NULL;
     CU(cudaMalloc(&buf, (size_t)blocks * tpb * sizeof(double)));

@@ -112,7 +112,7 @@ KMPC_HD Rows make_rows(int N, int O, int stagewise = 0) {
     L.rCsoc = r; r += 3 * (N + 1);
     L.rDsoc = r; r += NO;
     L.rFilt = r; r += 2 * K_FILTER_CAP;
-    L.rSc = r; r += 6 + 2 * O * (stagewise ? N : 1);   // x_cur, goal, circle centres (per obstacle, or per obstacle and stage)
+    L.rSc = r; r += 6 + 2 * O * (stagewise ? N : 1) + O;   // x_cur, goal, circle centres (per obstacle, or per obstacle and stage), radii
     L.rCtx = r; r += KMPC_NCTX;
     L.total = r;
     return L;
@@ -134,6 +134,7 @@ struct Cfg {
 // I/O pointers (device memory owned by the caller)
 struct IO {
     const double *x_cur, *goal, *X0, *U0, *obs;
+    const double *orad;     // per-slot obstacle radii [B][O] / [O][B] (optimizer.py:231-250: one radius per obstacle class); NULL: Cfg::obs_radius
     double *X_out, *U_out, *obj;
     int32_t *status, *iters;
     double *wscratch;       // warp solver: global scratch, WLay::GPRIV doubles per resident warp (owned by the handle)
@@ -185,6 +186,9 @@ KMPC_HD size_t io_obs_sw(const Cfg &c, int b, int o, int t, int j) {
 }
 // row (within the scalar rows of the thread solver's workspace) of coordinate j of obstacle o's centre at stage k >= 1
 #define CEN_ROW(o, k, j) (6 + 2 * (c.obs_sw ? (o) * c.N + ((k) - 1) : (o)) + (j))
+// row of obstacle o's radius (behind the centres)
+#define RAD_ROW(o) (6 + 2 * c.O * (c.obs_sw ? c.N : 1) + (o))
+KMPC_HD size_t io_orad(const Cfg &c, int b, int o) { return c.layout ? (size_t)o * c.B + b : (size_t)b * c.O + o; }
 
 // cost gradient of v (scaled) and its second derivative; optimizer.py:91-96 (literal) / README.md:23-24
 KMPC_HD void vcost(const Cfg &c, double df, double v, double *g, double *h) {
@@ -375,6 +379,7 @@ KMPC_HDN inline void pass_init(const Cfg &c, Ctx &t, double *wsp, size_t S, cons
     } else {
         for (int o = 0; o < O; ++o) for (int j = 0; j < 2; ++j) FD(sc, 6 + 2 * o + j) = io.obs[io_obs(c, b, o, j)];
     }
+    for (int o = 0; o < O; ++o) FD(sc, RAD_ROW(o)) = io.orad ? io.orad[io_orad(c, b, o)] : c.obs_radius;
     double gm = 0.0;
     const double dLpush = c.dL + K_BOUND_PUSH * fmax(1.0, fabs(c.dL));
     double *ps = wsp + (size_t)L.rState[0] * S;
@@ -409,7 +414,7 @@ KMPC_HDN inline void pass_init(const Cfg &c, Ctx &t, double *wsp, size_t S, cons
         if (k >= 1)
             for (int o = 0; o < O; ++o, po += (size_t)3 * S) {
                 const double ex = x[0] - FD(sc, CEN_ROW(o, k, 0)), ey = x[1] - FD(sc, CEN_ROW(o, k, 1));
-                const double d = sqrt(ex * ex + ey * ey) - c.obs_radius;
+                const double d = sqrt(ex * ex + ey * ey) - FD(sc, RAD_ROW(o));
                 FD(po, 0) = fmax(d, dLpush); FD(po, 1) = 0.0; FD(po, 2) = 1.0;
             }
     }
@@ -425,7 +430,7 @@ KMPC_HDN inline void pass_init(const Cfg &c, Ctx &t, double *wsp, size_t S, cons
 
 // per-(stage, obstacle) quantities shared by the sweep and the roll-out
 struct ObsT { double nx, ny, rr, Ds, bd, bs; };
-KMPC_HD ObsT obs_terms(const Cfg &c, double px, double py, double cx, double cy, double s, double yd, double vL,
+KMPC_HD ObsT obs_terms(const Cfg &c, double px, double py, double cx, double cy, double rad, double s, double yd, double vL,
                        double mu, double delta, bool lsq, bool soc, double dsoc) {
     ObsT r;
     const double ex = px - cx, ey = py - cy;
@@ -436,7 +441,7 @@ KMPC_HD ObsT obs_terms(const Cfg &c, double px, double py, double cx, double cy,
         const double sl = s - c.dL;
         r.Ds = vL / sl + delta;
         r.bs = yd + mu / sl - K_KAPPA_D * mu;
-        r.bd = soc ? -dsoc : -((r.rr - c.obs_radius) - s);
+        r.bd = soc ? -dsoc : -((r.rr - rad) - s);
     }
     return r;
 }
@@ -496,7 +501,7 @@ KMPC_HDN inline bool pass_sweep(const Cfg &c, const Ctx &t, double *wsp, size_t 
             for (int o = O - 1; o >= 0; --o) {
                 po -= (size_t)3 * S; pds -= S;
                 const double yd = FD(po, 1);
-                ObsT ot = obs_terms(c, x0, x1, FD(sc, CEN_ROW(o, k, 0)), FD(sc, CEN_ROW(o, k, 1)), FD(po, 0), yd, FD(po, 2), mu, delta, lsq,
+                ObsT ot = obs_terms(c, x0, x1, FD(sc, CEN_ROW(o, k, 0)), FD(sc, CEN_ROW(o, k, 1)), FD(sc, RAD_ROW(o)), FD(po, 0), yd, FD(po, 2), mu, delta, lsq,
                                     soc, soc ? FD(pds, 0) : 0.0);
                 if (!lsq) {
                     const double h = yd / ot.rr;
@@ -610,7 +615,7 @@ KMPC_HDN inline void pass_rollout(const Cfg &c, const Ctx &t, double *wsp, size_
 #pragma unroll 1
             for (int o = 0; o < O; ++o, po += (size_t)3 * S, pdo += (size_t)2 * S, pds += S) {
                 const double s = FD(po, 0), yd = FD(po, 1), vL = FD(po, 2);
-                ObsT ot = obs_terms(c, x0, x1, FD(sc, CEN_ROW(o, k, 0)), FD(sc, CEN_ROW(o, k, 1)), s, yd, vL, mu, delta, lsq, soc,
+                ObsT ot = obs_terms(c, x0, x1, FD(sc, CEN_ROW(o, k, 0)), FD(sc, CEN_ROW(o, k, 1)), FD(sc, RAD_ROW(o)), s, yd, vL, mu, delta, lsq, soc,
                                     soc ? FD(pds, 0) : 0.0);
                 const double ds = ot.nx * d0 + ot.ny * d1 - ot.bd;
                 const double dyd = ot.Ds * ds - ot.bs;
@@ -722,7 +727,7 @@ KMPC_HDN inline bool pass_trial(const Cfg &c, const Ctx &t, double *wsp, size_t 
                 const double s = so + alpha * ds;
                 const double ex = x0 - FD(sc, CEN_ROW(o, k, 0)), ey = x1 - FD(sc, CEN_ROW(o, k, 1));
                 const double rr = sqrt(ex * ex + ey * ey), nx = ex / rr, ny = ey / rr;
-                const double dm = (rr - c.obs_radius) - s;
+                const double dm = (rr - FD(sc, RAD_ROW(o))) - s;
                 st.theta += fabs(dm); st.pinf = maxabs_nan(st.pinf, dm);
                 const double slo = so - c.dL, sln = s - c.dL;
                 if (!(sln > 0)) valid = false;
@@ -807,10 +812,10 @@ KMPC_HDN inline void pass_soc_rhs(const Cfg &c, const Ctx &t, double *wsp, size_
             for (int o = 0; o < O; ++o, po += (size_t)3 * S, pto += (size_t)3 * S, pds += S) {
                 const double cx = FD(sc, CEN_ROW(o, k, 0)), cy = FD(sc, CEN_ROW(o, k, 1));
                 double base;
-                if (first) { const double ex = x0 - cx, ey = x1 - cy; base = (sqrt(ex * ex + ey * ey) - c.obs_radius) - FD(po, 0); }
+                if (first) { const double ex = x0 - cx, ey = x1 - cy; base = (sqrt(ex * ex + ey * ey) - FD(sc, RAD_ROW(o))) - FD(po, 0); }
                 else base = FD(pds, 0);
                 const double ex = t0 - cx, ey = t1 - cy;
-                FD(pds, 0) = al * base + ((sqrt(ex * ex + ey * ey) - c.obs_radius) - FD(pto, 0));
+                FD(pds, 0) = al * base + ((sqrt(ex * ex + ey * ey) - FD(sc, RAD_ROW(o))) - FD(pto, 0));
             }
         if (k < N) {
             cp0 = x0 + T * FD(ps, F_V) * FD(ps, F_CS); cp1 = x1 + T * FD(ps, F_V) * FD(ps, F_SN); cp2 = x2 + T * FD(ps, F_OM);

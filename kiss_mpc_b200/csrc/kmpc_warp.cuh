@@ -75,7 +75,7 @@ struct WLay {
     static constexpr int COOP = C_NF * NSTG + 1;
     static constexpr int PRIV = V_NF * NSTG;
     static constexpr int GPRIV = G_NF * NSTG;   // doubles of global scratch per resident warp
-    KMPC_HD static int obs_doubles(int O, int sw = 0) { return O > 0 ? B_NF * O * NSTG + 2 * O * (sw ? NSTG : 1) : 0; }
+    KMPC_HD static int obs_doubles(int O, int sw = 0) { return O > 0 ? B_NF * O * NSTG + 2 * O * (sw ? NSTG : 1) + O : 0; }   // rows, centres, radii
     static size_t bytes(int warps, int O = 0, int sw = 0) { return (size_t)warps * ((COOP + PRIV + obs_doubles(O, sw)) * sizeof(double) + sizeof(WScal)); }
 };
 
@@ -168,17 +168,19 @@ KMPC_W bool wb_trial(double d, double vt, double lb, double ub, bool hL, bool hU
 struct WObsT { double nx, ny, ir, rr, Ds, bd, bs, rsl; };  // unit normal, 1/|p-c|, |p-c|, condensed slack block, rhs terms, 1/(s - I)
 // terms of one (stage, obstacle) row at the current iterate (cf. obs_terms of kmpc_core.cuh); kind: lsq / soc / Newton
 // circle centres seen from stage s of this lane: one (x, y) per obstacle, or the obstacle's own track at that stage
-struct WCen { const double *p; int so, yo; };
+struct WCen { const double *p, *rp; int so, yo; };
 KMPC_W WCen w_cen(const Cfg &c, const double *ob, int O, int NSTG, int s) {
     const double *base = ob + B_NF * O * NSTG;
     WCen r;
     r.p = c.obs_sw ? base + s : base; r.so = c.obs_sw ? NSTG : 2; r.yo = c.obs_sw ? O * NSTG : 1;
+    r.rp = base + 2 * O * (c.obs_sw ? NSTG : 1);   // one radius per obstacle slot (optimizer.py:231-250)
     return r;
 }
 KMPC_W double w_cx(const WCen &cn, int o) { return cn.p[o * cn.so]; }
 KMPC_W double w_cy(const WCen &cn, int o) { return cn.p[o * cn.so + cn.yo]; }
+KMPC_W double w_cr(const WCen &cn, int o) { return cn.rp[o]; }
 
-KMPC_W WObsT w_obs_terms(const Cfg &c, double px, double py, double cx, double cy, double s, double yd, double vL, double mu,
+KMPC_W WObsT w_obs_terms(const Cfg &c, double px, double py, double cx, double cy, double rad, double s, double yd, double vL, double mu,
                          double delta, bool lsq, bool soc, double dsoc) {
     WObsT r;
     const double ex = px - cx, ey = py - cy;
@@ -190,7 +192,7 @@ KMPC_W WObsT w_obs_terms(const Cfg &c, double px, double py, double cx, double c
     else {
         r.Ds = fma(vL, r.rsl, delta);
         r.bs = yd + mu * r.rsl - K_KAPPA_D * mu;
-        r.bd = soc ? -dsoc : -((r.rr - c.obs_radius) - s);
+        r.bd = soc ? -dsoc : -((r.rr - rad) - s);
     }
     return r;
 }
@@ -226,6 +228,8 @@ KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<
         } else {
             for (int i = lane; i < 2 * O; i += 32) cxy[i] = io.obs[io_obs(c, b, i >> 1, i & 1)];
         }
+        double *rad = cxy + 2 * O * (c.obs_sw ? NSTG : 1);
+        for (int o = lane; o < O; o += 32) rad[o] = io.orad ? io.orad[io_orad(c, b, o)] : c.obs_radius;
         w_sync();
     }
     double xc[3], gl[3];
@@ -263,7 +267,7 @@ KMPC_WN inline void w_init(const Cfg &c, WScal *sc, const IO &io, int b, WState<
             const double dLpush = c.dL + K_BOUND_PUSH * fmax(1.0, fabs(c.dL));
             for (int o = 0; o < O; ++o) {
                 const double ex = x[0] - w_cx(cen, o), ey = x[1] - w_cy(cen, o);
-                const double d = sqrt(ex * ex + ey * ey) - c.obs_radius;
+                const double d = sqrt(ex * ex + ey * ey) - w_cr(cen, o);
                 double *po = ob + o * NSTG + s;
                 po[B_S * O * NSTG] = fmax(d, dLpush); po[B_YD * O * NSTG] = 0.0; po[B_VL * O * NSTG] = 1.0;
             }
@@ -335,7 +339,7 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
             for (int o = 0; o < O; ++o) {
                 const double *po = ob + o * NSTG + s;
                 const double yd = po[B_YD * O * NSTG];
-                const WObsT ot = w_obs_terms(c, x0, x1, w_cx(cen, o), w_cy(cen, o), po[B_S * O * NSTG], yd, po[B_VL * O * NSTG], mu, delta,
+                const WObsT ot = w_obs_terms(c, x0, x1, w_cx(cen, o), w_cy(cen, o), w_cr(cen, o), po[B_S * O * NSTG], yd, po[B_VL * O * NSTG], mu, delta,
                                              lsq, soc, soc ? po[B_DSOC * O * NSTG] : 0.0);
                 if (!lsq) {
                     const double h = yd * ot.ir;
@@ -590,7 +594,7 @@ KMPC_WN inline void w_step(const Cfg &c, const WScal *sc, const WState<SPL> &w, 
             for (int o = 0; o < O; ++o) {
                 const double *po = ob + o * NSTG + s;
                 const double vL = po[B_VL * O * NSTG];
-                const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], w_cx(cen, o), w_cy(cen, o), po[B_S * O * NSTG], po[B_YD * O * NSTG], vL, mu,
+                const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], w_cx(cen, o), w_cy(cen, o), w_cr(cen, o), po[B_S * O * NSTG], po[B_YD * O * NSTG], vL, mu,
                                              delta, lsq, soc, soc ? po[B_DSOC * O * NSTG] : 0.0);
                 const double ds = fma(ot.nx, d0, ot.ny * d1) - ot.bd;
                 ym = maxabs_nan(ym, fma(ot.Ds, ds, -ot.bs));
@@ -713,10 +717,10 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
                 double *po = ob + o * NSTG + s;
                 const double so = po[B_S * O * NSTG], ydo = po[B_YD * O * NSTG], vL = po[B_VL * O * NSTG];
                 const double cx = w_cx(cen, o), cy = w_cy(cen, o);
-                const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], cx, cy, so, ydo, vL, mu, delta, lsq, soc, soc ? po[B_DSOC * O * NSTG] : 0.0);
+                const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], cx, cy, w_cr(cen, o), so, ydo, vL, mu, delta, lsq, soc, soc ? po[B_DSOC * O * NSTG] : 0.0);
                 const WObsV tv = w_obs_vals(c, ot, so, ydo, vL, fma(ot.nx, d.dx0[j], ot.ny * d.dx1[j]), mu, alpha, ay, adu, clamp);
                 const double ex = x0 - cx, ey = x1 - cy, rr = sqrt(ex * ex + ey * ey), ir = KRCPF(rr);
-                const double dm = (rr - c.obs_radius) - tv.s;
+                const double dm = (rr - w_cr(cen, o)) - tv.s;
                 po[B_DM * O * NSTG] = dm;
                 st.theta += fabs(dm); st.pinf = maxabs_nan(st.pinf, dm);
                 valid &= tv.sln > 0;
@@ -794,7 +798,7 @@ KMPC_WN inline void w_obs_commit(const Cfg &c, const WState<SPL> &w, const WStep
         for (int o = 0; o < O; ++o) {
             double *po = ob + o * NSTG + s;
             const double so = po[B_S * O * NSTG], ydo = po[B_YD * O * NSTG], vL = po[B_VL * O * NSTG];
-            const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], w_cx(cen, o), w_cy(cen, o), so, ydo, vL, mu, delta, lsq, soc,
+            const WObsT ot = w_obs_terms(c, w.x0[j], w.x1[j], w_cx(cen, o), w_cy(cen, o), w_cr(cen, o), so, ydo, vL, mu, delta, lsq, soc,
                                          soc ? po[B_DSOC * O * NSTG] : 0.0);
             const WObsV tv = w_obs_vals(c, ot, so, ydo, vL, fma(ot.nx, d.dx0[j], ot.ny * d.dx1[j]), mu, alpha, ay, adu, clamp);
             po[B_S * O * NSTG] = tv.s; po[B_YD * O * NSTG] = tv.yd; po[B_VL * O * NSTG] = tv.z;
@@ -828,7 +832,7 @@ KMPC_WN inline void w_soc_rhs(const Cfg &c, const WScal *sc, const WState<SPL> &
             for (int o = 0; o < O; ++o) {
                 double *po = ob + o * NSTG + s;
                 double base;
-                if (first) { const double ex = w.x0[j] - w_cx(cen, o), ey = w.x1[j] - w_cy(cen, o); base = (sqrt(ex * ex + ey * ey) - c.obs_radius) - po[B_S * O * NSTG]; }
+                if (first) { const double ex = w.x0[j] - w_cx(cen, o), ey = w.x1[j] - w_cy(cen, o); base = (sqrt(ex * ex + ey * ey) - w_cr(cen, o)) - po[B_S * O * NSTG]; }
                 else base = po[B_DSOC * O * NSTG];
                 po[B_DSOC * O * NSTG] = al * base + po[B_DM * O * NSTG];
             }

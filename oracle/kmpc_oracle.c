@@ -47,7 +47,7 @@
 #include <omp.h>
 #endif
 
-#define KMO_VERSION 100
+#define KMO_VERSION 200
 
 /* ---- IPOPT 3.14 defaults (+ the four options optimizer.py:344-352 sets) ---- */
 #define BOUND_RELAX 1e-8
@@ -140,6 +140,7 @@ typedef struct {
     /* problem data */
     double xcur[3], goal[3], df;
     double *obs; /* [O][2], or [O][N][2] when the centres move with the stage */
+    double *orad; /* [O] radius subtracted in every row of obstacle o (optimizer.py:231-250: one radius per obstacle class) */
     int obs_sw;
     double *lb, *ub;
     int *hasL, *hasU;
@@ -175,7 +176,7 @@ static work_t *work_new(const kmo_config *cf) {
     w->linsolve = cf->linsolve;
     int n = w->n, ns = w->ns, mc = w->mc;
 #define D(name, cnt) w->name = (double *)xcalloc((cnt), sizeof(double))
-    w->obs_sw = cf->obs_stagewise != 0; D(obs, 2 * O * (w->obs_sw ? N : 1)); D(lb, n); D(ub, n);
+    w->obs_sw = cf->obs_stagewise != 0; D(obs, 2 * O * (w->obs_sw ? N : 1)); D(orad, O); D(lb, n); D(ub, n);
     w->hasL = (int *)xcalloc(n, sizeof(int)); w->hasU = (int *)xcalloc(n, sizeof(int));
     D(w, n); D(s, ns); D(yc, mc); D(yd, ns); D(zL, n); D(zU, n); D(vL, ns);
     D(g, n); D(c, mc); D(dms, ns); D(cs, N + 1); D(sn, N + 1); D(nrm, 2 * ns); D(dist, ns);
@@ -194,7 +195,7 @@ static work_t *work_new(const kmo_config *cf) {
 }
 
 static void work_free(work_t *w) {
-    double **ptrs[] = {&w->obs, &w->lb, &w->ub, &w->w, &w->s, &w->yc, &w->yd, &w->zL, &w->zU, &w->vL, &w->g, &w->c,
+    double **ptrs[] = {&w->obs, &w->orad, &w->lb, &w->ub, &w->w, &w->s, &w->yc, &w->yd, &w->zL, &w->zU, &w->vL, &w->g, &w->c,
         &w->dms, &w->cs, &w->sn, &w->nrm, &w->dist, &w->Wxx, &w->Wtv, &w->Wvv, &w->Www, &w->Dx, &w->Ds, &w->bx,
         &w->bs, &w->bc, &w->bd, &w->dx, &w->ds, &w->dyc, &w->dyd, &w->dzL, &w->dzU, &w->dvL, &w->dx2, &w->ds2,
         &w->dyc2, &w->dyd2, &w->csoc, &w->dsoc, &w->wt, &w->st, &w->ct, &w->dmst, &w->K, &w->L, &w->rhs, &w->Kg,
@@ -262,7 +263,7 @@ static void eval_d(const kmo_config *cf, const work_t *wk, const double *w, doub
             const double *cc = wk->obs + (wk->obs_sw ? 2 * ((size_t)o * N + (k - 1)) : 2 * (size_t)o);
             double ex = w[IX(k, 0)] - cc[0], ey = w[IX(k, 1)] - cc[1];
             double r = sqrt(ex * ex + ey * ey);
-            d[IS(o, k)] = r - cf->obs_radius;
+            d[IS(o, k)] = r - wk->orad[o];
             if (nrm) { nrm[2 * IS(o, k)] = ex / r; nrm[2 * IS(o, k) + 1] = ey / r; dist[IS(o, k)] = r; }
         }
 }
@@ -728,11 +729,12 @@ typedef struct {
 } trace_t;
 
 static void solve_one(const kmo_config *cf, work_t *wk, const double *xcur, const double *goal, const double *X0,
-                      const double *U0, const double *obs, double *Xout, double *Uout, double *duals_out,
+                      const double *U0, const double *obs, const double *orad, double *Xout, double *Uout, double *duals_out,
                       double *obj, int32_t *status, int32_t *iters, kmo_diag *dg, trace_t *tr) {
     int N = wk->N, O = wk->O, n = wk->n, ns = wk->ns, mc = wk->mc;
     memcpy(wk->xcur, xcur, 3 * sizeof(double)); memcpy(wk->goal, goal, 3 * sizeof(double));
     if (O) memcpy(wk->obs, obs, sizeof(double) * 2 * O * (wk->obs_sw ? N : 1));
+    for (int o = 0; o < O; ++o) wk->orad[o] = orad ? orad[o] : cf->obs_radius;
     kmo_diag dloc; memset(&dloc, 0, sizeof dloc);
 
     /* bounds, relaxed (optimizer.py:111-156 + IPOPT bound_relax_factor) */
@@ -966,9 +968,10 @@ int kmo_duals_len(const kmo_config *cf) { int N = cf->N, O = cf->O; return 3 * (
 
 /* Layouts (row-major, per-instance contiguous = numpy C order):
  *   x_cur[B][3], goal[B][3], X0[B][3][N+1] or NULL, U0[B][2][N] or NULL, obs[B][O][2] (obs_stagewise: [B][O][N][2]) or NULL,
+ *   obs_rad[B][O] or NULL (NULL: cf->obs_radius for every obstacle),
  *   X_out[B][3][N+1], U_out[B][2][N], obj[B], status[B], iters[B], duals[B][kmo_duals_len] or NULL, diag[B] or NULL */
 int kmo_solve(const kmo_config *cf, int B, const double *x_cur, const double *goal, const double *X0, const double *U0,
-              const double *obs, double *X_out, double *U_out, double *obj, int32_t *status, int32_t *iters,
+              const double *obs, const double *obs_rad, double *X_out, double *U_out, double *obj, int32_t *status, int32_t *iters,
               double *duals, kmo_diag *diag, int nthreads) {
     if (!cf || cf->N < 1 || cf->O < 0 || B < 0) return -1;
     if (cf->O > 0 && !obs) return -1;
@@ -985,7 +988,7 @@ int kmo_solve(const kmo_config *cf, int B, const double *x_cur, const double *go
         for (int b = 0; b < B; ++b) {
             solve_one(cf, wk, x_cur + 3 * (size_t)b, goal + 3 * (size_t)b, X0 ? X0 + (size_t)b * 3 * (N + 1) : NULL,
                       U0 ? U0 + (size_t)b * 2 * N : NULL, O ? obs + (size_t)b * 2 * O * (cf->obs_stagewise ? N : 1) : NULL,
-                      X_out + (size_t)b * 3 * (N + 1), U_out + (size_t)b * 2 * N, duals ? duals + (size_t)b * dl : NULL,
+                      (O && obs_rad) ? obs_rad + (size_t)b * O : NULL, X_out + (size_t)b * 3 * (N + 1), U_out + (size_t)b * 2 * N, duals ? duals + (size_t)b * dl : NULL,
                       obj + b, status + b, iters + b, diag ? diag + b : NULL, NULL);
         }
         work_free(wk);
@@ -995,12 +998,12 @@ int kmo_solve(const kmo_config *cf, int B, const double *x_cur, const double *go
 
 /* single instance with a per-iteration trace: rows[cap][8] = mu, alpha_pr, alpha_du, delta_w, theta, phi, E0, f */
 int kmo_solve_trace(const kmo_config *cf, const double *x_cur, const double *goal, const double *X0, const double *U0,
-                    const double *obs, double *X_out, double *U_out, double *obj, int32_t *status, int32_t *iters,
+                    const double *obs, const double *obs_rad, double *X_out, double *U_out, double *obj, int32_t *status, int32_t *iters,
                     double *rows, int cap, int32_t *len) {
     if (!cf || cf->N < 1) return -1;
     work_t *wk = work_new(cf);
     trace_t tr = {cap, 0, rows};
-    solve_one(cf, wk, x_cur, goal, X0, U0, obs, X_out, U_out, NULL, obj, status, iters, NULL, &tr);
+    solve_one(cf, wk, x_cur, goal, X0, U0, obs, obs_rad, X_out, U_out, NULL, obj, status, iters, NULL, &tr);
     *len = tr.len;
     work_free(wk);
     return 0;

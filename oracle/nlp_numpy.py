@@ -18,7 +18,7 @@ import numpy as np
 
 
 class NLP:
-    def __init__(self, cfg, x_cur, goal, obs=None):
+    def __init__(self, cfg, x_cur, goal, obs=None, obs_rad=None):
         self.cfg = cfg
         self.N = N = int(cfg.N)
         self.O = int(cfg.O)
@@ -30,6 +30,8 @@ class NLP:
         # own track, column t paired with X_{t+1} (dynamic_obstacle.py:47-56), when obs has a stage axis
         obs = None if not self.O else np.asarray(obs, float)
         self.obs = obs
+        # radius per obstacle (optimizer.py:231-250: one per obstacle class); default: cfg.obs_radius for all
+        self.rad = np.full(self.O, float(cfg.obs_radius)) if obs_rad is None else np.broadcast_to(np.asarray(obs_rad, float), (self.O,)).copy()
         if obs is not None:
             self.cen = obs.reshape(self.O, N, 2) if obs.ndim == 3 else np.repeat(obs.reshape(self.O, 1, 2), N, axis=1)
         self.n = 5 * N + 3
@@ -104,7 +106,7 @@ class NLP:
             return np.zeros(0)
         X, _ = self.unpack(z)
         diff = X[None, :2, 1:] - self.cen.transpose(0, 2, 1)
-        return (np.sqrt((diff ** 2).sum(1)) - self.cfg.obs_radius).reshape(-1)
+        return (np.sqrt((diff ** 2).sum(1)) - self.rad[:, None]).reshape(-1)
 
     def jac_d(self, z):
         N, O = self.N, self.O
@@ -200,3 +202,47 @@ def slsqp_polish(nlp: NLP, X, U, maxiter=200):
                  options={"maxiter": maxiter, "ftol": 1e-15})
     Xp, Up = nlp.unpack(r.x)
     return Xp.copy(), Up.copy(), float(r.fun)
+
+
+def dual_certificate(nlp: NLP, X, U, yc, zL, zU, df, inflation=None, yd=None, vL=None, relax=1e-8):
+    """First-order certificate of a returned primal-dual point on the UNSCALED problem: the oracle's multipliers belong to the
+    objective-scaled problem (factor df), so they are divided by df here.  Complementarity is measured against the bounds IPOPT
+    works with (relaxed by bound_relax_factor = 1e-8 max(1, |b|)).  Returns dict(stationarity, primal, complementarity,
+    bound_violation, dual_sign) -- all infinity norms."""
+    z = nlp.pack(X, U)
+    lo_r = nlp.lo - relax * np.maximum(1.0, np.abs(np.where(np.isfinite(nlp.lo), nlp.lo, 0.0)))
+    hi_r = nlp.hi + relax * np.maximum(1.0, np.abs(np.where(np.isfinite(nlp.hi), nlp.hi, 0.0)))
+    r = nlp.grad(z) + (nlp.jac_c(z).T @ yc - zL + zU) / df
+    comp = 0.0
+    if nlp.O:
+        r = r + nlp.jac_d(z).T @ yd / df
+        I = nlp.cfg.inflation if inflation is None else inflation
+        I_r = I - relax * max(1.0, abs(I))
+        comp = float(np.max(np.abs((nlp.d(z) - I_r) * vL))) / df
+    fl, fu = np.isfinite(nlp.lo), np.isfinite(nlp.hi)
+    comp = max(comp, float(np.max(np.abs((z - lo_r)[fl] * zL[fl]), initial=0.0)) / df, float(np.max(np.abs((hi_r - z)[fu] * zU[fu]), initial=0.0)) / df)
+    return {"stationarity": float(np.max(np.abs(r))), "primal": float(np.max(np.abs(nlp.c(z)))), "complementarity": comp,
+            "bound_violation": float(max(0.0, np.max(nlp.lo - z), np.max(z - nlp.hi))),
+            "dual_sign": float(max(0.0, -min(zL.min(), zU.min())))}
+
+
+def reduced_hessian_min_eig(nlp: NLP, X, U, yc, df, yd=None, act_tol=1e-6, inflation=None):
+    """Second-order sufficiency check: smallest eigenvalue of the Hessian of the (unscaled) Lagrangian projected onto the null
+    space of the equality Jacobian and of the active bounds / active obstacle rows.  > 0 at a strict local minimum."""
+    z = nlp.pack(X, U)
+    H = nlp.hess_lag(z, np.asarray(yc) / df, None if yd is None else np.asarray(yd) / df, 1.0)
+    rows = [nlp.jac_c(z)]
+    act = np.where((np.isfinite(nlp.lo) & (z - nlp.lo <= act_tol)) | (np.isfinite(nlp.hi) & (nlp.hi - z <= act_tol)))[0]
+    E = np.zeros((len(act), nlp.n)); E[np.arange(len(act)), act] = 1.0
+    rows.append(E)
+    if nlp.O:
+        I = nlp.cfg.inflation if inflation is None else inflation
+        d = nlp.d(z)
+        rows.append(nlp.jac_d(z)[d - I <= act_tol])
+    A = np.vstack(rows)
+    _, sv, Vt = np.linalg.svd(A, full_matrices=True)
+    rank = int((sv > 1e-10 * sv[0]).sum())
+    Z = Vt[rank:].T
+    if Z.shape[1] == 0:
+        return np.inf
+    return float(np.linalg.eigvalsh(Z.T @ H @ Z).min())

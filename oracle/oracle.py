@@ -108,9 +108,9 @@ def lib():
         L.kmo_duals_len.restype = C.c_int
         L.kmo_duals_len.argtypes = [C.POINTER(_Cfg)]
         L.kmo_solve.restype = C.c_int
-        L.kmo_solve.argtypes = [C.POINTER(_Cfg), C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, ip, ip, dp, C.c_void_p, C.c_int]
+        L.kmo_solve.argtypes = [C.POINTER(_Cfg), C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, dp, ip, ip, dp, C.c_void_p, C.c_int]
         L.kmo_solve_trace.restype = C.c_int
-        L.kmo_solve_trace.argtypes = [C.POINTER(_Cfg), dp, dp, dp, dp, dp, dp, dp, dp, ip, ip, dp, C.c_int, ip]
+        L.kmo_solve_trace.argtypes = [C.POINTER(_Cfg), dp, dp, dp, dp, dp, dp, dp, dp, dp, ip, ip, dp, C.c_int, ip]
         _lib = L
     return _lib
 
@@ -131,9 +131,10 @@ class OracleResult:
     meta: dict = field(default_factory=dict)
 
 
-def solve(cfg: OracleConfig, x_cur, goal, X0=None, U0=None, obs=None, want_duals=False, nthreads=0) -> OracleResult:
+def solve(cfg: OracleConfig, x_cur, goal, X0=None, U0=None, obs=None, want_duals=False, nthreads=0, obs_rad=None) -> OracleResult:
     """Solve B independent instances.  x_cur,goal: [B,3]; X0: [B,3,N+1]; U0: [B,2,N]; obs: [B,O,2], or [B,O,N,2] with
-    cfg.obs_stagewise (column t of an obstacle's track is paired with X_{t+1}, dynamic_obstacle.py:47-56)."""
+    cfg.obs_stagewise (column t of an obstacle's track is paired with X_{t+1}, dynamic_obstacle.py:47-56); obs_rad: [B,O] radius per
+    obstacle (optimizer.py:231-250 keeps one per obstacle class; None: cfg.obs_radius for all)."""
     L = lib()
     c = cfg.to_c()
     x_cur = np.ascontiguousarray(np.atleast_2d(x_cur), dtype=np.float64)
@@ -144,19 +145,20 @@ def solve(cfg: OracleConfig, x_cur, goal, X0=None, U0=None, obs=None, want_duals
     U0 = None if U0 is None else np.ascontiguousarray(U0, dtype=np.float64).reshape(B, 2, N)
     if O:
         obs = np.ascontiguousarray(obs, dtype=np.float64).reshape((B, O, N, 2) if cfg.obs_stagewise else (B, O, 2))
+    obs_rad = None if (not O or obs_rad is None) else np.ascontiguousarray(np.broadcast_to(np.asarray(obs_rad, dtype=np.float64), (B, O)))
     X = np.empty((B, 3, N + 1)); U = np.empty((B, 2, N)); obj = np.empty(B)
     status = np.empty(B, np.int32); iters = np.empty(B, np.int32)
     diag = np.zeros(B, DIAG_DTYPE)
     dl = L.kmo_duals_len(C.byref(c))
     duals = np.empty((B, dl)) if want_duals else None
-    rc = L.kmo_solve(C.byref(c), B, _p(x_cur), _p(goal), _p(X0), _p(U0), _p(obs) if O else None, _p(X), _p(U), _p(obj),
+    rc = L.kmo_solve(C.byref(c), B, _p(x_cur), _p(goal), _p(X0), _p(U0), _p(obs) if O else None, _p(obs_rad), _p(X), _p(U), _p(obj),
                      _p(status, C.c_int32), _p(iters, C.c_int32), _p(duals), diag.ctypes.data_as(C.c_void_p), int(nthreads))
     if rc != 0:
         raise ValueError(f"kmo_solve rejected its arguments (rc={rc})")
     return OracleResult(X, U, obj, status, iters, diag, duals, {"df": diag["obj_scaling"].copy()})
 
 
-def solve_trace(cfg: OracleConfig, x_cur, goal, X0=None, U0=None, obs=None, cap=2048):
+def solve_trace(cfg: OracleConfig, x_cur, goal, X0=None, U0=None, obs=None, cap=2048, obs_rad=None):
     """Single instance; returns (X,U,obj,status,iters, trace[len,8]) with rows mu,alpha_pr,alpha_du,delta_w,theta,phi,E0,f."""
     L = lib(); c = cfg.to_c(); N = cfg.N
     x_cur = np.ascontiguousarray(x_cur, dtype=np.float64).reshape(3); goal = np.ascontiguousarray(goal, dtype=np.float64).reshape(3)
@@ -165,7 +167,8 @@ def solve_trace(cfg: OracleConfig, x_cur, goal, X0=None, U0=None, obs=None, cap=
     obs = None if not cfg.O else np.ascontiguousarray(obs, dtype=np.float64).reshape((cfg.O, N, 2) if cfg.obs_stagewise else (cfg.O, 2))
     X = np.empty((3, N + 1)); U = np.empty((2, N)); obj = np.empty(1); st = np.empty(1, np.int32); it = np.empty(1, np.int32)
     rows = np.zeros((cap, 8)); ln = np.zeros(1, np.int32)
-    rc = L.kmo_solve_trace(C.byref(c), _p(x_cur), _p(goal), _p(X0), _p(U0), _p(obs), _p(X), _p(U), _p(obj),
+    obs_rad = None if (not cfg.O or obs_rad is None) else np.ascontiguousarray(np.broadcast_to(np.asarray(obs_rad, dtype=np.float64), (cfg.O,)))
+    rc = L.kmo_solve_trace(C.byref(c), _p(x_cur), _p(goal), _p(X0), _p(U0), _p(obs), _p(obs_rad), _p(X), _p(U), _p(obj),
                            _p(st, C.c_int32), _p(it, C.c_int32), _p(rows), cap, _p(ln, C.c_int32))
     if rc != 0:
         raise ValueError("kmo_solve_trace rejected its arguments")

@@ -44,11 +44,11 @@ def cfg_from_oracle(ocfg, B_max=1, layout=0):
     return c
 
 
-def solve(ocfg, x_cur, goal, X0=None, U0=None, obs=None, layout=0, warp=False):
+def solve(ocfg, x_cur, goal, X0=None, U0=None, obs=None, layout=0, warp=False, obs_rad=None):
     L = C.CDLL(build())
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
     L.emul_solve.restype = C.c_int
-    L.emul_solve.argtypes = [C.POINTER(KmpcConfig), C.c_int, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp,
+    L.emul_solve.argtypes = [C.POINTER(KmpcConfig), C.c_int, dp, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp,
                              dp, ip, ip, ip]
     x_cur = np.ascontiguousarray(x_cur, float); goal = np.ascontiguousarray(goal, float)
     B, N, O = x_cur.shape[0], ocfg.N, ocfg.O
@@ -63,17 +63,18 @@ def solve(ocfg, x_cur, goal, X0=None, U0=None, obs=None, layout=0, warp=False):
 
     xi, gi = tr_in(x_cur, (3,)), tr_in(goal, (3,))
     X0i, U0i, obi = tr_in(X0, (3, N + 1)), tr_in(U0, (2, N)), tr_in(obs if O else None, (O, N, 2) if sw else (O, 2))
+    ori = tr_in(None if (obs_rad is None or not O) else np.broadcast_to(np.asarray(obs_rad, float), (B, O)), (O,))
     Xo = np.full((3, N + 1, B) if layout else (B, 3, N + 1), np.nan); Uo = np.full((2, N, B) if layout else (B, 2, N), np.nan)
     obj = np.empty(B); st = np.empty(B, np.int32); it = np.empty(B, np.int32); tp = np.empty(B, np.int32)
     p = lambda a, t=C.c_double: None if a is None else a.ctypes.data_as(C.POINTER(t))
     if warp:
         L.emul_solve_warp.restype = C.c_int
-        L.emul_solve_warp.argtypes = [C.POINTER(KmpcConfig), C.c_int, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp,
+        L.emul_solve_warp.argtypes = [C.POINTER(KmpcConfig), C.c_int, dp, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp,
                                       dp, ip, ip, ip]
-        rc = L.emul_solve_warp(C.byref(c), B, p(xi), p(gi), p(X0i), p(U0i), p(obi), O, sw, ocfg.obs_radius, ocfg.inflation, p(Xo), p(Uo),
+        rc = L.emul_solve_warp(C.byref(c), B, p(xi), p(gi), p(X0i), p(U0i), p(obi), p(ori), O, sw, ocfg.obs_radius, ocfg.inflation, p(Xo), p(Uo),
                                p(obj), p(st, C.c_int32), p(it, C.c_int32), p(tp, C.c_int32))
     else:
-        rc = L.emul_solve(C.byref(c), B, p(xi), p(gi), p(X0i), p(U0i), p(obi), O, sw, ocfg.obs_radius, ocfg.inflation, p(Xo), p(Uo),
+        rc = L.emul_solve(C.byref(c), B, p(xi), p(gi), p(X0i), p(U0i), p(obi), p(ori), O, sw, ocfg.obs_radius, ocfg.inflation, p(Xo), p(Uo),
                           p(obj), p(st, C.c_int32), p(it, C.c_int32), p(tp, C.c_int32))
     assert rc == 0
     if layout:

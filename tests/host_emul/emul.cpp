@@ -64,11 +64,12 @@ static Cfg make_cfg(const kmpc_config *cf, int B, int O, int stagewise, double o
 }
 
 extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, const double *goal, const double *X0,
-                          const double *U0, const double *obs, int O, int stagewise, double obs_radius, double inflation, double *X_out,
+                          const double *U0, const double *obs, const double *obs_rad, int O, int stagewise, double obs_radius, double inflation, double *X_out,
                           double *U_out, double *obj, int32_t *status, int32_t *iters, int32_t *trips) {
     Cfg c = make_cfg(cf, B, O, stagewise, obs_radius, inflation);
     IO io;
-    io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs;
+    memset(&io, 0, sizeof io);
+    io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs; io.orad = O > 0 ? obs_rad : NULL;
     io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL; io.wscratch = NULL; io.order = NULL;
     // Mirrors the launch structure of kmpc.cu on the host: per trip, sweep(LA[p]) -> rollout(LT[p]) -> trial(LT[p]), with the
     // solver context stored in / reloaded from the workspace between the phases exactly as the kernels do.
@@ -129,12 +130,13 @@ extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, con
 
 // warp-per-instance solver (kmpc_warp.cuh) on the fibre emulator; N + 1 <= 64
 extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur, const double *goal, const double *X0,
-                               const double *U0, const double *obs, int O, int stagewise, double obs_radius, double inflation, double *X_out,
+                               const double *U0, const double *obs, const double *obs_rad, int O, int stagewise, double obs_radius, double inflation, double *X_out,
                                double *U_out, double *obj, int32_t *status, int32_t *iters, int32_t *trips) {
     if (cf->N + 1 > 64) return -1;
     Cfg c = make_cfg(cf, B, O, stagewise, obs_radius, inflation);
     IO io;
-    io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs;
+    memset(&io, 0, sizeof io);
+    io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs; io.orad = O > 0 ? obs_rad : NULL;
     io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL; io.wscratch = NULL; io.order = NULL;
     const int spl = cf->N + 1 <= 32 ? 1 : 2;
 #pragma omp parallel for schedule(dynamic, 1)

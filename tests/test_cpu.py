@@ -232,7 +232,11 @@ def test_abi_argument_errors_without_gpu():
     if not torch.cuda.is_available():
         ok = PlannerConfig().to_c(4, 0, 0)
         assert L.kmpc_create(C.byref(ok), C.byref(h)) == -4 and not h.value         # KMPC_E_NODEVICE: no CPU path
-    assert L.kmpc_solve(None, 1, None, None, None, None, None, 0, 0.0, 0.0, None, None, None, None, None, None) == -1
+    assert L.kmpc_solve(None, 1, None, None, None, None, None, 0, 0.0, None, 0.0, None, None, None, None, None, None) == -1
+    assert L.kmpc_solve_host_into(None, 1, None, None, None, None, None, 0, 0.0, None, 0.0, None, None, None, None, None) == -1
+    assert L.kmpc_host_sync(None) == -1 and L.kmpc_enable_peer(None, 0) == -1
+    assert L.kmpc_shared_buffer_create(None, 16, None, None) == -1 and L.kmpc_shared_buffer_open(None, None, None) == -1
+    assert L.kmpc_pinned_alloc(0, None) == -1 and L.kmpc_pinned_free(None) == 0
     L.kmpc_destroy(None)                                                              # no-op
 
 
