@@ -21,6 +21,7 @@ kiss_mpc_b200.RankGather) -- no collective in the solve, none after it.
 --impl reference times that CPU oracle alone (the reference's own CasADi/IPOPT path cannot run in this image).
 """
 import argparse
+import faulthandler
 import hashlib
 import json
 import os
@@ -33,6 +34,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+faulthandler.enable()      # a native crash leaves a Python traceback on stderr
 
 BATCH = 65536
 HORIZON = 30
@@ -367,7 +369,6 @@ def run_ours(args, rank, local_rank, world):
             chk += float(rh.objective[0]) + int(rh.status[-1])      # the host reads the result of every step
         e2e_s = time.perf_counter() - e0
         e2e_value = B * steps / e2e_s
-        sp.close()
     if world > 1:
         dist.barrier(group=host_group)     # the other ranks wait on the host: their GPUs are free for rank 0's per-device handles
 
@@ -422,6 +423,8 @@ def run_ours(args, rank, local_rank, world):
             "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "weak": weak, "gpu_launches": int(launches), "clocks": clocks, **extra,
         }))
+        rh = None
+        sp.close()          # (the pinned result buffer `rh` viewed)
     if gather is not None:
         barrier()
         gather.close()
