@@ -215,12 +215,17 @@ struct kmpc_handle {
 #endif
 // FULL: every bound of x, y, v, omega exists (the default problem), so the per-side tests are compiled away.
 // OBS: obstacle-distance rows present (their per-row state lives in shared memory; the block shrinks to what fits).
-template <int SPL, int NST, bool FULL, bool OBS, int WPB, int MINB>
+// TAIL: with the tail mode of w_worker (full-solve inertia candidates in borrowed instance slots once a block runs dry).
+template <int SPL, int NST, bool FULL, bool OBS, int WPB, int MINB, bool TAIL = false>
 __global__ void __launch_bounds__(32 * WPB, MINB)
 kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned long long *__restrict__ trips_total) {
     extern __shared__ double s_dyn[];  // WLay<SPL, NST>::bytes(warps per block, O)
-    w_worker<SPL, NST, FULL, OBS>(c, io, s_dyn, queue, trips_total);
+    w_worker<SPL, NST, FULL, OBS, TAIL>(c, io, s_dyn, queue, trips_total);
 }
+
+#ifndef KMPC_TAIL_WAVES
+#define KMPC_TAIL_WAVES 16   /* batches of at most this many waves of resident instances run the kernel with the tail mode */
+#endif
 
 // Queue order of the persistent kernel.  Iteration counts differ by more than 8x between instances and a long instance that is
 // fetched late sets the end of the launch; how long an instance takes is largely a function of its geometry, so the instances
@@ -305,12 +310,18 @@ static cudaError_t launch_warp_kernel(kmpc_handle *h, int device, int sm_count, 
     while (wpb > 0 && WLay<SPL, NST>::bytes(wpb, c.O, c.obs_sw) > (size_t)max_smem) --wpb;
     if (wpb < 1) return cudaErrorInvalidConfiguration;
     const size_t smem = WLay<SPL, NST>::bytes(wpb, c.O, c.obs_sw);
-    auto kern = kmpc_warp_kernel<SPL, NST, FULL, OBS, WPB, MINB>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    void (*kern)(const Cfg, const IO, int *, unsigned long long *) = kmpc_warp_kernel<SPL, NST, FULL, OBS, WPB, MINB, false>;
     int bpsm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsm, kern, 32 * wpb, smem);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsm, kern, 32 * wpb, smem);
     if (e != cudaSuccess) return e;
+    if (!OBS && (long long)B <= (long long)KMPC_TAIL_WAVES * sm_count * (bpsm > 0 ? bpsm : 1) * wpb && getenv("KMPC_NO_TAIL") == NULL) {
+        // few waves: the phase in which the queue is drained is a large part of the launch -- the kernel with the tail mode
+        kern = kmpc_warp_kernel<SPL, NST, FULL, OBS, WPB, MINB, !OBS>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsm, kern, 32 * wpb, smem);
+        if (e != cudaSuccess) return e;
+    }
     int grid = sm_count * (bpsm > 0 ? bpsm : 1);
     const int need = (B + wpb - 1) / wpb;
     if (grid > need) grid = need;

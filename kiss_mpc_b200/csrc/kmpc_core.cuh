@@ -204,6 +204,15 @@ KMPC_HD void vcost(const Cfg &c, double df, double v, double *g, double *h) {
 }
 
 // correctly rounded reciprocal (one MUFU + Newton steps on the device instead of a full division)
+// additions / multiplications the compiler must not contract into an FMA: expressions that two different functions have to
+// evaluate to the same bits (kmpc_warp.cuh: w_assemble and w_assemble_cands)
+#ifdef __CUDA_ARCH__
+#define KADD(a, b) __dadd_rn((a), (b))
+#define KMUL(a, b) __dmul_rn((a), (b))
+#else
+#define KADD(a, b) ((a) + (b))
+#define KMUL(a, b) ((a) * (b))
+#endif
 #ifdef __CUDA_ARCH__
 #define KRCP(x) __drcp_rn(x)
 // reciprocal for the Riccati pivots and slacks: MUFU.RCP64H seed (~20 bits) + one cubic step (<= 1-2 ulp), branch-free.  Operands

@@ -66,6 +66,7 @@ struct WScal {  // warp-uniform per-instance scalars
     double dshift[KMPC_NCAND];  // delta_w of candidate k minus the delta_w the stage blocks were assembled with (NaN: none)
     int pdc[KMPC_NCAND];        // candidate k has the right inertia
     int flag, ok, r, status;
+    int tinfo, ncand;           // tail mode (w_worker): slot borrowing of this trip, full candidates assembled this trip
 };
 
 // NST = stage slots allocated per field (>= N + 1, <= 32 * SPL): a smaller NST than 32 * SPL lets more instances fit
@@ -76,7 +77,7 @@ struct WLay {
     static constexpr int PRIV = V_NF * NSTG;
     static constexpr int GPRIV = G_NF * NSTG;   // doubles of global scratch per resident warp
     KMPC_HD static int obs_doubles(int O, int sw = 0) { return O > 0 ? B_NF * O * NSTG + 2 * O * (sw ? NSTG : 1) + O : 0; }   // rows, centres, radii
-    static size_t bytes(int warps, int O = 0, int sw = 0) { return (size_t)warps * ((COOP + PRIV + obs_doubles(O, sw)) * sizeof(double) + sizeof(WScal)); }
+    static size_t bytes(int warps, int O = 0, int sw = 0) { return (size_t)warps * ((COOP + PRIV + obs_doubles(O, sw)) * sizeof(double) + sizeof(WScal)) + 16; }   // + the block's live-instance masks
 };
 
 // value of the next / previous stage (neighbouring slot, or the neighbouring lane's edge slot)
@@ -331,7 +332,7 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
             Q00 = 1.0; Q11 = 1.0; Q22 = 1.0;
         } else {
             q0 = gx0 + w.y0[j] + rb0; q1 = gx1 + w.y1[j] + rb1; q2 = gx2 + w.y2[j];
-            Q00 = h0 + sg0 + delta; Q11 = h1 + sg1 + delta; Q22 = h2 + delta;
+            Q00 = KADD(KADD(h0, sg0), delta); Q11 = KADD(KADD(h1, sg1), delta); Q22 = KADD(h2, delta);   // (uncontracted: w_assemble_cands forms the same sums)
         }
         double Q01 = 0.0, S00 = 0.0, S01 = 0.0, S11 = 0.0;
         if (OBS && s >= 1) {  // slacks of the obstacle rows condensed into the x-y block
@@ -366,12 +367,12 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
             if (s < N) {
                 // J^T y of dynamics row s+1 and the curvature of the dynamics in the Lagrangian
                 q0 -= yn0[j]; q1 -= yn1[j]; q2 -= a13 * yn0[j] + a23 * yn1[j] + yn2[j];
-                Q22 += T * v * (yn0[j] * cs + yn1[j] * sn);
+                Q22 = KADD(Q22, KMUL(KMUL(T, v), fma(yn0[j], cs, KMUL(yn1[j], sn))));
                 htv = T * (yn0[j] * sn - yn1[j] * cs);
             }
             qv = gv - (b11 * yn0[j] + b21 * yn1[j]) + rbv;
             qw = gw - T * yn2[j] + rbw;
-            dv = hvv + (sgv + delta); dw = hww + (sgw + delta);
+            dv = KADD(hvv, KADD(sgv, delta)); dw = KADD(hww, KADD(sgw, delta));
             if (soc) {  // rhs of the dynamics row s+1 = -c_soc of stage s+1
                 const double *pn = gp + (s + 1 < NSTG ? s + 1 : s);
                 e0 = -pn[G_CS0 * NSTG]; e1 = -pn[G_CS1 * NSTG]; e2 = -pn[G_CS2 * NSTG];
@@ -392,6 +393,62 @@ KMPC_WN inline void w_assemble(const Cfg &c, WScal *sc, const WState<SPL> &w, do
             if (lsq) { sc->d0[0] = sc->d0[1] = sc->d0[2] = 0.0; }
             else if (soc) { sc->d0[0] = -gp[G_CS0 * NSTG]; sc->d0[1] = -gp[G_CS1 * NSTG]; sc->d0[2] = -gp[G_CS2 * NSTG]; }
             else { sc->d0[0] = -(x0 - sc->xc[0]); sc->d0[1] = -(x1 - sc->xc[1]); sc->d0[2] = -(x2 - sc->xc[2]); }
+        }
+    }
+}
+
+// Full-solve inertia candidates (tail mode, w_worker): the same Newton system with the NEXT perturbations delta_w of IPOPT's
+// sequence, written next to the base system into instance slots that are free, so that the Riccati warp solves all of them side
+// by side.  Runs after w_assemble on the same iterate: the entries that do not depend on delta_w are copied from the base
+// blocks, the ones that do are formed again exactly as w_assemble forms them (same operands -- the reciprocal slacks it left in
+// the private area -- same order), hence a candidate's solve has the bits of the retry trip it replaces.  No obstacle rows.
+struct WCands { int n; double *coop[KMPC_NCAND > 1 ? KMPC_NCAND - 1 : 1]; double delta[KMPC_NCAND > 1 ? KMPC_NCAND - 1 : 1]; WScal *sc[KMPC_NCAND > 1 ? KMPC_NCAND - 1 : 1]; };
+template <int SPL, int NST, bool FULL>
+KMPC_WN inline void w_assemble_cands(const Cfg &c, const WScal *sc, const WState<SPL> &w, const double *priv, const double *coop, const WCands &cand) {
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
+    const int N = c.N, lane = w_lane();
+    const double df = sc->t.df, T = c.T;
+    const bool hL0 = c.hasL[0], hU0 = c.hasU[0], hL1 = c.hasL[1], hU1 = c.hasU[1], hL2 = c.hasL[2], hU2 = c.hasU[2], hL3 = c.hasL[3], hU3 = c.hasU[3];
+    double yn0[SPL], yn1[SPL];
+    w_next<SPL>(w.y0, yn0); w_next<SPL>(w.y1, yn1);
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int s = lane * SPL + j;
+        if (s > N) continue;
+        const double v = w.v[j], cs = w.cs[j], sn = w.sn[j];
+        const bool ing = s >= c.gk_lo && s <= c.gk_hi;
+        const double h0 = ing ? df * 2.0 * c.W[0] : 0.0, h1 = ing ? df * 2.0 * c.W[1] : 0.0, h2 = ing ? df * 2.0 * c.W[2] : 0.0;
+        const double *pv = priv + s;
+        // sigma of a bounded variable as wb_terms forms it: zL * rsL, then fma(zU, rsU, .)
+        auto sigma = [](bool hL, bool hU, double zL, double zU, double rsL, double rsU) {
+            double sg = 0.0;
+            if (FULL || hL) sg = zL * rsL;
+            if (FULL || hU) sg = fma(zU, rsU, sg);
+            return sg;
+        };
+        const double sg0 = sigma(hL0, hU0, w.zLx[j], w.zUx[j], pv[V_RL0 * NSTG], pv[V_RU0 * NSTG]);
+        const double sg1 = sigma(hL1, hU1, w.zLy[j], w.zUy[j], pv[V_RL1 * NSTG], pv[V_RU1 * NSTG]);
+        const double sgv = sigma(hL2, hU2, w.zLv[j], w.zUv[j], pv[V_RL2 * NSTG], pv[V_RU2 * NSTG]);
+        const double sgw = sigma(hL3, hU3, w.zLw[j], w.zUw[j], pv[V_RL3 * NSTG], pv[V_RU3 * NSTG]);
+        double gv, hvv;
+        vcost(c, df, v, &gv, &hvv);
+        const double hww = df * 2.0 * c.Ww;
+        const double curv = KMUL(KMUL(T, v), fma(yn0[j], cs, KMUL(yn1[j], sn)));
+        const double *q = coop + s;
+#pragma unroll
+        for (int k = 0; k < (KMPC_NCAND > 1 ? KMPC_NCAND - 1 : 1); ++k) {
+            if (k >= cand.n) break;
+            const double dk = cand.delta[k];
+            double *qk = cand.coop[k] + s;
+            qk[C_A13 * NSTG] = q[C_A13 * NSTG]; qk[C_A23 * NSTG] = q[C_A23 * NSTG]; qk[C_B11 * NSTG] = q[C_B11 * NSTG]; qk[C_B21 * NSTG] = q[C_B21 * NSTG];
+            qk[C_E0 * NSTG] = q[C_E0 * NSTG]; qk[C_E1 * NSTG] = q[C_E1 * NSTG]; qk[C_E2 * NSTG] = q[C_E2 * NSTG];
+            qk[C_Q0 * NSTG] = q[C_Q0 * NSTG]; qk[C_Q1 * NSTG] = q[C_Q1 * NSTG]; qk[C_Q2 * NSTG] = q[C_Q2 * NSTG];
+            qk[C_QV * NSTG] = q[C_QV * NSTG]; qk[C_QW * NSTG] = q[C_QW * NSTG]; qk[C_HTV * NSTG] = q[C_HTV * NSTG];
+            // w_assemble: Q00 = h0 + sg0 + delta; Q22 = h2 + delta (+= curvature for s < N); dv = hvv + (sgv + delta); terminal stage: unit Quu
+            qk[C_Q00 * NSTG] = KADD(KADD(h0, sg0), dk); qk[C_Q11 * NSTG] = KADD(KADD(h1, sg1), dk);
+            qk[C_Q22 * NSTG] = s < N ? KADD(KADD(h2, dk), curv) : KADD(h2, dk);
+            qk[C_DV * NSTG] = s < N ? KADD(hvv, KADD(sgv, dk)) : 1.0; qk[C_DW * NSTG] = s < N ? KADD(hww, KADD(sgw, dk)) : 1.0;
+            if (s == 0) { cand.sc[k]->d0[0] = sc->d0[0]; cand.sc[k]->d0[1] = sc->d0[1]; cand.sc[k]->d0[2] = sc->d0[2]; }
         }
     }
 }
@@ -862,6 +919,9 @@ __device__ unsigned long long g_phase_cycles[KMPC_NPHASE];
 
 // rejected trial points re-evaluated within one trip before the instance goes round the block loop again (bounds what the
 // other warps of the block can be made to wait for)
+#ifndef KMPC_TAIL
+#define KMPC_TAIL 1   /* tail mode (full-solve inertia candidates in borrowed instance slots); 0 compiles it out (tuning builds) */
+#endif
 #ifndef KMPC_INLINE_BACKTRACKS
 #define KMPC_INLINE_BACKTRACKS 24
 #endif
@@ -892,7 +952,11 @@ KMPC_WN inline int w_fetch_active(const Cfg &c, const IO &io, int *queue) {
 // ---- persistent worker: one warp pulls instances from a queue and solves each start to finish; the warps of a block
 // walk through the phases of a trip in step (block barriers) so that warp 0 can run every instance's serial recursions.
 // smem: WLay<SPL, NST>::bytes(warps per block, O) bytes of block-shared scratch.
-template <int SPL, int NST, bool FULL, bool OBS>
+// TAIL: the tail mode is compiled in.  Its mere presence costs the common path 3 % (65,536 x N = 30: 12.95 vs 12.60 ms; neither
+// keeping its state in shared memory nor moving its code out of line changed that), so batches of many waves run the kernel
+// without it and only batches in which the drained-queue phase matters -- small ones, the slices of a batch sharded over
+// several GPUs -- run the kernel with it (launch_warp_kernel).
+template <int SPL, int NST, bool FULL, bool OBS, bool TAIL = true>
 KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queue, unsigned long long *trips_total) {
     typedef WLay<SPL, NST> LY;
     const int N = c.N, lane = w_lane(), wid = w_warp(), W = w_warps();
@@ -903,13 +967,15 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     double *ob = smem + (size_t)W * (LY::COOP + LY::PRIV) + (size_t)wid * OBD;
     WScal *scal0 = (WScal *)(smem + (size_t)W * (LY::COOP + LY::PRIV + OBD));
     WScal *sc = scal0 + wid;
+    unsigned *hmask = (unsigned *)(scal0 + W);   // which warps hold an instance, this trip / next trip
     Ctx &t = sc->t;
     WState<SPL> cur;
     WStep<SPL> act;
     bool have = false;
     int b = -1;
-    if (lane == 0) { t.mode = M_DONE; sc->flag = 0; sc->ok = 0; }
-    w_sync();
+    if (lane == 0) { t.mode = M_DONE; sc->flag = 0; sc->ok = 0; sc->tinfo = 0; sc->ncand = 0; for (int k = 0; k < KMPC_NCAND; ++k) { sc->dshift[k] = NAN; sc->pdc[k] = 0; } }
+    if (wid == 0 && lane == 0) { hmask[0] = 0; hmask[1] = 0; }
+    w_block_sync();
     PT_DECL
     bool drained = false;  // the queue has no more instances for this warp
     // the block's Riccati warp: co-resident blocks (b and b + gridDim/2 under round-robin placement) pick different warp
@@ -929,25 +995,77 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             if (b < c.B) { SCHED_START(b) w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
         }
         PT(0)
-        if (!w_block_any(have)) break;
+        const int nlive = w_block_warps_with(have);   // warps that hold an instance this trip
+        if (!nlive) break;
         PT(1)
         int status = 100;
+        // ---- tail mode: once at most a quarter of the block's instance slots are taken (the queue is drained, or the batch is
+        // small) every live instance borrows KMPC_NCAND - 1 free slots.  Into those it assembles the SAME Newton system with the
+        // next perturbations delta_w of IPOPT's inertia-correction sequence, the Riccati warp solves them side by side with the
+        // base system on lanes that would idle anyway, and a factorisation with the wrong inertia costs no retry trip: the
+        // instance continues at once with the first candidate that has the right one.  Same arithmetic as the retry, same bits.
+        // (All of its state lives in shared memory -- sc->tinfo, sc->ncand, hmask[1] -- so that the common path carries no
+        //  register for it: with them in registers the whole kernel ran 3 % slower.)
+        constexpr int NCF = KMPC_NCAND > 1 ? KMPC_NCAND - 1 : 1;
+        if (TAIL && KMPC_TAIL && !OBS && KMPC_NCAND > 1) {
+            if (W - nlive >= NCF * nlive) {          // uniform over the block: two more barriers, next to idle warps
+                if (lane == 0 && have) w_smem_or(hmask, 1u << wid);
+                w_block_sync();
+                const unsigned hm = *(volatile unsigned *)hmask;
+                if (wid == 0 && lane == 0) hmask[1] = hm;   // kept for the rest of the trip (read after the barrier below)
+                w_block_sync();
+                if (wid == 0 && lane == 0) hmask[0] = 0;    // (the next word is built after the next trip's first barrier)
+                // live: 1 + number of the first free slot it borrows (in the order of the free slots), shifted by 8; free: bit 0 = lent out
+                if (lane == 0) sc->tinfo = have ? (w_popc(hm & ((1u << wid) - 1u)) * NCF + 1) << 8 : (w_popc(~hm & ((1u << wid) - 1u)) < nlive * NCF ? 1 : 0);
+            } else if (lane == 0) sc->tinfo = 0;
+            w_sync();
+        }
         // ---- phase 1a: assemble the stage blocks ----
         const int mode = t.mode;
         const bool do_sweep = have && mode != M_TRIAL;
-        if (do_sweep) w_assemble<SPL, NST, FULL, OBS>(c, sc, cur, priv, gp, coop, ob);
-        if (lane == 0) {
-            sc->flag = do_sweep ? 1 : 0;
-            if (do_sweep) {
-                t.trips++;
-                // speculative inertia candidates (Newton systems; delta_w is a diagonal shift of the assembled blocks plus, with
-                // obstacle rows, delta_w * sum n n^T): the next perturbations IPOPT would try if this factorisation has the wrong inertia
+        {
+            const int tinfo = (TAIL && KMPC_TAIL && !OBS && KMPC_NCAND > 1) ? sc->tinfo : 0;
+            const bool full_cands = (tinfo >> 8) != 0 && do_sweep && mode == M_NEWTON;
+            int ncand = 0;       // full candidates of this trip (fewer than NCF when the sequence runs past delta_w_max)
+            if (do_sweep) w_assemble<SPL, NST, FULL, OBS>(c, sc, cur, priv, gp, coop, ob);   // (ONE call site: two inlined copies need not round alike)
+            if (full_cands) {
+                const unsigned hm = ((volatile unsigned *)hmask)[1];
+                WCands cand;     // (uniform over the warp: every lane forms the sequence itself)
                 double dk = t.delta;
-                sc->dshift[0] = 0.0;
-                for (int k = 1; k < KMPC_NCAND; ++k) {
+#pragma unroll
+                for (int k = 0; k < NCF; ++k) {
                     dk = inertia_next_delta(dk, t.delta_last);
-                    sc->dshift[k] = (W >= 2 && mode == M_NEWTON && dk <= K_DW_MAX && k * W <= 32 * ncw) ? dk - t.delta : NAN;
-                    sc->pdc[k] = 0;
+                    if (!(dk <= K_DW_MAX)) break;
+                    const int slot = w_nth_clear(hm, W, (tinfo >> 8) - 1 + k);
+                    cand.coop[k] = smem + (size_t)slot * LY::COOP; cand.delta[k] = dk; cand.sc[k] = scal0 + slot;
+                    ncand = k + 1;
+                }
+                cand.n = ncand;
+                w_sync();   // (the base blocks and d0 are read back below)
+                if (!OBS) w_assemble_cands<SPL, NST, FULL>(c, sc, cur, priv, coop, cand);
+            }
+            if (lane == 0) {
+                if (!(tinfo & 1)) sc->flag = do_sweep ? 1 : 0;   // (a lent slot's flag belongs to its borrower)
+                if (tinfo >> 8) {
+                    const unsigned hm = ((volatile unsigned *)hmask)[1];
+                    for (int k = 0; k < NCF; ++k) {
+                        WScal *sk = scal0 + w_nth_clear(hm, W, (tinfo >> 8) - 1 + k);
+                        sk->flag = k < ncand ? 1 : 0;
+                        for (int q = 1; q < KMPC_NCAND; ++q) sk->dshift[q] = NAN;
+                    }
+                }
+                if (do_sweep) {
+                    t.trips++;
+                    sc->ncand = ncand;
+                    // speculative inertia candidates (Newton systems; delta_w is a diagonal shift of the assembled blocks plus, with
+                    // obstacle rows, delta_w * sum n n^T): the next perturbations IPOPT would try if this factorisation has the wrong inertia
+                    double dk = t.delta;
+                    sc->dshift[0] = 0.0;
+                    for (int k = 1; k < KMPC_NCAND; ++k) {
+                        dk = inertia_next_delta(dk, t.delta_last);
+                        sc->dshift[k] = (!full_cands && W >= 2 && mode == M_NEWTON && dk <= K_DW_MAX && k * W <= 32 * ncw) ? dk - t.delta : NAN;
+                        sc->pdc[k] = 0;
+                    }
                 }
             }
         }
@@ -979,11 +1097,26 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         // ---- phase 2: search direction, step sizes, line-search set-up (or inertia correction) ----
         bool go_trial = have && !do_sweep;
         if (do_sweep) {
-            if (!sc->ok) {
+            // the system that was solved: the base one, or -- tail mode -- the first full candidate with the right inertia
+            const double *solved = coop;
+            bool ok = sc->ok != 0;
+            const int ncand = (TAIL && KMPC_TAIL && !OBS && KMPC_NCAND > 1 && !ok) ? sc->ncand : 0;
+            for (int k = 0; k < ncand; ++k) {
+                const int slot = w_nth_clear(((volatile unsigned *)hmask)[1], W, (sc->tinfo >> 8) - 1 + k);
+                if (scal0[slot].ok) {
+                    ok = true; solved = smem + (size_t)slot * LY::COOP;
+                    w_sync();
+                    if (lane == 0) { for (int q = 0; q <= k; ++q) t.delta = inertia_next_delta(t.delta, t.delta_last); }   // IPOPT's sequence up to the perturbation that works
+                    w_sync();
+                    break;
+                }
+            }
+            if (!ok) {
                 PT_COUNT(10)
                 if (lane == 0) {
                     // wrong inertia: raise delta_w (IPOPT's sequence) past the candidates already known to fail, sweep again next trip
                     int st = mode != M_NEWTON ? sweep_failure_status(t) : inertia_update(t);
+                    for (int k = 0; k < ncand && st == R_RETRY; ++k) st = inertia_update(t);
                     for (int k = 1; k < KMPC_NCAND && st == R_RETRY && sc->dshift[k] == sc->dshift[k] && !sc->pdc[k]; ++k) st = inertia_update(t);
                     sc->status = st;
                 }
@@ -991,7 +1124,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 status = sc->status;
             } else {
                 double apr, adu, gbd, ym;
-                w_step<SPL, NST, FULL, OBS>(c, sc, cur, coop, priv, ob, act, &apr, &adu, &gbd, &ym);
+                w_step<SPL, NST, FULL, OBS>(c, sc, cur, solved, priv, ob, act, &apr, &adu, &gbd, &ym);
                 if (lane == 0) rollout_logic(t, apr, adu, gbd, ym);
                 w_sync();
                 if (t.sel == 0) w_step_store<SPL, NST>(act, gp);

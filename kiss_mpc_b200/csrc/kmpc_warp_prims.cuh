@@ -23,6 +23,8 @@ KMPC_W unsigned w_ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 KMPC_W void w_reconverge(unsigned mask) { __syncwarp(mask); }  // re-join the lanes of `mask` after a divergent region
 KMPC_W void w_block_sync() { __syncthreads(); }
 KMPC_W bool w_block_any(bool p) { return __syncthreads_or(p ? 1 : 0) != 0; }
+KMPC_W unsigned w_smem_or(unsigned *p, unsigned v) { return atomicOr(p, v); }   // shared-memory word
+KMPC_W int w_block_warps_with(bool p) { return __syncthreads_count((p && (threadIdx.x & 31u) == 0) ? 1 : 0); }   // block barrier + number of warps whose (warp-uniform) p holds
 #ifndef KMPC_SERIAL_WARP_B
 #define KMPC_SERIAL_WARP_B 2
 #endif
@@ -56,6 +58,18 @@ KMPC_W double w_min_nn(double v) {
 #endif
 
 namespace kmpc {
+KMPC_W int w_popc(unsigned m) {
+#ifdef __CUDA_ARCH__
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
+}
+// position of the j-th (0-based) CLEAR bit of m among bits 0 .. W-1; W if there is none
+KMPC_W int w_nth_clear(unsigned m, int W, int j) {
+    for (int i = 0; i < W; ++i) if (!((m >> i) & 1u) && j-- == 0) return i;
+    return W;
+}
 // butterfly reductions: every lane ends with the same bits
 KMPC_W double w_sum(double v) { for (int m = 16; m > 0; m >>= 1) v += w_xor(v, m); return v; }
 KMPC_W double w_min(double v) { for (int m = 16; m > 0; m >>= 1) { const double o = w_xor(v, m); v = o < v ? o : v; } return v; }

@@ -44,7 +44,7 @@ def cfg_from_oracle(ocfg, B_max=1, layout=0):
     return c
 
 
-def solve(ocfg, x_cur, goal, X0=None, U0=None, obs=None, layout=0, warp=False, obs_rad=None):
+def solve(ocfg, x_cur, goal, X0=None, U0=None, obs=None, layout=0, warp=False, obs_rad=None, warps=1, chunk=0):
     L = C.CDLL(build())
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
     L.emul_solve.restype = C.c_int
@@ -70,9 +70,9 @@ def solve(ocfg, x_cur, goal, X0=None, U0=None, obs=None, layout=0, warp=False, o
     if warp:
         L.emul_solve_warp.restype = C.c_int
         L.emul_solve_warp.argtypes = [C.POINTER(KmpcConfig), C.c_int, dp, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp,
-                                      dp, ip, ip, ip]
+                                      dp, ip, ip, ip, C.c_int, C.c_int]
         rc = L.emul_solve_warp(C.byref(c), B, p(xi), p(gi), p(X0i), p(U0i), p(obi), p(ori), O, sw, ocfg.obs_radius, ocfg.inflation, p(Xo), p(Uo),
-                               p(obj), p(st, C.c_int32), p(it, C.c_int32), p(tp, C.c_int32))
+                               p(obj), p(st, C.c_int32), p(it, C.c_int32), p(tp, C.c_int32), int(warps), int(chunk))
     else:
         rc = L.emul_solve(C.byref(c), B, p(xi), p(gi), p(X0i), p(U0i), p(obi), p(ori), O, sw, ocfg.obs_radius, ocfg.inflation, p(Xo), p(Uo),
                           p(obj), p(st, C.c_int32), p(it, C.c_int32), p(tp, C.c_int32))

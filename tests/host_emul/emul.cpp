@@ -12,7 +12,7 @@
 
 using namespace kmpc;
 
-// ---- 32-fibre warp emulator (see simt.h) ----
+// ---- fibre emulator of a block of warps (see simt.h) ----
 namespace kmpc {
 thread_local Simt *g_simt = nullptr;
 static void simt_entry() {
@@ -20,15 +20,17 @@ static void simt_entry() {
     s.fn();
     // this lane is finished: hand over to the next unfinished lane, the last one returns to the caller
     const int me = s.cur;
-    if (me < 31) { s.cur = me + 1; setcontext(&s.ctx[me + 1]); }
+    if (me < 32 * s.nw - 1) { s.cur = me + 1; setcontext(&s.ctx[me + 1]); }
     setcontext(&s.main);
 }
-void simt_run(const std::function<void()> &fn) {
-    Simt s;
-    g_simt = &s;
+void simt_run(const std::function<void()> &fn, int warps) {
+    Simt *sp = new Simt;
+    Simt &s = *sp;
+    g_simt = sp;
     s.fn = fn;
-    for (int i = 0; i < 32; ++i) {
-        s.parity[i] = 0;
+    s.nw = warps;
+    for (int i = 0; i < 32 * warps; ++i) {
+        s.parity[i] = 0; s.bparity[i] = 0;
         s.stack[i].resize(1 << 20);
         getcontext(&s.ctx[i]);
         s.ctx[i].uc_stack.ss_sp = s.stack[i].data();
@@ -39,6 +41,7 @@ void simt_run(const std::function<void()> &fn) {
     s.cur = 0;
     swapcontext(&s.main, &s.ctx[0]);
     g_simt = nullptr;
+    delete sp;
 }
 }  // namespace kmpc
 
@@ -128,24 +131,35 @@ extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, con
     return 0;
 }
 
-// warp-per-instance solver (kmpc_warp.cuh) on the fibre emulator; N + 1 <= 64
+// warp-per-instance solver (kmpc_warp.cuh) on the fibre emulator; N + 1 <= 64.
+// warps <= 1: every instance on its own one-warp block.  warps > 1: blocks of `warps` warps, block j working through the
+// instances [j * chunk, (j + 1) * chunk) from its own queue -- the block-level machinery of the kernel (the Riccati warp
+// serving the other warps' instances, the speculative inertia candidates, refills in the serial window, the tail mode with
+// borrowed instance slots) runs exactly as on the device, only one fibre at a time.
 extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur, const double *goal, const double *X0,
                                const double *U0, const double *obs, const double *obs_rad, int O, int stagewise, double obs_radius, double inflation, double *X_out,
-                               double *U_out, double *obj, int32_t *status, int32_t *iters, int32_t *trips) {
+                               double *U_out, double *obj, int32_t *status, int32_t *iters, int32_t *trips, int warps, int chunk) {
     if (cf->N + 1 > 64) return -1;
+    if (warps > SIMT_MAX_WARPS) return -1;
     Cfg c = make_cfg(cf, B, O, stagewise, obs_radius, inflation);
     IO io;
     memset(&io, 0, sizeof io);
     io.x_cur = x_cur; io.goal = goal; io.X0 = X0; io.U0 = U0; io.obs = obs; io.orad = O > 0 ? obs_rad : NULL;
     io.X_out = X_out; io.U_out = U_out; io.obj = obj; io.status = status; io.iters = iters; io.active = NULL; io.wscratch = NULL; io.order = NULL;
     const int spl = cf->N + 1 <= 32 ? 1 : 2;
+    const int W = warps > 1 ? warps : 1;
+    if (W == 1) chunk = 1;
+    if (chunk < 1) chunk = B;
+    const int nblk = (B + chunk - 1) / chunk;
+    unsigned long long tr_total = 0;
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int b = 0; b < B; ++b) {
-        std::vector<double> smem((spl == 1 ? WLay<1, 32>::bytes(1, O, c.obs_sw) : cf->N + 1 <= 52 ? WLay<2, 52>::bytes(1, O, c.obs_sw) : WLay<2, 64>::bytes(1, O, c.obs_sw)) / sizeof(double), NAN);  // one emulated warp = one block
+    for (int j = 0; j < nblk; ++j) {
+        const int lo = j * chunk, hi = lo + chunk < B ? lo + chunk : B;
+        std::vector<double> smem((spl == 1 ? WLay<1, 32>::bytes(W, O, c.obs_sw) : cf->N + 1 <= 52 ? WLay<2, 52>::bytes(W, O, c.obs_sw) : WLay<2, 64>::bytes(W, O, c.obs_sw)) / sizeof(double) + 8, NAN);
         unsigned long long tr = 0;
-        int queue = b;          // this emulated warp is handed exactly instance b
-        Cfg cb = c; cb.B = b + 1;
-        std::vector<double> gscr(G_NF * 64, NAN);   // the warp's global scratch slot
+        int queue = lo;          // this emulated block is handed exactly the instances lo .. hi - 1
+        Cfg cb = c; cb.B = hi;
+        std::vector<double> gscr((size_t)G_NF * 64 * W, NAN);   // the block's global scratch slots
         IO iob = io; iob.wscratch = gscr.data();
         bool full = true;
         for (int i = 0; i < 4; ++i) full = full && c.hasL[i] && c.hasU[i];
@@ -155,9 +169,12 @@ extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur
             else { if (full) w_worker<SPL, NST, true, false>(cb, iob, smem.data(), &queue, &tr); else w_worker<SPL, NST, false, false>(cb, iob, smem.data(), &queue, &tr); } } while (0)
         simt_run([&]() {
             if (nst == 32) EMUL_RUN(1, 32); else if (nst == 52) EMUL_RUN(2, 52); else EMUL_RUN(2, 64);
-        });
+        }, W);
 #undef EMUL_RUN
-        if (trips) trips[b] = (int)tr;
+        if (W == 1 && trips) trips[lo] = (int)tr;
+#pragma omp atomic
+        tr_total += tr;
     }
+    if (W > 1 && trips) trips[0] = (int)tr_total;
     return 0;
 }

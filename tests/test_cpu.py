@@ -161,6 +161,43 @@ def test_warp_solver_source_matches_oracle(oracle_mod, case):
     assert (it == ref.iters).mean() >= (0.95 if O == 0 else 0.5)
 
 
+@pytest.mark.parametrize("case,W,chunk", [("box", 16, 40), ("box", 16, 2), ("box", 8, 1), ("N50", 12, 3), ("literal", 6, 1), ("obs", 10, 24),
+                                          ("warm", 16, 4), ("infeasible", 16, 40)])
+def test_warp_block_emulation_bit_identical(oracle_mod, case, W, chunk):
+    """The block-level machinery of the warp kernel on the multi-warp fibre emulator (tests/host_emul/simt.h): blocks of W warps
+    pulling `chunk` instances from their queue -- the Riccati warp serving every instance of the block, the matrix-only inertia
+    candidates, refills during the serial window and the TAIL MODE (at most a quarter of the slots taken: every live instance
+    borrows free slots for full-solve candidates of the next perturbations) -- must return bit for bit what one instance alone on a
+    one-warp block returns: scheduling and speculation never change the arithmetic of an instance."""
+    import emul
+    kw, B, seed, O = {}, 40, 1002, 0
+    if case == "N50":
+        kw, seed, B = dict(N=50), 1003, 12
+    elif case == "literal":
+        kw, B = dict(cost_mode="code_literal", goal_range="code", y_bounds=(-oracle_mod.INF, oracle_mod.INF)), 12
+    elif case == "obs":
+        kw, seed, O, B = dict(O=4), 1004, 4, 24
+    elif case == "infeasible":
+        kw = dict(max_iter=300)
+    cfg = oracle_mod.OracleConfig(linsolve="riccati", **kw)
+    b = make_batch(B, seed=seed, O=O)
+    X0 = U0 = None
+    x = b["x_cur"]
+    if case == "infeasible":
+        x[::4, 0] = 25.0
+    if case == "warm":
+        r0 = oracle_mod.solve(cfg, x, b["goal"])
+        X0, U0, x = r0.X, r0.U, r0.X[:, :, 1].copy()
+    one = emul.solve(cfg, x, b["goal"], X0=X0, U0=U0, obs=b["obs"], warp=True)
+    blk = emul.solve(cfg, x, b["goal"], X0=X0, U0=U0, obs=b["obs"], warp=True, warps=W, chunk=chunk)
+    for a, c in zip(one[:5], blk[:5]):
+        assert np.array_equal(a, c)
+    trips_one, trips_blk = int(one[5].sum()), int(blk[5][0])
+    assert trips_blk <= trips_one          # speculation only ever saves retry trips
+    if case == "box" and chunk <= 2:
+        assert trips_blk < 0.9 * trips_one  # tail mode: the inertia retries are gone
+
+
 @pytest.mark.parametrize("kw", [dict(), dict(O=2), dict(cost_mode="code_literal", goal_range="code", y_bounds=(-1e20, 1e20))])
 def test_non_finite_inputs_give_invalid_number(oracle_mod, kw):
     """NaN / inf in the current state, the goal or an obstacle centre: IPOPT's Invalid_Number_Detected (-13) for that instance

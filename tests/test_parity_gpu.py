@@ -740,3 +740,29 @@ def test_environment_loop_with_dynamic_obstacles(oracle_mod):
             d = (b["goal"][:, :2] - xc[:, :2]); act &= ~(np.linalg.norm(d, axis=1) - 0.5 <= 0)
         assert cd.max() >= 1 and cs.max() >= 1
         assert np.abs(x.cpu().numpy() - xc).max() <= 1e-4
+
+
+def test_tail_mode_kernel_is_bit_identical():
+    """Small batches run the kernel instantiation WITH the tail mode (borrowed instance slots solve the next inertia
+    perturbations next to the base system; launch_warp_kernel picks it for batches of at most KMPC_TAIL_WAVES waves), many-wave
+    batches the one without.  An instance must get the same bits from both, alone (B = 1) or among 3,000."""
+    from kiss_mpc_b200 import BatchedMotionPlanner, PlannerConfig
+    torch = _torch()
+    B = 40000
+    b = make_batch(B, seed=1000)
+    pl = BatchedMotionPlanner(PlannerConfig(), max_batch=B)
+    x, g = _dev(b["x_cur"]), _dev(b["goal"])
+    big = pl.solve(x, g)                      # 40,000 > 16 waves of 2,368 resident instances: no tail mode
+    small = pl.solve(x[:3000].contiguous(), g[:3000].contiguous())
+    for a, c in zip(small, big):
+        assert torch.equal(a, c[:3000])
+    for i in (0, 17, 2879, 30520 % 3000):
+        one = pl.solve(x[i:i + 1].contiguous(), g[i:i + 1].contiguous())
+        for a, c in zip(one, big):
+            assert torch.equal(a, c[i:i + 1])
+    # N = 50 (two stages per lane) as well
+    pl50 = BatchedMotionPlanner(PlannerConfig(N=50), max_batch=B)
+    big50 = pl50.solve(x[:24000].contiguous(), g[:24000].contiguous())
+    small50 = pl50.solve(x[:500].contiguous(), g[:500].contiguous())
+    for a, c in zip(small50, big50):
+        assert torch.equal(a, c[:500])
