@@ -182,6 +182,11 @@ struct kmpc_handle {
     double *env_rad;       //   ... their per-slot radii, cols x O_max
     int32_t *env_idx;      //   ... which dynamic candidate sits in every dynamic slot
     int max_smem;          // opt-in shared memory per block of the device
+    // restoration-phase hand-over (kmpc_finish_kernel): workspace columns, the instance in each, the number in use
+    double *resto_ws;
+    int32_t *resto_list;
+    int *resto_count;
+    int resto_cap, resto_rows;
     int last_path;         // 1: the last solve ran the warp kernel, 0: the thread-per-instance fall-back
     cudaStream_t stream;
     char err[256];
@@ -221,6 +226,17 @@ __global__ void __launch_bounds__(32 * WPB, MINB)
 kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned long long *__restrict__ trips_total) {
     extern __shared__ double s_dyn[];  // WLay<SPL, NST>::bytes(warps per block, O)
     w_worker<SPL, NST, FULL, OBS, TAIL>(c, io, s_dyn, queue, trips_total);
+}
+
+// Finisher of the warp solver: one thread per instance that was handed over because its regular line search failed -- IPOPT's
+// restoration phase, then the rest of the regular algorithm (kmpc_resto.cuh, finish_instance).  Launched after every warp-solver
+// launch with a fixed small grid; the number of columns in use is read on the device (no host round trip), normally zero.
+template <bool OBS>
+__global__ void __launch_bounds__(32)
+kmpc_finish_kernel(const Cfg c, const IO io) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *io.resto_count < io.resto_cap ? *io.resto_count : io.resto_cap;
+    if (i < n) finish_instance<OBS>(c, io, i);
 }
 
 #ifndef KMPC_TAIL_WAVES
@@ -337,7 +353,34 @@ static cudaError_t launch_warp_kernel(kmpc_handle *h, int device, int sm_count, 
     io.wscratch = h->wscratch;
     e = queue_order(h, B, grid * wpb, c, io, c.layout, st, &io.order);
     if (e != cudaSuccess) return e;
+    // hand-over workspace of the restoration phase (allocated on the first solve, sized for the handle's largest problem)
+    if (!h->resto_count) {
+        const int rows = make_resto_rows(make_rows(h->cfg.N, h->cfg.O_max, 1)).total;
+        long long cap = h->cfg.B_max < 1024 ? h->cfg.B_max : 1024;
+        const long long budget = 256ll << 20;   // bytes
+        if (cap * rows * 8ll > budget) cap = budget / (rows * 8ll);
+        double *ws = NULL; int32_t *li = NULL; int *cn = NULL;
+        if (cap >= 1) {
+            e = cudaMalloc(&ws, (size_t)cap * rows * sizeof(double));
+            if (e == cudaSuccess) e = cudaMalloc(&li, (size_t)cap * sizeof(int32_t));
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&cn, sizeof(int));
+        if (e != cudaSuccess) { cudaFree(ws); cudaFree(li); cudaFree(cn); return e; }
+        h->resto_ws = ws; h->resto_list = li; h->resto_count = cn; h->resto_cap = (int)(cap >= 1 ? cap : 0); h->resto_rows = rows;
+    }
+    io.resto_ws = h->resto_cap ? h->resto_ws : NULL; io.resto_list = h->resto_list; io.resto_count = h->resto_count;
+    io.resto_cap = h->resto_cap; io.resto_rows = h->resto_rows;
+    e = cudaMemsetAsync(h->resto_count, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
     kern<<<grid, 32 * wpb, smem, st>>>(c, io, queue, trips);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (h->resto_cap) {
+        const int cap = h->resto_cap < B ? h->resto_cap : B;
+        if (OBS) kmpc_finish_kernel<true><<<(cap + 31) / 32, 32, 0, st>>>(c, io);
+        else kmpc_finish_kernel<false><<<(cap + 31) / 32, 32, 0, st>>>(c, io);
+        h->launches++;
+    }
     return cudaGetLastError();
 }
 
@@ -519,7 +562,7 @@ extern "C" int kmpc_version(void) { return KMPC_VERSION; }
 extern "C" size_t kmpc_workspace_bytes(const kmpc_config *cfg) {
     if (!check_cfg(cfg)) return 0;
     Rows r = make_rows(cfg->N, cfg->O_max, 1);
-    return (size_t)r.total * cols_for(cfg) * sizeof(double) + (size_t)4 * cols_for(cfg) * sizeof(int);
+    return (size_t)make_resto_rows(r).total * cols_for(cfg) * sizeof(double) + (size_t)4 * cols_for(cfg) * sizeof(int);
 }
 
 extern "C" const char *kmpc_last_error(const kmpc_handle *h) { return h ? h->err : g_err; }
@@ -536,6 +579,9 @@ extern "C" void kmpc_destroy(kmpc_handle *h) {
     if (h->okey) cudaFree(h->okey);
     if (h->env_obs) cudaFree(h->env_obs);
     if (h->env_rad) cudaFree(h->env_rad);
+    if (h->resto_ws) cudaFree(h->resto_ws);
+    if (h->resto_list) cudaFree(h->resto_list);
+    if (h->resto_count) cudaFree(h->resto_count);
     if (h->env_idx) cudaFree(h->env_idx);
     if (h->oval) cudaFree(h->oval);
     if (h->osort_tmp) cudaFree(h->osort_tmp);
@@ -694,7 +740,7 @@ static int solve_impl(kmpc_handle *h, int B, const SolveArgs &a, void *cuda_stre
     }
     if (!h->lists) {   // first thread-solver solve on this handle (both buffers are committed together)
         double *ws = NULL; int *li = NULL;
-        cudaError_t e = cudaMalloc(&ws, (size_t)h->rows.total * h->cols * sizeof(double));
+        cudaError_t e = cudaMalloc(&ws, (size_t)make_resto_rows(h->rows).total * h->cols * sizeof(double));   // (solver rows + the rows of the restoration phase)
         if (e == cudaSuccess) e = cudaMalloc(&li, (size_t)4 * h->cols * sizeof(int));
         if (e != cudaSuccess) { cudaFree(ws); cudaFree(li); CU(e); }
         h->ws = ws; h->lists = li;

@@ -71,10 +71,10 @@ namespace kmpc {
 #define K_CONSTR_VIOL_TOL 1e-4
 #define K_COMPL_INF_TOL 1e-4
 #define K_DIVERGING 1e20
-#define K_FILTER_CAP 24
+#define K_FILTER_CAP 64          /* filter entries kept per instance (IPOPT's filter is unbounded; a full filter ends the instance with Internal_Error) */
 #define KMPC_NCTX 40  /* rows reserved for the per-instance solver context in the workspace */
 
-enum { ST_SUCCESS = 0, ST_MAXITER = -1, ST_RESTORATION = -2, ST_STEP_ERROR = -3, ST_DIVERGING = 4, ST_INVALID = -13 };
+enum { ST_SUCCESS = 0, ST_MAXITER = -1, ST_RESTORATION = -2, ST_STEP_ERROR = -3, ST_DIVERGING = 4, ST_INVALID = -13, ST_INTERNAL = -199 };
 enum { M_FETCH = 0, M_LSQ = 1, M_NEWTON = 2, M_SOC = 3, M_TRIAL = 4, M_DONE = 5 };
 enum { TU_INIT = 0, TU_STEP = 1 };
 
@@ -140,6 +140,12 @@ struct IO {
     double *wscratch;       // warp solver: global scratch, WLay::GPRIV doubles per resident warp (owned by the handle)
     const int32_t *active;  // optional per-instance mask (closed loop: agents that reached their goal are not solved again)
     const int32_t *order;   // warp solver: instance handed out at queue position q (NULL: q itself); a permutation of 0..B-1
+    // warp solver -> finisher hand-over of the instances whose line search failed (restoration phase, kmpc_resto.cuh): a workspace
+    // column per instance (resto_rows doubles each, contiguous), the instance each column holds, the number of columns in use
+    double *resto_ws;
+    int32_t *resto_list;
+    int *resto_count;
+    int resto_cap, resto_rows;
 };
 #define KMPC_STATUS_SKIPPED 1000  /* status_log value of an agent that was not solved in a closed-loop step */
 
@@ -868,14 +874,18 @@ KMPC_HD bool filter_ok(const Ctx &t, const double *filt, size_t FS, double theta
         if (!(theta <= filt[(size_t)(2 * i) * FS] || phi <= filt[(size_t)(2 * i + 1) * FS])) return false;
     return true;
 }
-KMPC_HD void filter_add(Ctx &t, double *filt, size_t FS, double theta, double phi) {
+// false: the filter is full (the entry is NOT recorded; the caller ends the instance with ST_INTERNAL rather than go on with a
+// filter that has forgotten an entry)
+KMPC_HD bool filter_add(Ctx &t, double *filt, size_t FS, double theta, double phi) {
     int m = 0;
     for (int i = 0; i < t.fn; ++i) {
         const double th = filt[(size_t)(2 * i) * FS], ph = filt[(size_t)(2 * i + 1) * FS];
         if (!(th >= theta && ph >= phi)) { filt[(size_t)(2 * m) * FS] = th; filt[(size_t)(2 * m + 1) * FS] = ph; ++m; }
     }
     t.fn = m;
-    if (t.fn < K_FILTER_CAP) { filt[(size_t)(2 * t.fn) * FS] = theta; filt[(size_t)(2 * t.fn + 1) * FS] = phi; t.fn++; }
+    if (t.fn >= K_FILTER_CAP) return false;
+    filt[(size_t)(2 * t.fn) * FS] = theta; filt[(size_t)(2 * t.fn + 1) * FS] = phi; t.fn++;
+    return true;
 }
 
 // FilterLSAcceptor::CheckAcceptabilityOfTrialPoint
@@ -1053,6 +1063,10 @@ KMPC_HD int trial_decide(Ctx &t, const double *filt, size_t FS, const Stats &tri
     return R_ACCEPT;
 }
 
+}  // namespace kmpc
+#include "kmpc_resto.cuh"   // the feasibility restoration phase (uses everything above)
+namespace kmpc {
+
 template <bool OBS>
 KMPC_HDN inline int phase_trial(const Cfg &c, Ctx &t, double *wsp, size_t S) {
     trial_setup(t);
@@ -1061,9 +1075,11 @@ KMPC_HDN inline int phase_trial(const Cfg &c, Ctx &t, double *wsp, size_t S) {
     bool aug; double ath, aph;
     double *filt = wsp + (size_t)c.L.rFilt * S;
     const int r = trial_decide(t, filt, S, tri, evok, &aug, &ath, &aph);
-    if (aug) filter_add(t, filt, S, ath, aph);
+    if (aug && !filter_add(t, filt, S, ath, aph)) return ST_INTERNAL;
     if (r == R_SOC1 || r == R_SOC2) { pass_soc_rhs(c, t, wsp, S, t.alpha_soc, r == R_SOC1); return 100; }
     if (r == R_BACKTRACK) return 100;
+    // the step size fell below alpha_min: IPOPT's restoration phase (100: it handed a point back, the next trip is a Newton step there)
+    if (r == ST_RESTORATION) return resto_enter<OBS>(c, t, make_resto_rows(c.L), wsp, S);
     if (r != R_ACCEPT) return r;
     // the trial buffer becomes the current iterate
     t.c = tri; t.cur ^= 1;
@@ -1081,6 +1097,8 @@ KMPC_HDN inline int trip(const Cfg &c, Ctx &t, double *wsp, size_t S) {
     }
     return phase_trial<OBS>(c, t, wsp, S);
 }
+
+// (finish_instance is defined at the end of the file: it needs ctx_load)
 
 // ---- solver context <-> workspace (the kernels keep no state between launches) -------------------
 enum { X_MODE = 0, X_ITER, X_CUR, X_NSTEPS, X_SOCC, X_FN, X_TRIPS, X_SEL, X_TU, X_MU, X_TAU, X_DELTA, X_DLAST, X_DF, X_THMAX,
@@ -1111,6 +1129,21 @@ KMPC_HD void ctx_load(Ctx &t, const Rows &L, const double *wsp, size_t S) {
     t.c.f = FD(p, X_CF); t.c.bar = FD(p, X_CBAR); t.c.damp = FD(p, X_CDAMP); t.c.theta = FD(p, X_CTHETA); t.c.dinf = FD(p, X_CDINF);
     t.c.pinf = FD(p, X_CPINF); t.c.mn = FD(p, X_CMN); t.c.mx = FD(p, X_CMX); t.c.sumy = FD(p, X_CSUMY); t.c.sumz = FD(p, X_CSUMZ);
     t.c.wmax = FD(p, X_CWMAX); t.pw_g = FD(p, X_PWG); t.pw_t = FD(p, X_PWT);
+}
+
+// Finisher of the warp solver (kmpc_finish_kernel): column i of the hand-over workspace holds an instance whose regular line search
+// failed (its iterate, multipliers, filter and solver context as the warp solver left them, w_hand_over in kmpc_warp.cuh).  One thread
+// runs IPOPT's restoration phase on it and, if that hands a point back, the rest of the regular algorithm (the thread solver's trips),
+// then writes the instance's outputs.
+template <bool OBS>
+KMPC_HDN inline void finish_instance(const Cfg &c, const IO &io, int i) {
+    double *wsp = io.resto_ws + (size_t)i * io.resto_rows;
+    Ctx t;
+    ctx_load(t, c.L, wsp, 1);
+    t.inst = io.resto_list[i];
+    int r = resto_enter<OBS>(c, t, make_resto_rows(c.L), wsp, 1);
+    while (r == 100) r = trip<OBS>(c, t, wsp, 1);
+    pass_output(c, t, wsp, 1, io, r);
 }
 
 }  // namespace kmpc

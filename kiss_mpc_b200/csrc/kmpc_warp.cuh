@@ -938,6 +938,58 @@ __device__ __forceinline__ unsigned kmpc_smid() { unsigned r; asm volatile("mov.
 #define SCHED_END(b, trips)
 #endif
 
+// The regular line search of this instance has failed (trial_decide returned ST_RESTORATION) and the point is not "almost feasible":
+// IPOPT's restoration phase is due.  It is rare and serial in nature, so it does not run here: the instance is handed over to the
+// finisher (finish_instance, kmpc_core.cuh) -- iterate, multipliers, obstacle-row state, problem data, filter and solver context go
+// to a column of the hand-over workspace in the thread solver's layout.  False: no column left (the caller reports Restoration_Failed).
+template <int SPL, int NST, bool OBS>
+KMPC_WN inline bool w_hand_over(const Cfg &c, WScal *sc, const WState<SPL> &w, const double *ob, const IO &io, int b) {
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
+    const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
+    const Rows &L = c.L;
+    int slot = -1;
+    if (lane == 0 && io.resto_ws) slot = w_take_slot(io.resto_count);
+    slot = w_bcast_i(slot, 0);
+    if (slot < 0 || slot >= io.resto_cap) return false;
+    double *base = io.resto_ws + (size_t)slot * io.resto_rows;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int s = lane * SPL + j;
+        if (s > N) continue;
+        double *ps = base + L.rState[0] + NSTATE * s;
+        ps[F_X0] = w.x0[j]; ps[F_X1] = w.x1[j]; ps[F_X2] = w.x2[j]; ps[F_V] = w.v[j]; ps[F_OM] = w.om[j];
+        ps[F_Y0] = w.y0[j]; ps[F_Y1] = w.y1[j]; ps[F_Y2] = w.y2[j];
+        ps[F_ZLX] = w.zLx[j]; ps[F_ZUX] = w.zUx[j]; ps[F_ZLY] = w.zLy[j]; ps[F_ZUY] = w.zUy[j];
+        ps[F_ZLV] = w.zLv[j]; ps[F_ZUV] = w.zUv[j]; ps[F_ZLW] = w.zLw[j]; ps[F_ZUW] = w.zUw[j];
+        ps[F_CS] = w.cs[j]; ps[F_SN] = w.sn[j];
+        if (OBS && s >= 1) {
+            const WCen cen = w_cen(c, ob, O, NSTG, s);
+            for (int o = 0; o < O; ++o) {
+                const double *po = ob + o * NSTG + s;
+                double *pr = base + L.rState[0] + L.sObs + 3 * ((s - 1) * O + o);
+                pr[0] = po[B_S * O * NSTG]; pr[1] = po[B_YD * O * NSTG]; pr[2] = po[B_VL * O * NSTG];
+                if (c.obs_sw) { base[L.rSc + CEN_ROW(o, s, 0)] = w_cx(cen, o); base[L.rSc + CEN_ROW(o, s, 1)] = w_cy(cen, o); }
+            }
+        }
+    }
+    if (OBS) {
+        const WCen cen = w_cen(c, ob, O, NSTG, 1);
+        for (int o = lane; o < O; o += 32) {
+            base[L.rSc + RAD_ROW(o)] = w_cr(cen, o);
+            if (!c.obs_sw) { base[L.rSc + CEN_ROW(o, 1, 0)] = w_cx(cen, o); base[L.rSc + CEN_ROW(o, 1, 1)] = w_cy(cen, o); }
+        }
+    }
+    for (int i = lane; i < 2 * sc->t.fn; i += 32) base[L.rFilt + i] = sc->filt[i];
+    if (lane == 0) {
+        for (int j = 0; j < 3; ++j) { base[L.rSc + j] = sc->xc[j]; base[L.rSc + 3 + j] = sc->gl[j]; }
+        sc->t.cur = 0; sc->t.inst = b;
+        ctx_store(sc->t, L, base, 1);
+        io.resto_list[slot] = b;
+    }
+    w_sync();
+    return true;
+}
+
 // next instance of the queue that is to be solved (masked-out instances only get their status / iteration records)
 KMPC_WN inline int w_fetch_active(const Cfg &c, const IO &io, int *queue) {
     for (;;) {
@@ -1149,8 +1201,8 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             PT(7)
             if (lane == 0) {
                 bool aug; double ath, aph;
-                const int r = trial_decide(t, sc->filt, 1, ts, evok, &aug, &ath, &aph);
-                if (aug) filter_add(t, sc->filt, 1, ath, aph);
+                int r = trial_decide(t, sc->filt, 1, ts, evok, &aug, &ath, &aph);
+                if (aug && !filter_add(t, sc->filt, 1, ath, aph)) r = ST_INTERNAL;   // filter full: ends the instance loudly (Internal_Error)
                 sc->r = r;
             }
             w_sync();
@@ -1173,6 +1225,15 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             break;
         }
         PT(8)
+        if (have && status == ST_RESTORATION) {
+            // IPOPT's BacktrackingLineSearch: restoration phase, unless the point is almost feasible ("Restoration phase called, but
+            // point is almost feasible": Restoration_Failed).  The phase itself runs in the finisher kernel.
+            if (!(t.c.theta <= 1e-2 * c.tol) && w_hand_over<SPL, NST, OBS>(c, sc, cur, ob, io, b)) {
+                if (lane == 0) { w_count_trips(trips_total, t.trips); SCHED_END(b, t.trips) t.mode = M_DONE; }
+                have = false;
+                status = 100;
+            }
+        }
         if (have && status != 100 && status != R_RETRY) {
             // returned matrices (optimizer.py:392-400): every lane writes its stages
 #pragma unroll

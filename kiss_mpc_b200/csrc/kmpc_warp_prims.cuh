@@ -35,6 +35,7 @@ KMPC_W int w_fetch(int *queue) {  // next instance index for this warp
     return __shfl_sync(0xffffffffu, b, 0);
 }
 KMPC_W void w_count_trips(unsigned long long *total, int trips) { if (total) atomicAdd(total, (unsigned long long)trips); }
+KMPC_W int w_take_slot(int *counter) { return atomicAdd(counter, 1); }   // global-memory counter
 // max / min over the warp of doubles whose sign bit is clear (non-negative numbers, +inf, NaN with a clear sign bit): their
 // bit patterns order like unsigned integers, so two 32-bit warp reductions (CREDUX) replace a 5-level shuffle butterfly.
 // A NaN (pattern above +inf) wins the max, i.e. it propagates, exactly like w_maxabs_nan.

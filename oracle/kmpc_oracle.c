@@ -26,9 +26,15 @@
  *     mu_superlinear_decrease_power 1.5, mu_allow_fast_monotone_decrease yes]
  *   - termination on the scaled optimality error E_0 <= tol [tol 1e-8, s_max 100] plus the unscaled
  *     dual_inf_tol 1 / constr_viol_tol 1e-4 / compl_inf_tol 1e-4 tests; max_iter 2000.
- * What is NOT restated (documented deviations; the step that would call them is flagged in the status):
- *   - the restoration phase (status -2 is returned where IPOPT would enter it), watchdog, soft restoration,
- *     iterative refinement of the linear solve, tiny-step detection, slack safeguards at machine precision.
+ *   - the feasibility restoration phase [MinC_1NrmRestorationPhase: resto_penalty_parameter 1000, resto_proximity_weight 1,
+ *     required_infeasibility_reduction 0.9, bound_mult_reset_threshold 1000, constr_mult_reset_threshold 0,
+ *     resto.theta_max_fact 1e8]: entered when the line search runs below alpha_min; "almost feasible" entry -> Restoration_Failed
+ *     (-2); converged to a stationary point of the infeasibility that is not feasible -> Infeasible_Problem_Detected (2).
+ *     Restated from the published algorithm (Waechter & Biegler 2006, section 3.3) and IPOPT 3.14's documented behaviour; like the
+ *     rest of this file it cannot be held against IPOPT itself here.
+ * What is NOT restated (documented deviations):
+ *   - watchdog, soft restoration phase, iterative refinement of the linear solve, tiny-step detection, slack safeguards at
+ *     machine precision, the recursive restoration inside the restoration phase.
  *
  * Linear algebra: linsolve=0 assembles the full IPOPT augmented system (x, s, y_c, y_d) densely and factors it
  * with a Bunch-Kaufman LDL^T, reading the inertia off D exactly as IPOPT does with MUMPS.  linsolve=1 solves the
@@ -90,9 +96,14 @@
 #define COMPL_INF_TOL 1e-4
 #define DIVERGING_TOL 1e20
 #define FILTER_CAP 512
+#define RESTO_RHO 1000.0          /* resto_penalty_parameter */
+#define RESTO_KAPPA 0.9           /* required_infeasibility_reduction */
+#define RESTO_THETA_MAX_FACT 1e8  /* resto.theta_max_fact */
+#define BOUND_MULT_RESET 1000.0   /* bound_mult_reset_threshold */
 
 /* IPOPT ApplicationReturnStatus numbering */
 #define ST_SUCCESS 0
+#define ST_INFEASIBLE 2
 #define ST_MAXITER (-1)
 #define ST_RESTORATION (-2)
 #define ST_STEP_ERROR (-3)
@@ -130,6 +141,8 @@ typedef struct {
     double err;          /* final scaled E_0 */
     double obj_scaling;  /* df */
     double max_delta_w;  /* largest Hessian perturbation used */
+    int32_t n_resto;     /* restoration phases entered */
+    int32_t reserved;
 } kmo_diag;
 
 /* ------------------------------------------------------------------ */
@@ -164,6 +177,10 @@ typedef struct {
     /* riccati solver */
     double *Kg /*[N][6]*/, *Quui /*[N][3]*/, *Pm /*[N+1][6]*/, *pv, *Sigc /*[ns]*/;
     int linsolve;
+    /* restoration phase: -Dc / -Dd on the diagonal of the constraint blocks (eliminated n, p), proximity Hessian eta * DR^2 instead of the objective's */
+    double *Dc, *Dd, *DR2;
+    double eta;
+    int resto;
 } work_t;
 
 static void *xcalloc(size_t n, size_t sz) { void *p = calloc(n ? n : 1, sz); if (!p) abort(); return p; }
@@ -190,6 +207,7 @@ static work_t *work_new(const kmo_config *cf) {
         w->perm = (int *)xcalloc(w->nk, sizeof(int)); w->pivtype = (int *)xcalloc(w->nk, sizeof(int));
     }
     D(Kg, 6 * N); D(Quui, 3 * N); D(Pm, 6 * (N + 1)); D(pv, 3 * (N + 1)); D(Sigc, ns);
+    D(Dc, mc); D(Dd, ns); D(DR2, n);
 #undef D
     return w;
 }
@@ -199,7 +217,7 @@ static void work_free(work_t *w) {
         &w->dms, &w->cs, &w->sn, &w->nrm, &w->dist, &w->Wxx, &w->Wtv, &w->Wvv, &w->Www, &w->Dx, &w->Ds, &w->bx,
         &w->bs, &w->bc, &w->bd, &w->dx, &w->ds, &w->dyc, &w->dyd, &w->dzL, &w->dzU, &w->dvL, &w->dx2, &w->ds2,
         &w->dyc2, &w->dyd2, &w->csoc, &w->dsoc, &w->wt, &w->st, &w->ct, &w->dmst, &w->K, &w->L, &w->rhs, &w->Kg,
-        &w->Quui, &w->Pm, &w->pv, &w->Sigc};
+        &w->Quui, &w->Pm, &w->pv, &w->Sigc, &w->Dc, &w->Dd, &w->DR2};
     for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i) free(*ptrs[i]);
     free(w->hasL); free(w->hasU); free(w->perm); free(w->pivtype);
     free(w);
@@ -300,7 +318,9 @@ static void eval_hess(const kmo_config *cf, work_t *wk, const double *w, const d
     int N = wk->N, O = wk->O; double T = cf->T, df = wk->df;
     memset(wk->Wxx, 0, sizeof(double) * 6 * (N + 1));
     for (int k = 0; k <= N; ++k) {
-        if (k >= cf->goal_k_lo && k <= cf->goal_k_hi) {
+        if (wk->resto) {   /* restoration objective: rho (n + p) + eta/2 |DR (x - x_ref)|^2 -> eta DR^2 on the diagonal */
+            wk->Wxx[6 * k + 0] = wk->eta * wk->DR2[IX(k, 0)]; wk->Wxx[6 * k + 2] = wk->eta * wk->DR2[IX(k, 1)]; wk->Wxx[6 * k + 5] = wk->eta * wk->DR2[IX(k, 2)];
+        } else if (k >= cf->goal_k_lo && k <= cf->goal_k_hi) {
             wk->Wxx[6 * k + 0] = df * 2.0 * cf->W[0]; wk->Wxx[6 * k + 2] = df * 2.0 * cf->W[1]; wk->Wxx[6 * k + 5] = df * 2.0 * cf->W[2];
         }
         wk->Wtv[k] = 0; wk->Wvv[k] = 0; wk->Www[k] = 0;
@@ -309,6 +329,7 @@ static void eval_hess(const kmo_config *cf, work_t *wk, const double *w, const d
         double v = w[IU(k, 0)]; const double *yn = yc + 3 * (k + 1);
         wk->Wxx[6 * k + 5] += T * v * (yn[0] * cs[k] + yn[1] * sn[k]);
         wk->Wtv[k] = T * (yn[0] * sn[k] - yn[1] * cs[k]);
+        if (wk->resto) { wk->Wvv[k] = wk->eta * wk->DR2[IU(k, 0)]; wk->Www[k] = wk->eta * wk->DR2[IU(k, 1)]; continue; }
         if (cf->cost_mode == 0) { double a = dmin0(v), b = dmax0(v); wk->Wvv[k] = df * (2.0 * cf->Wv_neg * a * a + 2.0 * cf->Wv_pos * b * b); }
         wk->Www[k] = df * 2.0 * cf->Ww;
     }
@@ -452,6 +473,10 @@ static int kkt_factor_dense(const kmo_config *cf, work_t *wk, const double *w, i
     for (int o = 0; o < O; ++o) for (int k = 1; k <= N; ++k) {
         int i = IS(o, k);
         KS(rd + i, IX(k, 0), wk->nrm[2 * i]); KS(rd + i, IX(k, 1), wk->nrm[2 * i + 1]); KS(rd + i, n + i, -1.0);
+    }
+    if (wk->resto) {
+        for (int i = 0; i < mc; ++i) KS(rc + i, rc + i, -wk->Dc[i]);
+        for (int i = 0; i < ns; ++i) KS(rd + i, rd + i, -wk->Dd[i]);
     }
 #undef KS
     int npos, nneg, nzero;
@@ -721,6 +746,325 @@ static void build_rhs(const kmo_config *cf, work_t *wk, double mu, double delta_
 }
 
 /* ------------------------------------------------------------------ */
+/* feasibility restoration phase (IPOPT MinC_1NrmRestorationPhase / RestoIpoptNLP / RestoIterateInitializer /
+ * RestoFilterConvergenceCheck; Waechter & Biegler 2006, section 3.3):
+ *     min  rho (sum n_c + p_c + n_d + p_d) + eta/2 |D_R (x - x_ref)|^2      rho = 1000, eta = sqrt(mu), D_R = diag 1/max(1,|x_ref|)
+ *     s.t. c(x) + n_c - p_c = 0,   d(x) - s + n_d - p_d = 0,   x and s within their bounds,   n, p >= 0
+ * solved by the same interior-point algorithm (own filter, own barrier parameter starting at max(mu, |c|_inf, |d - s|_inf)); n and p
+ * are eliminated from the step system, which leaves -(n/z_n + p/z_p) on the diagonal of the constraint blocks.  It returns to the
+ * regular algorithm as soon as an iterate reduces the ORIGINAL constraint violation to 0.9 of its value at entry and is acceptable
+ * to the original filter and current point; if instead it converges on its own problem the original NLP is locally infeasible.
+ * Always uses the dense augmented system.  Returns 0 (x, s, bound multipliers replaced; y = 0) or a final status.
+ * ------------------------------------------------------------------ */
+typedef struct {
+    double *nc, *pc, *znc, *zpc, *nd, *pd, *znd, *zpd, *xref;
+    double *dnc, *dpc, *dnd, *dpd, *nct, *pct, *ndt, *pdt;
+    double *rc, *rd, *gR, *rnc, *rpc, *rnd, *rpd;
+} resto_t;
+
+static double resto_f(const work_t *wk, const resto_t *R, const double *w, const double *nc, const double *pc, const double *nd, const double *pd) {
+    double f = 0, q = 0;
+    for (int i = 0; i < wk->mc; ++i) f += nc[i] + pc[i];
+    for (int i = 0; i < wk->ns; ++i) f += nd[i] + pd[i];
+    for (int i = 0; i < wk->n; ++i) { double e = w[i] - R->xref[i]; q += wk->DR2[i] * e * e; }
+    return RESTO_RHO * f + 0.5 * wk->eta * q;
+}
+
+/* barrier objective and constraint violation of the restoration problem; leaves c + n - p in ct, d - s + n - p in dt */
+static int resto_merit(const kmo_config *cf, work_t *wk, const resto_t *R, const double *w, const double *s, const double *nc, const double *pc,
+                       const double *nd, const double *pd, double mu, double *ct, double *dt, merit_t *m) {
+    int n = wk->n, ns = wk->ns, mc = wk->mc;
+    double bar = 0, damp = 0;
+    for (int i = 0; i < n; ++i) {
+        if (wk->hasL[i]) { double sl = w[i] - wk->lb[i]; if (!(sl > 0)) return 0; bar += log(sl); if (!wk->hasU[i]) damp += sl; }
+        if (wk->hasU[i]) { double su = wk->ub[i] - w[i]; if (!(su > 0)) return 0; bar += log(su); if (!wk->hasL[i]) damp += su; }
+    }
+    for (int i = 0; i < ns; ++i) { double sl = s[i] - wk->dL; if (!(sl > 0)) return 0; bar += log(sl); damp += sl; }
+    for (int i = 0; i < mc; ++i) { if (!(nc[i] > 0) || !(pc[i] > 0)) return 0; bar += log(nc[i]) + log(pc[i]); damp += nc[i] + pc[i]; }
+    for (int i = 0; i < ns; ++i) { if (!(nd[i] > 0) || !(pd[i] > 0)) return 0; bar += log(nd[i]) + log(pd[i]); damp += nd[i] + pd[i]; }
+    eval_c(cf, wk, w, ct);
+    double theta = 0;
+    for (int i = 0; i < mc; ++i) { ct[i] += nc[i] - pc[i]; theta += fabs(ct[i]); }
+    if (ns) { eval_d(cf, wk, w, dt, NULL, NULL); for (int i = 0; i < ns; ++i) { dt[i] += -s[i] + nd[i] - pd[i]; theta += fabs(dt[i]); } }
+    m->f = resto_f(wk, R, w, nc, pc, nd, pd); m->phi = m->f - mu * bar + KAPPA_D * mu * damp; m->theta = theta;
+    return isfinite(m->phi) && isfinite(m->theta);
+}
+
+static int resto_acceptable(const filter_t *F, const merit_t *cur, const merit_t *tri, double gBD, double alpha_test, double theta_max, double theta_min) {
+    if (tri->theta > theta_max) return 0;
+    int acc;
+    int ftype = gBD < 0 && alpha_test * pow(-gBD, S_PHI) > DELTA_LS * pow(cur->theta, S_THETA);
+    if (ftype && cur->theta <= theta_min) acc = compare_le(tri->phi - cur->phi, ETA_PHI * alpha_test * gBD, cur->phi);
+    else {
+        acc = 1;
+        if (tri->phi > cur->phi) { double bas = fabs(cur->phi) > 10.0 ? log10(fabs(cur->phi)) : 1.0; if (log10(tri->phi - cur->phi) > OBJ_MAX_INC + bas) acc = 0; }
+        if (acc) acc = compare_le(tri->theta, (1.0 - GAMMA_THETA) * cur->theta, cur->theta) || compare_le(tri->phi - cur->phi, -GAMMA_PHI * cur->theta, cur->phi);
+    }
+    if (acc) acc = filter_ok(F, tri->theta, tri->phi);
+    return acc;
+}
+
+static int restoration(const kmo_config *cf, work_t *wk, double mu_orig, const filter_t *F_orig, double theta_ref, double phi_ref,
+                       int *iter, kmo_diag *dg) {
+    const int n = wk->n, ns = wk->ns, mc = wk->mc;
+    const double rho = RESTO_RHO;
+    int st = -100;
+    if (!wk->K) {   /* the restoration phase always factors the dense augmented system */
+        wk->K = (double *)xcalloc((size_t)wk->nk * wk->nk, sizeof(double)); wk->L = (double *)xcalloc((size_t)wk->nk * wk->nk, sizeof(double));
+        wk->rhs = (double *)xcalloc(wk->nk, sizeof(double)); wk->perm = (int *)xcalloc(wk->nk, sizeof(int)); wk->pivtype = (int *)xcalloc(wk->nk, sizeof(int));
+    }
+    resto_t R;
+    const size_t tot = (size_t)16 * mc + 16 * (ns ? ns : 1) + 2 * n + 16;
+    double *pool = (double *)xcalloc(tot, sizeof(double)), *q = pool;
+#define TAKE(name, cnt) R.name = q; q += (cnt)
+    TAKE(nc, mc); TAKE(pc, mc); TAKE(znc, mc); TAKE(zpc, mc); TAKE(dnc, mc); TAKE(dpc, mc); TAKE(nct, mc); TAKE(pct, mc); TAKE(rc, mc); TAKE(rnc, mc); TAKE(rpc, mc);
+    TAKE(nd, ns); TAKE(pd, ns); TAKE(znd, ns); TAKE(zpd, ns); TAKE(dnd, ns); TAKE(dpd, ns); TAKE(ndt, ns); TAKE(pdt, ns); TAKE(rd, ns); TAKE(rnd, ns); TAKE(rpd, ns);
+    TAKE(xref, n); TAKE(gR, n);
+#undef TAKE
+    filter_t *F = (filter_t *)xcalloc(1, sizeof(filter_t));
+    const int saved_linsolve = wk->linsolve;
+    wk->linsolve = 0; wk->resto = 1;
+
+    /* RestoIterateInitializer: x, s kept; mu = max(mu, |c|_inf, |d - s|_inf); n, p from the complementarity-consistent formula */
+    eval_trig(wk, wk->w, wk->cs, wk->sn);
+    eval_c(cf, wk, wk->w, wk->c);
+    if (ns) { eval_d(cf, wk, wk->w, wk->dms, wk->nrm, wk->dist); for (int i = 0; i < ns; ++i) wk->dms[i] -= wk->s[i]; }
+    double mu = fmax(mu_orig, fmax(vmaxabs(wk->c, mc), ns ? vmaxabs(wk->dms, ns) : 0.0)), tau = fmax(TAU_MIN, 1.0 - mu);
+    wk->eta = sqrt(mu_orig);
+    for (int i = 0; i < n; ++i) { R.xref[i] = wk->w[i]; double dr = 1.0 / fmax(1.0, fabs(wk->w[i])); wk->DR2[i] = dr * dr; }
+    for (int i = 0; i < mc + ns; ++i) {
+        double cv = i < mc ? wk->c[i] : wk->dms[i - mc];
+        double a = (mu - rho * cv) / (2.0 * rho), nn = a + sqrt(a * a + mu * cv / (2.0 * rho)), pp = cv + nn;
+        if (i < mc) { R.nc[i] = nn; R.pc[i] = pp; R.znc[i] = mu / nn; R.zpc[i] = mu / pp; }
+        else { R.nd[i - mc] = nn; R.pd[i - mc] = pp; R.znd[i - mc] = mu / nn; R.zpd[i - mc] = mu / pp; }
+    }
+    for (int i = 0; i < n; ++i) { if (wk->hasL[i]) wk->zL[i] = fmin(rho, wk->zL[i]); if (wk->hasU[i]) wk->zU[i] = fmin(rho, wk->zU[i]); }
+    for (int i = 0; i < ns; ++i) wk->vL[i] = fmin(rho, wk->vL[i]);
+    memset(wk->yc, 0, sizeof(double) * mc); if (ns) memset(wk->yd, 0, sizeof(double) * ns);
+
+    double theta_max = -1, theta_min = -1, delta_last = 0.0;
+    int first = 1;
+    double *rx = wk->dx2, *rs = wk->ds2;
+    for (;;) {
+        /* ---- residuals of the restoration problem at the current iterate ---- */
+        eval_trig(wk, wk->w, wk->cs, wk->sn);
+        eval_c(cf, wk, wk->w, wk->c);
+        if (ns) { eval_d(cf, wk, wk->w, wk->dms, wk->nrm, wk->dist); for (int i = 0; i < ns; ++i) wk->dms[i] -= wk->s[i]; }
+        for (int i = 0; i < n; ++i) R.gR[i] = wk->eta * wk->DR2[i] * (wk->w[i] - R.xref[i]);
+        memcpy(rx, R.gR, sizeof(double) * n);
+        add_JcT(cf, wk, wk->w, wk->cs, wk->sn, wk->yc, rx);
+        if (ns) add_JdT(wk, wk->nrm, wk->yd, rx);
+        double mn = INFINITY, mx = 0, sz = 0, dinf = 0, pinf = 0; int nb = 0;
+#define CP(slack, z) do { double p_ = (slack) * (z); mn = fmin(mn, p_); mx = fmax(mx, p_); sz += fabs(z); nb++; } while (0)
+        for (int i = 0; i < n; ++i) {
+            if (wk->hasL[i]) { rx[i] -= wk->zL[i]; CP(wk->w[i] - wk->lb[i], wk->zL[i]); }
+            if (wk->hasU[i]) { rx[i] += wk->zU[i]; CP(wk->ub[i] - wk->w[i], wk->zU[i]); }
+        }
+        for (int i = 0; i < ns; ++i) { rs[i] = -wk->yd[i] - wk->vL[i]; CP(wk->s[i] - wk->dL, wk->vL[i]); }
+        for (int i = 0; i < mc; ++i) {
+            R.rc[i] = wk->c[i] + R.nc[i] - R.pc[i];
+            dinf = fmax(dinf, fmax(fabs(rho + wk->yc[i] - R.znc[i]), fabs(rho - wk->yc[i] - R.zpc[i])));
+            CP(R.nc[i], R.znc[i]); CP(R.pc[i], R.zpc[i]);
+        }
+        for (int i = 0; i < ns; ++i) {
+            R.rd[i] = wk->dms[i] + R.nd[i] - R.pd[i];
+            dinf = fmax(dinf, fmax(fabs(rho + wk->yd[i] - R.znd[i]), fabs(rho - wk->yd[i] - R.zpd[i])));
+            CP(R.nd[i], R.znd[i]); CP(R.pd[i], R.zpd[i]);
+        }
+#undef CP
+        { double a = vmaxabs(rx, n), b = ns ? vmaxabs(rs, ns) : 0.0; dinf = (a != a || b != b) ? NAN : fmax(dinf, fmax(a, b)); }
+        { double a = vmaxabs(R.rc, mc), b = ns ? vmaxabs(R.rd, ns) : 0.0; pinf = (a != a || b != b) ? NAN : fmax(a, b); }
+        const double sum_y = vsumabs(wk->yc, mc) + (ns ? vsumabs(wk->yd, ns) : 0.0);
+        const double sd = fmax(S_MAX, (sum_y + sz) / (double)(mc + ns + nb)) / S_MAX, sc = fmax(S_MAX, sz / (double)nb) / S_MAX;
+#define RCOMPL(m_) fmax(fabs(mx - (m_)), fabs(mn - (m_)))
+#define RERR(m_) fmax(dinf / sd, fmax(pinf, RCOMPL(m_) / sc))
+        const double E0 = RERR(0.0);
+        if (!isfinite(E0) || !isfinite(dinf) || !isfinite(pinf)) { st = ST_INVALID_NUMBER; break; }
+
+        /* ---- RestoFilterConvergenceCheck (not in the first iteration: the start is the point the line search failed at) ---- */
+        if (!first) {
+            const double theta_o = vsumabs(wk->c, mc) + (ns ? vsumabs(wk->dms, ns) : 0.0);
+            if (theta_o <= RESTO_KAPPA * theta_ref) {
+                merit_t mo;
+                if (eval_merit(cf, wk, wk->w, wk->s, mu_orig, wk->ct, wk->dmst, &mo) && filter_ok(F_orig, mo.theta, mo.phi) &&
+                    (compare_le(mo.theta, (1.0 - GAMMA_THETA) * theta_ref, theta_ref) || compare_le(mo.phi - phi_ref, -GAMMA_PHI * theta_ref, phi_ref))) { st = 0; break; }
+            }
+            if (E0 <= cf->tol && dinf <= DUAL_INF_TOL && pinf <= CONSTR_VIOL_TOL && RCOMPL(0.0) <= COMPL_INF_TOL) {
+                const double po = fmax(vmaxabs(wk->c, mc), ns ? vmaxabs(wk->dms, ns) : 0.0);
+                st = po <= 1e2 * cf->tol ? ST_RESTORATION : ST_INFEASIBLE;   /* converged to a feasible point the filter rejects / local infeasibility */
+                break;
+            }
+        }
+        first = 0;
+        if (*iter >= cf->max_iter) { st = ST_MAXITER; break; }
+        if (vmaxabs(wk->w, n) > DIVERGING_TOL) { st = ST_DIVERGING; break; }
+
+        /* monotone barrier update */
+        {
+            int done = 0;
+            while (!done && RERR(mu) <= KAPPA_EPS * mu) {
+                double nm = fmax(fmin(MU_LIN * mu, pow(mu, MU_SUPER)), fmin(cf->tol, COMPL_INF_TOL) / (KAPPA_EPS + 1.0));
+                int changed = nm != mu;
+                mu = nm; tau = fmax(TAU_MIN, 1.0 - mu);
+                if (changed) F->n = 0; else done = 1;
+            }
+        }
+#undef RERR
+#undef RCOMPL
+
+        /* ---- search direction: n, p eliminated (their blocks leave -Dc, -Dd on the constraint diagonals) ---- */
+        eval_hess(cf, wk, wk->w, wk->yc, wk->yd, wk->cs, wk->sn);
+        for (int i = 0; i < mc; ++i) {
+            R.rnc[i] = rho + wk->yc[i] - mu / R.nc[i] + KAPPA_D * mu; R.rpc[i] = rho - wk->yc[i] - mu / R.pc[i] + KAPPA_D * mu;
+            wk->Dc[i] = R.nc[i] / R.znc[i] + R.pc[i] / R.zpc[i];
+        }
+        for (int i = 0; i < ns; ++i) {
+            R.rnd[i] = rho + wk->yd[i] - mu / R.nd[i] + KAPPA_D * mu; R.rpd[i] = rho - wk->yd[i] - mu / R.pd[i] + KAPPA_D * mu;
+            wk->Dd[i] = R.nd[i] / R.znd[i] + R.pd[i] / R.zpd[i];
+        }
+        double delta = 0.0; int ok = 0;
+        for (;;) {
+            memcpy(wk->g, R.gR, sizeof(double) * n);            /* build_rhs works on wk->g */
+            build_rhs(cf, wk, mu, delta, R.rc, R.rd);
+            for (int i = 0; i < mc; ++i) wk->bc[i] += R.rnc[i] * R.nc[i] / R.znc[i] - R.rpc[i] * R.pc[i] / R.zpc[i];
+            for (int i = 0; i < ns; ++i) wk->bd[i] += R.rnd[i] * R.nd[i] / R.znd[i] - R.rpd[i] * R.pd[i] / R.zpd[i];
+            ok = kkt_factor_dense(cf, wk, wk->w, 1); if (dg) dg->n_factor++;
+            if (ok) break;
+            if (delta == 0.0) delta = delta_last == 0.0 ? DELTA_W_INIT : fmax(DELTA_W_MIN, delta_last * DELTA_W_DEC);
+            else delta = (delta_last == 0.0 || 1e5 * delta_last < delta) ? DELTA_W_INC_FIRST * delta : DELTA_W_INC * delta;
+            if (delta > DELTA_W_MAX) break;
+        }
+        if (!ok) { st = ST_STEP_ERROR; break; }
+        if (delta > 0.0) delta_last = delta;
+        kkt_solve_dense(wk, wk->bx, wk->bs, wk->bc, wk->bd, wk->dx, wk->ds, wk->dyc, wk->dyd);
+#define ELIM(dyc_, dyd_) do { \
+        for (int i = 0; i < mc; ++i) { R.dnc[i] = -(R.rnc[i] + (dyc_)[i]) * R.nc[i] / R.znc[i]; R.dpc[i] = -(R.rpc[i] - (dyc_)[i]) * R.pc[i] / R.zpc[i]; } \
+        for (int i = 0; i < ns; ++i) { R.dnd[i] = -(R.rnd[i] + (dyd_)[i]) * R.nd[i] / R.znd[i]; R.dpd[i] = -(R.rpd[i] - (dyd_)[i]) * R.pd[i] / R.zpd[i]; } } while (0)
+#define FTB_NP(a_) do { \
+        for (int i = 0; i < mc; ++i) { if (R.dnc[i] < 0) (a_) = fmin((a_), -tau * R.nc[i] / R.dnc[i]); if (R.dpc[i] < 0) (a_) = fmin((a_), -tau * R.pc[i] / R.dpc[i]); } \
+        for (int i = 0; i < ns; ++i) { if (R.dnd[i] < 0) (a_) = fmin((a_), -tau * R.nd[i] / R.dnd[i]); if (R.dpd[i] < 0) (a_) = fmin((a_), -tau * R.pd[i] / R.dpd[i]); } } while (0)
+        ELIM(wk->dyc, wk->dyd);
+
+        /* ---- line search on the restoration problem ---- */
+        merit_t cur;
+        if (!resto_merit(cf, wk, &R, wk->w, wk->s, R.nc, R.pc, R.nd, R.pd, mu, wk->ct, wk->dmst, &cur)) { st = ST_INVALID_NUMBER; break; }
+        double gBD = 0;
+        for (int i = 0; i < n; ++i) {
+            double gp = R.gR[i];
+            if (wk->hasL[i]) { gp -= mu / (wk->w[i] - wk->lb[i]); if (!wk->hasU[i]) gp += KAPPA_D * mu; }
+            if (wk->hasU[i]) { gp += mu / (wk->ub[i] - wk->w[i]); if (!wk->hasL[i]) gp -= KAPPA_D * mu; }
+            gBD += gp * wk->dx[i];
+        }
+        for (int i = 0; i < ns; ++i) gBD += (-mu / (wk->s[i] - wk->dL) + KAPPA_D * mu) * wk->ds[i];
+        for (int i = 0; i < mc; ++i) gBD += (rho - mu / R.nc[i] + KAPPA_D * mu) * R.dnc[i] + (rho - mu / R.pc[i] + KAPPA_D * mu) * R.dpc[i];
+        for (int i = 0; i < ns; ++i) gBD += (rho - mu / R.nd[i] + KAPPA_D * mu) * R.dnd[i] + (rho - mu / R.pd[i] + KAPPA_D * mu) * R.dpd[i];
+        if (theta_max < 0) { theta_max = RESTO_THETA_MAX_FACT * fmax(1.0, cur.theta); theta_min = THETA_MIN_FACT * fmax(1.0, cur.theta); }
+        double alpha_min = GAMMA_THETA;
+        if (gBD < 0) {
+            alpha_min = fmin(GAMMA_THETA, GAMMA_PHI * cur.theta / (-gBD));
+            if (cur.theta <= theta_min) alpha_min = fmin(alpha_min, DELTA_LS * pow(cur.theta, S_THETA) / pow(-gBD, S_PHI));
+        }
+        alpha_min *= ALPHA_MIN_FRAC;
+        double alpha_max = ftb_primal(wk, wk->dx, wk->ds, tau);
+        FTB_NP(alpha_max);
+        double alpha = alpha_max, alpha_test = alpha_max;
+        /* the step finally taken (the corrected one after an accepted second-order correction) */
+        double *sdx = wk->dx, *sds = wk->ds, *sdyc = wk->dyc, *sdyd = wk->dyd;
+        int accept = 0, nsteps = 0;
+        merit_t tri;
+#define TRIAL(a_, dx_, ds_) do { \
+        for (int i = 0; i < n; ++i) wk->wt[i] = wk->w[i] + (a_) * (dx_)[i]; \
+        for (int i = 0; i < ns; ++i) wk->st[i] = wk->s[i] + (a_) * (ds_)[i]; \
+        for (int i = 0; i < mc; ++i) { R.nct[i] = R.nc[i] + (a_) * R.dnc[i]; R.pct[i] = R.pc[i] + (a_) * R.dpc[i]; } \
+        for (int i = 0; i < ns; ++i) { R.ndt[i] = R.nd[i] + (a_) * R.dnd[i]; R.pdt[i] = R.pd[i] + (a_) * R.dpd[i]; } } while (0)
+        while (alpha > alpha_min || nsteps == 0) {
+            TRIAL(alpha, wk->dx, wk->ds);
+            int evok = resto_merit(cf, wk, &R, wk->wt, wk->st, R.nct, R.pct, R.ndt, R.pdt, mu, wk->ct, wk->dmst, &tri); if (dg) dg->n_trials++;
+            alpha_test = alpha;
+            if (evok) accept = resto_acceptable(F, &cur, &tri, gBD, alpha_test, theta_max, theta_min);
+            if (accept) break;
+            if (evok && alpha == alpha_max && cur.theta <= tri.theta) {   /* second-order correction */
+                double theta_soc_old = 0, theta_trial = tri.theta, alpha_soc = alpha;
+                memcpy(wk->csoc, R.rc, sizeof(double) * mc); if (ns) memcpy(wk->dsoc, R.rd, sizeof(double) * ns);
+                int count = 0;
+                while (count < MAX_SOC && !accept && (count == 0 || theta_trial <= KAPPA_SOC * theta_soc_old)) {
+                    theta_soc_old = theta_trial;
+                    for (int i = 0; i < mc; ++i) { wk->csoc[i] = alpha_soc * wk->csoc[i] + wk->ct[i]; wk->bc[i] = -wk->csoc[i] + R.rnc[i] * R.nc[i] / R.znc[i] - R.rpc[i] * R.pc[i] / R.zpc[i]; }
+                    for (int i = 0; i < ns; ++i) { wk->dsoc[i] = alpha_soc * wk->dsoc[i] + wk->dmst[i]; wk->bd[i] = -wk->dsoc[i] + R.rnd[i] * R.nd[i] / R.znd[i] - R.rpd[i] * R.pd[i] / R.zpd[i]; }
+                    kkt_solve_dense(wk, wk->bx, wk->bs, wk->bc, wk->bd, wk->dx2, wk->ds2, wk->dyc2, wk->dyd2); if (dg) dg->n_soc++;
+                    ELIM(wk->dyc2, wk->dyd2);
+                    alpha_soc = ftb_primal(wk, wk->dx2, wk->ds2, tau);
+                    FTB_NP(alpha_soc);
+                    TRIAL(alpha_soc, wk->dx2, wk->ds2);
+                    merit_t ts; int e2 = resto_merit(cf, wk, &R, wk->wt, wk->st, R.nct, R.pct, R.ndt, R.pdt, mu, wk->ct, wk->dmst, &ts); if (dg) dg->n_trials++;
+                    if (!e2) break;
+                    if (resto_acceptable(F, &cur, &ts, gBD, alpha_test, theta_max, theta_min)) { accept = 1; tri = ts; alpha = alpha_soc; sdx = wk->dx2; sds = wk->ds2; sdyc = wk->dyc2; sdyd = wk->dyd2; }
+                    else { count++; theta_trial = ts.theta; }
+                }
+                if (accept) break;
+                ELIM(wk->dyc, wk->dyd);   /* back to the original step */
+            }
+            alpha *= ALPHA_RED; nsteps++;
+        }
+        if (!accept) { st = ST_RESTORATION; break; }   /* the restoration phase's own line search failed: Restoration_Failed */
+        {
+            int ftype = gBD < 0 && alpha_test * pow(-gBD, S_PHI) > DELTA_LS * pow(cur.theta, S_THETA);
+            if (!ftype || !compare_le(tri.phi - cur.phi, ETA_PHI * alpha_test * gBD, cur.phi)) filter_add(F, (1.0 - GAMMA_THETA) * cur.theta, cur.phi - GAMMA_PHI * cur.theta);
+        }
+        /* ---- accept: primal with alpha, y with alpha, every bound multiplier with its own fraction-to-the-boundary step ---- */
+        double adu = dual_steps(wk, sdx, sds, mu, tau);
+        for (int i = 0; i < mc; ++i) {   /* dz = mu/slack - z - z/slack d */
+            double a = mu / R.nc[i] - R.znc[i] - R.znc[i] / R.nc[i] * R.dnc[i], b = mu / R.pc[i] - R.zpc[i] - R.zpc[i] / R.pc[i] * R.dpc[i];
+            if (a < 0) adu = fmin(adu, -tau * R.znc[i] / a);
+            if (b < 0) adu = fmin(adu, -tau * R.zpc[i] / b);
+        }
+        for (int i = 0; i < ns; ++i) {
+            double a = mu / R.nd[i] - R.znd[i] - R.znd[i] / R.nd[i] * R.dnd[i], b = mu / R.pd[i] - R.zpd[i] - R.zpd[i] / R.pd[i] * R.dpd[i];
+            if (a < 0) adu = fmin(adu, -tau * R.znd[i] / a);
+            if (b < 0) adu = fmin(adu, -tau * R.zpd[i] / b);
+        }
+#define ZUP(z_, sl_old, d_, sl_new) do { double dz_ = mu / (sl_old) - (z_) - (z_) / (sl_old) * (d_), zn_ = (z_) + adu * dz_; (z_) = fmax(fmin(zn_, KAPPA_SIGMA * mu / (sl_new)), mu / (KAPPA_SIGMA * (sl_new))); } while (0)
+        for (int i = 0; i < mc; ++i) {
+            double nn = R.nc[i] + alpha * R.dnc[i], pp = R.pc[i] + alpha * R.dpc[i];
+            ZUP(R.znc[i], R.nc[i], R.dnc[i], nn); ZUP(R.zpc[i], R.pc[i], R.dpc[i], pp);
+            R.nc[i] = nn; R.pc[i] = pp;
+        }
+        for (int i = 0; i < ns; ++i) {
+            double nn = R.nd[i] + alpha * R.dnd[i], pp = R.pd[i] + alpha * R.dpd[i];
+            ZUP(R.znd[i], R.nd[i], R.dnd[i], nn); ZUP(R.zpd[i], R.pd[i], R.dpd[i], pp);
+            R.nd[i] = nn; R.pd[i] = pp;
+        }
+#undef ZUP
+        for (int i = 0; i < n; ++i) wk->w[i] += alpha * sdx[i];
+        for (int i = 0; i < ns; ++i) wk->s[i] += alpha * sds[i];
+        for (int i = 0; i < mc; ++i) wk->yc[i] += alpha * sdyc[i];
+        for (int i = 0; i < ns; ++i) wk->yd[i] += alpha * sdyd[i];
+        for (int i = 0; i < n; ++i) {
+            if (wk->hasL[i]) { double sl = wk->w[i] - wk->lb[i], z = wk->zL[i] + adu * wk->dzL[i]; wk->zL[i] = fmax(fmin(z, KAPPA_SIGMA * mu / sl), mu / (KAPPA_SIGMA * sl)); }
+            if (wk->hasU[i]) { double su = wk->ub[i] - wk->w[i], z = wk->zU[i] + adu * wk->dzU[i]; wk->zU[i] = fmax(fmin(z, KAPPA_SIGMA * mu / su), mu / (KAPPA_SIGMA * su)); }
+        }
+        for (int i = 0; i < ns; ++i) { double sl = wk->s[i] - wk->dL, z = wk->vL[i] + adu * wk->dvL[i]; wk->vL[i] = fmax(fmin(z, KAPPA_SIGMA * mu / sl), mu / (KAPPA_SIGMA * sl)); }
+        (*iter)++;
+#undef ELIM
+#undef FTB_NP
+#undef TRIAL
+    }
+    if (st == 0) {
+        /* back to the regular algorithm: bound multipliers kept unless one exceeds bound_mult_reset_threshold (then all 1); equality
+         * multipliers zero (constr_mult_reset_threshold 0) */
+        double zm = fmax(vmaxabs(wk->zL, n), fmax(vmaxabs(wk->zU, n), ns ? vmaxabs(wk->vL, ns) : 0.0));
+        if (zm > BOUND_MULT_RESET) {
+            for (int i = 0; i < n; ++i) { wk->zL[i] = wk->hasL[i] ? 1.0 : 0.0; wk->zU[i] = wk->hasU[i] ? 1.0 : 0.0; }
+            for (int i = 0; i < ns; ++i) wk->vL[i] = 1.0;
+        }
+        memset(wk->yc, 0, sizeof(double) * mc); if (ns) memset(wk->yd, 0, sizeof(double) * ns);
+    }
+    wk->resto = 0; wk->linsolve = saved_linsolve;
+    free(F); free(pool);
+    return st;
+}
+
+/* ------------------------------------------------------------------ */
 /* one NLP                                                             */
 /* ------------------------------------------------------------------ */
 typedef struct {
@@ -921,7 +1265,17 @@ static void solve_one(const kmo_config *cf, work_t *wk, const double *xcur, cons
             }
             alpha *= ALPHA_RED; nsteps++;
         }
-        if (!accept) { st = ST_RESTORATION; break; } /* IPOPT would enter the restoration phase here */
+        if (!accept) {
+            /* BacktrackingLineSearch: the step size fell below alpha_min -> restoration phase, unless the point is almost feasible */
+            if (cur.theta <= 1e-2 * cf->tol) { st = ST_RESTORATION; break; }   /* "Restoration phase called, but point is almost feasible" */
+            filter_add(F, (1.0 - GAMMA_THETA) * cur.theta, cur.phi - GAMMA_PHI * cur.theta);   /* PrepareRestoPhaseStart */
+            if (F->n > dloc.max_filter) dloc.max_filter = F->n;
+            const int rs_ = restoration(cf, wk, mu, F, cur.theta, cur.phi, &iter, &dloc);
+            dloc.n_resto++;
+            if (rs_ != 0) { st = rs_; break; }
+            iter++;
+            continue;
+        }
 
         /* filter augmentation (FilterLSAcceptor::UpdateForNextIteration) */
         if (!IS_FTYPE(alpha_test) || !ARMIJO(alpha_test, tri)) {

@@ -37,11 +37,12 @@ class _Diag(C.Structure):
     _fields_ = [
         ("n_factor", C.c_int32), ("n_trials", C.c_int32), ("n_soc", C.c_int32), ("max_filter", C.c_int32),
         ("mu", C.c_double), ("err", C.c_double), ("obj_scaling", C.c_double), ("max_delta_w", C.c_double),
+        ("n_resto", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
 DIAG_DTYPE = np.dtype([("n_factor", "i4"), ("n_trials", "i4"), ("n_soc", "i4"), ("max_filter", "i4"),
-                       ("mu", "f8"), ("err", "f8"), ("obj_scaling", "f8"), ("max_delta_w", "f8")])
+                       ("mu", "f8"), ("err", "f8"), ("obj_scaling", "f8"), ("max_delta_w", "f8"), ("n_resto", "i4"), ("reserved", "i4")])
 
 
 @dataclass

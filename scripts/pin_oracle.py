@@ -4,7 +4,7 @@
   * the second-order check (reduced Hessian of the Lagrangian on the null space of the active constraints),
   * a SciPy SLSQP polish (independent solver, analytic derivatives) started from the oracle's point,
 and the dense LDL^T path is compared with the Riccati path.  CPU only; writes profiles/r02_oracle_pins.json.
-    python scripts/pin_oracle.py [count] [workers]
+    python scripts/pin_oracle.py [count] [workers] [form,form,...]    (results are merged into the existing record)
 tests/test_pins_cpu.py runs the same checks on smaller samples in the routine suite."""
 import json
 import multiprocessing as mp
@@ -37,8 +37,10 @@ def one(args):
 def main():
     count = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
     workers = int(sys.argv[2]) if len(sys.argv) > 2 else os.cpu_count()
-    out = {"count_per_form": count, "forms": {}}
-    for name in FORMS:
+    names = sys.argv[3].split(",") if len(sys.argv) > 3 else list(FORMS)
+    path = os.path.join(ROOT, "profiles", "r02_oracle_pins.json")
+    out = json.load(open(path)) if os.path.exists(path) else {"count_per_form": count, "forms": {}}
+    for name in names:
         t0 = time.time()
         cfg, b = form_batch(ok, name, count)
         r = ok.solve(cfg, b["x_cur"], b["goal"], obs=b["obs"], want_duals=True)
@@ -61,7 +63,7 @@ def main():
                                  "max_control_diff": float(np.abs(rd.U - r.U[:nd])[cd].max())},
             "seconds": time.time() - t0}
         print(name, json.dumps(out["forms"][name]), flush=True)
-    json.dump(out, open(os.path.join(ROOT, "profiles", "r02_oracle_pins.json"), "w"), indent=1)
+        json.dump(out, open(path, "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -21,7 +21,9 @@ class KmpcConfig(C.Structure):
 
 
 def build():
-    newest = max(os.path.getmtime(p) for p in (_SRC, _CORE, _WARP, os.path.join(_HERE, "host_emul", "simt.h")))
+    csrc = os.path.dirname(_CORE)
+    deps = [_SRC, os.path.join(_HERE, "host_emul", "simt.h")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+    newest = max(os.path.getmtime(p) for p in deps)
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.check_call(["g++", "-O2", "-fopenmp", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-I", os.path.join(_HERE, "host_emul"), "-o", _SO, _SRC])
     return _SO

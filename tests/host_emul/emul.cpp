@@ -77,8 +77,9 @@ extern "C" int emul_solve(const kmpc_config *cf, int B, const double *x_cur, con
     // Mirrors the launch structure of kmpc.cu on the host: per trip, sweep(LA[p]) -> rollout(LT[p]) -> trial(LT[p]), with the
     // solver context stored in / reloaded from the workspace between the phases exactly as the kernels do.
     const size_t S = (size_t)((B + 31) / 32 * 32);
-    double *ws = (double *)malloc(sizeof(double) * S * c.L.total);
-    for (size_t i = 0; i < S * c.L.total; ++i) ws[i] = NAN;  // poison: reads of never-written rows show up
+    const size_t rows_total = (size_t)make_resto_rows(c.L).total;   // solver rows + the rows of the restoration phase
+    double *ws = (double *)malloc(sizeof(double) * S * rows_total);
+    for (size_t i = 0; i < S * rows_total; ++i) ws[i] = NAN;  // poison: reads of never-written rows show up
     std::vector<int> LA[2], LT[2];
     for (int b = 0; b < B; ++b) {
         Ctx t; memset(&t, 0, sizeof t); t.inst = b;
@@ -161,6 +162,12 @@ extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur
         Cfg cb = c; cb.B = hi;
         std::vector<double> gscr((size_t)G_NF * 64 * W, NAN);   // the block's global scratch slots
         IO iob = io; iob.wscratch = gscr.data();
+        // hand-over workspace of the restoration phase: a column per instance of this block, run by finish_instance below
+        const int rrows = make_resto_rows(c.L).total;
+        std::vector<double> rws((size_t)rrows * (hi - lo), NAN);
+        std::vector<int32_t> rlist(hi - lo, -1);
+        int rcount = 0;
+        iob.resto_ws = rws.data(); iob.resto_list = rlist.data(); iob.resto_count = &rcount; iob.resto_cap = hi - lo; iob.resto_rows = rrows;
         bool full = true;
         for (int i = 0; i < 4; ++i) full = full && c.hasL[i] && c.hasU[i];
         const int nst = spl == 1 ? 32 : cf->N + 1 <= 52 ? 52 : 64;
@@ -171,6 +178,7 @@ extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur
             if (nst == 32) EMUL_RUN(1, 32); else if (nst == 52) EMUL_RUN(2, 52); else EMUL_RUN(2, 64);
         }, W);
 #undef EMUL_RUN
+        for (int i = 0; i < rcount; ++i) { if (O > 0) finish_instance<true>(cb, iob, i); else finish_instance<false>(cb, iob, i); }   // kmpc_finish_kernel
         if (W == 1 && trips) trips[lo] = (int)tr;
 #pragma omp atomic
         tr_total += tr;

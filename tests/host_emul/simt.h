@@ -88,6 +88,7 @@ inline int w_fetch(int *queue) {  // lane 0 takes the next index, everybody lear
     return (int)b[0];
 }
 inline void w_count_trips(unsigned long long *total, int trips) { if (total) *total += (unsigned long long)trips; }
+inline int w_take_slot(int *counter) { return (*counter)++; }
 
 void simt_run(const std::function<void()> &fn, int warps = 1);  // runs fn on 32 * warps lanes (emul.cpp)
 }  // namespace kmpc
