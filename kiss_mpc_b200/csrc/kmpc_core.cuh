@@ -71,7 +71,7 @@ namespace kmpc {
 #define K_CONSTR_VIOL_TOL 1e-4
 #define K_COMPL_INF_TOL 1e-4
 #define K_DIVERGING 1e20
-#define K_FILTER_CAP 64          /* filter entries kept per instance (IPOPT's filter is unbounded; a full filter ends the instance with Internal_Error) */
+#define K_FILTER_CAP 512         /* filter entries kept per instance, as in the oracle (IPOPT's filter is unbounded; a full filter ends the instance with Internal_Error) */
 #define KMPC_NCTX 40  /* rows reserved for the per-instance solver context in the workspace */
 
 enum { ST_SUCCESS = 0, ST_MAXITER = -1, ST_RESTORATION = -2, ST_STEP_ERROR = -3, ST_DIVERGING = 4, ST_INVALID = -13, ST_INTERNAL = -199 };

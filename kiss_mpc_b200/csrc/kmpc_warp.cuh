@@ -61,7 +61,6 @@ enum { B_S = 0, B_YD, B_VL, B_DSOC, B_DM, B_NF };
 
 struct WScal {  // warp-uniform per-instance scalars
     Ctx t;
-    double filt[2 * K_FILTER_CAP];
     double xc[3], gl[3], d0[3];
     double dshift[KMPC_NCAND];  // delta_w of candidate k minus the delta_w the stage blocks were assembled with (NaN: none)
     int pdc[KMPC_NCAND];        // candidate k has the right inertia
@@ -75,7 +74,8 @@ struct WLay {
     static constexpr int NSTG = NST;
     static constexpr int COOP = C_NF * NSTG + 1;
     static constexpr int PRIV = V_NF * NSTG;
-    static constexpr int GPRIV = G_NF * NSTG;   // doubles of global scratch per resident warp
+    static constexpr int GFILT = G_NF * NSTG;                  // the filter of the instance sits behind the per-stage fields of the global scratch slot
+    static constexpr int GPRIV = G_NF * NSTG + 2 * K_FILTER_CAP;   // doubles of global scratch per resident warp
     KMPC_HD static int obs_doubles(int O, int sw = 0) { return O > 0 ? B_NF * O * NSTG + 2 * O * (sw ? NSTG : 1) + O : 0; }   // rows, centres, radii
     static size_t bytes(int warps, int O = 0, int sw = 0) { return (size_t)warps * ((COOP + PRIV + obs_doubles(O, sw)) * sizeof(double) + sizeof(WScal)) + 16; }   // + the block's live-instance masks
 };
@@ -943,7 +943,7 @@ __device__ __forceinline__ unsigned kmpc_smid() { unsigned r; asm volatile("mov.
 // finisher (finish_instance, kmpc_core.cuh) -- iterate, multipliers, obstacle-row state, problem data, filter and solver context go
 // to a column of the hand-over workspace in the thread solver's layout.  False: no column left (the caller reports Restoration_Failed).
 template <int SPL, int NST, bool OBS>
-KMPC_WN inline bool w_hand_over(const Cfg &c, WScal *sc, const WState<SPL> &w, const double *ob, const IO &io, int b) {
+KMPC_WN inline bool w_hand_over(const Cfg &c, WScal *sc, const WState<SPL> &w, const double *ob, const double *filt, const IO &io, int b) {
     constexpr int NSTG = WLay<SPL, NST>::NSTG;
     const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     const Rows &L = c.L;
@@ -979,7 +979,7 @@ KMPC_WN inline bool w_hand_over(const Cfg &c, WScal *sc, const WState<SPL> &w, c
             if (!c.obs_sw) { base[L.rSc + CEN_ROW(o, 1, 0)] = w_cx(cen, o); base[L.rSc + CEN_ROW(o, 1, 1)] = w_cy(cen, o); }
         }
     }
-    for (int i = lane; i < 2 * sc->t.fn; i += 32) base[L.rFilt + i] = sc->filt[i];
+    for (int i = lane; i < 2 * sc->t.fn; i += 32) base[L.rFilt + i] = filt[i];
     if (lane == 0) {
         for (int j = 0; j < 3; ++j) { base[L.rSc + j] = sc->xc[j]; base[L.rSc + 3 + j] = sc->gl[j]; }
         sc->t.cur = 0; sc->t.inst = b;
@@ -1015,6 +1015,8 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     double *coop = smem + (size_t)wid * LY::COOP;
     double *priv = smem + (size_t)W * LY::COOP + (size_t)wid * LY::PRIV;
     double *gp = io.wscratch + ((size_t)w_block() * W + wid) * LY::GPRIV;
+    // the filter (touched by lane 0 only, a handful of entries as a rule, 512 at most as in the oracle) lives in the global scratch slot too
+    double *filt = gp + LY::GFILT;
     const int OBD = LY::obs_doubles(OBS ? c.O : 0, c.obs_sw);
     double *ob = smem + (size_t)W * (LY::COOP + LY::PRIV) + (size_t)wid * OBD;
     WScal *scal0 = (WScal *)(smem + (size_t)W * (LY::COOP + LY::PRIV + OBD));
@@ -1201,8 +1203,8 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             PT(7)
             if (lane == 0) {
                 bool aug; double ath, aph;
-                int r = trial_decide(t, sc->filt, 1, ts, evok, &aug, &ath, &aph);
-                if (aug && !filter_add(t, sc->filt, 1, ath, aph)) r = ST_INTERNAL;   // filter full: ends the instance loudly (Internal_Error)
+                int r = trial_decide(t, filt, 1, ts, evok, &aug, &ath, &aph);
+                if (aug && !filter_add(t, filt, 1, ath, aph)) r = ST_INTERNAL;   // filter full: ends the instance loudly (Internal_Error)
                 sc->r = r;
             }
             w_sync();
@@ -1228,7 +1230,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         if (have && status == ST_RESTORATION) {
             // IPOPT's BacktrackingLineSearch: restoration phase, unless the point is almost feasible ("Restoration phase called, but
             // point is almost feasible": Restoration_Failed).  The phase itself runs in the finisher kernel.
-            if (!(t.c.theta <= 1e-2 * c.tol) && w_hand_over<SPL, NST, OBS>(c, sc, cur, ob, io, b)) {
+            if (!(t.c.theta <= 1e-2 * c.tol) && w_hand_over<SPL, NST, OBS>(c, sc, cur, ob, filt, io, b)) {
                 if (lane == 0) { w_count_trips(trips_total, t.trips); SCHED_END(b, t.trips) t.mode = M_DONE; }
                 have = false;
                 status = 100;

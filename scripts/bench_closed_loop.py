@@ -29,4 +29,5 @@ print(json.dumps({"workload": f"closed loop, {B} agents x {steps} steps, N=30, w
                   "goal_radius": goal_radius, "agent_radius": agent_radius, "solves": n_solved, "solves_per_sec": n_solved / (ms * 1e-3),
                   "active_agents_last_step": int(solved[-1].sum().item()), "mean_iters_step0": float(it[0]), "mean_iters_steps_1_10": float(it[1:11].mean()),
                   "mean_iters_last_10": float(it[-10:].mean()), "converged_fraction_of_solved": float(((status == 0) & solved).sum().item() / max(1, n_solved)),
-                  "agents_within_0.5m_of_goal": float((dist < 0.5).float().mean().item())}))
+                  "agents_within_0.5m_of_goal": float((dist < 0.5).float().mean().item()),
+                  "status_counts_of_solved": {int(k): int(v) for k, v in zip(*[t.tolist() for t in torch.unique(status[solved], return_counts=True)])}}))

@@ -160,7 +160,7 @@ extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur
         unsigned long long tr = 0;
         int queue = lo;          // this emulated block is handed exactly the instances lo .. hi - 1
         Cfg cb = c; cb.B = hi;
-        std::vector<double> gscr((size_t)G_NF * 64 * W, NAN);   // the block's global scratch slots
+        std::vector<double> gscr((size_t)(G_NF * 64 + 2 * K_FILTER_CAP) * W, NAN);   // the block's global scratch slots (>= WLay::GPRIV each)
         IO iob = io; iob.wscratch = gscr.data();
         // hand-over workspace of the restoration phase: a column per instance of this block, run by finish_instance below
         const int rrows = make_resto_rows(c.L).total;

@@ -778,6 +778,9 @@ def test_tail_mode_kernel_is_bit_identical():
     small = pl.solve(x[:3000].contiguous(), g[:3000].contiguous())
     for a, c in zip(small, big):
         assert torch.equal(a, c[:3000])
+    tiny = pl.solve(x[:500].contiguous(), g[:500].contiguous())     # one wave of 4-instance blocks: the low-latency launch shape
+    for a, c in zip(tiny, big):
+        assert torch.equal(a, c[:500])
     for i in (0, 17, 2879, 30520 % 3000):
         one = pl.solve(x[i:i + 1].contiguous(), g[i:i + 1].contiguous())
         for a, c in zip(one, big):
