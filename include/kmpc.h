@@ -215,6 +215,18 @@ int kmpc_environment_loop(kmpc_handle *h, int B, int steps, double *x_cur, const
                           double pad_y, double *applied_log, int32_t *iters_log, int32_t *status_log, int32_t *count_log,
                           int32_t *dyn_count_log, int32_t *active, double goal_radius, double agent_radius, void *cuda_stream);
 
+/* Occupancy map -> packed circles: the static-obstacle candidates of a map.  Replaces the stand-alone script
+ * obstacle_handling/static_obstacle.py:12-56 (threshold at 127 :23, distance transform of the occupied region :35, then greedily the
+ * largest inscribed circle, its disc blanked, until the largest remaining distance is below MIN_RADIUS :38-57) and returns what the
+ * script only paints: centres (x, y in pixels, raster order of discovery) and integer radii.  The arithmetic is OpenCV's and is
+ * restated to the bit (5x5 chamfer transform in fixed point, first maximum in raster order, filled midpoint circle), so the circle
+ * list equals the script's on the same image.  HOST pointers; image[h][w] 8-bit grey; at most max_circles are written, *count_out is
+ * the number found.  One-off preprocessing on the host (no device is touched). */
+/* the distance map alone (static_obstacle.py:23-35): depth of every occupied pixel inside the occupied region, float32 [h][w] */
+int kmpc_map_distance(const unsigned char *image, int w, int h, int threshold, float *dist_out);
+int kmpc_map_to_circles(const unsigned char *image, int w, int h, int threshold, double min_radius, int max_circles,
+                        int32_t *centers_out /*[max_circles][2]*/, int32_t *radii_out /*[max_circles]*/, int32_t *count_out);
+
 /* Scheduling of the batch inside kmpc_solve (no reference equivalent; results never depend on it).  The solver kernel is
  * persistent: warps pull instances from a queue, and interior-point iteration counts differ by more than 8x between instances,
  * so an instance that is fetched late and runs long sets the end of the launch.  KMPC_ORDER_PRIOR (default) hands the

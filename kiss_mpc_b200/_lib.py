@@ -18,7 +18,7 @@ SYMBOLS = ["kmpc_version", "kmpc_workspace_bytes", "kmpc_create", "kmpc_destroy"
            "kmpc_solve_tracks", "kmpc_solve_host", "kmpc_solve_host_into", "kmpc_host_sync", "kmpc_pinned_alloc", "kmpc_pinned_free",
            "kmpc_host_result", "kmpc_shared_buffer_create", "kmpc_shared_buffer_open", "kmpc_shared_buffer_close", "kmpc_enable_peer",
            "kmpc_agent_handoff", "kmpc_closed_loop", "kmpc_environment_loop", "kmpc_select_obstacles", "kmpc_predict_tracks",
-           "kmpc_set_queue_order", "kmpc_set_timing", "kmpc_get_stats", "kmpc_measure_fp64_peak"]
+           "kmpc_map_distance", "kmpc_map_to_circles", "kmpc_set_queue_order", "kmpc_set_timing", "kmpc_get_stats", "kmpc_measure_fp64_peak"]
 IPC_HANDLE_BYTES = 64
 
 
@@ -99,6 +99,10 @@ def load():
     L.kmpc_select_obstacles.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double, dp, ip, ip, dp, vp]
     L.kmpc_predict_tracks.restype = C.c_int
     L.kmpc_predict_tracks.argtypes = [vp, C.c_int, C.c_int, C.c_int, ip, dp, dp, dp, C.c_double, C.c_int, C.c_double, C.c_double, dp, vp]
+    L.kmpc_map_distance.restype = C.c_int
+    L.kmpc_map_distance.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    L.kmpc_map_to_circles.restype = C.c_int
+    L.kmpc_map_to_circles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     L.kmpc_set_queue_order.restype = C.c_int
     L.kmpc_set_queue_order.argtypes = [vp, C.c_int]
     L.kmpc_set_timing.restype = C.c_int

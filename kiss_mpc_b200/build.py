@@ -6,7 +6,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "kmpc.cu")
-DEPS = [SRC, os.path.join(_HERE, "..", "include", "kmpc.h")] + [os.path.join(_HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(_HERE, "csrc"))) if f.endswith((".cuh", ".h"))]
+DEPS = [SRC, os.path.join(_HERE, "..", "include", "kmpc.h")] + [os.path.join(_HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(_HERE, "csrc"))) if f.endswith((".cuh", ".h", ".inl"))]
 SO = os.path.join(_HERE, "libkmpc.so")
 # -fmad=false: no implicit contraction of a * b + c into an FMA -- every fused operation of the solver is an explicit fma() in
 # the source.  What the compiler contracts depends on the inlining context, so two instantiations of the same function (the

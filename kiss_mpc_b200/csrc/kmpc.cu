@@ -1156,6 +1156,8 @@ extern "C" int kmpc_environment_loop(kmpc_handle *h, int B, int steps, double *x
     return 0;
 }
 
+#include "kmpc_map.inl"   // occupancy map -> packed circles (host code)
+
 extern "C" int kmpc_set_queue_order(kmpc_handle *h, int mode) {
     if (!h || (mode != KMPC_ORDER_NATURAL && mode != KMPC_ORDER_PRIOR)) return KMPC_E_BADARG;
     h->order_mode = mode;

@@ -251,3 +251,54 @@ def test_reference_agent_unmodified_on_drop_in(oracle_mod, monkeypatch):
     far2.planner.on_failure = "raise"
     with pytest.raises(P.KmpcError):
         far2.step()
+
+
+# ---------------- occupancy map -> circles (obstacle_handling/static_obstacle.py:12-56) ----------------
+def _synthetic_map(seed, h=240, w=320):
+    rng = np.random.default_rng(seed)
+    img = np.full((h, w), 254, np.uint8)                      # free space
+    for _ in range(14):                                       # dark blobs: walls, pillars, clutter (some cut by the border)
+        y, x = int(rng.integers(-10, h)), int(rng.integers(-10, w))
+        hh, ww = int(rng.integers(3, 60)), int(rng.integers(3, 60))
+        img[max(y, 0):y + hh, max(x, 0):x + ww] = int(rng.integers(0, 120))
+    img[rng.random((h, w)) < 0.002] = 0                       # speckle
+    img[rng.random((h, w)) < 0.01] = 205                      # "unknown" grey of a ROS map: free for the script (> 127)
+    return img
+
+
+def test_map_to_circles_equals_reference_script():
+    """kmpc_map_to_circles against the reference script run with its own OpenCV calls (oracle/map_circles_cv2.py): the same circles
+    in the same order, on synthetic maps and -- where the reference tree is present -- on its rrc_lab.pgm (27,262 circles)."""
+    cv2 = pytest.importorskip("cv2")
+    import ctypes as C
+    from kiss_mpc_b200 import _lib, map_to_circles, read_pgm
+    from oracle.map_circles_cv2 import circles_cv2
+    images = [_synthetic_map(s) for s in (1, 2, 3)]
+    # (an all-occupied map has no free pixel to measure from: the script's own cv2.circle call rejects the resulting radius)
+    images.append(np.full((40, 50), 255, np.uint8))           # all free: no circle
+    real = os.path.join(REF, "obstacle_handling", "rrc_lab.pgm")
+    if os.path.exists(real):
+        img = read_pgm(real)
+        assert np.array_equal(img, cv2.imread(real, cv2.IMREAD_GRAYSCALE))
+        images.append(img)
+    L = _lib.load()
+    for img in images:
+        cen, rad = map_to_circles(img)
+        c2, r2, _ = circles_cv2(img)
+        assert len(cen) == len(c2) and np.array_equal(cen, c2) and np.array_equal(rad, r2)
+        h, w = img.shape
+        d = np.empty((h, w), np.float32)
+        assert L.kmpc_map_distance(img.ctypes.data, w, h, 127, d.ctypes.data) == 0
+        _, binary = cv2.threshold(img, 127, 255, cv2.THRESH_BINARY)
+        assert np.abs(d - cv2.distanceTransform(cv2.bitwise_not(binary), cv2.DIST_L2, 5)).max() <= 1e-5
+    # metres: resolution / origin of a map_server YAML, y up; truncation of the list
+    img = images[0]
+    cen, rad = map_to_circles(img)
+    cm, rm = map_to_circles(img, resolution=0.05, origin=(-8.0, -6.0))
+    assert np.allclose(cm[:, 0], -8.0 + (cen[:, 0] + 0.5) * 0.05) and np.allclose(cm[:, 1], -6.0 + (img.shape[0] - cen[:, 1] - 0.5) * 0.05)
+    assert np.allclose(rm, rad * 0.05)
+    c5, r5 = map_to_circles(img, max_circles=5)
+    assert np.array_equal(c5, cen[:5]) and np.array_equal(r5, rad[:5])
+    assert (np.diff(rad) <= 0).all()                           # largest first
+    with pytest.raises(ValueError):
+        map_to_circles(np.zeros((2, 3, 4), np.uint8))
