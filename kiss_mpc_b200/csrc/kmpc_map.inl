@@ -110,7 +110,8 @@ extern "C" int kmpc_map_to_circles(const unsigned char *image, int w, int h, int
         const int i = order[q];
         const float v = dist[i];
         if (!(v >= (float)min_radius)) continue;        // blanked by an earlier circle
-        const int cx = i % w, cy = i / w, r = (int)v;  // radius = int(maxVal), centre = maxLoc
+        // radius = int(maxVal), centre = maxLoc (a map without a single free pixel has no finite distance: the radius is capped at the image)
+        const int cx = i % w, cy = i / w, r = v < (float)(w + h) ? (int)v : w + h;
         if (n < max_circles) { centers_out[2 * n] = cx; centers_out[2 * n + 1] = cy; radii_out[n] = r; }
         ++n;
         kmpc_map::filled_circle(cx, cy, r, w, h, [&](int y, int x0, int x1) { for (int x = x0; x <= x1; ++x) dist[(size_t)y * w + x] = 0.f; });
