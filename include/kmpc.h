@@ -19,8 +19,10 @@
  *            structure-of-arrays with the instance index fastest (fully coalesced loads/stores on the device).
  *   - per-instance solver outcome uses IPOPT's ApplicationReturnStatus numbering (the reference discards it,
  *     optimizer.py:375-400 reads only solution["x"]):
- *         0 Solve_Succeeded, -1 Maximum_Iterations_Exceeded, -2 Restoration_Failed (restoration phase would be
- *         needed), -3 Error_In_Step_Computation, 4 Diverging_Iterates, -13 Invalid_Number_Detected.
+ *         0 Solve_Succeeded, 2 Infeasible_Problem_Detected (the restoration phase ended at a stationary point of the
+ *         constraint violation), 4 Diverging_Iterates, -1 Maximum_Iterations_Exceeded, -2 Restoration_Failed (restoration
+ *         entered at an almost feasible point or could not make progress), -3 Error_In_Step_Computation,
+ *         -13 Invalid_Number_Detected, -199 Internal_Error (the 512-entry filter is full; never seen by the oracle either).
  *   - functions return 0 on success, a negative KMPC_E_* code otherwise; nothing throws across the ABI.
  */
 #ifndef KMPC_H
@@ -219,7 +221,7 @@ int kmpc_environment_loop(kmpc_handle *h, int B, int steps, double *x_cur, const
  * obstacle_handling/static_obstacle.py:12-56 (threshold at 127 :23, distance transform of the occupied region :35, then greedily the
  * largest inscribed circle, its disc blanked, until the largest remaining distance is below MIN_RADIUS :38-57) and returns what the
  * script only paints: centres (x, y in pixels, raster order of discovery) and integer radii.  The arithmetic is OpenCV's and is
- * restated to the bit (5x5 chamfer transform in fixed point, first maximum in raster order, filled midpoint circle), so the circle
+ * restated to the bit (OpenCV 4.x's float32 5x5 chamfer transform with weights 1 / 1.4 / 2.1969, first maximum in raster order, filled midpoint circle), so the circle
  * list equals the script's on the same image.  HOST pointers; image[h][w] 8-bit grey; at most max_circles are written, *count_out is
  * the number found.  One-off preprocessing on the host (no device is touched). */
 /* the distance map alone (static_obstacle.py:23-35): depth of every occupied pixel inside the occupied region, float32 [h][w] */

@@ -868,25 +868,35 @@ KMPC_HD double opt_error(const Cfg &c, const Stats &s, double mu) {
 }
 KMPC_HD double phi_of(const Stats &s, double mu) { return s.f - mu * s.bar + K_KAPPA_D * mu * s.damp; }
 
-// the filter: entry i = (theta, phi) at filt[(2 i) * FS], filt[(2 i + 1) * FS]
-KMPC_HD bool filter_ok(const Ctx &t, const double *filt, size_t FS, double theta, double phi) {
+// the filter: entry i = (theta, phi).  Two stores: FiltStrided -- entry i at filt[(2 i) * FS], filt[(2 i + 1) * FS] (a band of the
+// thread solver's workspace); FiltSplit -- the first KMPC_FILTER_NEAR entries in a small fast array (the warp solver's shared
+// memory: nearly every instance keeps fewer), the others at the same index of a far array (its global scratch slot).
+#ifndef KMPC_FILTER_NEAR
+#define KMPC_FILTER_NEAR 6
+#endif
+struct FiltStrided { double *p; size_t FS; KMPC_HD double &at(int i, int k) const { return p[(size_t)(2 * i + k) * FS]; } };
+struct FiltSplit { double *nearp; double *farp; KMPC_HD double &at(int i, int k) const { return i < KMPC_FILTER_NEAR ? nearp[2 * i + k] : farp[2 * i + k]; } };
+template <class F>
+KMPC_HD bool filter_ok(const Ctx &t, const F &filt, double theta, double phi) {
     for (int i = 0; i < t.fn; ++i)
-        if (!(theta <= filt[(size_t)(2 * i) * FS] || phi <= filt[(size_t)(2 * i + 1) * FS])) return false;
+        if (!(theta <= filt.at(i, 0) || phi <= filt.at(i, 1))) return false;
     return true;
 }
 // false: the filter is full (the entry is NOT recorded; the caller ends the instance with ST_INTERNAL rather than go on with a
 // filter that has forgotten an entry)
-KMPC_HD bool filter_add(Ctx &t, double *filt, size_t FS, double theta, double phi) {
+template <class F>
+KMPC_HD bool filter_add(Ctx &t, const F &filt, double theta, double phi) {
     int m = 0;
     for (int i = 0; i < t.fn; ++i) {
-        const double th = filt[(size_t)(2 * i) * FS], ph = filt[(size_t)(2 * i + 1) * FS];
-        if (!(th >= theta && ph >= phi)) { filt[(size_t)(2 * m) * FS] = th; filt[(size_t)(2 * m + 1) * FS] = ph; ++m; }
+        const double th = filt.at(i, 0), ph = filt.at(i, 1);
+        if (!(th >= theta && ph >= phi)) { filt.at(m, 0) = th; filt.at(m, 1) = ph; ++m; }
     }
     t.fn = m;
     if (t.fn >= K_FILTER_CAP) return false;
-    filt[(size_t)(2 * t.fn) * FS] = theta; filt[(size_t)(2 * t.fn + 1) * FS] = phi; t.fn++;
+    filt.at(t.fn, 0) = theta; filt.at(t.fn, 1) = phi; t.fn++;
     return true;
 }
+KMPC_HD bool filter_add(Ctx &t, double *filt, size_t FS, double theta, double phi) { return filter_add(t, FiltStrided{filt, FS}, theta, phi); }
 
 // FilterLSAcceptor::CheckAcceptabilityOfTrialPoint
 // switching condition  gBD < 0  and  a (-gBD)^s_phi > delta theta^s_theta  (theta, gBD of the current iterate).
@@ -912,7 +922,8 @@ KMPC_HD double alpha_min_of(const Ctx &t) {
     return amin * K_ALPHA_MIN_FRAC;
 }
 KMPC_HD bool armijo(const Ctx &t, double a, double tphi, double cphi) { return cmp_le(tphi - cphi, K_ETA_PHI * a * t.gBD, cphi); }
-KMPC_HD bool acceptable(const Ctx &t, const double *filt, size_t FS, const Stats &tri) {
+template <class F>
+KMPC_HD bool acceptable(const Ctx &t, const F &filt, const Stats &tri) {
     const double cphi = phi_of(t.c, t.mu), tphi = phi_of(tri, t.mu), cth = t.c.theta;
     bool acc;
     if (tri.theta > t.theta_max) return false;
@@ -925,7 +936,7 @@ KMPC_HD bool acceptable(const Ctx &t, const double *filt, size_t FS, const Stats
         }
         if (acc) acc = cmp_le(tri.theta, (1.0 - K_GAMMA_THETA) * cth, cth) || cmp_le(tphi - cphi, -K_GAMMA_PHI * cth, cphi);
     }
-    if (acc) acc = filter_ok(t, filt, FS, tri.theta, tphi);
+    if (acc) acc = filter_ok(t, filt, tri.theta, tphi);
     return acc;
 }
 
@@ -1025,13 +1036,13 @@ KMPC_HD void trial_setup(Ctx &t) {
 //   R_BACKTRACK      next trip evaluates a shorter step;   R_ACCEPT  caller makes the trial point current, then begin_iteration
 //   a final status (ST_RESTORATION)
 enum { R_CONTINUE = 100, R_RETRY = 101, R_ACCEPT = 102, R_SOC1 = 103, R_SOC2 = 104, R_BACKTRACK = 105 };
-KMPC_HD int trial_decide(Ctx &t, const double *filt, size_t FS, const Stats &tri, bool evok, bool *augment, double *aug_theta,
-                        double *aug_phi) {
+template <class F>
+KMPC_HD int trial_decide(Ctx &t, const F &filt, const Stats &tri, bool evok, bool *augment, double *aug_theta, double *aug_phi) {
     *augment = false; *aug_theta = 0.0; *aug_phi = 0.0;
     if (t.tu == TU_INIT) return R_ACCEPT;
     bool accept = false;
     int soc_rhs = 0;
-    if (evok) accept = acceptable(t, filt, FS, tri);
+    if (evok) accept = acceptable(t, filt, tri);
     if (!accept && evok) {
         if (t.mode == M_SOC) {
             t.soc_count++; t.theta_trial = tri.theta;
@@ -1074,7 +1085,7 @@ KMPC_HDN inline int phase_trial(const Cfg &c, Ctx &t, double *wsp, size_t S) {
     const bool evok = pass_trial<OBS>(c, t, wsp, S, t.sel, t.tu, t.a_pr, t.a_y, t.a_du, &tri);
     bool aug; double ath, aph;
     double *filt = wsp + (size_t)c.L.rFilt * S;
-    const int r = trial_decide(t, filt, S, tri, evok, &aug, &ath, &aph);
+    const int r = trial_decide(t, FiltStrided{filt, S}, tri, evok, &aug, &ath, &aph);
     if (aug && !filter_add(t, filt, S, ath, aph)) return ST_INTERNAL;
     if (r == R_SOC1 || r == R_SOC2) { pass_soc_rhs(c, t, wsp, S, t.alpha_soc, r == R_SOC1); return 100; }
     if (r == R_BACKTRACK) return 100;

@@ -66,6 +66,7 @@ struct WScal {  // warp-uniform per-instance scalars
     int pdc[KMPC_NCAND];        // candidate k has the right inertia
     int flag, ok, r, status;
     int tinfo, ncand;           // tail mode (w_worker): slot borrowing of this trip, full candidates assembled this trip
+    double fnear[2 * KMPC_FILTER_NEAR];   // the first entries of the instance's filter (FiltSplit); the others in its global scratch slot
 };
 
 // NST = stage slots allocated per field (>= N + 1, <= 32 * SPL): a smaller NST than 32 * SPL lets more instances fit
@@ -922,6 +923,9 @@ __device__ unsigned long long g_phase_cycles[KMPC_NPHASE];
 #ifndef KMPC_TAIL
 #define KMPC_TAIL 1   /* tail mode (full-solve inertia candidates in borrowed instance slots); 0 compiles it out (tuning builds) */
 #endif
+#ifndef KMPC_HOLD_TRIPS
+#define KMPC_HOLD_TRIPS 256   /* an instance older than this many trips gets its block to itself (w_block_holds); 0 switches that off */
+#endif
 #ifndef KMPC_INLINE_BACKTRACKS
 #define KMPC_INLINE_BACKTRACKS 24
 #endif
@@ -943,7 +947,7 @@ __device__ __forceinline__ unsigned kmpc_smid() { unsigned r; asm volatile("mov.
 // finisher (finish_instance, kmpc_core.cuh) -- iterate, multipliers, obstacle-row state, problem data, filter and solver context go
 // to a column of the hand-over workspace in the thread solver's layout.  False: no column left (the caller reports Restoration_Failed).
 template <int SPL, int NST, bool OBS>
-KMPC_WN inline bool w_hand_over(const Cfg &c, WScal *sc, const WState<SPL> &w, const double *ob, const double *filt, const IO &io, int b) {
+KMPC_WN inline bool w_hand_over(const Cfg &c, WScal *sc, const WState<SPL> &w, const double *ob, const FiltSplit &filt, const IO &io, int b) {
     constexpr int NSTG = WLay<SPL, NST>::NSTG;
     const int N = c.N, lane = w_lane(), O = OBS ? c.O : 0;
     const Rows &L = c.L;
@@ -979,7 +983,7 @@ KMPC_WN inline bool w_hand_over(const Cfg &c, WScal *sc, const WState<SPL> &w, c
             if (!c.obs_sw) { base[L.rSc + CEN_ROW(o, 1, 0)] = w_cx(cen, o); base[L.rSc + CEN_ROW(o, 1, 1)] = w_cy(cen, o); }
         }
     }
-    for (int i = lane; i < 2 * sc->t.fn; i += 32) base[L.rFilt + i] = filt[i];
+    for (int i = lane; i < 2 * sc->t.fn; i += 32) base[L.rFilt + i] = filt.at(i >> 1, i & 1);
     if (lane == 0) {
         for (int j = 0; j < 3; ++j) { base[L.rSc + j] = sc->xc[j]; base[L.rSc + 3 + j] = sc->gl[j]; }
         sc->t.cur = 0; sc->t.inst = b;
@@ -1001,6 +1005,20 @@ KMPC_WN inline int w_fetch_active(const Cfg &c, const IO &io, int *queue) {
     }
 }
 
+// A block that carries a very old instance stops taking new ones: the trips of a block are as long as its busiest phase, an
+// instance in a full block of 16 advances at ~17 us per trip but at ~8 us when it is alone, and the one instance in 10^4..10^5
+// that needs many hundred trips otherwise sets the end of the whole launch (65,536 x N = 30: a 770-trip instance = 13.5 ms of
+// a 12.6 ms batch).  The other blocks absorb the work of the 15 slots that drain, < 1 % of the grid.  Scheduling only: which
+// warp solves an instance never changes its arithmetic.  (Reads the neighbours' contexts in shared memory; a stale value costs
+// or saves one fetch, nothing else -- the caller never lets a hold empty the block, see the two-pass fetch in w_worker.)
+KMPC_WN inline bool w_block_holds(const WScal *scal0, int W) {
+    if (KMPC_HOLD_TRIPS <= 0) return false;
+    const int l = w_lane();
+    bool old = false;
+    if (l < W) { const Ctx &o = scal0[l].t; old = o.mode != M_DONE && o.trips > KMPC_HOLD_TRIPS; }
+    return w_any(old);
+}
+
 // ---- persistent worker: one warp pulls instances from a queue and solves each start to finish; the warps of a block
 // walk through the phases of a trip in step (block barriers) so that warp 0 can run every instance's serial recursions.
 // smem: WLay<SPL, NST>::bytes(warps per block, O) bytes of block-shared scratch.
@@ -1015,12 +1033,13 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     double *coop = smem + (size_t)wid * LY::COOP;
     double *priv = smem + (size_t)W * LY::COOP + (size_t)wid * LY::PRIV;
     double *gp = io.wscratch + ((size_t)w_block() * W + wid) * LY::GPRIV;
-    // the filter (touched by lane 0 only, a handful of entries as a rule, 512 at most as in the oracle) lives in the global scratch slot too
-    double *filt = gp + LY::GFILT;
     const int OBD = LY::obs_doubles(OBS ? c.O : 0, c.obs_sw);
     double *ob = smem + (size_t)W * (LY::COOP + LY::PRIV) + (size_t)wid * OBD;
     WScal *scal0 = (WScal *)(smem + (size_t)W * (LY::COOP + LY::PRIV + OBD));
     WScal *sc = scal0 + wid;
+    // the filter (touched by lane 0 only; 512 entries at most as in the oracle, a handful as a rule): the first few entries in shared
+    // memory, the others in the global scratch slot (all of it there cost 5 % of the batch: a dependent L2 round trip per entry and trial)
+    const FiltSplit filt{sc->fnear, gp + LY::GFILT};
     unsigned *hmask = (unsigned *)(scal0 + W);   // which warps hold an instance, this trip / next trip
     Ctx &t = sc->t;
     WState<SPL> cur;
@@ -1044,12 +1063,17 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     for (;;) {
         // warp 0 is busy in the serial window below, so it takes its next instance here; the other warps take theirs
         // in that window (the global-memory round trip then costs the block nothing)
-        if (!have && !drained && (wid == swid || is_cand)) {
-            b = w_fetch_active(c, io, queue);
-            if (b < c.B) { SCHED_START(b) w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
+        // (second pass: nothing is live, so a hold -- possibly read stale -- is void and every warp may fetch)
+        int nlive = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2 && !nlive; ++pass) {
+            if (!have && !drained && (pass || wid == swid || is_cand) && (pass || !w_block_holds(scal0, W))) {
+                b = w_fetch_active(c, io, queue);
+                if (b < c.B) { SCHED_START(b) w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
+            }
+            PT(0)
+            nlive = w_block_warps_with(have);   // warps that hold an instance this trip
         }
-        PT(0)
-        const int nlive = w_block_warps_with(have);   // warps that hold an instance this trip
         if (!nlive) break;
         PT(1)
         int status = 100;
@@ -1141,7 +1165,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             WScal *so = scal0 + inst;
             const double ds = cand < KMPC_NCAND ? so->dshift[cand] : NAN;
             if (so->flag && ds == ds) so->pdc[cand] = w_serial_candidate<OBS>(c, smem + (size_t)inst * LY::COOP, LY::NSTG, ds) ? 1 : 0;
-        } else if (!have && !drained) {
+        } else if (!have && !drained && !w_block_holds(scal0, W)) {
             b = w_fetch_active(c, io, queue);
             if (b < c.B) { SCHED_START(b) w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); fresh = true; } else drained = true;
         }
@@ -1203,8 +1227,8 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             PT(7)
             if (lane == 0) {
                 bool aug; double ath, aph;
-                int r = trial_decide(t, filt, 1, ts, evok, &aug, &ath, &aph);
-                if (aug && !filter_add(t, filt, 1, ath, aph)) r = ST_INTERNAL;   // filter full: ends the instance loudly (Internal_Error)
+                int r = trial_decide(t, filt, ts, evok, &aug, &ath, &aph);
+                if (aug && !filter_add(t, filt, ath, aph)) r = ST_INTERNAL;   // filter full: ends the instance loudly (Internal_Error)
                 sc->r = r;
             }
             w_sync();

@@ -32,5 +32,6 @@ for prior in (False, True):
     out[name] = {"ms": e0.elapsed_time(e1), "end_ms": float(en.max()), "trips_sum": int(trips.sum()), "us_per_trip_mean": float((dur * 1e3).sum() / trips.sum()),
                  "us_per_trip_by_quartile_of_start": [float((dur[q] * 1e3).sum() / trips[q].sum()) for q in np.array_split(np.argsort(st), 4)],
                  "concurrency_at_5pct_steps": conc,
+                 "longest": [(int(i), round(float(st[i]), 2), round(float(en[i]), 2), int(trips[i]), int(t[i, 3] >> 32)) for i in np.argsort(-trips)[:6]],
                  "last_finishers": [(round(float(st[i]), 2), round(float(en[i]), 2), int(trips[i])) for i in late]}
 print(json.dumps(out))
