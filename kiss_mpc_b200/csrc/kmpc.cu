@@ -178,6 +178,8 @@ struct kmpc_handle {
     int32_t *oval;         // 2 x cols; the second half is the order the kernel reads
     void *osort_tmp;
     size_t osort_bytes;
+    int32_t *cost_buf;     // closed loops: trips every agent's solve took this step / last step (2 x cols); the next step's queue is ordered by it
+    const int32_t *order_hint;   // set by the closed loops for steps >= 1: the per-instance cost of the previous step (device pointer)
     double *env_obs;       // kmpc_environment_loop: the circles each agent kept this step: cols x O_max x 2 centres, then their N-column tracks
     double *env_rad;       //   ... their per-slot radii, cols x O_max
     int32_t *env_idx;      //   ... which dynamic candidate sits in every dynamic slot
@@ -294,6 +296,16 @@ __global__ void kmpc_order_key_kernel(int B, int layout, const double *__restric
     val[b] = b;
 }
 
+// closed loops, step >= 1: an agent's solve costs about what its previous one did (same agent, one control interval later, warm-started
+// from that solution), so the previous step's trip count is the key -- no model of the problem geometry involved.
+__global__ void kmpc_order_hint_kernel(int B, const int32_t *__restrict__ cost, unsigned *__restrict__ key, int32_t *__restrict__ val) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int cst = cost[b];
+    key[b] = cst < 0 ? 0u : (cst > 65535 ? 65535u : (unsigned)cst);
+    val[b] = b;
+}
+
 // fills h->oval[cols..] with the queue order of this batch; returns NULL in *order when the natural order is kept
 static cudaError_t queue_order(kmpc_handle *h, int B, int resident, const Cfg &c, const IO &io, int layout, cudaStream_t st, const int32_t **order) {
     *order = NULL;
@@ -309,8 +321,9 @@ static cudaError_t queue_order(kmpc_handle *h, int B, int resident, const Cfg &c
         h->okey = k; h->oval = v; h->osort_tmp = tmp; h->osort_bytes = nb;
     }
     const double inflation = c.dL + K_BOUND_RELAX * fmax(1.0, fabs(c.dL));   // (c.dL is the relaxed bound; close enough for a heuristic)
-    kmpc_order_key_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, layout, io.x_cur, io.goal, io.obs, io.orad, c.O, c.obs_sw, c.N, c.ub[2] * c.T * c.N,
-                                                          c.obs_radius + inflation + 0.4, inflation + 0.4, h->okey, h->oval);
+    if (h->order_hint) kmpc_order_hint_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, h->order_hint, h->okey, h->oval);
+    else kmpc_order_key_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, layout, io.x_cur, io.goal, io.obs, io.orad, c.O, c.obs_sw, c.N, c.ub[2] * c.T * c.N,
+                                                               c.obs_radius + inflation + 0.4, inflation + 0.4, h->okey, h->oval);
     size_t bytes = h->osort_bytes;
     if ((e = cub::DeviceRadixSort::SortPairsDescending(h->osort_tmp, bytes, h->okey, h->okey + S, h->oval, h->oval + S, B, 0, 16, st)) != cudaSuccess) return e;
     h->launches += 2;
@@ -386,6 +399,15 @@ static cudaError_t launch_warp_kernel(kmpc_handle *h, int device, int sm_count, 
     }
     return cudaGetLastError();
 }
+
+#ifdef KMPC_TUNE_HEADLINE
+template <int SPL, int NST, bool OBS, int WPB, int MINB>
+static cudaError_t kmpc_tune_launch(bool full, kmpc_handle *h, int device, int sm_count, int B, const Cfg &c, const IO &io, int *queue,
+                                    unsigned long long *trips, cudaStream_t st) {
+    if constexpr (SPL == 1 && !OBS) { if (full) return launch_warp_kernel<SPL, NST, true, OBS, WPB, MINB>(h, device, sm_count, B, c, io, queue, trips, st); }
+    return cudaErrorInvalidConfiguration;
+}
+#endif
 
 // Batched EgoAgent.step hand-off (agent.py:139-155, :70-72): applied control = U[:,0]; next current state = X[:,1].
 // With a mask: agents already at their goal keep their state (the reference stops stepping an agent whose final goal is
@@ -588,6 +610,7 @@ extern "C" void kmpc_destroy(kmpc_handle *h) {
     if (h->env_idx) cudaFree(h->env_idx);
     if (h->oval) cudaFree(h->oval);
     if (h->osort_tmp) cudaFree(h->osort_tmp);
+    if (h->cost_buf) cudaFree(h->cost_buf);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_iout) cudaFree(h->d_iout);
@@ -668,6 +691,7 @@ struct SolveArgs {
     double *X_out, *U_out, *obj;
     int32_t *status, *iters;
     const int32_t *active;
+    int32_t *cost;   // optional: trips per instance (closed loops)
 };
 
 // One batch solve, asynchronous on `cuda_stream`.  Warp path: one persistent launch (+ the queue-order kernels).  Thread path:
@@ -699,7 +723,7 @@ static int solve_impl(kmpc_handle *h, int B, const SolveArgs &a, void *cuda_stre
     IO io;
     memset(&io, 0, sizeof io);
     io.x_cur = a.x_cur; io.goal = a.goal; io.X0 = a.X0; io.U0 = a.U0; io.obs = a.obs; io.orad = O > 0 ? a.orad : NULL;
-    io.X_out = a.X_out; io.U_out = a.U_out; io.obj = a.obj; io.status = a.status; io.iters = a.iters; io.active = a.active;
+    io.X_out = a.X_out; io.U_out = a.U_out; io.obj = a.obj; io.status = a.status; io.iters = a.iters; io.active = a.active; io.cost_out = a.cost;
     const size_t S = (size_t)h->cols;
     Lists ls;
     ls.LA[0] = h->lists; ls.LA[1] = h->lists + S; ls.LT[0] = h->lists + 2 * S; ls.LT[1] = h->lists + 3 * S;
@@ -717,9 +741,13 @@ static int solve_impl(kmpc_handle *h, int B, const SolveArgs &a, void *cuda_stre
         for (int i = 0; i < 4; ++i) full = full && c.hasL[i] && c.hasU[i];
         cudaError_t le;
         const int dv = h->device, sms = h->sm_count;
+#ifdef KMPC_TUNE_HEADLINE   /* tuning builds only (scripts/variants.sh): nothing but the N <= 31, box-bounds, no-obstacle kernels -- compiles in a sixth of the time */
+#define KMPC_LAUNCH(SPL, NST, OBS, WPB, MINB) kmpc_tune_launch<SPL, NST, OBS, WPB, MINB>(full, h, dv, sms, B, c, io, h->cnt, ls.trips, st)
+#else
 #define KMPC_LAUNCH(SPL, NST, OBS, WPB, MINB)                                                                          \
     (full ? launch_warp_kernel<SPL, NST, true, OBS, WPB, MINB>(h, dv, sms, B, c, io, h->cnt, ls.trips, st)                 \
           : launch_warp_kernel<SPL, NST, false, OBS, WPB, MINB>(h, dv, sms, B, c, io, h->cnt, ls.trips, st))
+#endif
         // stage slots per field: 32 (N <= 31), 52 (N <= 51, e.g. the N = 50 configuration), 64 (N <= 63)
         // (a batch that fits one wave of 4-instance blocks runs those: 222 registers per thread instead of 128, nothing spilled, and a
         //  lone instance's trip is 12 % shorter -- B = 1: 321 -> 284 us at N = 30, 147 -> 124 us at N = 7)
@@ -816,7 +844,7 @@ static SolveArgs solve_args(const double *x_cur, const double *goal, const doubl
     SolveArgs a;
     a.x_cur = x_cur; a.goal = goal; a.X0 = X0; a.U0 = U0; a.obs = obs; a.orad = obs_radii; a.O = O; a.stagewise = stagewise;
     a.obs_radius = obs_radius; a.inflation = inflation; a.X_out = X_out; a.U_out = U_out; a.obj = obj_out; a.status = status_out;
-    a.iters = iters_out; a.active = active;
+    a.iters = iters_out; a.active = active; a.cost = NULL;
     return a;
 }
 
@@ -1067,6 +1095,18 @@ extern "C" int kmpc_predict_tracks(kmpc_handle *h, int B, int O, int M, const in
     return 0;
 }
 
+// closed loops: where step s records what every agent's solve cost (trips), and -- from the second step on -- the previous step's record
+// as the queue-order key of this one (kmpc_order_hint_kernel).  KMPC_ORDER_NATURAL switches the ordering off as everywhere else.
+static int loop_cost_buffers(kmpc_handle *h, int s, int32_t **cost_now) {
+    if (!h->cost_buf) {
+        CU(cudaMalloc(&h->cost_buf, (size_t)2 * h->cols * sizeof(int32_t)));
+        CU(cudaMemset(h->cost_buf, 0, (size_t)2 * h->cols * sizeof(int32_t)));
+    }
+    *cost_now = h->cost_buf + (size_t)(s & 1) * h->cols;
+    h->order_hint = (s > 0 && getenv("KMPC_NO_ORDER_HINT") == NULL) ? h->cost_buf + (size_t)((s - 1) & 1) * h->cols : NULL;
+    return 0;
+}
+
 extern "C" int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur, const double *goal, double *X, double *U,
                                 double *applied_log, int32_t *iters_log, int32_t *status_log, int32_t *active, double goal_radius,
                                 double agent_radius, void *cuda_stream) {
@@ -1078,8 +1118,12 @@ extern "C" int kmpc_closed_loop(kmpc_handle *h, int B, int steps, double *x_cur,
     cudaStream_t st = (cudaStream_t)cuda_stream;
     for (int s = 0; s < steps; ++s) {
         // in place: every instance reads its own warm-start rows before it writes its result rows
-        int rc = solve_impl(h, B, solve_args(x_cur, goal, X, U, NULL, 0, 0, 0.0, NULL, 0.0, X, U, NULL, status_log ? status_log + (size_t)s * B : NULL,
-                                             iters_log ? iters_log + (size_t)s * B : NULL, active), cuda_stream);
+        SolveArgs sa = solve_args(x_cur, goal, X, U, NULL, 0, 0, 0.0, NULL, 0.0, X, U, NULL, status_log ? status_log + (size_t)s * B : NULL,
+                                  iters_log ? iters_log + (size_t)s * B : NULL, active);
+        int rc = loop_cost_buffers(h, s, &sa.cost);
+        if (rc) return rc;
+        rc = solve_impl(h, B, sa, cuda_stream);
+        h->order_hint = NULL;
         if (rc) return rc;
         kmpc_handoff_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, h->cfg.N, h->cfg.layout, X, U, x_cur,
                                                             applied_log ? applied_log + (size_t)s * B * 2 : NULL, goal, active, goal_radius, agent_radius);
@@ -1144,9 +1188,12 @@ extern "C" int kmpc_environment_loop(kmpc_handle *h, int B, int steps, double *x
             h->launches++;
             obs = trk;
         }
-        int rc = solve_impl(h, B, solve_args(x_cur, goal, X, U, obs, Ot, tracks ? 1 : 0, 0.0, h->env_rad, inflation, X, U, NULL,
-                                             status_log ? status_log + (size_t)s * B : NULL, iters_log ? iters_log + (size_t)s * B : NULL, active),
-                            cuda_stream);
+        SolveArgs sa = solve_args(x_cur, goal, X, U, obs, Ot, tracks ? 1 : 0, 0.0, h->env_rad, inflation, X, U, NULL,
+                                  status_log ? status_log + (size_t)s * B : NULL, iters_log ? iters_log + (size_t)s * B : NULL, active);
+        int rc = loop_cost_buffers(h, s, &sa.cost);
+        if (rc) return rc;
+        rc = solve_impl(h, B, sa, cuda_stream);
+        h->order_hint = NULL;
         if (rc) return rc;
         kmpc_handoff_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, h->cfg.N, h->cfg.layout, X, U, x_cur,
                                                             applied_log ? applied_log + (size_t)s * B * 2 : NULL, goal, active, goal_radius, agent_radius);

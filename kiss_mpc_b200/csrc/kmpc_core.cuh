@@ -137,6 +137,7 @@ struct IO {
     const double *orad;     // per-slot obstacle radii [B][O] / [O][B] (optimizer.py:231-250: one radius per obstacle class); NULL: Cfg::obs_radius
     double *X_out, *U_out, *obj;
     int32_t *status, *iters;
+    int32_t *cost_out;      // optional: trips the instance took (what it cost; the closed loops order the next step's queue by it)
     double *wscratch;       // warp solver: global scratch, WLay::GPRIV doubles per resident warp (owned by the handle)
     const int32_t *active;  // optional per-instance mask (closed loop: agents that reached their goal are not solved again)
     const int32_t *order;   // warp solver: instance handed out at queue position q (NULL: q itself); a permutation of 0..B-1
@@ -861,6 +862,7 @@ KMPC_HD double compl_inf(const Cfg &c, const Stats &s, double mu) {
 }
 KMPC_HD double opt_error(const Cfg &c, const Stats &s, double mu) {
     // s_d = max(s_max, (|y|_1 + |z|_1) / (m + n_b)) / s_max, s_c likewise; both are >= 1 and almost always exactly 1
+    // (tried: the two rare divisions behind a branch in an out-of-line function -- 0.7 % slower than these selects)
     const double sd = kfmax(K_S_MAX, (s.sumy + s.sumz) * c.r_mnb) * (1.0 / K_S_MAX);
     const double sc = c.nb ? kfmax(K_S_MAX, s.sumz * c.r_nb) * (1.0 / K_S_MAX) : 1.0;
     const double di = sd > 1.0 ? s.dinf / sd : s.dinf, ci = compl_inf(c, s, mu);

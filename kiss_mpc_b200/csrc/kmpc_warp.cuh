@@ -29,8 +29,9 @@ template <int SPL>
 struct WStep { double dx0[SPL], dx1[SPL], dx2[SPL], du0[SPL], du1[SPL], dy0[SPL], dy1[SPL], dy2[SPL]; };
 
 // ---- shared-memory layout ----------------------------------------------------------------------------------------
-// coop area of one instance: C_NF fields x NSTG stages (field-major: the owner lanes touch consecutive stages, the
-// Riccati lanes -- one per instance -- are COOP doubles apart, COOP odd => both patterns are bank-conflict free).
+// coop area of one instance: C_NF fields x NSTG stages (field-major: the owner lanes touch consecutive stages; the
+// Riccati lanes -- one per instance -- are COOP doubles apart and read / write an even-odd pair of stages with one 128-bit
+// access: COOP = 2 mod 32 doubles puts 8 lanes x 16 bytes on the 32 banks, the minimum of two wavefronts per access).
 // Fields 7..17 (+ Q01) are the stage blocks going in.  The backward sweep adds K and P and overwrites the blocks its vector
 // part has consumed (q, qv, qw) with p and k_ff; the forward roll-out overwrites K with (dx, du).  The matrix blocks
 // (Q00 Q11 Q22 Q01 dv dw htv) are never overwritten: the speculative inertia candidates read them at their own pace.
@@ -66,6 +67,7 @@ struct WScal {  // warp-uniform per-instance scalars
     int pdc[KMPC_NCAND];        // candidate k has the right inertia
     int flag, ok, r, status;
     int tinfo, ncand;           // tail mode (w_worker): slot borrowing of this trip, full candidates assembled this trip
+    int pred, pstat;            // inertia prediction (w_worker): element of IPOPT's perturbation sequence this sweep was assembled with (0: none), status once it is judged
     double fnear[2 * KMPC_FILTER_NEAR];   // the first entries of the instance's filter (FiltSplit); the others in its global scratch slot
 };
 
@@ -73,7 +75,7 @@ struct WScal {  // warp-uniform per-instance scalars
 template <int SPL, int NST = 32 * SPL>
 struct WLay {
     static constexpr int NSTG = NST;
-    static constexpr int COOP = C_NF * NSTG + 1;
+    static constexpr int COOP = C_NF * NSTG + 2;   // (even: the Riccati lanes move two stages per 128-bit access, w_ld2 / w_st2)
     static constexpr int PRIV = V_NF * NSTG;
     static constexpr int GFILT = G_NF * NSTG;                  // the filter of the instance sits behind the per-stage fields of the global scratch slot
     static constexpr int GPRIV = G_NF * NSTG + 2 * K_FILTER_CAP;   // doubles of global scratch per resident warp
@@ -454,6 +456,15 @@ KMPC_WN inline void w_assemble_cands(const Cfg &c, const WScal *sc, const WState
     }
 }
 
+// two consecutive stages (an even one and the next) of one field in one shared-memory access.  The serial warp is bound by
+// instruction issue, and a 64-bit shared-memory access costs it ~4 issue cycles (ncu, r02d): half as many accesses.
+#ifdef __CUDA_ARCH__
+KMPC_W void w_ld2(const double *p, double &lo, double &hi) { const double2 v = *reinterpret_cast<const double2 *>(p); lo = v.x; hi = v.y; }
+KMPC_W void w_st2(double *p, double lo, double hi) { *reinterpret_cast<double2 *>(p) = make_double2(lo, hi); }
+#else
+KMPC_W void w_ld2(const double *p, double &lo, double &hi) { lo = p[0]; hi = p[1]; }
+KMPC_W void w_st2(double *p, double lo, double hi) { p[0] = lo; p[1] = hi; }
+#endif
 // ---- phase 1b, RICCATI: the two serial recursions of ONE instance, executed by ONE lane of the block's Riccati warp ----
 // Backward sweep (K, k_ff, P, p of every stage; false = some Q_uu not positive definite = wrong inertia), then the
 // forward substitution dx+ = A dx + B du + e, du = K dx + k_ff.  Same algebra as riccati_step (kmpc_core.cuh) for the
@@ -476,18 +487,20 @@ KMPC_W void w_ric_vec(const WRicCarry &cy, const double *q, double *qs, const in
     qs[C_KF0 * NSTG] = kf0; qs[C_KF1 * NSTG] = kf1; qs[C_PV0 * NSTG] = p0; qs[C_PV1 * NSTG] = p1; qs[C_PV2 * NSTG] = p2;
 }
 // matrix part of stage k: (P of stage k+1 in P..) -> K, M = -Quu^-1, P of stage k; leaves what the vector part needs in cy
-// dshift / dshift_u: extra delta_w on the x-x / u-u diagonal (0 here; the candidates have their own loop); qs: where K, P go
+// qs: where K, P go.  (The blocks are used as assembled: the candidates of other delta_w have their own loop.  An added shift of 0.0
+// and the x-y coupling 0.0 of the rows-free problem are not folded by the compiler -- x + 0.0 is not x for x = -0.0 -- and cost six
+// FP64 issue slots per stage on the one warp the whole block waits for.)
 template <bool OBS>
 KMPC_W bool w_ric_mat(WRicCarry &cy, double *q, const int NSTG, const double T, const double TT, double &P00, double &P10,
-                      double &P11, double &P20, double &P21, double &P22, const double dshift, const double dshift_u, double *qs) {
+                      double &P11, double &P20, double &P21, double &P22, double *qs) {
     const double a13 = q[C_A13 * NSTG], a23 = q[C_A23 * NSTG], b11 = q[C_B11 * NSTG], b21 = q[C_B21 * NSTG];
-    const double Q00 = q[C_Q00 * NSTG] + dshift, Q11 = q[C_Q11 * NSTG] + dshift, Q22 = q[C_Q22 * NSTG] + dshift, Q01 = OBS ? q[C_Q01 * NSTG] : 0.0;
-    const double dv = q[C_DV * NSTG] + dshift_u, dw = q[C_DW * NSTG] + dshift_u, htv = q[C_HTV * NSTG];
+    const double Q00 = q[C_Q00 * NSTG], Q11 = q[C_Q11 * NSTG], Q22 = q[C_Q22 * NSTG];
+    const double dv = q[C_DV * NSTG], dw = q[C_DW * NSTG], htv = q[C_HTV * NSTG];
     cy.P00 = P00; cy.P10 = P10; cy.P11 = P11; cy.P20 = P20; cy.P21 = P21; cy.P22 = P22;
     cy.a13 = a13; cy.a23 = a23; cy.b11 = b11; cy.b21 = b21;
     // P A (third column), symmetric Qxx = A^T P A + Q
     const double PA02 = fma(P00, a13, fma(P10, a23, P20)), PA12 = fma(P10, a13, fma(P11, a23, P21)), PA22 = fma(P20, a13, fma(P21, a23, P22));
-    const double X00 = P00 + Q00, X10 = P10 + Q01, X11 = P11 + Q11, X20 = PA02, X21 = PA12;
+    const double X00 = P00 + Q00, X10 = OBS ? P10 + q[C_Q01 * NSTG] : P10, X11 = P11 + Q11, X20 = PA02, X21 = PA12;
     const double X22 = fma(a13, PA02, fma(a23, PA12, PA22)) + Q22;
     // Qux = B^T P A (+ W_v,theta)
     const double U00 = fma(b11, P00, b21 * P10), U01 = fma(b11, P10, b21 * P11), U02 = fma(b11, PA02, fma(b21, PA12, htv));
@@ -546,6 +559,23 @@ KMPC_WN inline bool w_serial_candidate(const Cfg &c, const double *coop, const i
     return pd;
 }
 struct WFwdIn { double K00, K01, K02, K10, K11, K12, kf0, kf1, a13, a23, b11, b21, e0, e1, e2; };
+KMPC_W void w_fwd_load2(WFwdIn &a, WFwdIn &b, const double *q, const int NSTG) {   // q: an even stage
+    w_ld2(q + C_K00 * NSTG, a.K00, b.K00); w_ld2(q + C_K01 * NSTG, a.K01, b.K01); w_ld2(q + C_K02 * NSTG, a.K02, b.K02);
+    w_ld2(q + C_K10 * NSTG, a.K10, b.K10); w_ld2(q + C_K11 * NSTG, a.K11, b.K11); w_ld2(q + C_K12 * NSTG, a.K12, b.K12);
+    w_ld2(q + C_KF0 * NSTG, a.kf0, b.kf0); w_ld2(q + C_KF1 * NSTG, a.kf1, b.kf1);
+    w_ld2(q + C_A13 * NSTG, a.a13, b.a13); w_ld2(q + C_A23 * NSTG, a.a23, b.a23); w_ld2(q + C_B11 * NSTG, a.b11, b.b11); w_ld2(q + C_B21 * NSTG, a.b21, b.b21);
+    w_ld2(q + C_E0 * NSTG, a.e0, b.e0); w_ld2(q + C_E1 * NSTG, a.e1, b.e1); w_ld2(q + C_E2 * NSTG, a.e2, b.e2);
+}
+// one stage of the roll-out without the stores: (dx, du) of the stage come back in o[0..4], x0..x2 become dx of the next stage
+KMPC_W void w_fwd_step(const WFwdIn &f, const double T, double &x0, double &x1, double &x2, double (&o)[5]) {
+    const double du0 = fma(f.K00, x0, fma(f.K01, x1, fma(f.K02, x2, f.kf0)));
+    const double du1 = fma(f.K10, x0, fma(f.K11, x1, fma(f.K12, x2, f.kf1)));
+    o[0] = x0; o[1] = x1; o[2] = x2; o[3] = du0; o[4] = du1;
+    const double n0 = fma(f.b11, du0, fma(f.a13, x2, x0 + f.e0));
+    const double n1 = fma(f.b21, du0, fma(f.a23, x2, x1 + f.e1));
+    const double n2 = fma(T, du1, x2 + f.e2);
+    x0 = n0; x1 = n1; x2 = n2;
+}
 KMPC_W void w_fwd_load(WFwdIn &r, const double *q, const int NSTG) {
     r.K00 = q[C_K00 * NSTG]; r.K01 = q[C_K01 * NSTG]; r.K02 = q[C_K02 * NSTG];
     r.K10 = q[C_K10 * NSTG]; r.K11 = q[C_K11 * NSTG]; r.K12 = q[C_K12 * NSTG];
@@ -558,9 +588,10 @@ KMPC_W void w_fwd_stage(const WFwdIn &f, double *q, const int NSTG, const double
     const double du0 = fma(f.K00, x0, fma(f.K01, x1, fma(f.K02, x2, f.kf0)));
     const double du1 = fma(f.K10, x0, fma(f.K11, x1, fma(f.K12, x2, f.kf1)));
     q[C_DX0 * NSTG] = x0; q[C_DX1 * NSTG] = x1; q[C_DX2 * NSTG] = x2; q[C_DU0 * NSTG] = du0; q[C_DU1 * NSTG] = du1;
-    const double n0 = x0 + f.a13 * x2 + f.b11 * du0 + f.e0;
-    const double n1 = x1 + f.a23 * x2 + f.b21 * du0 + f.e1;
-    const double n2 = x2 + T * du1 + f.e2;
+    // (fused form: one FMA behind du on the dependency chain of the recursion instead of a multiply and two additions)
+    const double n0 = fma(f.b11, du0, fma(f.a13, x2, x0 + f.e0));
+    const double n1 = fma(f.b21, du0, fma(f.a23, x2, x1 + f.e1));
+    const double n2 = fma(T, du1, x2 + f.e2);
     x0 = n0; x1 = n1; x2 = n2;
 }
 // forward roll-out dx+ = A dx + B du + e, du = K dx + k_ff over all stages
@@ -568,24 +599,23 @@ KMPC_WN inline void w_serial_fwd(const Cfg &c, double *coop, const int NSTG, con
     const int N = c.N;
     const double T = c.T;
     double x0 = d0[0], x1 = d0[1], x2 = d0[2];
-    // two stages per trip, the two operand sets swapping roles (no register copies, no guarded load block -- the guarded
-    // block of a one-stage loop kept the shared-window address arithmetic, an S2R per stage, inside the loop: 255 cycles/stage)
-    WFwdIn fa, fb;
-    w_fwd_load(fa, coop, NSTG);
+    // two stages (an even one and the next) per trip: their operands arrive and their results leave in 128-bit accesses.  Every
+    // address is the loop base plus a constant, so the loads move freely above the stores.
     int s = 0;
 #pragma unroll 1
-    for (; s + 2 <= N; s += 2) {   // every address is the loop base plus a constant: loads move freely above the stores
+    for (; s + 1 <= N; s += 2) {
         double *q = coop + s;
-        w_fwd_load(fb, q + 1, NSTG);
-        w_fwd_stage(fa, q, NSTG, T, x0, x1, x2);
-        w_fwd_load(fa, q + 2, NSTG);
-        w_fwd_stage(fb, q + 1, NSTG, T, x0, x1, x2);
+        WFwdIn fa, fb;
+        double oa[5], ob[5];
+        w_fwd_load2(fa, fb, q, NSTG);
+        w_fwd_step(fa, T, x0, x1, x2, oa);
+        w_fwd_step(fb, T, x0, x1, x2, ob);
+        w_st2(q + C_DX0 * NSTG, oa[0], ob[0]); w_st2(q + C_DX1 * NSTG, oa[1], ob[1]); w_st2(q + C_DX2 * NSTG, oa[2], ob[2]);
+        w_st2(q + C_DU0 * NSTG, oa[3], ob[3]); w_st2(q + C_DU1 * NSTG, oa[4], ob[4]);
     }
-    if (s + 1 <= N) {              // the last one or two stages
-        w_fwd_load(fb, coop + s + 1, NSTG);
-        w_fwd_stage(fa, coop + s, NSTG, T, x0, x1, x2);
-        w_fwd_stage(fb, coop + s + 1, NSTG, T, x0, x1, x2);
-    } else {
+    if (s == N) {   // N even: the terminal stage is left
+        WFwdIn fa;
+        w_fwd_load(fa, coop + s, NSTG);
         w_fwd_stage(fa, coop + s, NSTG, T, x0, x1, x2);
     }
 }
@@ -598,20 +628,22 @@ KMPC_WN inline bool w_serial(const Cfg &c, double *coop, const int NSTG, const d
     double P00 = 0, P10 = 0, P11 = 0, P20 = 0, P21 = 0, P22 = 0, p0 = 0, p1 = 0, p2 = 0;
     WRicCarry cy;
     double *const st = coop;      // loads and stores through ONE base: the compiler can tell the fields apart and keeps hoisting
-    const double dshift = 0.0;    // the next stage's loads above this stage's stores (a second base pointer cost 15 %)
-    bool pd = w_ric_mat<OBS>(cy, coop + N, NSTG, T, TT, P00, P10, P11, P20, P21, P22, dshift, 0.0, st + N);
+                                  // the next stage's loads above this stage's stores (a second base pointer cost 15 %)
+    bool pd = w_ric_mat<OBS>(cy, coop + N, NSTG, T, TT, P00, P10, P11, P20, P21, P22, st + N);
     // two stages per trip of the loop with the carry structs swapping roles (no register copies between iterations)
+    // (tried: the blocks of an even-odd stage pair loaded, and their K, P stored, with 128-bit accesses as the roll-out below does --
+    //  2.6 % faster for the sweep alone, 3 % SLOWER inside the kernel, whose 128-register budget the longer live ranges do not fit)
     WRicCarry cz;
     int s = N - 1;
 #pragma unroll 1
     for (; s >= 1; s -= 2) {
-        pd = w_ric_mat<OBS>(cz, coop + s, NSTG, T, TT, P00, P10, P11, P20, P21, P22, dshift, dshift, st + s) && pd;
+        pd = w_ric_mat<OBS>(cz, coop + s, NSTG, T, TT, P00, P10, P11, P20, P21, P22, st + s) && pd;
         w_ric_vec(cy, coop + s + 1, st + s + 1, NSTG, T, p0, p1, p2);
-        pd = w_ric_mat<OBS>(cy, coop + s - 1, NSTG, T, TT, P00, P10, P11, P20, P21, P22, dshift, dshift, st + s - 1) && pd;
+        pd = w_ric_mat<OBS>(cy, coop + s - 1, NSTG, T, TT, P00, P10, P11, P20, P21, P22, st + s - 1) && pd;
         w_ric_vec(cz, coop + s, st + s, NSTG, T, p0, p1, p2);
     }
     if (s == 0) {  // (only when the pair loop did not end on stage 0)
-        pd = w_ric_mat<OBS>(cz, coop, NSTG, T, TT, P00, P10, P11, P20, P21, P22, dshift, dshift, st) && pd;
+        pd = w_ric_mat<OBS>(cz, coop, NSTG, T, TT, P00, P10, P11, P20, P21, P22, st) && pd;
         w_ric_vec(cy, coop + 1, st + 1, NSTG, T, p0, p1, p2);
         cy = cz;
     }
@@ -1019,6 +1051,25 @@ KMPC_WN inline bool w_block_holds(const WScal *scal0, int W) {
     return w_any(old);
 }
 
+// Inertia prediction.  IPOPT factorises every new iteration's KKT matrix with delta_w = 0 first and walks its perturbation sequence
+// (0, d1 = max(delta_min, delta_last / 3) or 1e-4, d2 = 8 d1 or 100 d1, ...) until the inertia is right.  A wrong inertia costs this
+// solver a whole trip (the instance sits out the rest of the block's trip), and it clusters: after an iteration that needed a
+// perturbation the first factorisation of the next one fails in 87 % of the cases (after an unperturbed one: 1.6 %; 65,536 x N = 30),
+// and which element then works follows from the last one -- after d1 mostly d2 (a third of the last value is too small), after d2 or
+// later mostly d1.  So such an iteration is ASSEMBLED AND SOLVED with the predicted element right away, and the candidate lanes
+// test the other elements of the sequence, delta_w = 0 included (diagonal shifts of the assembled blocks, as before).  The decision
+// rule is IPOPT's: the first element of the sequence with the right inertia is the one used -- if that is not the predicted one, the
+// instance repeats the sweep with it (what a failed first factorisation costs anyway).  Same iterates, 5 % fewer trips.
+#ifndef KMPC_PREDICT_INERTIA
+#define KMPC_PREDICT_INERTIA 1
+#endif
+// element i of the sequence that starts at delta_w = 0 (i = 0: no perturbation)
+KMPC_W double w_inertia_seq(int i, double delta_last) {
+    double d = 0.0;
+    for (int k = 0; k < i; ++k) d = inertia_next_delta(d, delta_last);
+    return d;
+}
+
 // ---- persistent worker: one warp pulls instances from a queue and solves each start to finish; the warps of a block
 // walk through the phases of a trip in step (block barriers) so that warp 0 can run every instance's serial recursions.
 // smem: WLay<SPL, NST>::bytes(warps per block, O) bytes of block-shared scratch.
@@ -1046,7 +1097,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     WStep<SPL> act;
     bool have = false;
     int b = -1;
-    if (lane == 0) { t.mode = M_DONE; sc->flag = 0; sc->ok = 0; sc->tinfo = 0; sc->ncand = 0; for (int k = 0; k < KMPC_NCAND; ++k) { sc->dshift[k] = NAN; sc->pdc[k] = 0; } }
+    if (lane == 0) { t.mode = M_DONE; sc->flag = 0; sc->ok = 0; sc->tinfo = 0; sc->ncand = 0; sc->pred = 0; sc->pstat = 0; for (int k = 0; k < KMPC_NCAND; ++k) { sc->dshift[k] = NAN; sc->pdc[k] = 0; } }
     if (wid == 0 && lane == 0) { hmask[0] = 0; hmask[1] = 0; }
     w_block_sync();
     PT_DECL
@@ -1059,6 +1110,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     const int ncw = W >= 2 ? ((KMPC_NCAND - 1) * W + 31) / 32 < W - 1 ? ((KMPC_NCAND - 1) * W + 31) / 32 : W - 1 : 0;
     const int cj = (wid - swid - 1 + W) % W;          // 0 .. ncw - 1: this warp is a candidate warp
     const bool is_cand = W >= 2 && wid != swid && cj < ncw;
+    const bool can_predict = W >= 2 && (KMPC_NCAND - 1) * W <= 32 * ncw && KMPC_NCAND >= 3;   // every other element of the sequence has a candidate lane
 #pragma unroll 1
     for (;;) {
         // warp 0 is busy in the serial window below, so it takes its next instance here; the other warps take theirs
@@ -1104,6 +1156,11 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         {
             const int tinfo = (TAIL && KMPC_TAIL && !OBS && KMPC_NCAND > 1) ? sc->tinfo : 0;
             const bool full_cands = (tinfo >> 8) != 0 && do_sweep && mode == M_NEWTON;
+            if (KMPC_PREDICT_INERTIA && full_cands && sc->pred) {   // borrowed slots solve the whole sequence side by side: no prediction needed
+                w_sync();
+                if (lane == 0) { t.delta = 0.0; t.alpha_min = 0.0; sc->pred = 0; }
+                w_sync();
+            }
             int ncand = 0;       // full candidates of this trip (fewer than NCF when the sequence runs past delta_w_max)
             if (do_sweep) w_assemble<SPL, NST, FULL, OBS>(c, sc, cur, priv, gp, coop, ob);   // (ONE call site: two inlined copies need not round alike)
             if (full_cands) {
@@ -1139,6 +1196,17 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                     // obstacle rows, delta_w * sum n n^T): the next perturbations IPOPT would try if this factorisation has the wrong inertia
                     double dk = t.delta;
                     sc->dshift[0] = 0.0;
+                    if (KMPC_PREDICT_INERTIA && sc->pred) {
+                        // predicted sweep: the candidates are the OTHER elements of the sequence, in its order (delta_w = 0 first)
+                        int k = 1;
+                        for (int i = 0; i < KMPC_NCAND; ++i) {
+                            if (i == sc->pred) continue;
+                            const double di = w_inertia_seq(i, t.delta_last);
+                            sc->dshift[k] = di <= K_DW_MAX ? di - t.delta : NAN;
+                            sc->pdc[k] = 0;
+                            ++k;
+                        }
+                    } else
                     for (int k = 1; k < KMPC_NCAND; ++k) {
                         dk = inertia_next_delta(dk, t.delta_last);
                         sc->dshift[k] = (!full_cands && W >= 2 && mode == M_NEWTON && dk <= K_DW_MAX && k * W <= 32 * ncw) ? dk - t.delta : NAN;
@@ -1177,6 +1245,24 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         if (do_sweep) {
             // the system that was solved: the base one, or -- tail mode -- the first full candidate with the right inertia
             const double *solved = coop;
+            if (KMPC_PREDICT_INERTIA && sc->pred) {
+                // IPOPT's rule over the tested elements: the first one of the sequence with the right inertia is the one to use
+                if (lane == 0) {
+                    const int pj = sc->pred;
+                    int first = -1, k = 1;
+                    for (int i = 0; i < KMPC_NCAND && first < 0; ++i) {
+                        const bool works = i == pj ? sc->ok != 0 : (sc->dshift[k] == sc->dshift[k] && sc->pdc[k] != 0);
+                        if (i != pj) ++k;
+                        if (works) first = i;
+                    }
+                    if (first != pj) {
+                        sc->ok = 0;
+                        if (first >= 0) { t.delta = w_inertia_seq(first, t.delta_last); t.alpha_min = (double)first; sc->pstat = R_RETRY; }
+                        else { t.delta = w_inertia_seq(KMPC_NCAND - 1, t.delta_last); t.alpha_min = (double)KMPC_NCAND; sc->pstat = inertia_update(t); }
+                    }
+                }
+                w_sync();
+            }
             bool ok = sc->ok != 0;
             const int ncand = (TAIL && KMPC_TAIL && !OBS && KMPC_NCAND > 1 && !ok) ? sc->ncand : 0;
             for (int k = 0; k < ncand; ++k) {
@@ -1184,7 +1270,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 if (scal0[slot].ok) {
                     ok = true; solved = smem + (size_t)slot * LY::COOP;
                     w_sync();
-                    if (lane == 0) { for (int q = 0; q <= k; ++q) t.delta = inertia_next_delta(t.delta, t.delta_last); }   // IPOPT's sequence up to the perturbation that works
+                    if (lane == 0) { for (int q = 0; q <= k; ++q) t.delta = inertia_next_delta(t.delta, t.delta_last); t.alpha_min += (double)(k + 1); }   // IPOPT's sequence up to the perturbation that works
                     w_sync();
                     break;
                 }
@@ -1192,18 +1278,27 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             if (!ok) {
                 PT_COUNT(10)
                 if (lane == 0) {
-                    // wrong inertia: raise delta_w (IPOPT's sequence) past the candidates already known to fail, sweep again next trip
-                    int st = mode != M_NEWTON ? sweep_failure_status(t) : inertia_update(t);
-                    for (int k = 0; k < ncand && st == R_RETRY; ++k) st = inertia_update(t);
-                    for (int k = 1; k < KMPC_NCAND && st == R_RETRY && sc->dshift[k] == sc->dshift[k] && !sc->pdc[k]; ++k) st = inertia_update(t);
-                    sc->status = st;
+                    if (KMPC_PREDICT_INERTIA && sc->pred) { sc->status = sc->pstat; sc->pred = 0; }   // (judged above)
+                    else {
+                        // wrong inertia: raise delta_w (IPOPT's sequence) past the candidates already known to fail, sweep again next trip
+                        // (t.alpha_min -- a field the warp solver has no other use for -- counts the elements of the sequence tried)
+                        int st = mode != M_NEWTON ? sweep_failure_status(t) : inertia_update(t);
+                        t.alpha_min += 1.0;
+                        for (int k = 0; k < ncand && st == R_RETRY; ++k) { st = inertia_update(t); t.alpha_min += 1.0; }
+                        for (int k = 1; k < KMPC_NCAND && st == R_RETRY && sc->dshift[k] == sc->dshift[k] && !sc->pdc[k]; ++k) { st = inertia_update(t); t.alpha_min += 1.0; }
+                        sc->status = st;
+                    }
                 }
                 w_sync();
                 status = sc->status;
             } else {
                 double apr, adu, gbd, ym;
                 w_step<SPL, NST, FULL, OBS>(c, sc, cur, solved, priv, ob, act, &apr, &adu, &gbd, &ym);
-                if (lane == 0) rollout_logic(t, apr, adu, gbd, ym);
+                if (lane == 0) {
+                    if (mode == M_NEWTON) t.pw_t = t.alpha_min;   // which element of the perturbation sequence this iteration needed (0: none)
+                    sc->pred = 0;
+                    rollout_logic(t, apr, adu, gbd, ym);
+                }
                 w_sync();
                 if (t.sel == 0) w_step_store<SPL, NST>(act, gp);
                 go_trial = true;
@@ -1239,7 +1334,15 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 if (mode == M_SOC) { PT_COUNT(14) }
                 if (OBS) w_obs_commit<SPL, NST>(c, cur, act, ta_mu, ta_delta, ta_pr, ta_y, ta_du, tclamp, tlsq, tsoc, ob);
                 cur = tri;
-                if (lane == 0) { t.c = ts; sc->status = begin_iteration(c, t); }
+                if (lane == 0) {
+                    t.c = ts; sc->status = begin_iteration(c, t);
+                    t.alpha_min = 0.0;
+                    if (KMPC_PREDICT_INERTIA && can_predict && sc->status == 100 && t.pw_t > 0.0) {
+                        const int pj = t.pw_t == 1.0 ? 2 : 1;
+                        const double dj = w_inertia_seq(pj, t.delta_last);
+                        if (dj <= K_DW_MAX) { t.delta = dj; t.alpha_min = (double)pj; sc->pred = pj; }
+                    }
+                }
                 w_sync();
                 status = sc->status;
             } else if (r != R_BACKTRACK) status = r;
@@ -1276,6 +1379,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
 #else
                 if (io.iters) io.iters[b] = t.iter;
 #endif
+                if (io.cost_out) io.cost_out[b] = t.trips;
                 w_count_trips(trips_total, t.trips);
                 SCHED_END(b, t.trips)
                 t.mode = M_DONE;

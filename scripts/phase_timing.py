@@ -11,7 +11,7 @@ pl = BatchedMotionPlanner(PlannerConfig(N=N), max_batch=B)
 pl.set_timing(True)
 x = torch.tensor(b["x_cur"], device="cuda"); g = torch.tensor(b["goal"], device="cuda")
 L = _lib.load()
-out = (C.c_double * 18)()
+out = (C.c_double * 48)()
 for rep in range(2):
     r = pl.solve(x, g); torch.cuda.synchronize()
     n = L.kmpc_debug_phase_cycles(out)
