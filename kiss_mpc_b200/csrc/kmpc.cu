@@ -157,7 +157,7 @@ struct kmpc_handle {
     int device, sm_count, cols;  // cols = workspace columns (B_max rounded up to a multiple of 32)
     double *ws;
     int *lists;  // 4 x cols ints
-    int *cnt;    // 4 counters
+    int *cnt;    // 4 counters of the thread solver's lists (cnt[0] doubles as the warp solver's queue head) + cnt[4]: restoration hand-over count
     unsigned long long *trips;
     int *h_cnt;  // pinned: KMPC_LOOKAHEAD x 4 counters
     cudaEvent_t ev0, ev1, evq[KMPC_LOOKAHEAD];
@@ -184,6 +184,8 @@ struct kmpc_handle {
     double *env_rad;       //   ... their per-slot radii, cols x O_max
     int32_t *env_idx;      //   ... which dynamic candidate sits in every dynamic slot
     int max_smem;          // opt-in shared memory per block of the device
+    struct { const void *fn; size_t smem; int bpsm; } kattr[16];   // per kernel instantiation: shared-memory opt-in done, resident blocks per SM
+    int n_kattr;
     // restoration-phase hand-over (kmpc_finish_kernel): workspace columns, the instance in each, the number in use
     double *resto_ws;
     int32_t *resto_list;
@@ -335,23 +337,38 @@ static cudaError_t queue_order(kmpc_handle *h, int B, int resident, const Cfg &c
 template <int SPL, int NST, bool FULL, bool OBS, int WPB, int MINB>
 static cudaError_t launch_warp_kernel(kmpc_handle *h, int device, int sm_count, int B, const Cfg &c, const IO &io_in, int *queue,
                                       unsigned long long *trips, cudaStream_t st) {
-    int max_smem = 0;
-    cudaError_t e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
+    int max_smem = h->max_smem;
+    if (max_smem <= 0) {
+        e = cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        if (e != cudaSuccess) return e;
+    }
     int wpb = WPB;
     while (wpb > 0 && WLay<SPL, NST>::bytes(wpb, c.O, c.obs_sw) > (size_t)max_smem) --wpb;
     if (wpb < 1) return cudaErrorInvalidConfiguration;
     const size_t smem = WLay<SPL, NST>::bytes(wpb, c.O, c.obs_sw);
+    // shared-memory opt-in + occupancy of a kernel instantiation: asked once per handle and shared-memory size, not once per solve
+    // (three runtime calls, ~10 us of host time that a B = 1 solve of ~130 us would pay every time)
+    auto prepare = [&](void (*k)(const Cfg, const IO, int *, unsigned long long *), int *bp) -> cudaError_t {
+        for (int i = 0; i < h->n_kattr; ++i)
+            if (h->kattr[i].fn == (const void *)k && h->kattr[i].smem == smem) { *bp = h->kattr[i].bpsm; return cudaSuccess; }
+        cudaError_t r = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);   // (the device's limit: the attribute belongs to the function, not to this handle's problem size)
+        if (r == cudaSuccess) r = cudaOccupancyMaxActiveBlocksPerMultiprocessor(bp, k, 32 * wpb, smem);
+        if (r == cudaSuccess) {
+            const int i = h->n_kattr < 16 ? h->n_kattr++ : 15;
+            h->kattr[i].fn = (const void *)k; h->kattr[i].smem = smem; h->kattr[i].bpsm = *bp;
+        }
+        return r;
+    };
     void (*kern)(const Cfg, const IO, int *, unsigned long long *) = kmpc_warp_kernel<SPL, NST, FULL, OBS, WPB, MINB, false>;
     int bpsm = 0;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsm, kern, 32 * wpb, smem);
+    e = prepare(kern, &bpsm);
     if (e != cudaSuccess) return e;
-    if (!OBS && (long long)B <= (long long)KMPC_TAIL_WAVES * sm_count * (bpsm > 0 ? bpsm : 1) * wpb && getenv("KMPC_NO_TAIL") == NULL) {
+    static const bool no_tail = getenv("KMPC_NO_TAIL") != NULL;
+    if (!OBS && (long long)B <= (long long)KMPC_TAIL_WAVES * sm_count * (bpsm > 0 ? bpsm : 1) * wpb && !no_tail) {
         // few waves: the phase in which the queue is drained is a large part of the launch -- the kernel with the tail mode
         kern = kmpc_warp_kernel<SPL, NST, FULL, OBS, WPB, MINB, !OBS>;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpsm, kern, 32 * wpb, smem);
+        e = prepare(kern, &bpsm);
         if (e != cudaSuccess) return e;
     }
     int grid = sm_count * (bpsm > 0 ? bpsm : 1);
@@ -375,19 +392,17 @@ static cudaError_t launch_warp_kernel(kmpc_handle *h, int device, int sm_count, 
         long long cap = h->cfg.B_max < 1024 ? h->cfg.B_max : 1024;
         const long long budget = 256ll << 20;   // bytes
         if (cap * rows * 8ll > budget) cap = budget / (rows * 8ll);
-        double *ws = NULL; int32_t *li = NULL; int *cn = NULL;
+        double *ws = NULL; int32_t *li = NULL;
         if (cap >= 1) {
             e = cudaMalloc(&ws, (size_t)cap * rows * sizeof(double));
             if (e == cudaSuccess) e = cudaMalloc(&li, (size_t)cap * sizeof(int32_t));
         }
-        if (e == cudaSuccess) e = cudaMalloc(&cn, sizeof(int));
-        if (e != cudaSuccess) { cudaFree(ws); cudaFree(li); cudaFree(cn); return e; }
-        h->resto_ws = ws; h->resto_list = li; h->resto_count = cn; h->resto_cap = (int)(cap >= 1 ? cap : 0); h->resto_rows = rows;
+        if (e != cudaSuccess) { cudaFree(ws); cudaFree(li); return e; }
+        h->resto_ws = ws; h->resto_list = li; h->resto_count = h->cnt + 4; h->resto_cap = (int)(cap >= 1 ? cap : 0); h->resto_rows = rows;
     }
     io.resto_ws = h->resto_cap ? h->resto_ws : NULL; io.resto_list = h->resto_list; io.resto_count = h->resto_count;
     io.resto_cap = h->resto_cap; io.resto_rows = h->resto_rows;
-    e = cudaMemsetAsync(h->resto_count, 0, sizeof(int), st);
-    if (e != cudaSuccess) return e;
+    // (queue head and hand-over count were zeroed together by solve_impl: one memset of h->cnt[0..7])
     kern<<<grid, 32 * wpb, smem, st>>>(c, io, queue, trips);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -606,7 +621,6 @@ extern "C" void kmpc_destroy(kmpc_handle *h) {
     if (h->env_rad) cudaFree(h->env_rad);
     if (h->resto_ws) cudaFree(h->resto_ws);
     if (h->resto_list) cudaFree(h->resto_list);
-    if (h->resto_count) cudaFree(h->resto_count);
     if (h->env_idx) cudaFree(h->env_idx);
     if (h->oval) cudaFree(h->oval);
     if (h->osort_tmp) cudaFree(h->osort_tmp);
@@ -646,7 +660,7 @@ extern "C" int kmpc_create(const kmpc_config *cfg, kmpc_handle **out) {
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
     // (the thread solver's HBM workspace -- 1.2 GB at B_max = 65,536, N = 30 -- is allocated on its first use: the warp solver
     //  that serves N <= 63 keeps its state on chip and never touches it)
-    if (e == cudaSuccess) e = cudaMalloc(&h->cnt, 4 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&h->cnt, 8 * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&h->trips, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_cnt, KMPC_LOOKAHEAD * 4 * sizeof(int));
     if (e == cudaSuccess) e = cudaEventCreate(&h->ev0);
@@ -736,7 +750,7 @@ static int solve_impl(kmpc_handle *h, int B, const SolveArgs &a, void *cuda_stre
     h->last_path = use_warp ? 1 : 0;
     if (use_warp) {
         // warp-per-instance path: one persistent launch, instances pulled from a queue, no workspace traffic
-        CU(cudaMemsetAsync(h->cnt, 0, sizeof(int), st));
+        CU(cudaMemsetAsync(h->cnt, 0, 8 * sizeof(int), st));   // queue head + restoration hand-over count (cnt[4])
         bool full = true;
         for (int i = 0; i < 4; ++i) full = full && c.hasL[i] && c.hasU[i];
         cudaError_t le;
@@ -913,7 +927,11 @@ static int solve_host_impl(kmpc_handle *h, int B, const double *x_cur, const dou
     if (X0) { oX = o; memcpy(h->h_in + o, X0, nX * sizeof(double)); o += nX; oU = o; memcpy(h->h_in + o, U0, nU * sizeof(double)); o += nU; }
     if (O) { oO = o; memcpy(h->h_in + o, obs_centers, b * 2 * O * sizeof(double)); o += b * 2 * O; }
     if (O && obs_radii) { oR = o; memcpy(h->h_in + o, obs_radii, b * O * sizeof(double)); o += b * O; }
-    CU(cudaMemcpyAsync(h->d_in, h->h_in, o * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    // Inputs: one H2D copy of the packed buffer -- or, for a handful of instances (the single-agent call of agent.py:139-152), none at
+    // all: the kernel reads the few hundred bytes straight from the mapped pinned buffer, which saves a stream operation (~5 us) per call.
+    const bool zc_in = b * (6 + (X0 ? 5 * N + 3 : 0) + 3 * (size_t)O) <= 4096;
+    double *din = zc_in ? h->h_in : h->d_in;
+    if (!zc_in) CU(cudaMemcpyAsync(h->d_in, h->h_in, o * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     // Results: the warp solver writes each finished instance straight into pinned host memory (device-visible under unified
     // addressing), so the 81 MB of D2H traffic at B = 65,536 rides over PCIe while later instances are still being solved; the
     // thread solver (piecemeal 8-byte writes) goes through device staging and one copy.
@@ -923,8 +941,8 @@ static int solve_host_impl(kmpc_handle *h, int B, const double *x_cur, const dou
     int32_t *dst, *dit;
     if (pinned_out) { dX = X_out; dU = U_out; dobj = obj_out; dst = status_out; dit = iters_out; }
     else { dX = direct ? h->h_out : h->d_out; dU = dX + nX; dobj = dX + nX + nU; dst = direct ? h->h_iout : h->d_iout; dit = dst + b; }
-    rc = solve_impl(h, B, solve_args(h->d_in, h->d_in + b * 3, X0 ? h->d_in + oX : NULL, X0 ? h->d_in + oU : NULL, O ? h->d_in + oO : NULL, O, 0,
-                                     obs_radius, (O && obs_radii) ? h->d_in + oR : NULL, inflation, dX, dU, dobj, dst, dit, NULL), h->stream);
+    rc = solve_impl(h, B, solve_args(din, din + b * 3, X0 ? din + oX : NULL, X0 ? din + oU : NULL, O ? din + oO : NULL, O, 0,
+                                     obs_radius, (O && obs_radii) ? din + oR : NULL, inflation, dX, dU, dobj, dst, dit, NULL), h->stream);
     if (rc) return rc;
     if (!direct) {
         CU(cudaMemcpyAsync(h->h_out, h->d_out, (nX + nU + b) * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

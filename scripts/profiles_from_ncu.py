@@ -4,7 +4,7 @@
 Writes profiles/<tag>_bench_launches.md (every kernel launch of the bench command with its duration and the solver kernel's
 share), profiles/<tag>_kernel_ncu_details.txt (ncu --page details of the full capture) and profiles/<tag>_traffic.json
 (dram__bytes_read/write of that capture)."""
-import csv, io, json, os, subprocess, sys
+import csv, hashlib, io, json, os, subprocess, sys
 tag, launches, rep, cmd = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rows = [r for r in csv.reader(open(launches)) if r]
@@ -40,7 +40,10 @@ def byt(k):
     v = float(d[k].replace(",", "")); u = units[k].lower()
     return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
 rd, wr = byt("dram__bytes_read.sum"), byt("dram__bytes_write.sum")
-json.dump({"kernel": d.get("Kernel Name", "kmpc_warp_kernel"), "workload": "65536 instances, N=30, cold start (scripts/one_solve.py 65536 30 1)",
+_h = hashlib.sha256()   # same hash as bench.py kernel_source_sha(): the capture belongs to these kernel sources and no others
+for f in ("kmpc.cu", "kmpc_core.cuh", "kmpc_warp.cuh", "kmpc_warp_prims.cuh", "kmpc_order_prior.h"):
+    _h.update(open(os.path.join(ROOT, "kiss_mpc_b200", "csrc", f), "rb").read())
+json.dump({"kernel": d.get("Kernel Name", "kmpc_warp_kernel"), "kernel_source_sha": _h.hexdigest()[:16], "workload": "65536 instances, N=30, cold start (scripts/one_solve.py 65536 30 1)",
            "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr, "algorithmic_bytes_per_launch": 65536 * 1288,
            "duration_ms_under_ncu": float(d["gpu__time_duration.sum"].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1, "msecond": 1, "usecond": 1e-3, "nsecond": 1e-6}.get(units["gpu__time_duration.sum"], 1e-6),
            "fp64_pipe_pct_of_peak_active": float(d["sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"]),
