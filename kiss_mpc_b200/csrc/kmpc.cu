@@ -186,6 +186,7 @@ struct kmpc_handle {
     int max_smem;          // opt-in shared memory per block of the device
     struct { const void *fn; size_t smem; int bpsm; } kattr[16];   // per kernel instantiation: shared-memory opt-in done, resident blocks per SM
     int n_kattr;
+    size_t fin_smem[2];    // shared-memory opt-in of the two finisher kernels done (bytes)
     // restoration-phase hand-over (kmpc_finish_kernel): workspace columns, the instance in each, the number in use
     double *resto_ws;
     int32_t *resto_list;
@@ -235,15 +236,26 @@ kmpc_warp_kernel(const Cfg c, const IO io, int *__restrict__ queue, unsigned lon
     w_worker<SPL, NST, FULL, OBS, TAIL>(c, io, s_dyn, queue, trips_total);
 }
 
-// Finisher of the warp solver: one thread per instance that was handed over because its regular line search failed -- IPOPT's
-// restoration phase, then the rest of the regular algorithm (kmpc_resto.cuh, finish_instance).  Launched after every warp-solver
-// launch with a fixed small grid; the number of columns in use is read on the device (no host round trip), normally zero.
+// Finisher of the warp solver: one block (one working thread) per instance that was handed over because its regular line search failed --
+// IPOPT's restoration phase, then the rest of the regular algorithm (kmpc_resto.cuh, finish_instance).  Launched after every warp-solver
+// launch with a fixed grid; the number of columns in use is read on the device (no host round trip), normally zero.
 template <bool OBS>
 __global__ void __launch_bounds__(32)
-kmpc_finish_kernel(const Cfg c, const IO io) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+kmpc_finish_kernel(const Cfg c, const IO io, int in_smem) {
+    extern __shared__ double s_fin[];
+    const int i = blockIdx.x;   // one instance per block: the whole column of an instance fits the block's shared memory
     const int n = *io.resto_count < io.resto_cap ? *io.resto_count : io.resto_cap;
-    if (i < n) finish_instance<OBS>(c, io, i);
+    if (i >= n) return;
+    double *col = io.resto_ws + (size_t)i * io.resto_rows;
+    if (in_smem) {
+        // The phase is a long serial computation of ONE thread on ~5-15 k doubles of state: from HBM / L2 every dependent access costs
+        // hundreds of cycles (2 ms per interior-point iteration at O = 10), from shared memory a tenth of that.
+        const int rows = make_resto_rows(c.L).total;
+        for (int r = threadIdx.x; r < rows; r += 32) s_fin[r] = col[r];
+        __syncwarp();
+        col = s_fin;
+    }
+    if (threadIdx.x == 0) finish_instance<OBS>(c, io, i, col);
 }
 
 #ifndef KMPC_TAIL_WAVES
@@ -408,8 +420,15 @@ static cudaError_t launch_warp_kernel(kmpc_handle *h, int device, int sm_count, 
     if (e != cudaSuccess) return e;
     if (h->resto_cap) {
         const int cap = h->resto_cap < B ? h->resto_cap : B;
-        if (OBS) kmpc_finish_kernel<true><<<(cap + 31) / 32, 32, 0, st>>>(c, io);
-        else kmpc_finish_kernel<false><<<(cap + 31) / 32, 32, 0, st>>>(c, io);
+        void (*fin)(const Cfg, const IO, int) = OBS ? kmpc_finish_kernel<true> : kmpc_finish_kernel<false>;
+        const size_t fbytes = (size_t)make_resto_rows(c.L).total * sizeof(double);
+        const int in_smem = fbytes <= (size_t)max_smem ? 1 : 0;     // (else: the column stays in HBM, as large N x O needs)
+        if (in_smem && h->fin_smem[OBS ? 1 : 0] < fbytes) {
+            e = cudaFuncSetAttribute(fin, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+            if (e != cudaSuccess) return e;
+            h->fin_smem[OBS ? 1 : 0] = (size_t)max_smem;
+        }
+        fin<<<cap, 32, in_smem ? fbytes : 0, st>>>(c, io, in_smem);
         h->launches++;
     }
     return cudaGetLastError();

@@ -159,7 +159,7 @@ struct Ctx {  // per-thread solver state (registers / local memory)
     double mu, tau, delta, delta_last, df, theta_max, theta_min;
     double alpha, alpha_test, alpha_min, alpha_du0, alpha_soc, gBD, theta_soc_old, theta_trial;
     double a_pr, a_y, a_du;  // step sizes of the pending trial: primal, equality multipliers, bound multipliers
-    double pw_g, pw_t;       // (-gBD)^s_phi and theta^s_theta of the current line search (switching condition)
+    double pw_g, pw_t;       // pw_g: alpha_min of the current line search once a trial point has been rejected (0: not computed yet); pw_t: warp solver, inertia prediction
     Stats c;  // current iterate
 };
 
@@ -933,8 +933,15 @@ KMPC_HD bool acceptable(const Ctx &t, const F &filt, const Stats &tri) {
     else {
         acc = true;
         if (tphi > cphi) {
-            const double bas = fabs(cphi) > 10.0 ? log10(fabs(cphi)) : 1.0;
-            if (log10(tphi - cphi) > K_OBJ_MAX_INC + bas) acc = false;
+            // obj_max_inc test: log10(tphi - cphi) > obj_max_inc + max(1, log10 |cphi|), i.e. an increase by more than a factor 10^5 of
+            // max(10, |cphi|).  Screened without the logarithms: 10 % on either side of that threshold the outcome cannot depend on
+            // their rounding (a few ulp), and only inside the band are they evaluated -- same decisions, two log10() less per trial.
+            const double d = tphi - cphi, sc = fabs(cphi) > 10.0 ? fabs(cphi) : 10.0;
+            if (d >= 1.1e5 * sc) acc = false;
+            else if (d > 0.9e5 * sc) {
+                const double bas = fabs(cphi) > 10.0 ? log10(fabs(cphi)) : 1.0;
+                if (log10(d) > K_OBJ_MAX_INC + bas) acc = false;
+            }
         }
         if (acc) acc = cmp_le(tri.theta, (1.0 - K_GAMMA_THETA) * cth, cth) || cmp_le(tphi - cphi, -K_GAMMA_PHI * cth, cphi);
     }
@@ -1007,7 +1014,7 @@ KMPC_HD void rollout_logic(Ctx &t, double apr, double adu, double gbd, double ym
         t.a_y = (ym <= K_YINIT_MAX && isfinite(ym)) ? -1.0 : 0.0;
     } else if (t.mode == M_NEWTON) {
         if (t.delta > 0.0) t.delta_last = t.delta;
-        t.gBD = gbd;
+        t.gBD = gbd; t.pw_g = 0.0;   // (new search direction: alpha_min of the line search is not known yet)
         if (t.theta_max < 0) { t.theta_max = K_THETA_MAX_FACT * fmax(1.0, t.c.theta); t.theta_min = K_THETA_MIN_FACT * fmax(1.0, t.c.theta); }
         t.alpha = apr; t.alpha_test = apr; t.alpha_du0 = adu; t.nsteps = 0; t.soc_count = 0;
         t.a_pr = apr; t.a_y = apr; t.a_du = adu;
@@ -1063,7 +1070,11 @@ KMPC_HD int trial_decide(Ctx &t, const F &filt, const Stats &tri, bool evok, boo
     if (!accept) {
         // back-track on the original step (also after a failed correction)
         t.alpha *= K_ALPHA_RED; t.nsteps++;
-        if (!(t.alpha > alpha_min_of(t))) return ST_RESTORATION;  // IPOPT would enter the restoration phase here
+        // (alpha_min depends on gBD, theta and theta_min of the current iterate only -- two pow() and two divisions -- and an instance with a
+        //  difficult line search rejects hundreds of trial points: computed at the first rejection of a line search, then reused)
+        double amin = t.pw_g;
+        if (!(amin > 0.0)) { amin = alpha_min_of(t); t.pw_g = amin; }
+        if (!(t.alpha > amin)) return ST_RESTORATION;  // IPOPT would enter the restoration phase here
         t.mode = M_TRIAL;
         return R_BACKTRACK;
     }
@@ -1149,8 +1160,7 @@ KMPC_HD void ctx_load(Ctx &t, const Rows &L, const double *wsp, size_t S) {
 // runs IPOPT's restoration phase on it and, if that hands a point back, the rest of the regular algorithm (the thread solver's trips),
 // then writes the instance's outputs.
 template <bool OBS>
-KMPC_HDN inline void finish_instance(const Cfg &c, const IO &io, int i) {
-    double *wsp = io.resto_ws + (size_t)i * io.resto_rows;
+KMPC_HDN inline void finish_instance(const Cfg &c, const IO &io, int i, double *wsp /* the instance's column (HBM, or a copy of it in shared memory) */) {
     Ctx t;
     ctx_load(t, c.L, wsp, 1);
     t.inst = io.resto_list[i];

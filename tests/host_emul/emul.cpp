@@ -178,7 +178,7 @@ extern "C" int emul_solve_warp(const kmpc_config *cf, int B, const double *x_cur
             if (nst == 32) EMUL_RUN(1, 32); else if (nst == 52) EMUL_RUN(2, 52); else EMUL_RUN(2, 64);
         }, W);
 #undef EMUL_RUN
-        for (int i = 0; i < rcount; ++i) { if (O > 0) finish_instance<true>(cb, iob, i); else finish_instance<false>(cb, iob, i); }   // kmpc_finish_kernel
+        for (int i = 0; i < rcount; ++i) { double *col = iob.resto_ws + (size_t)i * iob.resto_rows; if (O > 0) finish_instance<true>(cb, iob, i, col); else finish_instance<false>(cb, iob, i, col); }   // kmpc_finish_kernel
         if (W == 1 && trips) trips[lo] = (int)tr;
 #pragma omp atomic
         tr_total += tr;
