@@ -791,3 +791,66 @@ def test_tail_mode_kernel_is_bit_identical():
     small50 = pl50.solve(x[:500].contiguous(), g[:500].contiguous())
     for a, c in zip(small50, big50):
         assert torch.equal(a, c[:500])
+
+
+def test_cfg3_full_size_N50(oracle_mod):
+    """BASELINE configs[2] at its full size (65,536 x N = 50): a 2,048-instance prefix against the oracle (status, iterate, objective)
+    and, over the whole batch, the size-independent properties -- dynamics and bounds satisfied, objective reproduced from the
+    returned trajectory, and the 1/8 slice an 8-GPU run gives rank 5 reproduces the full-batch result bit for bit."""
+    from kiss_mpc_b200 import BatchedMotionPlanner, shard_range
+    torch = _torch()
+    B, N, T = 65536, 50, 0.1
+    ocfg, pcfg = _pair(oracle_mod, N=N)
+    b = make_batch(B, seed=1003)
+    pl = BatchedMotionPlanner(pcfg, max_batch=B)
+    x, g = _dev(b["x_cur"]), _dev(b["goal"])
+    r = pl.solve(x, g)
+    n = 2048
+    ref = oracle_mod.solve(ocfg, b["x_cur"][:n], b["goal"][:n])
+    pre = type(r)(r.states[:n], r.controls[:n], r.objective[:n], r.status[:n], r.iters[:n])
+    conv = _check(pre, ref)
+    assert (r.iters[:n].cpu().numpy() == ref.iters)[conv].mean() >= 0.999
+    assert (r.status == 0).all()
+    X, U = r.states, r.controls
+    nxt = X[:, :, :-1] + T * torch.stack([U[:, 0] * torch.cos(X[:, 2, :-1]), U[:, 0] * torch.sin(X[:, 2, :-1]), U[:, 1]], 1)
+    assert (X[:, :, 1:] - nxt).abs().max().item() <= 1e-7 and (X[:, :, 0] - x).abs().max().item() <= 1e-7
+    assert U[:, 0].min().item() >= -0.2 - 1e-7 and U[:, 0].max().item() <= 0.5 + 1e-7 and U[:, 1].abs().max().item() <= 0.5 + 1e-7
+    e = X[:, :, 1:] - g[:, :, None]
+    f = (torch.tensor([100.0, 100.0, 50.0], device=X.device, dtype=X.dtype)[None, :, None] * e * e).sum((1, 2)) \
+        + (300.0 * U[:, 0].clamp(max=0) ** 2 + 10.0 * U[:, 1] ** 2).sum(1)
+    assert ((f - r.objective).abs() / f.abs().clamp(min=1)).max().item() <= 1e-10
+    lo, hi = shard_range(B, 5, 8)
+    rs = pl.solve(x[lo:hi].contiguous(), g[lo:hi].contiguous())
+    assert torch.equal(rs.controls, U[lo:hi]) and torch.equal(rs.status, r.status[lo:hi]) and torch.equal(rs.iters, r.iters[lo:hi])
+
+
+def test_cfg5_full_size_closed_loop():
+    """BASELINE configs[4] at its full size (16,384 agents x 200 steps, warm-started, agents stop at the goal radius as
+    environment.py:31-33 does): every solve converges, every applied control is inside its bounds, the state hand-off is the
+    model step of the applied control (agent.py:70-72 "perfect model": x <- X[:,1] = f(x, U[:,0])), stopped agents never move again,
+    and most agents arrive."""
+    from kiss_mpc_b200 import BatchedMotionPlanner, PlannerConfig
+    torch = _torch()
+    B, steps, T = 16384, 200, 0.1
+    b = make_batch(B, seed=1005)
+    pl = BatchedMotionPlanner(PlannerConfig(), max_batch=B)
+    x0, g = _dev(b["x_cur"]), _dev(b["goal"])
+    x = x0.clone()
+    X, U, applied, iters, status = pl.closed_loop(x, g, steps, goal_radius=0.5)
+    solved = status != 1000
+    assert ((status == 0) | ~solved).all()
+    assert solved[0].all() and int(solved.sum()) > 1_000_000
+    # a stopped agent stays stopped
+    assert (solved[1:] & ~solved[:-1]).sum().item() == 0
+    a = torch.where(solved[:, :, None], applied, torch.zeros_like(applied))     # [steps, B, 2]; rows of stopped agents are not written
+    assert a[:, :, 0].min().item() >= -0.2 - 1e-7 and a[:, :, 0].max().item() <= 0.5 + 1e-7 and a[:, :, 1].abs().max().item() <= 0.5 + 1e-7
+    # roll the unicycle model forward with the applied controls: must land on the final states (dynamics rows hold to 1e-8 per step)
+    p = x0.clone()
+    for t in range(steps):
+        m = solved[t]
+        th = p[:, 2]
+        q = p + T * torch.stack([a[t, :, 0] * torch.cos(th), a[t, :, 0] * torch.sin(th), a[t, :, 1]], 1)
+        p = torch.where(m[:, None], q, p)
+    assert (p - x).abs().max().item() <= 1e-5
+    assert ((x[:, :2] - g[:, :2]).norm(dim=1) <= 0.5 + 1e-9).float().mean().item() >= 0.85
+    assert iters[1:][solved[1:]].float().mean().item() < 0.7 * iters[0].float().mean().item()      # the warm start pays
