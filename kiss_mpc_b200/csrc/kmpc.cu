@@ -259,7 +259,11 @@ kmpc_finish_kernel(const Cfg c, const IO io, int in_smem) {
 }
 
 #ifndef KMPC_TAIL_WAVES
-#define KMPC_TAIL_WAVES 16   /* batches of at most this many waves of resident instances run the kernel with the tail mode */
+#define KMPC_TAIL_WAVES 0   /* batches of at most this many waves of resident instances run the kernel with the tail mode; 0: never.
+   r02b: 16.  Since the inertia prediction (1.05 instead of 2.36 retry trips per solve) the mode saves less than its two extra block
+   barriers and the candidate assembly cost: B = 1 307 -> 266 us (N = 30), 137 -> 113 us (N = 7); 4,096 instances 4.59 -> 4.47 ms;
+   the 1/2, 1/4, 1/8 slices of the headline batch 9.88 / 8.39 / 7.30 -> 9.69 / 8.25 / 7.24 ms (scripts/tail_onoff.py, strong_slices.py).
+   The instantiation stays (KMPC_FORCE_TAIL=1 in the environment selects it, tests/test_parity_gpu.py keeps it bit-identical). */
 #endif
 
 // Queue order of the persistent kernel.  Iteration counts differ by more than 8x between instances and a long instance that is
@@ -376,8 +380,8 @@ static cudaError_t launch_warp_kernel(kmpc_handle *h, int device, int sm_count, 
     int bpsm = 0;
     e = prepare(kern, &bpsm);
     if (e != cudaSuccess) return e;
-    static const bool no_tail = getenv("KMPC_NO_TAIL") != NULL;
-    if (!OBS && (long long)B <= (long long)KMPC_TAIL_WAVES * sm_count * (bpsm > 0 ? bpsm : 1) * wpb && !no_tail) {
+    const bool no_tail = getenv("KMPC_NO_TAIL") != NULL, force_tail = getenv("KMPC_FORCE_TAIL") != NULL;
+    if (!OBS && !no_tail && (force_tail || (long long)B <= (long long)KMPC_TAIL_WAVES * sm_count * (bpsm > 0 ? bpsm : 1) * wpb)) {
         // few waves: the phase in which the queue is drained is a large part of the launch -- the kernel with the tail mode
         kern = kmpc_warp_kernel<SPL, NST, FULL, OBS, WPB, MINB, !OBS>;
         e = prepare(kern, &bpsm);

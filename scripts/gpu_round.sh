@@ -16,3 +16,13 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:kmpc_warp_kernel -c 1 -o gpurun_out/${tag}_full -f \
   python scripts/one_solve.py 65536 30 1 > gpurun_out/${tag}_ncu_full.log 2>&1
 ls -la gpurun_out
+# obstacle batches: warp kernel vs restoration finisher (per-launch durations under ncu)
+for args in "65536 10 0" "4096 10 1" "65536 10 1"; do
+  echo "== diag_resto $args" >> gpurun_out/${tag}_resto_split.txt
+  python scripts/diag_resto.py $args >> gpurun_out/${tag}_resto_split.txt 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none --csv python scripts/diag_resto.py $args 2>/dev/null | grep -E "kmpc_(warp|finish)" | awk -F'","' '{print $5, $NF}' | tail -2 >> gpurun_out/${tag}_resto_split.txt
+done
+python scripts/bench_configs.py 3 > gpurun_out/${tag}_all_configs.json 2> gpurun_out/${tag}_all_configs.err
+python scripts/strong_slices.py > gpurun_out/${tag}_strong_slices.json 2>/dev/null
+python scripts/b1_breakdown.py 30 0.1 > gpurun_out/${tag}_b1_breakdown.txt 2>&1; python scripts/b1_breakdown.py 7 0.8 >> gpurun_out/${tag}_b1_breakdown.txt 2>&1
+cat gpurun_out/${tag}_resto_split.txt gpurun_out/${tag}_b1_breakdown.txt

@@ -764,30 +764,36 @@ def test_environment_loop_with_dynamic_obstacles(oracle_mod):
         assert np.abs(x.cpu().numpy() - xc).max() <= 1e-4
 
 
-def test_tail_mode_kernel_is_bit_identical():
-    """Small batches run the kernel instantiation WITH the tail mode (borrowed instance slots solve the next inertia
-    perturbations next to the base system; launch_warp_kernel picks it for batches of at most KMPC_TAIL_WAVES waves), many-wave
-    batches the one without.  An instance must get the same bits from both, alone (B = 1) or among 3,000."""
+def test_tail_mode_kernel_is_bit_identical(monkeypatch):
+    """The kernel instantiation WITH the tail mode (borrowed instance slots solve the next inertia perturbations next to the base
+    system; off by default since r02c, KMPC_FORCE_TAIL=1 selects it) must give every instance the same bits as the one without,
+    alone (B = 1), in the low-latency launch shape (one wave of 4-instance blocks) or among 3,000."""
     from kiss_mpc_b200 import BatchedMotionPlanner, PlannerConfig
     torch = _torch()
     B = 40000
     b = make_batch(B, seed=1000)
     pl = BatchedMotionPlanner(PlannerConfig(), max_batch=B)
     x, g = _dev(b["x_cur"]), _dev(b["goal"])
-    big = pl.solve(x, g)                      # 40,000 > 16 waves of 2,368 resident instances: no tail mode
-    small = pl.solve(x[:3000].contiguous(), g[:3000].contiguous())
-    for a, c in zip(small, big):
-        assert torch.equal(a, c[:3000])
-    tiny = pl.solve(x[:500].contiguous(), g[:500].contiguous())     # one wave of 4-instance blocks: the low-latency launch shape
-    for a, c in zip(tiny, big):
-        assert torch.equal(a, c[:500])
-    for i in (0, 17, 2879, 30520 % 3000):
-        one = pl.solve(x[i:i + 1].contiguous(), g[i:i + 1].contiguous())
-        for a, c in zip(one, big):
-            assert torch.equal(a, c[i:i + 1])
+    big = pl.solve(x, g)                      # no tail mode
+    for force in (True, False):
+        if force:
+            monkeypatch.setenv("KMPC_FORCE_TAIL", "1")
+        else:
+            monkeypatch.delenv("KMPC_FORCE_TAIL", raising=False)
+        small = pl.solve(x[:3000].contiguous(), g[:3000].contiguous())
+        for a, c in zip(small, big):
+            assert torch.equal(a, c[:3000])
+        tiny = pl.solve(x[:500].contiguous(), g[:500].contiguous())     # one wave of 4-instance blocks: the low-latency launch shape
+        for a, c in zip(tiny, big):
+            assert torch.equal(a, c[:500])
+        for i in (0, 17, 2879, 30520 % 3000):
+            one = pl.solve(x[i:i + 1].contiguous(), g[i:i + 1].contiguous())
+            for a, c in zip(one, big):
+                assert torch.equal(a, c[i:i + 1])
     # N = 50 (two stages per lane) as well
     pl50 = BatchedMotionPlanner(PlannerConfig(N=50), max_batch=B)
     big50 = pl50.solve(x[:24000].contiguous(), g[:24000].contiguous())
+    monkeypatch.setenv("KMPC_FORCE_TAIL", "1")
     small50 = pl50.solve(x[:500].contiguous(), g[:500].contiguous())
     for a, c in zip(small50, big50):
         assert torch.equal(a, c[:500])
