@@ -745,6 +745,38 @@ KMPC_W void w_step_load(WStep<SPL> &d, const double *gp) {
     }
 }
 
+// kept search direction <-> the instance's own coop area.  Between the step phase and the trial evaluations the direction (8 doubles
+// per stage) does not stay in registers: at 128 registers per thread the compiler spilled it to local memory (8 STL.64 + ~10 LDL.64
+// per trip, and 106 KB of stack per block do not fit the L1 left beside 185 KB of shared memory -- ncu r02e: a third of all
+// long-scoreboard stalls sat on those reloads).  dx, du already are in the coop area (the roll-out left them in C_DX0.. C_DU1); dy
+// goes to the fields of p, which the step phase has consumed (C_PV0..2).  The reduction scratch of w_trial (the first 7 x 33
+// doubles of the area) does not reach either.
+#ifndef KMPC_STEP_SMEM
+#define KMPC_STEP_SMEM 1
+#endif
+template <int SPL, int NST>
+KMPC_W void w_step_park(const WStep<SPL> &d, double *coop) {
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        if (w_lane() * SPL + j >= NSTG) continue;
+        double *p = coop + w_lane() * SPL + j;
+        p[C_DX0 * NSTG] = d.dx0[j]; p[C_DX1 * NSTG] = d.dx1[j]; p[C_DX2 * NSTG] = d.dx2[j]; p[C_DU0 * NSTG] = d.du0[j];
+        p[C_DU1 * NSTG] = d.du1[j]; p[C_PV0 * NSTG] = d.dy0[j]; p[C_PV1 * NSTG] = d.dy1[j]; p[C_PV2 * NSTG] = d.dy2[j];
+    }
+}
+template <int SPL, int NST>
+KMPC_W void w_step_fetch(WStep<SPL> &d, const double *coop) {
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        if (w_lane() * SPL + j >= NSTG) { d.dx0[j] = d.dx1[j] = d.dx2[j] = d.du0[j] = d.du1[j] = d.dy0[j] = d.dy1[j] = d.dy2[j] = 0.0; continue; }
+        const double *p = coop + w_lane() * SPL + j;
+        d.dx0[j] = p[C_DX0 * NSTG]; d.dx1[j] = p[C_DX1 * NSTG]; d.dx2[j] = p[C_DX2 * NSTG]; d.du0[j] = p[C_DU0 * NSTG];
+        d.du1[j] = p[C_DU1 * NSTG]; d.dy0[j] = p[C_PV0 * NSTG]; d.dy1[j] = p[C_PV1 * NSTG]; d.dy2[j] = p[C_PV2 * NSTG];
+    }
+}
+
 // ---- phase 3, TRIAL: trial point + speculative multiplier update + residual norms (all stages at once) ----
 template <int SPL, int NST, bool FULL, bool OBS>
 KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w, const WStep<SPL> &d, double alpha, double ay,
@@ -1094,7 +1126,9 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     unsigned *hmask = (unsigned *)(scal0 + W);   // which warps hold an instance, this trip / next trip
     Ctx &t = sc->t;
     WState<SPL> cur;
+#if !KMPC_STEP_SMEM
     WStep<SPL> act;
+#endif
     bool have = false;
     int b = -1;
     if (lane == 0) { t.mode = M_DONE; sc->flag = 0; sc->ok = 0; sc->tinfo = 0; sc->ncand = 0; sc->pred = 0; sc->pstat = 0; for (int k = 0; k < KMPC_NCAND; ++k) { sc->dshift[k] = NAN; sc->pdc[k] = 0; } }
@@ -1293,6 +1327,9 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 status = sc->status;
             } else {
                 double apr, adu, gbd, ym;
+#if KMPC_STEP_SMEM
+                WStep<SPL> act;
+#endif
                 w_step<SPL, NST, FULL, OBS>(c, sc, cur, solved, priv, ob, act, &apr, &adu, &gbd, &ym);
                 if (lane == 0) {
                     if (mode == M_NEWTON) t.pw_t = t.alpha_min;   // which element of the perturbation sequence this iteration needed (0: none)
@@ -1301,12 +1338,19 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 }
                 w_sync();
                 if (t.sel == 0) w_step_store<SPL, NST>(act, gp);
+#if KMPC_STEP_SMEM
+                w_step_park<SPL, NST>(act, coop);   // (every lane parks and later fetches its own stages only: no warp barrier needed)
+#endif
                 go_trial = true;
             }
         } else if (have) {
             if (lane == 0) trial_setup(t);
             w_sync();
+#if KMPC_STEP_SMEM
+            { WStep<SPL> act; w_step_load<SPL, NST>(act, gp); w_step_park<SPL, NST>(act, coop); }
+#else
             w_step_load<SPL, NST>(act, gp);
+#endif
         }
         PT(6)
         // ---- phase 3: trial point + acceptance logic ----
@@ -1315,6 +1359,10 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
         for (int nbt = 0; go_trial; ++nbt) {
             Stats ts;
             WState<SPL> tri;
+#if KMPC_STEP_SMEM
+            WStep<SPL> act;
+            w_step_fetch<SPL, NST>(act, coop);
+#endif
             // step sizes / barrier parameters of THIS trial, read before lane 0 moves the context on (begin_iteration)
             const double ta_pr = t.a_pr, ta_y = t.a_y, ta_du = t.a_du, ta_mu = t.mu, ta_delta = t.delta;
             const bool tclamp = t.tu == TU_STEP, tlsq = t.mode == M_LSQ, tsoc = t.mode == M_SOC;
