@@ -777,6 +777,37 @@ KMPC_W void w_step_fetch(WStep<SPL> &d, const double *coop) {
     }
 }
 
+// The bound multipliers of a trial point (8 doubles per stage) are needed again only if the point is accepted: they wait in fields of
+// the coop area that are dead during the trial phase (k_ff, the Q_uu diagonal, W_v,theta, the first P entries -- read by the sweep,
+// its candidates and the step phase only) instead of 16 registers of the most register-starved function of the kernel.
+#ifndef KMPC_TRIZ_SMEM
+#define KMPC_TRIZ_SMEM 1
+#endif
+#if KMPC_TRIZ_SMEM
+#define TRIZ(reg, field, val) (scr + s)[(field) * NSTG] = (val)
+#else
+#define TRIZ(reg, field, val) (reg) = (val)
+#endif
+// accepted trial point -> current iterate
+template <int SPL, int NST>
+KMPC_W void w_accept(const Cfg &c, WState<SPL> &cur, const WState<SPL> &tri, const double *coop) {
+#if KMPC_TRIZ_SMEM
+    constexpr int NSTG = WLay<SPL, NST>::NSTG;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+        const int s = w_lane() * SPL + j;
+        cur.x0[j] = tri.x0[j]; cur.x1[j] = tri.x1[j]; cur.x2[j] = tri.x2[j]; cur.v[j] = tri.v[j]; cur.om[j] = tri.om[j];
+        cur.y0[j] = tri.y0[j]; cur.y1[j] = tri.y1[j]; cur.y2[j] = tri.y2[j]; cur.cs[j] = tri.cs[j]; cur.sn[j] = tri.sn[j];
+        const bool in = s <= c.N;
+        const double *p = coop + (in ? s : 0);
+        cur.zLx[j] = in ? p[C_QV * NSTG] : 0.0; cur.zUx[j] = in ? p[C_QW * NSTG] : 0.0; cur.zLy[j] = in ? p[C_DV * NSTG] : 0.0; cur.zUy[j] = in ? p[C_DW * NSTG] : 0.0;
+        cur.zLv[j] = in ? p[C_HTV * NSTG] : 0.0; cur.zUv[j] = in ? p[C_P00 * NSTG] : 0.0; cur.zLw[j] = in ? p[C_P10 * NSTG] : 0.0; cur.zUw[j] = in ? p[C_P11 * NSTG] : 0.0;
+    }
+#else
+    cur = tri;
+#endif
+}
+
 // ---- phase 3, TRIAL: trial point + speculative multiplier update + residual norms (all stages at once) ----
 template <int SPL, int NST, bool FULL, bool OBS>
 KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w, const WStep<SPL> &d, double alpha, double ay,
@@ -798,7 +829,9 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
         n.x0[j] = w.x0[j] + alpha * d.dx0[j]; n.x1[j] = w.x1[j] + alpha * d.dx1[j]; n.x2[j] = w.x2[j] + alpha * d.dx2[j];
         n.v[j] = w.v[j] + alpha * d.du0[j]; n.om[j] = w.om[j] + alpha * d.du1[j];
         n.y0[j] = w.y0[j] + ay * d.dy0[j]; n.y1[j] = w.y1[j] + ay * d.dy1[j]; n.y2[j] = w.y2[j] + ay * d.dy2[j];
+#if !KMPC_TRIZ_SMEM
         n.zLx[j] = n.zUx[j] = n.zLy[j] = n.zUy[j] = n.zLv[j] = n.zUv[j] = n.zLw[j] = n.zUw[j] = 0.0;
+#endif
         double sn = 0.0, cs = 1.0;
         if (s < N) sincos_(n.x2[j], &sn, &cs);
         n.cs[j] = cs; n.sn[j] = sn;
@@ -829,10 +862,10 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
         double prod = 1.0, zLn, zUn;
         valid &= wb_trial<FULL>(d.dx0[j], x0, c.lb[0], c.ub[0], hL0, hU0, w.zLx[j], w.zUx[j], pv[V_RL0 * NSTG], pv[V_RU0 * NSTG], mu, adu,
                                 clamp, zLn, zUn, prod, st);
-        n.zLx[j] = zLn; n.zUx[j] = zUn; r0 += zUn - zLn;
+        TRIZ(n.zLx[j], C_QV, zLn); TRIZ(n.zUx[j], C_QW, zUn); r0 += zUn - zLn;
         valid &= wb_trial<FULL>(d.dx1[j], x1, c.lb[1], c.ub[1], hL1, hU1, w.zLy[j], w.zUy[j], pv[V_RL1 * NSTG], pv[V_RU1 * NSTG], mu, adu,
                                 clamp, zLn, zUn, prod, st);
-        n.zLy[j] = zLn; n.zUy[j] = zUn; r1 += zUn - zLn;
+        TRIZ(n.zLy[j], C_DV, zLn); TRIZ(n.zUy[j], C_DW, zUn); r1 += zUn - zLn;
         if (OBS && s >= 1) {  // obstacle rows at the trial point
             const WCen cen = w_cen(c, ob, O, NSTG, s);
             for (int o = 0; o < O; ++o) {
@@ -867,13 +900,13 @@ KMPC_WN inline bool w_trial(const Cfg &c, const WScal *sc, const WState<SPL> &w,
             st.f += c.Ww * om * om;
             valid &= wb_trial<FULL>(d.du0[j], v, c.lb[2], c.ub[2], hL2, hU2, w.zLv[j], w.zUv[j], pv[V_RL2 * NSTG], pv[V_RU2 * NSTG], mu, adu,
                                     clamp, zLn, zUn, prod, st);
-            n.zLv[j] = zLn; n.zUv[j] = zUn; rv += zUn - zLn;
+            TRIZ(n.zLv[j], C_HTV, zLn); TRIZ(n.zUv[j], C_P00, zUn); rv += zUn - zLn;
             valid &= wb_trial<FULL>(d.du1[j], om, c.lb[3], c.ub[3], hL3, hU3, w.zLw[j], w.zUw[j], pv[V_RL3 * NSTG], pv[V_RU3 * NSTG], mu, adu,
                                     clamp, zLn, zUn, prod, st);
-            n.zLw[j] = zLn; n.zUw[j] = zUn; rw += zUn - zLn;
+            TRIZ(n.zLw[j], C_P10, zLn); TRIZ(n.zUw[j], C_P11, zUn); rw += zUn - zLn;
             st.dinf = maxabs_nan(maxabs_nan(st.dinf, rv), rw);
         } else {
-            n.zLv[j] = n.zUv[j] = n.zLw[j] = n.zUw[j] = 0.0;
+            TRIZ(n.zLv[j], C_HTV, 0.0); TRIZ(n.zUv[j], C_P00, 0.0); TRIZ(n.zLw[j], C_P10, 0.0); TRIZ(n.zUw[j], C_P11, 0.0);
         }
         st.dinf = maxabs_nan(maxabs_nan(maxabs_nan(st.dinf, r0), r1), r2);
         st.bar += log(prod);
@@ -1381,7 +1414,7 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
                 PT_COUNT(12)
                 if (mode == M_SOC) { PT_COUNT(14) }
                 if (OBS) w_obs_commit<SPL, NST>(c, cur, act, ta_mu, ta_delta, ta_pr, ta_y, ta_du, tclamp, tlsq, tsoc, ob);
-                cur = tri;
+                w_accept<SPL, NST>(c, cur, tri, coop);
                 if (lane == 0) {
                     t.c = ts; sc->status = begin_iteration(c, t);
                     t.alpha_min = 0.0;
