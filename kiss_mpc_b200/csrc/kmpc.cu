@@ -360,9 +360,9 @@ static cudaError_t launch_warp_kernel(kmpc_handle *h, int device, int sm_count, 
         if (e != cudaSuccess) return e;
     }
     int wpb = WPB;
-    while (wpb > 0 && WLay<SPL, NST>::bytes(wpb, c.O, c.obs_sw) > (size_t)max_smem) --wpb;
+    while (wpb > 0 && WLay<SPL, NST, OBS>::bytes(wpb, c.O, c.obs_sw) > (size_t)max_smem) --wpb;
     if (wpb < 1) return cudaErrorInvalidConfiguration;
-    const size_t smem = WLay<SPL, NST>::bytes(wpb, c.O, c.obs_sw);
+    const size_t smem = WLay<SPL, NST, OBS>::bytes(wpb, c.O, c.obs_sw);
     // shared-memory opt-in + occupancy of a kernel instantiation: asked once per handle and shared-memory size, not once per solve
     // (three runtime calls, ~10 us of host time that a B = 1 solve of ~130 us would pay every time)
     auto prepare = [&](void (*k)(const Cfg, const IO, int *, unsigned long long *), int *bp) -> cudaError_t {

@@ -37,8 +37,9 @@ struct WStep { double dx0[SPL], dx1[SPL], dx2[SPL], du0[SPL], du1[SPL], dy0[SPL]
 // (Q00 Q11 Q22 Q01 dv dw htv) are never overwritten: the speculative inertia candidates read them at their own pace.
 enum { C_A13 = 0, C_A23, C_B11, C_B21, C_E0, C_E1, C_E2,
        C_Q00 = 7, C_Q11, C_Q22, C_Q0, C_Q1, C_Q2, C_QV, C_QW, C_DV, C_DW, C_HTV,
-       C_P00 = 18, C_P10, C_P11, C_P20, C_P21, C_P22, C_Q01 = 24,   // Q01: x-y coupling of the obstacle rows
-       C_K00 = 25, C_K01, C_K02, C_K10, C_K11, C_K12,
+       C_P00 = 18, C_P10, C_P11, C_P20, C_P21, C_P22,
+       C_K00 = 24, C_K01, C_K02, C_K10, C_K11, C_K12, C_NF_BOX = 30,   // (problems without obstacle rows end here: 30 fields)
+       C_Q01 = 30,                                                      // x-y coupling of the obstacle rows
        C_S00 = 31, C_S01, C_S11, C_NF = 34 };   // sum of n n^T over the obstacle rows of a stage: d(x-y block) / d(delta_w) - I
 enum { C_PV0 = C_Q0, C_PV1 = C_Q1, C_PV2 = C_Q2, C_KF0 = C_QV, C_KF1 = C_QW };
 #ifndef KMPC_NCAND
@@ -72,10 +73,12 @@ struct WScal {  // warp-uniform per-instance scalars
 };
 
 // NST = stage slots allocated per field (>= N + 1, <= 32 * SPL): a smaller NST than 32 * SPL lets more instances fit
-template <int SPL, int NST = 32 * SPL>
+// OBS = false: the four fields only obstacle rows use are not allocated (1.0 / 1.7 / 2.0 KB per instance at 32 / 52 / 64 stage slots: at
+// N <= 51 that is the 13th instance per SM)
+template <int SPL, int NST = 32 * SPL, bool OBS = true>
 struct WLay {
     static constexpr int NSTG = NST;
-    static constexpr int COOP = C_NF * NSTG + 2;   // (even: the Riccati lanes move two stages per 128-bit access, w_ld2 / w_st2)
+    static constexpr int COOP = (OBS ? C_NF : C_NF_BOX) * NSTG + 2;   // (even: the Riccati lanes move two stages per 128-bit access, w_ld2 / w_st2)
     static constexpr int PRIV = V_NF * NSTG;
     static constexpr int GFILT = G_NF * NSTG;                  // the filter of the instance sits behind the per-stage fields of the global scratch slot
     static constexpr int GPRIV = G_NF * NSTG + 2 * K_FILTER_CAP;   // doubles of global scratch per resident warp
@@ -1144,7 +1147,7 @@ KMPC_W double w_inertia_seq(int i, double delta_last) {
 // several GPUs -- run the kernel with it (launch_warp_kernel).
 template <int SPL, int NST, bool FULL, bool OBS, bool TAIL = true>
 KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queue, unsigned long long *trips_total) {
-    typedef WLay<SPL, NST> LY;
+    typedef WLay<SPL, NST, OBS> LY;
     const int N = c.N, lane = w_lane(), wid = w_warp(), W = w_warps();
     double *coop = smem + (size_t)wid * LY::COOP;
     double *priv = smem + (size_t)W * LY::COOP + (size_t)wid * LY::PRIV;
