@@ -1131,6 +1131,9 @@ KMPC_WN inline bool w_block_holds(const WScal *scal0, int W) {
 #ifndef KMPC_PREDICT_INERTIA
 #define KMPC_PREDICT_INERTIA 1
 #endif
+#ifndef KMPC_MERGE_TOP
+#define KMPC_MERGE_TOP 1   /* the top-of-trip barrier merged into the one behind the assemble phase (kernels without the tail mode) */
+#endif
 // element i of the sequence that starts at delta_w = 0 (i = 0: no perturbation)
 KMPC_W double w_inertia_seq(int i, double delta_last) {
     double d = 0.0;
@@ -1181,22 +1184,36 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
     const int cj = (wid - swid - 1 + W) % W;          // 0 .. ncw - 1: this warp is a candidate warp
     const bool is_cand = W >= 2 && wid != swid && cj < ncw;
     const bool can_predict = W >= 2 && (KMPC_NCAND - 1) * W <= 32 * ncw && KMPC_NCAND >= 3;   // every other element of the sequence has a candidate lane
+    bool fetch_all = false;   // (merged top barrier only)
 #pragma unroll 1
     for (;;) {
         // warp 0 is busy in the serial window below, so it takes its next instance here; the other warps take theirs
         // in that window (the global-memory round trip then costs the block nothing)
         // (second pass: nothing is live, so a hold -- possibly read stale -- is void and every warp may fetch)
         int nlive = 0;
+        // Without the tail mode nothing needs the number of live warps before the stage blocks are assembled, so the count rides on the
+        // barrier behind the assemble phase (one block barrier less per trip; a warp that is done with its trial phase goes straight on
+        // to assemble -- between the barrier behind the serial window and the next one every warp touches its own areas only).
+        constexpr bool top_barrier = (TAIL && KMPC_TAIL && !OBS && KMPC_NCAND > 1) || !KMPC_MERGE_TOP;
+        if (top_barrier) {
 #pragma unroll 1
-        for (int pass = 0; pass < 2 && !nlive; ++pass) {
-            if (!have && !drained && (pass || wid == swid || is_cand) && (pass || !w_block_holds(scal0, W))) {
+            for (int pass = 0; pass < 2 && !nlive; ++pass) {
+                if (!have && !drained && (pass || wid == swid || is_cand) && (pass || !w_block_holds(scal0, W))) {
+                    b = w_fetch_active(c, io, queue);
+                    if (b < c.B) { SCHED_START(b) w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
+                }
+                PT(0)
+                nlive = w_block_warps_with(have);   // warps that hold an instance this trip
+            }
+            if (!nlive) break;
+        } else {
+            // (fetch_all: the last count found nothing live, so a hold -- possibly read stale -- is void and every warp may fetch)
+            if (!have && !drained && (fetch_all || wid == swid || is_cand) && (fetch_all || !w_block_holds(scal0, W))) {
                 b = w_fetch_active(c, io, queue);
                 if (b < c.B) { SCHED_START(b) w_init<SPL, NST, OBS>(c, sc, io, b, cur, ob); have = true; } else drained = true;
             }
             PT(0)
-            nlive = w_block_warps_with(have);   // warps that hold an instance this trip
         }
-        if (!nlive) break;
         PT(1)
         int status = 100;
         // ---- tail mode: once at most a quarter of the block's instance slots are taken (the queue is drained, or the batch is
@@ -1286,7 +1303,12 @@ KMPC_WN inline void w_worker(const Cfg &c, const IO &io, double *smem, int *queu
             }
         }
         PT(2)
-        w_block_sync();
+        if (top_barrier) w_block_sync();
+        else {
+            nlive = w_block_warps_with(have);
+            if (!nlive) { if (fetch_all) break; fetch_all = true; continue; }   // (uniform over the block)
+            fetch_all = false;
+        }
         PT(3)
         // ---- phase 1b: the serial recursions of all the block's instances, one lane each ----
         bool fresh = false;  // an instance taken in this window joins the next trip
