@@ -924,12 +924,17 @@ KMPC_HD double alpha_min_of(const Ctx &t) {
     return amin * K_ALPHA_MIN_FRAC;
 }
 KMPC_HD bool armijo(const Ctx &t, double a, double tphi, double cphi) { return cmp_le(tphi - cphi, K_ETA_PHI * a * t.gBD, cphi); }
+// ftype: 0 / 1 = the switching condition at alpha_test as evaluated here (the caller needs it again for the filter augmentation of an
+// accepted point), -1 = not evaluated
 template <class F>
-KMPC_HD bool acceptable(const Ctx &t, const F &filt, const Stats &tri) {
+KMPC_HD bool acceptable(const Ctx &t, const F &filt, const Stats &tri, int *ftype) {
     const double cphi = phi_of(t.c, t.mu), tphi = phi_of(tri, t.mu), cth = t.c.theta;
     bool acc;
+    *ftype = -1;
     if (tri.theta > t.theta_max) return false;
-    if (is_ftype(t, t.alpha_test) && cth <= t.theta_min) acc = armijo(t, t.alpha_test, tphi, cphi);
+    const bool ft = is_ftype(t, t.alpha_test);
+    *ftype = ft ? 1 : 0;
+    if (ft && cth <= t.theta_min) acc = armijo(t, t.alpha_test, tphi, cphi);
     else {
         acc = true;
         if (tphi > cphi) {
@@ -951,8 +956,23 @@ KMPC_HD bool acceptable(const Ctx &t, const F &filt, const Stats &tri) {
 
 // Top of IPOPT's main loop at a (new) current iterate: termination tests, monotone barrier update.
 // Returns a status < 100 to finish the instance, 100 to continue with a Newton step.
+// opt_error(c, s, mu) with the parts that do not depend on mu (the scaled dual infeasibility, the scale of the complementarity) taken
+// from the caller: begin_iteration evaluates the error for mu = 0 and then for one or more barrier parameters on the same point
+struct OptErrParts { double di, sc; };
+KMPC_HD OptErrParts opt_error_parts(const Cfg &c, const Stats &s) {
+    const double sd = kfmax(K_S_MAX, (s.sumy + s.sumz) * c.r_mnb) * (1.0 / K_S_MAX);
+    OptErrParts p;
+    p.sc = c.nb ? kfmax(K_S_MAX, s.sumz * c.r_nb) * (1.0 / K_S_MAX) : 1.0;
+    p.di = sd > 1.0 ? s.dinf / sd : s.dinf;
+    return p;
+}
+KMPC_HD double opt_error_with(const Cfg &c, const Stats &s, double mu, const OptErrParts &p) {
+    const double ci = compl_inf(c, s, mu);
+    return kfmax(p.di, kfmax(s.pinf, p.sc > 1.0 ? ci / p.sc : ci));
+}
 KMPC_HD int begin_iteration(const Cfg &c, Ctx &t) {
-    const double E0 = opt_error(c, t.c, 0.0);
+    const OptErrParts ep = opt_error_parts(c, t.c);
+    const double E0 = opt_error_with(c, t.c, 0.0, ep);
     // (IPOPT checks every evaluated quantity for non-finite numbers; the max-norms carry a NaN / inf through, the scaled max may lose it)
     if (!isfinite(E0) || !isfinite(t.c.pinf) || !isfinite(t.c.dinf)) return ST_INVALID;
     if (E0 <= c.tol && t.c.dinf / t.df <= K_DUAL_INF_TOL && t.c.pinf <= K_CONSTR_VIOL_TOL &&
@@ -961,7 +981,7 @@ KMPC_HD int begin_iteration(const Cfg &c, Ctx &t) {
     if (t.iter >= c.max_iter) return ST_MAXITER;
     if (t.c.wmax > K_DIVERGING) return ST_DIVERGING;
     bool done = false;
-    while (!done && opt_error(c, t.c, t.mu) <= K_KAPPA_EPS * t.mu) {
+    while (!done && opt_error_with(c, t.c, t.mu, ep) <= K_KAPPA_EPS * t.mu) {
         const double nm = kfmax(kfmin(K_MU_LIN * t.mu, t.mu * sqrt(t.mu)), kfmin(c.tol, K_COMPL_INF_TOL) / (K_KAPPA_EPS + 1.0));  // mu^1.5 (mu_superlinear_decrease_power)
         const bool changed = nm != t.mu;
         t.mu = nm; t.tau = kfmax(K_TAU_MIN, 1.0 - t.mu);
@@ -1051,7 +1071,8 @@ KMPC_HD int trial_decide(Ctx &t, const F &filt, const Stats &tri, bool evok, boo
     if (t.tu == TU_INIT) return R_ACCEPT;
     bool accept = false;
     int soc_rhs = 0;
-    if (evok) accept = acceptable(t, filt, tri);
+    int ftype = -1;
+    if (evok) accept = acceptable(t, filt, tri, &ftype);
     if (!accept && evok) {
         if (t.mode == M_SOC) {
             t.soc_count++; t.theta_trial = tri.theta;
@@ -1080,7 +1101,7 @@ KMPC_HD int trial_decide(Ctx &t, const F &filt, const Stats &tri, bool evok, boo
     }
     // accepted: filter augmentation (FilterLSAcceptor::UpdateForNextIteration)
     const double cphi = phi_of(t.c, t.mu), tphi = phi_of(tri, t.mu);
-    if (!is_ftype(t, t.alpha_test) || !armijo(t, t.alpha_test, tphi, cphi)) {
+    if (!(ftype < 0 ? is_ftype(t, t.alpha_test) : ftype != 0) || !armijo(t, t.alpha_test, tphi, cphi)) {
         *augment = true; *aug_theta = (1.0 - K_GAMMA_THETA) * t.c.theta; *aug_phi = cphi - K_GAMMA_PHI * t.c.theta;
     }
     t.iter++;
