@@ -756,7 +756,7 @@ static int solve_impl(kmpc_handle *h, int B, const SolveArgs &a, void *cuda_stre
     c.L = make_rows(cf->N, O, c.obs_sw);
     c.nb = (cf->N + 1) * (c.hasL[0] + c.hasU[0] + c.hasL[1] + c.hasU[1]) + cf->N * (c.hasL[2] + c.hasU[2] + c.hasL[3] + c.hasU[3]) + cf->N * O;
     c.m = 3 * (cf->N + 1) + cf->N * O;
-    c.r_mnb = 1.0 / (double)(c.m + c.nb); c.r_nb = c.nb ? 1.0 / (double)c.nb : 0.0;
+    c.r_mnb = 1.0 / (double)(c.m + c.nb); c.r_nb = c.nb ? 1.0 / (double)c.nb : 0.0; c.mu_floor = cfg_mu_floor(c.tol);
     IO io;
     memset(&io, 0, sizeof io);
     io.x_cur = a.x_cur; io.goal = a.goal; io.X0 = a.X0; io.U0 = a.U0; io.obs = a.obs; io.orad = O > 0 ? a.orad : NULL;

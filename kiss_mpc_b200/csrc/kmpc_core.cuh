@@ -125,6 +125,7 @@ struct Cfg {
     int hasL[4], hasU[4];  // x, y, v, omega
     int nb, m;             // number of bound sides incl. obstacle slacks; number of constraint rows
     double r_mnb, r_nb;    // 1 / (m + nb), 1 / nb (0 if nb == 0): the averaging factors of IPOPT's s_d, s_c
+    double mu_floor;       // min(tol, compl_inf_tol) / (barrier_tol_factor + 1): the smallest barrier parameter (mu_min of IPOPT's monotone update)
     double T, W[3], Wvn, Wvp, Ww;
     double lb[4], ub[4];   // relaxed bounds
     double tol, obs_radius, dL;
@@ -857,6 +858,7 @@ KMPC_HDN inline void pass_output(const Cfg &c, const Ctx &t, double *wsp, size_t
 }
 
 // ---- scalar logic -------------------------------------------------------------------------------
+KMPC_HD double cfg_mu_floor(double tol) { return kfmin(tol, K_COMPL_INF_TOL) / (K_KAPPA_EPS + 1.0); }   // (an IEEE division wherever it is evaluated)
 KMPC_HD double compl_inf(const Cfg &c, const Stats &s, double mu) {
     return c.nb ? kfmax(fabs(s.mx - mu), fabs(s.mn - mu)) : 0.0;
 }
@@ -982,7 +984,7 @@ KMPC_HD int begin_iteration(const Cfg &c, Ctx &t) {
     if (t.c.wmax > K_DIVERGING) return ST_DIVERGING;
     bool done = false;
     while (!done && opt_error_with(c, t.c, t.mu, ep) <= K_KAPPA_EPS * t.mu) {
-        const double nm = kfmax(kfmin(K_MU_LIN * t.mu, t.mu * sqrt(t.mu)), kfmin(c.tol, K_COMPL_INF_TOL) / (K_KAPPA_EPS + 1.0));  // mu^1.5 (mu_superlinear_decrease_power)
+        const double nm = kfmax(kfmin(K_MU_LIN * t.mu, t.mu * sqrt(t.mu)), c.mu_floor);  // mu^1.5 (mu_superlinear_decrease_power); the floor is formed once, on the host (cfg_mu_floor)
         const bool changed = nm != t.mu;
         t.mu = nm; t.tau = kfmax(K_TAU_MIN, 1.0 - t.mu);
         if (changed) t.fn = 0; else done = true;

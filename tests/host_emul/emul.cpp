@@ -62,7 +62,7 @@ static Cfg make_cfg(const kmpc_config *cf, int B, int O, int stagewise, double o
     c.L = make_rows(cf->N, O, c.obs_sw);
     c.nb = (cf->N + 1) * (c.hasL[0] + c.hasU[0] + c.hasL[1] + c.hasU[1]) + cf->N * (c.hasL[2] + c.hasU[2] + c.hasL[3] + c.hasU[3]) + cf->N * O;
     c.m = 3 * (cf->N + 1) + cf->N * O;
-    c.r_mnb = 1.0 / (double)(c.m + c.nb); c.r_nb = c.nb ? 1.0 / (double)c.nb : 0.0;
+    c.r_mnb = 1.0 / (double)(c.m + c.nb); c.r_nb = c.nb ? 1.0 / (double)c.nb : 0.0; c.mu_floor = cfg_mu_floor(c.tol);
     return c;
 }
 
