@@ -965,12 +965,14 @@ KMPC_HD OptErrParts opt_error_parts(const Cfg &c, const Stats &s) {
     const double sd = kfmax(K_S_MAX, (s.sumy + s.sumz) * c.r_mnb) * (1.0 / K_S_MAX);
     OptErrParts p;
     p.sc = c.nb ? kfmax(K_S_MAX, s.sumz * c.r_nb) * (1.0 / K_S_MAX) : 1.0;
-    p.di = sd > 1.0 ? s.dinf / sd : s.dinf;
+    p.di = s.dinf;
+    if (__builtin_expect(sd > 1.0, 0)) p.di = s.dinf / sd;   // (s_d is 1 unless the multipliers are huge: keep the division off the common path)
     return p;
 }
 KMPC_HD double opt_error_with(const Cfg &c, const Stats &s, double mu, const OptErrParts &p) {
-    const double ci = compl_inf(c, s, mu);
-    return kfmax(p.di, kfmax(s.pinf, p.sc > 1.0 ? ci / p.sc : ci));
+    double ci = compl_inf(c, s, mu);
+    if (__builtin_expect(p.sc > 1.0, 0)) ci = ci / p.sc;
+    return kfmax(p.di, kfmax(s.pinf, ci));
 }
 KMPC_HD int begin_iteration(const Cfg &c, Ctx &t) {
     const OptErrParts ep = opt_error_parts(c, t.c);
